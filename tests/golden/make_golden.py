@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference modules are imported from where they lie (``/root/reference/{GCN,GAT,QC}``); nothing is
+copied.  Two shims are needed to import them under this image and both are import-only:
+
+* ``torchdiffeq`` is absent -> ``sys.modules['torchdiffeq']`` is pointed at ``oracle/odeint.py`` (the
+  restated solver; parity for the solver itself is therefore *unpinned*, see oracle/odeint.py);
+* ``GCN/utils.py`` imports matplotlib and a removed scipy path at module level (utils.py:5-8) ->
+  empty stub modules satisfy the import; the loader body (utils.py:154-202) then runs unmodified.
+
+Outputs (all small, committed):
+  planetoid_<ds>.npz   reference loader output (adjacency COO, GAT edge list, labels, splits, features)
+  gcn_golden.npz       GraphConvolution / ODEfunc / ODEfunc2 / ODEBlock / whole-model outputs + grads
+  gat_golden.npz       GAT GraphConvolution + ODEfunc outputs + grads
+  qc_golden.npz        QC EdgeGraphConvolution / EdgeEncoderMLP / EdgeGCN_K_Sum outputs + grads
+"""
+from __future__ import annotations
+
+import functools
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+from oracle import odeint as restated  # noqa: E402
+from oracle import graph_ops  # noqa: E402
+
+STATS = {}
+
+
+def _install_shims():
+    td = types.ModuleType("torchdiffeq")
+    td.odeint = restated.odeint
+    td.odeint_adjoint = restated.odeint_adjoint
+    sys.modules["torchdiffeq"] = td
+    for name in ["matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.colors",
+                 "scipy.sparse.linalg.eigen", "scipy.sparse.linalg.eigen.arpack"]:
+        m = types.ModuleType(name)
+        sys.modules[name] = m
+    sys.modules["matplotlib.colors"].colorConverter = None
+    sys.modules["scipy.sparse.linalg.eigen.arpack"].eigsh = None
+
+
+def load_ref(subdir, names=("layers", "models", "utils")):
+    """Import the reference's bare-named modules from one experiment directory."""
+    for n in ("layers", "models", "utils", "mpnn", "set2set", "torch_scatter", "layer_models"):
+        sys.modules.pop(n, None)
+    sys.path.insert(0, os.path.join(REF, subdir))
+    try:
+        mods = types.SimpleNamespace(**{n: importlib.import_module(n) for n in names})
+    finally:
+        sys.path.pop(0)
+    for n in ("layers", "models", "utils", "mpnn", "set2set", "torch_scatter", "layer_models"):
+        sys.modules.pop(n, None)
+    return mods
+
+
+def rnd(seed, *shape, scale=1.0):
+    """Inputs come from numpy's legacy RandomState (stream frozen by numpy policy) so the fixtures only
+    need to hold the seed; tests regenerate the same float32 arrays with ``tests/_golden.py:rnd``."""
+    return torch.from_numpy((np.random.RandomState(seed).standard_normal(shape) * scale).astype(np.float32))
+
+
+def sd_np(module, prefix=""):
+    return {prefix + k: v.detach().numpy().copy() for k, v in module.state_dict().items()}
+
+
+def set_method(models_mod, method, options=None, stats=None):
+    """Route the reference ODEBlock's odeint call (models.py:192) to a given solver method."""
+    models_mod.odeint = functools.partial(restated.odeint_adjoint, method=method, options=options, stats=stats)
+
+
+def main():
+    _install_shims()
+    gcn = load_ref("GCN")
+    gat = load_ref("GAT")
+    cwd = os.getcwd()
+    os.chdir(REF)
+
+    # ------------------------------------------------------------------ planetoid loader output
+    import pickle as pkl
+    import scipy.sparse as sp
+    data = {}
+    for ds in ["cora", "citeseer", "pubmed"]:
+        out = {}
+        with open("data/ind.%s.graph" % ds, "rb") as f:
+            graph = pkl.load(f, encoding="latin1")
+        # reference pipeline, verbatim calls (GCN/utils.py:180,186,222-229)
+        import networkx as nx
+        adj_raw = nx.adjacency_matrix(nx.from_dict_of_lists(graph))
+        adj = gcn.utils.normalize(adj_raw + sp.eye(adj_raw.shape[0]))
+        adj_t = gcn.utils.sparse_mx_to_torch_sparse_tensor(adj)
+        idx, val = adj_t._indices().numpy(), adj_t._values().numpy()
+        out.update(n=np.int64(adj_raw.shape[0]), coo_row=idx[0].astype(np.int32), coo_col=idx[1].astype(np.int32),
+                   coo_val=val.astype(np.float32))
+        raw = adj_raw.tocoo()
+        out.update(raw_row=raw.row.astype(np.int32), raw_col=raw.col.astype(np.int32),
+                   raw_val=raw.data.astype(np.float32))
+        # oracle restatement of the same pipeline must agree bit for bit
+        n, r, c = graph_ops.adjacency_from_dict_of_lists(graph)
+        assert n == adj_raw.shape[0]
+        rr, cc, vv = graph_ops.add_self_loops(n, r, c, np.ones(len(r)))
+        vv = graph_ops.normalize_rows(n, rr, cc, vv)
+        rr, cc, vv = graph_ops.to_coo_f32(rr, cc, vv)
+        o1 = np.lexsort((idx[1], idx[0]))
+        assert np.array_equal(rr, idx[0][o1]) and np.array_equal(cc, idx[1][o1]), ds
+        assert np.array_equal(vv.view(np.uint32), val[o1].view(np.uint32)), ds
+        # GAT edge list (GAT/utils.py:187-196)
+        G = nx.from_dict_of_lists(graph)
+        edges = np.array(G.edges, dtype=np.int64).reshape(-1, 2)
+        out.update(gat_src=edges[:, 0].astype(np.int32), gat_tgt=edges[:, 1].astype(np.int32))
+        if ds != "pubmed":  # ind.pubmed.allx is missing from the reference checkout
+            a, feats, labels, itr, iva, ite = gcn.utils.load_data_new(ds)
+            assert torch.equal(a._indices(), adj_t._indices()) and torch.equal(a._values(), adj_t._values())
+            fs = sp.csr_matrix(feats.numpy())
+            out.update(feat_indptr=fs.indptr.astype(np.int32), feat_indices=fs.indices.astype(np.int32),
+                       feat_data=fs.data.astype(np.float32), nfeat=np.int64(feats.shape[1]),
+                       labels=labels.numpy().astype(np.int16), idx_train=itr.numpy().astype(np.int32),
+                       idx_val=iva.numpy().astype(np.int32), idx_test=ite.numpy().astype(np.int32))
+            data[ds] = (a, feats, labels, itr)
+        else:
+            data[ds] = (adj_t, None, None, None)
+        np.savez_compressed(os.path.join(HERE, "planetoid_%s.npz" % ds), **out)
+        print(ds, "N", out["n"], "nnz", len(val), "gatE", len(edges))
+    os.chdir(cwd)
+
+    adj, feats, labels, idx_train = data["cora"]
+    N = adj.shape[0]
+    G = {}
+    # a 512-node induced subgraph of Cora, normalised by the reference's own functions: keeps d=128 fixtures small
+    c = np.load(os.path.join(HERE, "planetoid_cora.npz"))
+    raw = sp.coo_matrix((c["raw_val"], (c["raw_row"], c["raw_col"])), shape=(N, N)).tocsr()[:512, :512]
+    adj_s = gcn.utils.sparse_mx_to_torch_sparse_tensor(gcn.utils.normalize(raw + sp.eye(512)))
+    G.update({"sub/row": adj_s._indices()[0].numpy().astype(np.int32), "sub/col": adj_s._indices()[1].numpy().astype(np.int32),
+              "sub/val": adj_s._values().numpy()})
+    NS = 512
+
+    # ------------------------------------------------------------------ GraphConvolution fwd + grads
+    # (inputs are regenerated in the tests from the recorded seeds: rnd(seed, shape))
+    torch.manual_seed(42)
+    layer = gcn.layers.GraphConvolution(32, 16)
+    x = rnd(1, N, 32).requires_grad_(True)
+    g = rnd(2, N, 16)
+    y = layer(x, adj)
+    y.backward(g)
+    G.update({"gc/out": y.detach().numpy(), "gc/grad_x": x.grad.numpy(),
+              "gc/grad_weight": layer.weight.grad.numpy(), "gc/grad_bias": layer.bias.grad.numpy(),
+              **sd_np(layer, "gc/p/")})
+
+    # ------------------------------------------------------------------ ODEfunc / ODEfunc2 fwd + VJP
+    for d, A_, n_ in ((16, adj, N), (128, adj_s, NS)):
+        torch.manual_seed(100 + d)
+        f = gcn.models.ODEfunc(d)
+        with torch.no_grad():  # non-trivial affine so gamma/beta grads are exercised
+            f.norm1.weight.uniform_(0.5, 1.5)
+            f.norm1.bias.uniform_(-0.5, 0.5)
+        f.set_adj(A_)
+        x = rnd(10 + d, n_, d).requires_grad_(True)
+        t = torch.tensor(0.37, requires_grad=True)
+        g = rnd(20 + d, n_, d)
+        y = f(t, x)
+        grads = torch.autograd.grad(y, (x, t) + tuple(f.parameters()), g)
+        k = "odefunc%d/" % d
+        G.update({k + "out": y.detach().numpy(), k + "grad_x": grads[0].numpy(), k + "grad_t": grads[1].numpy(),
+                  **sd_np(f, k + "p/")})
+        for (name, _), gr in zip(f.named_parameters(), grads[2:]):
+            G[k + "grad/" + name] = gr.numpy()
+
+    torch.manual_seed(7)
+    f2 = gcn.models.ODEfunc2(32, 0.0)
+    f2.set_adj(adj_s)
+    x = rnd(31, NS, 32).requires_grad_(True)
+    t = torch.tensor(0.61, requires_grad=True)
+    g = rnd(32, NS, 32)
+    y = f2(t, x)
+    grads = torch.autograd.grad(y, (x, t) + tuple(f2.parameters()), g)
+    G.update({"odefunc2/out": y.detach().numpy(), "odefunc2/grad_x": grads[0].numpy(),
+              "odefunc2/grad_t": grads[1].numpy(), **sd_np(f2, "odefunc2/p/")})
+    for (name, _), gr in zip(f2.named_parameters(), grads[2:]):
+        G["odefunc2/grad/" + name] = gr.numpy()
+
+    # ------------------------------------------------------------------ ODEBlock: fixed-step + dopri5, fwd + adjoint grads
+    cases = [(16, "cora", "rk4", None), (16, "cora", "dopri5", None),
+             (16, "sub", "rk4", {"step_size": 0.25}), (16, "sub", "euler", {"step_size": 0.5}),
+             (16, "sub", "midpoint", None), (128, "sub", "rk4", None), (128, "sub", "dopri5", None),
+             (64, "sub", "rk4", None), (64, "sub", "dopri5", None)]
+    for d, gname, method, opts in cases:
+        A_, n_ = (adj, N) if gname == "cora" else (adj_s, NS)
+        tag = method + ("" if not opts else "_h%g" % opts["step_size"])
+        torch.manual_seed(200 + d)
+        blk = gcn.models.ODEBlock(gcn.models.ODEfunc(d))
+        with torch.no_grad():
+            blk.odefunc.norm1.weight.uniform_(0.5, 1.5)
+            blk.odefunc.norm1.bias.uniform_(-0.5, 0.5)
+        x = rnd(40 + d, n_, d, scale=0.5).requires_grad_(True)
+        g = rnd(50 + d, n_, d, scale=1.0 / n_)
+        stats = {}
+        set_method(gcn.models, method, opts, stats)
+        blk.nfe = 0
+        y = blk(x, A_)
+        nfe_f = blk.nfe
+        blk.nfe = 0
+        y.backward(g)
+        nfe_b = blk.nfe
+        k = "odeblock%d_%s_%s/" % (d, gname, tag)
+        G.update({k + "out": y.detach().numpy(), k + "grad_x": x.grad.numpy(),
+                  k + "nfe_f": np.int64(nfe_f), k + "nfe_b": np.int64(nfe_b),
+                  k + "acc_f": np.int64(stats["forward"].get("accepted", 0)),
+                  k + "rej_f": np.int64(stats["forward"].get("rejected", 0)),
+                  k + "acc_b": np.int64(stats["backward"].get("accepted", 0)),
+                  k + "rej_b": np.int64(stats["backward"].get("rejected", 0)),
+                  **sd_np(blk, k + "p/")})
+        for name, p in blk.named_parameters():
+            G[k + "grad/" + name] = p.grad.numpy().copy()
+        print(k, "nfe", nfe_f, nfe_b, stats)
+
+    # ------------------------------------------------------------------ whole models on Cora (eval mode)
+    for name, cls, method in (("GCN3", gcn.models.GCN3, None), ("RGCN3", gcn.models.RGCN3, None),
+                              ("RGCN3norm", gcn.models.RGCN3norm, None),
+                              ("ODEGCN3_dopri5", gcn.models.ODEGCN3, "dopri5"),
+                              ("ODEGCN3_rk4", gcn.models.ODEGCN3, "rk4")):
+        torch.manual_seed(42)
+        if method:
+            set_method(gcn.models, method, None, None)
+        model = cls(nfeat=feats.shape[1], nhid=16, nclass=int(labels.max()) + 1, dropout=0.5)
+        model.eval()
+        if method:
+            model.nfe = 0
+        out = model(feats, adj)
+        nfe_f = model.nfe if method else 0
+        if method:
+            model.nfe = 0
+        loss = torch.nn.functional.nll_loss(out[idx_train], labels[idx_train])
+        loss.backward()
+        k = "model_%s/" % name
+        G.update({k + "out": out.detach().numpy(), k + "loss": np.float32(loss.item()),
+                  k + "nfe_f": np.int64(nfe_f), k + "nfe_b": np.int64(model.nfe if method else 0),
+                  **sd_np(model, k + "p/")})
+        for pn, p in model.named_parameters():
+            G[k + "grad/" + pn] = p.grad.numpy().copy()
+        print(k, "loss", loss.item(), "nfe", nfe_f, model.nfe if method else 0)
+    np.savez_compressed(os.path.join(HERE, "gcn_golden.npz"), **G)
+
+    # ------------------------------------------------------------------ GAT (Cora edge list)
+    src = torch.from_numpy(c["gat_src"].astype(np.int64))
+    tgt = torch.from_numpy(c["gat_tgt"].astype(np.int64))
+    E = len(src)
+    Mtgt = torch.sparse_coo_tensor(torch.stack([tgt, torch.arange(E)]), torch.ones(E), (N, E))
+    A = {}
+    torch.manual_seed(11)
+    layer = gat.layers.GraphConvolution(16, 8)
+    x = rnd(61, N, 16).requires_grad_(True)
+    g = rnd(62, N, 8)
+    y = layer(x, src, tgt, Mtgt)
+    y.backward(g)
+    A.update({"gc/out": y.detach().numpy(), "gc/grad_x": x.grad.numpy(), **sd_np(layer, "gc/p/")})
+    for pn, p in layer.named_parameters():
+        A["gc/grad/" + pn] = p.grad.numpy().copy()
+    torch.manual_seed(12)
+    f = gat.models.ODEfunc(16)
+    f.set_adj(src, tgt, Mtgt)
+    x = rnd(63, N, 16).requires_grad_(True)
+    t = torch.tensor(0.25, requires_grad=True)
+    g = rnd(64, N, 16)
+    y = f(t, x)
+    grads = torch.autograd.grad(y, (x, t) + tuple(f.parameters()), g)
+    A.update({"odefunc/out": y.detach().numpy(), "odefunc/grad_x": grads[0].numpy(),
+              "odefunc/grad_t": grads[1].numpy(), **sd_np(f, "odefunc/p/")})
+    for (pn, _), gr in zip(f.named_parameters(), grads[2:]):
+        A["odefunc/grad/" + pn] = gr.numpy()
+    np.savez_compressed(os.path.join(HERE, "gat_golden.npz"), **A)
+
+    # ------------------------------------------------------------------ QC
+    qc = load_ref("QC", names=("layers",))
+    Q = {}
+    for nf, nN, nE in ((24, 60, 130), (73, 18, 16)):
+        torch.manual_seed(300 + nf)
+        layer = qc.layers.EdgeGraphConvolution(nf, nf)
+        x = rnd(70 + nf, nN, nf).requires_grad_(True)
+        rs = np.random.RandomState(80 + nf)
+        esrc = torch.from_numpy(rs.randint(0, nN, nE).astype(np.int64))
+        etgt = torch.from_numpy(rs.randint(0, nN, nE).astype(np.int64))
+        Etgt = torch.zeros(nN, nE)
+        Etgt[etgt, torch.arange(nE)] = 1.0
+        ed = rnd(90 + nf, nE, nf, nf, scale=1.0 / nf ** 0.5).requires_grad_(True)
+        g = rnd(95 + nf, nN, nf)
+        y = layer(x, esrc, Etgt, ed)
+        y.backward(g)
+        k = "egc%d/" % nf
+        Q.update({k + "esrc": esrc.numpy().astype(np.int32), k + "etgt": etgt.numpy().astype(np.int32),
+                  k + "out": y.detach().numpy(), k + "grad_x": x.grad.numpy(),
+                  k + "grad_edge_data": ed.grad.numpy(), k + "grad_weight": layer.weight.grad.numpy(),
+                  k + "grad_bias": layer.bias.grad.numpy(), **sd_np(layer, k + "p/")})
+    torch.manual_seed(5)
+    ee = qc.layers.EdgeEncoderMLP(5, 8)
+    e = rnd(99, 20, 5)
+    Q.update({"ee/out": ee(e).detach().numpy(), **sd_np(ee, "ee/p/")})
+    np.savez_compressed(os.path.join(HERE, "qc_golden.npz"), **Q)
+    for fn in sorted(os.listdir(HERE)):
+        if fn.endswith(".npz"):
+            print(fn, os.path.getsize(os.path.join(HERE, fn)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
