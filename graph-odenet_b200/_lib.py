@@ -1,0 +1,96 @@
+"""ctypes binding of libgode.so (the C ABI in include/gode.h).  No torch types cross this boundary:
+device pointers are passed as integers, sizes as int64, the stream as the raw cudaStream_t handle."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libgode.so")
+
+MAX_STAGES = 8
+HEAVY_ROW = 2048
+PREC_FP32, PREC_TF32 = 0, 1
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "libgode.so is missing (%s). Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "from the repository root; there is no CPU fallback." % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+
+vp, i64, i32, f32, sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
+
+
+class SpmmEpilogue(C.Structure):
+    _fields_ = [("bias", vp), ("relu", i32), ("residual", vp), ("y0", vp), ("kprev", vp * MAX_STAGES),
+                ("coef", f32 * MAX_STAGES), ("n_prev", i32), ("coef_self", f32), ("ynext", vp),
+                ("mask_src", vp), ("mask_scale", f32), ("gp_out", vp)]
+
+
+class GcnOdeFunc(C.Structure):
+    _fields_ = [("n_rows", i64), ("n_cols", i64), ("n_cols_t", i64), ("d", i32), ("groups", i32), ("gn_eps", f32),
+                ("precision", i32),
+                ("rowptr", vp), ("colidx", vp), ("vals", vp),
+                ("rowptr_t", vp), ("colidx_t", vp), ("vals_t", vp),
+                ("heavy", vp), ("n_heavy", i32), ("heavy_t", vp), ("n_heavy_t", i32),
+                ("W", vp), ("b", vp), ("gamma", vp), ("beta", vp)]
+
+
+_PROTOS = {
+    "gode_version": (C.c_int, []),
+    "gode_last_error": (C.c_char_p, []),
+    "gode_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "gode_launch_count": (C.c_ulonglong, []),
+    "gode_csr_from_coo_workspace_bytes": (sz, [i64, i64]),
+    "gode_csr_from_coo": (C.c_int, [i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "gode_csr_transpose_workspace_bytes": (sz, [i64, i64, i64]),
+    "gode_csr_transpose": (C.c_int, [i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "gode_csr_heavy_rows": (C.c_int, [i64, vp, vp, vp, vp]),
+    "gode_spmm_csr_f32": (C.c_int, [i64, vp, vp, vp, vp, i32, vp, i64, i32, vp, i64, C.POINTER(SpmmEpilogue), vp]),
+    "gode_gemm_f32": (C.c_int, [i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, f32, vp, i64, i32, i32, vp, sz, vp]),
+    "gode_groupnorm_fwd": (C.c_int, [i64, i32, i32, f32, vp, i64, vp, vp, vp, i64, vp]),
+    "gode_groupnorm_bwd": (C.c_int, [i64, i32, i32, f32, vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, sz, vp]),
+    "gode_colreduce_workspace_bytes": (sz, [i32]),
+    "gode_colsum_f32": (C.c_int, [i64, i32, vp, i64, vp, vp, sz, vp]),
+    "gode_rk_combine": (C.c_int, [i64, vp, C.POINTER(vp), C.POINTER(f32), i32, vp, vp]),
+    "gode_rk_error_sumsq": (C.c_int, [i64, vp, vp, C.POINTER(vp), C.POINTER(f32), i32, f32, f32, vp, vp, sz, vp]),
+    "gode_gcn_workspace_bytes": (sz, [C.POINTER(GcnOdeFunc)]),
+    "gode_gcn_transform": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, sz, vp]),
+    "gode_gcn_stage_fwd": (C.c_int, [C.POINTER(GcnOdeFunc), vp, vp, vp, C.POINTER(vp), C.POINTER(f32), i32, f32, vp,
+                                     f32, vp, vp, sz, vp]),
+    "gode_gcn_stage_vjp": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, f32, vp, vp, vp, vp, sz, vp]),
+    "gode_gcn_vjp_phase1": (C.c_int, [C.POINTER(GcnOdeFunc), vp, vp, f32, vp, vp, vp]),
+    "gode_gcn_vjp_phase2": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, vp, vp, sz, vp]),
+}
+
+EXPORTS = tuple(_PROTOS)
+
+for _name, (_res, _args) in _PROTOS.items():
+    _fn = getattr(lib, _name)  # AttributeError here = header / library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class GodeError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib.gode_last_error()
+        raise GodeError("%s failed (code %d): %s" % (what or "libgode call", rc, msg.decode() if msg else "?"))
+
+
+def ptr_array(ptrs):
+    arr = (vp * MAX_STAGES)()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr
+
+
+def f32_array(vals):
+    arr = (f32 * MAX_STAGES)()
+    for i, v in enumerate(vals):
+        arr[i] = v
+    return arr

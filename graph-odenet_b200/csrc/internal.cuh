@@ -1,0 +1,19 @@
+// Internal (non-ABI) entry points shared between the translation units of libgode.
+#pragma once
+#include "common.cuh"
+
+namespace gode {
+int spmm_dispatch(int64_t n_rows, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                  const int32_t* heavy_rows, int32_t n_heavy, const float* X, int64_t ldx, int32_t d, float* Y,
+                  int64_t ldy, const gode_spmm_epilogue_t& ep, cudaStream_t st);
+int gemm_simt(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B,
+              int64_t ldb, float beta, float* C, int64_t ldc, int splits, void* ws, size_t ws_bytes, cudaStream_t st,
+              const float* rowvec, float rowvec_scale);
+int colsum(int64_t n, int d, const float* x, int64_t ldx, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+int groupnorm_fwd(int64_t n, int d, int groups, float eps, const float* x, int64_t ldx, const float* gamma,
+                  const float* beta, float* y, int64_t ldy, cudaStream_t st);
+int groupnorm_bwd(int64_t n, int d, int groups, float eps, const float* x, int64_t ldx, const float* gamma,
+                  const float* dy, int64_t lddy, float* dx, int64_t lddx, float* dgamma, float* dbeta, void* ws,
+                  size_t ws_bytes, cudaStream_t st);
+int rk_combine(int64_t n, const float* y0, const float* const* k, const float* c, int nk, float* out, cudaStream_t st);
+}  // namespace gode

@@ -1,0 +1,228 @@
+// libgode: the GCN ODE function  f(t,y) = relu(A_hat ([t || GroupNorm(y)] W) + b)  and its VJP, composed
+// from the gather (spmm.cu), dense (gemm.cu / transform_tc.cu) and row-local (rowops.cu) kernels.
+//
+// Reference: ODEfunc.forward GCN/models.py:172-179; FixedGraphConvolution.forward GCN/layers.py:69-75;
+// the adjoint's torch.autograd.grad over (t, y, theta) restated in oracle/odeint.py:_Adjoint.
+//
+// The time column is never materialised: [t || z] W = t * W[0,:] + z * W[1:,:].
+#include "internal.cuh"
+#include <string.h>
+
+namespace gode {
+
+int transform_tc(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, cudaStream_t st);  // transform_tc.cu
+bool transform_tc_supported(const gode_gcn_odefunc_t* f);
+
+struct GcnWs {
+  float* bufA;
+  float* bufB;
+  float* bufC;
+  float* red;      // column-reduction workspace (width 2d)
+  size_t red_bytes;
+  float* splitk;
+  size_t splitk_bytes;
+  float* small;    // [d] scratch
+};
+
+static int64_t max_rows(const gode_gcn_odefunc_t* f) {
+  int64_t m = f->n_rows;
+  if (f->n_cols > m) m = f->n_cols;
+  if (f->n_cols_t > m) m = f->n_cols_t;
+  return m;
+}
+
+static int splits_for(int64_t k) {
+  int64_t s = k / 4096;
+  int64_t cap = 2LL * sm_count();
+  if (s > cap) s = cap;
+  if (s < 1) s = 1;
+  return static_cast<int>(s);
+}
+
+static size_t ws_bytes_for(const gode_gcn_odefunc_t* f) {
+  const size_t nd = align_up(sizeof(float) * static_cast<size_t>(max_rows(f)) * f->d, 256);
+  const size_t red = align_up(gode_colreduce_workspace_bytes(2 * f->d), 256);
+  const size_t sk = align_up(sizeof(float) * static_cast<size_t>(splits_for(f->n_rows)) * f->d * f->d, 256);
+  return 3 * nd + red + sk + 4096;
+}
+
+static int carve(const gode_gcn_odefunc_t* f, void* ws, size_t ws_bytes, GcnWs& w) {
+  if (!ws || ws_bytes < ws_bytes_for(f)) {
+    set_error("gcn: workspace too small (%zu < %zu)", ws_bytes, ws_bytes_for(f));
+    return GODE_EWORKSPACE;
+  }
+  Arena ar(ws, ws_bytes);
+  const size_t nd = static_cast<size_t>(max_rows(f)) * f->d;
+  w.bufA = ar.take<float>(nd);
+  w.bufB = ar.take<float>(nd);
+  w.bufC = ar.take<float>(nd);
+  w.red_bytes = gode_colreduce_workspace_bytes(2 * f->d);
+  w.red = reinterpret_cast<float*>(ar.take<char>(w.red_bytes));
+  w.splitk_bytes = sizeof(float) * static_cast<size_t>(splits_for(f->n_rows)) * f->d * f->d;
+  w.splitk = reinterpret_cast<float*>(ar.take<char>(w.splitk_bytes));
+  w.small = ar.take<float>(1024);
+  if (!w.small) {
+    set_error("gcn: workspace arena exhausted");
+    return GODE_EWORKSPACE;
+  }
+  return GODE_OK;
+}
+
+static int check(const gode_gcn_odefunc_t* f) {
+  GODE_REQUIRE(f != nullptr, "gcn: null descriptor");
+  GODE_REQUIRE(f->n_rows >= 0 && f->d > 0 && f->groups > 0 && f->d % f->groups == 0, "gcn: bad shape");
+  GODE_REQUIRE(f->W && f->gamma && f->beta && f->rowptr, "gcn: null parameter pointer");
+  return GODE_OK;
+}
+
+// gW[0,:] = t * cs ; gt = <cs, W[0,:]>      (cs = column sums of gS)
+__global__ void k_time_terms(int d, float t, const float* __restrict__ cs, const float* __restrict__ W0,
+                             float* __restrict__ gW0, float* __restrict__ gt) {
+  __shared__ float sm[32];
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float v = cs[c];
+    gW0[c] = t * v;
+    acc += v * W0[c];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) s += sm[i];
+    *gt = s;
+  }
+}
+
+static int transform_impl(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, GcnWs& w, cudaStream_t st) {
+  if (transform_tc_supported(f)) return transform_tc(f, y, t, S, st);
+  const int d = f->d;
+  int rc = groupnorm_fwd(f->n_rows, d, f->groups, f->gn_eps, y, d, f->gamma, f->beta, w.bufC, d, st);
+  if (rc) return rc;
+  return gemm_simt(0, 0, f->n_rows, d, d, 1.f, w.bufC, d, f->W + d, d, 0.f, S, d, 1, nullptr, 0, st, f->W, t);
+}
+
+}  // namespace gode
+
+using namespace gode;
+
+extern "C" size_t gode_gcn_workspace_bytes(const gode_gcn_odefunc_t* f) {
+  if (!f || f->d <= 0) return 0;
+  return ws_bytes_for(f);
+}
+
+extern "C" int gode_gcn_transform(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  int rc = check(f);
+  if (rc) return rc;
+  GODE_REQUIRE(f->n_rows == 0 || (y && S), "gcn_transform: null pointer");
+  GcnWs w;
+  rc = carve(f, ws, ws_bytes, w);
+  if (rc) return rc;
+  return transform_impl(f, y, t, S, w, as_stream(stream));
+}
+
+extern "C" int gode_gcn_stage_fwd(const gode_gcn_odefunc_t* f, const float* S, float* k_out, const float* y0,
+                                  const float* const* kprev_host, const float* coef_host, int32_t n_prev, float coef_self,
+                                  float* y_next, float t_next, float* S_next, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check(f);
+  if (rc) return rc;
+  GODE_REQUIRE(n_prev >= 0 && n_prev <= GODE_MAX_STAGES, "gcn_stage_fwd: n_prev out of range");
+  GODE_REQUIRE(!S_next || y_next, "gcn_stage_fwd: S_next needs y_next");
+  GODE_REQUIRE(!y_next || y0, "gcn_stage_fwd: y_next needs y0");
+  cudaStream_t st = as_stream(stream);
+  gode_spmm_epilogue_t ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.bias = f->b;
+  ep.relu = 1;
+  if (y_next) {
+    ep.y0 = y0;
+    ep.n_prev = n_prev;
+    for (int j = 0; j < n_prev; ++j) {
+      ep.kprev[j] = kprev_host[j];
+      ep.coef[j] = coef_host[j];
+    }
+    ep.coef_self = coef_self;
+    ep.ynext = y_next;
+  }
+  rc = spmm_dispatch(f->n_rows, f->rowptr, f->colidx, f->vals, f->heavy, f->n_heavy, S, f->d, f->d, k_out, f->d, ep, st);
+  if (rc) return rc;
+  if (S_next) {
+    GcnWs w;
+    rc = carve(f, ws, ws_bytes, w);
+    if (rc) return rc;
+    rc = transform_impl(f, y_next, t_next, S_next, w, st);
+  }
+  return rc;
+}
+
+extern "C" int gode_gcn_vjp_phase1(const gode_gcn_odefunc_t* f, const float* S, const float* a, float sign, float* k_y,
+                                   float* gP, void* stream) {
+  int rc = check(f);
+  if (rc) return rc;
+  GODE_REQUIRE(f->n_rows == 0 || (S && a && gP), "gcn_vjp_phase1: null pointer");
+  gode_spmm_epilogue_t ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.bias = f->b;
+  ep.relu = 1;
+  ep.mask_src = a;
+  ep.mask_scale = sign;
+  ep.gp_out = gP;
+  return spmm_dispatch(f->n_rows, f->rowptr, f->colidx, f->vals, f->heavy, f->n_heavy, S, f->d, f->d, k_y, f->d, ep,
+                       as_stream(stream));
+}
+
+extern "C" int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, float t, const float* gP, float* k_a,
+                                   float* gtheta, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check(f);
+  if (rc) return rc;
+  GODE_REQUIRE(f->rowptr_t && (f->n_rows == 0 || (y && gP && k_a)) && gtheta, "gcn_vjp_phase2: null pointer");
+  GcnWs w;
+  rc = carve(f, ws, ws_bytes, w);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  const int d = f->d;
+  const int64_t n = f->n_rows;
+  float* gW = gtheta;
+  float* gb = gtheta + static_cast<size_t>(d + 1) * d;
+  float* ggamma = gb + d;
+  float* gbeta = ggamma + d;
+  float* gt = gbeta + d;
+  float* gS = w.bufB;
+  float* z = w.bufC;
+  float* gz = w.bufA;
+  float* cs = w.small;
+  // gS = A_hat^T gP
+  gode_spmm_epilogue_t ep;
+  memset(&ep, 0, sizeof(ep));
+  rc = spmm_dispatch(n, f->rowptr_t, f->colidx_t, f->vals_t, f->heavy_t, f->n_heavy_t, gP, d, d, gS, d, ep, st);
+  if (rc) return rc;
+  // bias gradient and the two time-column terms
+  if ((rc = colsum(n, d, gP, d, gb, w.red, w.red_bytes, st))) return rc;
+  if ((rc = colsum(n, d, gS, d, cs, w.red, w.red_bytes, st))) return rc;
+  k_time_terms<<<1, 128, 0, st>>>(d, t, cs, f->W, gW, gt);
+  GODE_LAUNCH_CHECK();
+  // gW[1:,:] = z^T gS
+  if ((rc = groupnorm_fwd(n, d, f->groups, f->gn_eps, y, d, f->gamma, f->beta, z, d, st))) return rc;
+  if ((rc = gemm_simt(1, 0, d, d, n, 1.f, z, d, gS, d, 0.f, gW + d, d, splits_for(n), w.splitk, w.splitk_bytes, st, nullptr, 0.f)))
+    return rc;
+  // gz = gS W[1:,:]^T ; GroupNorm backward
+  if ((rc = gemm_simt(0, 1, n, d, d, 1.f, gS, d, f->W + d, d, 0.f, gz, d, 1, nullptr, 0, st, nullptr, 0.f))) return rc;
+  return groupnorm_bwd(n, d, f->groups, f->gn_eps, y, d, f->gamma, gz, d, k_a, d, ggamma, gbeta, w.red, w.red_bytes, st);
+}
+
+extern "C" int gode_gcn_stage_vjp(const gode_gcn_odefunc_t* f, const float* y, float t, const float* S, const float* a,
+                                  float sign, float* k_y, float* k_a, float* gtheta, void* ws, size_t ws_bytes,
+                                  void* stream) {
+  int rc = check(f);
+  if (rc) return rc;
+  GODE_REQUIRE(f->n_cols == f->n_rows && f->n_cols_t == f->n_rows,
+               "gcn_stage_vjp: partitioned graphs must call phase1 / exchange / phase2");
+  GcnWs w;
+  rc = carve(f, ws, ws_bytes, w);
+  if (rc) return rc;
+  if ((rc = gode_gcn_vjp_phase1(f, S, a, sign, k_y, w.bufA, stream))) return rc;
+  // phase2 reuses bufA for gz only after the bias column sum has consumed gP
+  return gode_gcn_vjp_phase2(f, y, t, w.bufA, k_a, gtheta, ws, ws_bytes, stream);
+}

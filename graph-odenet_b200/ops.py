@@ -1,0 +1,344 @@
+"""Tensor-level wrappers over the C ABI (libgode.so) + autograd Functions used by the layer modules.
+
+PyTorch is plumbing here: it owns device memory (caching allocator) and the current stream; every
+arithmetic step of the hot path is a libgode kernel.  Nothing in this file falls back to ATen math on
+the hot path -- tensors that are not CUDA fp32 raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+_NULL = None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _req(t, name, dtype=torch.float32):
+    if not (torch.is_tensor(t) and t.is_cuda and t.dtype == dtype):
+        raise TypeError("%s must be a CUDA %s tensor (got %s); graph-odenet_b200 has no CPU path" % (
+            name, dtype, (t.device, t.dtype) if torch.is_tensor(t) else type(t)))
+    return t
+
+
+def _rowmajor(t, name):
+    _req(t, name)
+    if t.dim() != 2 or t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device, tag="ws"):
+    """Grow-only per-(device, tag) scratch buffer from the caching allocator."""
+    key = (device.index, tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+# --------------------------------------------------------------------------------------------------
+# graph plan
+# --------------------------------------------------------------------------------------------------
+
+
+class GraphPlan:
+    """Canonical CSR and CSR^T (int32) of an adjacency, built once on the device.
+
+    replaces the per-call COO handling inside ``torch.spmm`` (GCN/layers.py:33,71).  ``from_coo`` accepts
+    what the reference loader produces (GCN/utils.py:222-229): int64 indices [2, nnz], fp32 values,
+    uncoalesced, unsorted columns.
+    """
+
+    def __init__(self, n_rows, n_cols, rowptr, colidx, vals, build_transpose=True):
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
+        self.nnz = int(colidx.numel())
+        self.device = rowptr.device
+        self.heavy, self.n_heavy = self._heavy(rowptr, self.n_rows)
+        self.rowptr_t = self.colidx_t = self.vals_t = self.perm_t = None
+        self.heavy_t, self.n_heavy_t = None, 0
+        if build_transpose:
+            self._build_transpose()
+
+    @staticmethod
+    def _heavy(rowptr, n_rows):
+        if n_rows == 0:
+            return None, 0
+        out = torch.empty(n_rows, dtype=torch.int32, device=rowptr.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=rowptr.device)
+        check(lib.gode_csr_heavy_rows(n_rows, _p(rowptr), _p(out), _p(cnt), _stream()), "gode_csr_heavy_rows")
+        n = int(cnt.item())
+        return (out[:n].clone() if n else None), n
+
+    def _build_transpose(self):
+        dev = self.device
+        nnz = self.nnz
+        self.rowptr_t = torch.empty(self.n_cols + 1, dtype=torch.int32, device=dev)
+        self.colidx_t = torch.empty(nnz, dtype=torch.int32, device=dev)
+        self.vals_t = torch.empty(nnz, dtype=torch.float32, device=dev)
+        self.perm_t = torch.empty(nnz, dtype=torch.int32, device=dev)
+        nb = lib.gode_csr_transpose_workspace_bytes(nnz, self.n_rows, self.n_cols)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        check(lib.gode_csr_transpose(self.n_rows, self.n_cols, nnz, _p(self.rowptr), _p(self.colidx), _p(self.vals),
+                                     _p(self.rowptr_t), _p(self.colidx_t), _p(self.vals_t), _p(self.perm_t),
+                                     _p(ws), nb, _stream()), "gode_csr_transpose")
+        self.heavy_t, self.n_heavy_t = self._heavy(self.rowptr_t, self.n_cols)
+        del ws
+
+    @classmethod
+    def from_coo(cls, row, col, val, n_rows, n_cols, build_transpose=True):
+        dev = val.device
+        if not val.is_cuda:
+            raise TypeError("GraphPlan.from_coo needs CUDA tensors")
+        row = row.to(torch.int64).contiguous()
+        col = col.to(torch.int64).contiguous()
+        val = val.to(torch.float32).contiguous()
+        nnz = int(val.numel())
+        rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+        colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        vals = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+        nnz_out = torch.zeros(1, dtype=torch.int64, device=dev)
+        nb = lib.gode_csr_from_coo_workspace_bytes(nnz, n_rows)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        check(lib.gode_csr_from_coo(n_rows, n_cols, nnz, _p(row), _p(col), _p(val), _p(rowptr), _p(colidx), _p(vals),
+                                    _p(nnz_out), _p(ws), nb, _stream()), "gode_csr_from_coo")
+        n_u = int(nnz_out.item())
+        if n_u < 0:
+            raise IndexError("adjacency index out of range for shape (%d, %d)" % (n_rows, n_cols))
+        del ws
+        return cls(n_rows, n_cols, rowptr, colidx[:n_u].clone() if n_u < nnz else colidx[:n_u],
+                   vals[:n_u].clone() if n_u < nnz else vals[:n_u], build_transpose)
+
+    @classmethod
+    def from_sparse(cls, adj, build_transpose=True):
+        """``adj``: torch sparse COO (as the reference passes) or a dense matrix (GCN-dense-paper passes one)."""
+        if adj.layout == torch.sparse_coo:
+            idx, val = adj._indices(), adj._values()
+            return cls.from_coo(idx[0], idx[1], val, adj.shape[0], adj.shape[1], build_transpose)
+        if adj.layout == torch.strided and adj.dim() == 2:
+            idx = adj.nonzero(as_tuple=False).t()
+            return cls.from_coo(idx[0], idx[1], adj[idx[0], idx[1]], adj.shape[0], adj.shape[1], build_transpose)
+        raise TypeError("unsupported adjacency layout %s" % adj.layout)
+
+    def transposed(self):
+        """Plan of A^T sharing storage (used by the backward of the discrete layers)."""
+        t = object.__new__(GraphPlan)
+        t.n_rows, t.n_cols, t.nnz, t.device = self.n_cols, self.n_rows, self.nnz, self.device
+        t.rowptr, t.colidx, t.vals = self.rowptr_t, self.colidx_t, self.vals_t
+        t.heavy, t.n_heavy = self.heavy_t, self.n_heavy_t
+        t.rowptr_t, t.colidx_t, t.vals_t, t.perm_t = self.rowptr, self.colidx, self.vals, None
+        t.heavy_t, t.n_heavy_t = self.heavy, self.n_heavy
+        return t
+
+
+_plan_cache = {}
+
+
+def plan_for(adj):
+    """Plan cache keyed on the adjacency tensor's storage (the reference passes the same ``adj`` every epoch)."""
+    if isinstance(adj, GraphPlan):
+        return adj
+    if adj.layout == torch.sparse_coo:
+        key = (adj._indices().data_ptr(), adj._values().data_ptr(), tuple(adj.shape), adj._nnz(), adj.device.index)
+    else:
+        key = (adj.data_ptr(), 0, tuple(adj.shape), adj.numel(), adj.device.index)
+    hit = _plan_cache.get(key)
+    if hit is not None and hit[0]() is adj:
+        return hit[1]
+    if not adj.is_cuda:
+        raise TypeError("adjacency must live on a CUDA device (call adj.cuda() as GCN/train_res.py:57 does)")
+    plan = GraphPlan.from_sparse(adj)
+    try:
+        _plan_cache[key] = (weakref.ref(adj), plan)
+    except TypeError:
+        pass
+    if len(_plan_cache) > 64:
+        for k in [k for k, v in _plan_cache.items() if v[0]() is None]:
+            _plan_cache.pop(k, None)
+    return plan
+
+
+# --------------------------------------------------------------------------------------------------
+# raw kernels
+# --------------------------------------------------------------------------------------------------
+
+
+def spmm(plan, x, bias=None, relu=False, residual=None, out=None, transpose=False):
+    """out = relu?(A x + bias) + residual  via gode_spmm_csr_f32."""
+    x = _rowmajor(x, "x")
+    if transpose:
+        rowptr, colidx, vals, heavy, n_heavy, n_rows, n_in = (plan.rowptr_t, plan.colidx_t, plan.vals_t, plan.heavy_t,
+                                                              plan.n_heavy_t, plan.n_cols, plan.n_rows)
+    else:
+        rowptr, colidx, vals, heavy, n_heavy, n_rows, n_in = (plan.rowptr, plan.colidx, plan.vals, plan.heavy,
+                                                              plan.n_heavy, plan.n_rows, plan.n_cols)
+    if x.shape[0] != n_in:
+        raise ValueError("spmm: operand has %d rows, adjacency expects %d" % (x.shape[0], n_in))
+    d = x.shape[1]
+    if out is None:
+        out = torch.empty(n_rows, d, dtype=torch.float32, device=x.device)
+    ep = _lib.SpmmEpilogue()
+    ep.bias = _p(_req(bias, "bias").contiguous()) if bias is not None else None
+    ep.relu = 1 if relu else 0
+    if residual is not None:
+        residual = _rowmajor(residual, "residual")
+        if residual.stride(0) != out.stride(0):
+            residual = residual.contiguous()
+        ep.residual = _p(residual)
+    check(lib.gode_spmm_csr_f32(n_rows, _p(rowptr), _p(colidx), _p(vals), _p(heavy), n_heavy, _p(x), x.stride(0), d,
+                                _p(out), out.stride(0), C.byref(ep), _stream()), "gode_spmm_csr_f32")
+    return out
+
+
+def gemm(a, b, trans_a=False, trans_b=False, out=None, alpha=1.0, beta=0.0, splits=1):
+    """out = alpha * op(a) @ op(b) + beta * out  via gode_gemm_f32."""
+    a = _rowmajor(a, "a")
+    b = _rowmajor(b, "b")
+    M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    K2, N = (b.shape[1], b.shape[0]) if trans_b else b.shape
+    if K != K2:
+        raise ValueError("gemm: inner dimensions differ (%d vs %d)" % (K, K2))
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+        beta = 0.0
+    ws, nb = None, 0
+    if splits > 1:
+        nb = 4 * splits * M * N
+        ws = workspace(nb, a.device, "gemm")
+    check(lib.gode_gemm_f32(int(trans_a), int(trans_b), M, N, K, alpha, _p(a), a.stride(0), _p(b), b.stride(0), beta,
+                            _p(out), out.stride(0), _lib.PREC_FP32, splits, _p(ws), nb, _stream()), "gode_gemm_f32")
+    return out
+
+
+def _splits_for(k, m, n):
+    if k < 8192 or m * n > 512 * 512:
+        return 1
+    return int(min(k // 4096, 256))
+
+
+def colsum(x):
+    x = _rowmajor(x, "x")
+    out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    nb = lib.gode_colreduce_workspace_bytes(x.shape[1])
+    ws = workspace(nb, x.device, "colreduce")
+    check(lib.gode_colsum_f32(x.shape[0], x.shape[1], _p(x), x.stride(0), _p(out), _p(ws), nb, _stream()), "gode_colsum_f32")
+    return out
+
+
+def groupnorm_fwd(x, groups, gamma, beta, eps):
+    x = _rowmajor(x, "x")
+    y = torch.empty_like(x, memory_format=torch.contiguous_format)
+    check(lib.gode_groupnorm_fwd(x.shape[0], x.shape[1], groups, eps, _p(x), x.stride(0), _p(gamma.contiguous()),
+                                 _p(beta.contiguous()), _p(y), y.stride(0), _stream()), "gode_groupnorm_fwd")
+    return y
+
+
+def groupnorm_bwd(x, groups, gamma, dy, eps):
+    x = _rowmajor(x, "x")
+    dy = _rowmajor(dy, "dy")
+    d = x.shape[1]
+    dx = torch.empty_like(x, memory_format=torch.contiguous_format)
+    dg = torch.empty(d, dtype=torch.float32, device=x.device)
+    db = torch.empty(d, dtype=torch.float32, device=x.device)
+    nb = lib.gode_colreduce_workspace_bytes(2 * d)
+    ws = workspace(nb, x.device, "colreduce")
+    check(lib.gode_groupnorm_bwd(x.shape[0], d, groups, eps, _p(x), x.stride(0), _p(gamma.contiguous()), _p(dy),
+                                 dy.stride(0), _p(dx), dx.stride(0), _p(dg), _p(db), _p(ws), nb, _stream()),
+          "gode_groupnorm_bwd")
+    return dx, dg, db
+
+
+def rk_combine(y0, ks, coefs, out=None):
+    """out = y0 + sum_j coefs[j] * ks[j]   (y0 may be None)."""
+    ref = ks[0] if y0 is None else y0
+    if out is None:
+        out = torch.empty_like(ref)
+    karr = (C.c_void_p * _lib.MAX_STAGES)(*[k.data_ptr() for k in ks])
+    carr = (C.c_float * _lib.MAX_STAGES)(*[float(c) for c in coefs])
+    check(lib.gode_rk_combine(ref.numel(), _p(y0), karr, carr, len(ks), _p(out), _stream()), "gode_rk_combine")
+    return out
+
+
+def rk_error_sumsq(y0, y1, ks, coefs, rtol, atol):
+    """Device scalar: sum_i (sum_j c_j k_j[i] / (atol + rtol*max(|y0_i|,|y1_i|)))^2."""
+    out = torch.empty(1, dtype=torch.float32, device=y0.device)
+    nb = lib.gode_colreduce_workspace_bytes(1)
+    ws = workspace(nb, y0.device, "colreduce")
+    karr = (C.c_void_p * _lib.MAX_STAGES)(*[k.data_ptr() for k in ks])
+    carr = (C.c_float * _lib.MAX_STAGES)(*[float(c) for c in coefs])
+    check(lib.gode_rk_error_sumsq(y0.numel(), _p(y0), _p(y1), karr, carr, len(ks), rtol, atol, _p(out), _p(ws), nb,
+                                  _stream()), "gode_rk_error_sumsq")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# autograd Functions for the discrete layers
+# --------------------------------------------------------------------------------------------------
+
+
+class GraphConvFn(torch.autograd.Function):
+    """``spmm(adj, mm(x, W)) + b`` (GCN/layers.py:31-37) and its backward, all on libgode kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, plan, relu):
+        x = _rowmajor(x, "input")
+        w = _rowmajor(weight, "weight")
+        support = gemm(x, w)
+        out = spmm(plan, support, bias=bias, relu=relu)
+        ctx.plan, ctx.relu, ctx.has_bias = plan, relu, bias is not None
+        ctx.save_for_backward(x, w, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, out = ctx.saved_tensors
+        g = _rowmajor(g, "grad")
+        if ctx.relu:
+            g = g * (out > 0).to(g.dtype)
+        gb = colsum(g) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        gs = spmm(ctx.plan, g, transpose=True)                       # A^T g
+        gx = gemm(gs, w, trans_b=True) if ctx.needs_input_grad[0] else None
+        gw = None
+        if ctx.needs_input_grad[1]:
+            gw = gemm(x, gs, trans_a=True, splits=_splits_for(x.shape[0], x.shape[1], gs.shape[1]))
+        return gx, gw, gb, None, None
+
+
+class GroupNormFn(torch.autograd.Function):
+    """nn.GroupNorm on [N, d] (GCN/models.py:88,129,143,165)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps):
+        ctx.groups, ctx.eps = groups, eps
+        ctx.save_for_backward(x, gamma)
+        return groupnorm_fwd(x, groups, gamma, beta, eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma = ctx.saved_tensors
+        dx, dg, db = groupnorm_bwd(x, ctx.groups, gamma, dy, ctx.eps)
+        return dx, dg, db, None, None
+
+
+def graph_conv(x, adj, weight, bias, relu=False):
+    return GraphConvFn.apply(x, weight, bias, plan_for(adj), relu)
+
+
+def group_norm(x, groups, gamma, beta, eps=1e-5):
+    return GroupNormFn.apply(x, gamma, beta, groups, eps)

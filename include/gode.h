@@ -1,0 +1,213 @@
+/*
+ * gode.h -- C ABI of libgode.so, the B200 (sm_100a) hot path of graph-odenet.
+ *
+ * The reference (phcavelar/graph-odenet) is pure Python: its "operator interface" for this path is the
+ * set of ATen calls its layers make.  Each entry point below names the reference call site it replaces
+ * (file:line under /root/reference).  The reference-side binding (a ctypes stub) is in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function is extern "C", takes plain pointers and sizes, returns 0 on success and a negative
+ *     GODE_E* code on failure; gode_last_error() returns a thread-local message for the last failure;
+ *   - all pointers are DEVICE pointers unless the name ends in _host; all matrices are row-major fp32
+ *     with an explicit leading dimension where one is given; indices are int32 (the plan builder takes
+ *     the reference's int64 COO and range-checks it);
+ *   - nothing here allocates caller-visible memory: workspaces are sized by *_workspace_bytes() and
+ *     owned by the caller (the PyTorch caching allocator in the shipped host code);
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*); none synchronises;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with GODE_ENODEV.
+ */
+#ifndef GODE_H_
+#define GODE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GODE_OK 0
+#define GODE_EINVAL (-1)   /* bad argument (shape, alignment, null pointer) */
+#define GODE_ECUDA (-2)    /* a CUDA runtime call failed; see gode_last_error() */
+#define GODE_ENODEV (-3)   /* no usable CUDA device */
+#define GODE_EWORKSPACE (-4) /* workspace too small */
+
+#define GODE_MAX_STAGES 8
+
+/* precision of the dense H*W products (GCN/layers.py:32,70 torch.mm) */
+#define GODE_PREC_FP32 0   /* fp32 result: SIMT FFMA, or 3xTF32 split on tcgen05 where the shape allows */
+#define GODE_PREC_TF32 1   /* single-pass TF32 on tcgen05 (flagged option) */
+
+int gode_version(void);
+const char* gode_last_error(void);
+/* sm_count / compute capability of the current device */
+int gode_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* number of CUDA kernels this library has launched in this process (monotonic) */
+unsigned long long gode_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph plan: canonical CSR from the reference's COO.
+ * replaces: the implicit COO->CSR conversion inside torch.spmm (GCN/layers.py:33,71) fed by
+ *           sparse_mx_to_torch_sparse_tensor (GCN/utils.py:222-229).
+ * Entries are ordered by (row, col), stable; entries with equal (row, col) are summed in fp32 in input
+ * order.  *nnz_out (device int64) receives the number of stored entries after merging.
+ * rowptr [n_rows+1], colidx/vals [nnz] must be provided at full nnz capacity.
+ * ---------------------------------------------------------------------------------------------- */
+size_t gode_csr_from_coo_workspace_bytes(int64_t nnz, int64_t n_rows);
+int gode_csr_from_coo(int64_t n_rows, int64_t n_cols, int64_t nnz,
+                      const int64_t* row, const int64_t* col, const float* val,
+                      int32_t* rowptr, int32_t* colidx, float* vals, int64_t* nnz_out,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* CSR of the transpose (entries ordered by (col,row)); perm_t[e'] = index of the source entry.
+ * Needed because the reference's row-normalised adjacency is not symmetric (GCN/utils.py:186,205-212):
+ * autograd's backward of torch.spmm multiplies by A^T. */
+size_t gode_csr_transpose_workspace_bytes(int64_t nnz, int64_t n_rows, int64_t n_cols);
+int gode_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz,
+                       const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                       int32_t* rowptr_t, int32_t* colidx_t, float* vals_t, int32_t* perm_t,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* rows with more than GODE_HEAVY_ROW stored entries, ascending; *n_heavy_out is a device int32.
+ * The SpMM processes these with one thread block each instead of one warp each. */
+#define GODE_HEAVY_ROW 2048
+int gode_csr_heavy_rows(int64_t n_rows, const int32_t* rowptr, int32_t* heavy_rows, int32_t* n_heavy_out,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CSR SpMM with a fused row epilogue.
+ * replaces: torch.spmm(adj, support) (+ bias, + F.relu, + residual) -- GCN/layers.py:33-35,71-73,
+ *           GCN/models.py:76-80,110-116,178.
+ *   acc   = sum_e vals[e] * X[colidx[e], :]
+ *   v     = acc + bias (if bias)          ; v = max(v,0) (if relu)
+ *   Y     = v + residual (if residual)    (Y may be NULL)
+ *   fused Runge-Kutta stage combination (torchdiffeq rk_common._runge_kutta_step, restated in
+ *   oracle/odeint.py):  Ynext = y0 + sum_j coef[j]*kprev[j] + coef_self*v     (if ynext)
+ *   fused adjoint preparation:   gP = mask_scale * mask_src * (v > 0)         (if gp_out)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* bias;       /* [d] or NULL */
+  int32_t relu;            /* 0/1 */
+  const float* residual;   /* [n_rows, ld] or NULL */
+  const float* y0;         /* RK base state or NULL */
+  const float* kprev[GODE_MAX_STAGES];
+  float coef[GODE_MAX_STAGES];
+  int32_t n_prev;
+  float coef_self;
+  float* ynext;            /* [n_rows, ld] or NULL */
+  const float* mask_src;   /* adjoint state a, or NULL */
+  float mask_scale;
+  float* gp_out;           /* [n_rows, ld] or NULL */
+} gode_spmm_epilogue_t;
+
+int gode_spmm_csr_f32(int64_t n_rows, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                      const int32_t* heavy_rows, int32_t n_heavy,
+                      const float* X, int64_t ldx, int32_t d, float* Y, int64_t ldy,
+                      const gode_spmm_epilogue_t* epi, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense GEMM  C = alpha * op(A) op(B) + beta * C      (row-major, fp32 in/out)
+ * replaces: torch.mm(input, weight) -- GCN/layers.py:32,70; its autograd transposes.
+ * splits > 1 partitions K (used for the tall weight-gradient products); ws must hold
+ * splits*M*N floats; the partial sums are reduced in a fixed order (deterministic).
+ * ---------------------------------------------------------------------------------------------- */
+int gode_gemm_f32(int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K, float alpha,
+                  const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
+                  float* C, int64_t ldc, int32_t precision, int32_t splits, void* ws, size_t ws_bytes,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-wise GroupNorm on [n, d] (groups of d/groups contiguous channels per row).
+ * replaces: nn.GroupNorm(min(32,d), d) -- GCN/models.py:165,175 (ATen formula
+ *           y = x*(gamma*rstd) + (beta - mean*gamma*rstd)).
+ * bwd: dx, and column reductions dgamma/dbeta written (not accumulated) to [d] each.
+ * ws for bwd: gode_colreduce_workspace_bytes(2*d).
+ * ---------------------------------------------------------------------------------------------- */
+int gode_groupnorm_fwd(int64_t n, int32_t d, int32_t groups, float eps, const float* x, int64_t ldx,
+                       const float* gamma, const float* beta, float* y, int64_t ldy, void* stream);
+int gode_groupnorm_bwd(int64_t n, int32_t d, int32_t groups, float eps, const float* x, int64_t ldx,
+                       const float* gamma, const float* dy, int64_t lddy, float* dx, int64_t lddx,
+                       float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+
+size_t gode_colreduce_workspace_bytes(int32_t width);
+/* out[c] = sum_r x[r, c]   (bias gradients; GCN/layers.py:35 autograd) */
+int gode_colsum_f32(int64_t n, int32_t d, const float* x, int64_t ldx, float* out,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Runge-Kutta helpers (torchdiffeq rk_common / dopri5, restated in oracle/odeint.py).
+ * combine : out = y0 + sum_j coef[j]*k[j]                 (y0 may be NULL -> plain linear combination)
+ * error   : sumsq_out[0] = sum_i ( (sum_j coef[j]*k[j][i]) / (atol + rtol*max(|y0_i|,|y1_i|)) )^2
+ *           (the caller divides by n: "mean-square error ratio", accept iff <= 1)
+ * ws for error: gode_colreduce_workspace_bytes(1).
+ * ---------------------------------------------------------------------------------------------- */
+int gode_rk_combine(int64_t n_elems, const float* y0, const float* const* k_host, const float* coef_host,
+                    int32_t n_k, float* out, void* stream);
+int gode_rk_error_sumsq(int64_t n_elems, const float* y0, const float* y1, const float* const* k_host,
+                        const float* coef_host, int32_t n_k, float rtol, float atol, float* sumsq_out,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GCN ODE function   f(t, y) = relu( A_hat * ([t || GroupNorm(y)] * W) + b )
+ * replaces: ODEfunc.forward (GCN/models.py:172-179) = GroupNorm + cat + FixedGraphConvolution.forward
+ *           (GCN/layers.py:69-75) + F.relu; and, for the adjoint, the torch.autograd.grad call
+ *           torchdiffeq makes on it (restated in oracle/odeint.py:_Adjoint).
+ *
+ * The function is evaluated in two halves so the Runge-Kutta stage combination can be fused between
+ * them ("support" S is the only [N,d] tensor that crosses a stage boundary):
+ *   transform : S = [t || GroupNorm(y)] * W                               (dense, row-local)
+ *   aggregate : k = relu(A_hat * S + b), y_next = y0 + sum c_j k_j, S_next = transform(y_next, t_next)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t n_rows;          /* rows owned (outputs) */
+  int64_t n_cols;          /* rows of the gather operand S (= n_rows, or owned + halo when partitioned) */
+  int64_t n_cols_t;        /* rows of the gather operand of A_hat^T (= n_rows, or owned + halo of the transpose) */
+  int32_t d;
+  int32_t groups;
+  float gn_eps;
+  int32_t precision;       /* GODE_PREC_* */
+  const int32_t* rowptr;   const int32_t* colidx;   const float* vals;     /* A_hat   */
+  const int32_t* rowptr_t; const int32_t* colidx_t; const float* vals_t;   /* A_hat^T */
+  const int32_t* heavy;    int32_t n_heavy;
+  const int32_t* heavy_t;  int32_t n_heavy_t;
+  const float* W;          /* [d+1, d]; row 0 multiplies the time column */
+  const float* b;          /* [d] or NULL */
+  const float* gamma;      /* [d] */
+  const float* beta;       /* [d] */
+} gode_gcn_odefunc_t;
+
+size_t gode_gcn_workspace_bytes(const gode_gcn_odefunc_t* f);
+
+/* S[n_rows, d] = [t || GN(y)] W */
+int gode_gcn_transform(const gode_gcn_odefunc_t* f, const float* y, float t, float* S,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* k_out = relu(A_hat S + b); optional y_next (RK combination, see gode_spmm_epilogue_t);
+ * optional S_next = transform(y_next, t_next) (needs y_next). */
+int gode_gcn_stage_fwd(const gode_gcn_odefunc_t* f, const float* S, float* k_out,
+                       const float* y0, const float* const* kprev_host, const float* coef_host, int32_t n_prev,
+                       float coef_self, float* y_next, float t_next, float* S_next,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* One evaluation of the augmented (adjoint) dynamics at (t, y, a) with upstream = sign * a:
+ *   k_y  = f(t, y)                                   [n_rows, d]
+ *   k_a  = sign * a^T df/dy                          [n_rows, d]
+ *   gtheta = sign * a^T df/d(theta, t), laid out as  [ W (d+1)*d | b d | gamma d | beta d | t 1 ]
+ * S must hold transform(y, t).  (torchdiffeq passes -a: sign = -1.) */
+int gode_gcn_stage_vjp(const gode_gcn_odefunc_t* f, const float* y, float t, const float* S,
+                       const float* a, float sign, float* k_y, float* k_a, float* gtheta,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* The same evaluation in two halves, for the row-partitioned (multi-GPU) path where the rows of gP that
+ * other ranks own must be exchanged between them:
+ *   phase1: k_y = relu(A_hat S + b);  gP[0:n_rows] = sign * a * (k_y > 0)
+ *   phase2: gS = A_hat^T gP (gP has n_cols_t rows);  k_a, gtheta as above (gtheta = this rank's partial sum) */
+int gode_gcn_vjp_phase1(const gode_gcn_odefunc_t* f, const float* S, const float* a, float sign,
+                        float* k_y, float* gP, void* stream);
+int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, float t, const float* gP,
+                        float* k_a, float* gtheta, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GODE_H_ */
