@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: GCN-ODE (one ODE block, RK4 3/8-rule, t in [0,1]) forward + adjoint backward
+on a synthetic power-law graph -- BASELINE.json's metric ("ODE func-evals/sec and edges/sec ... HBM GB/s").
+
+    python bench.py --gpus N --steps K --warmup W            # ours (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the reference arithmetic on the host CPU (oracle port)
+
+One JSON line on stdout (rank 0).  A *step* = ODEBlock forward + loss + adjoint backward + optimiser step on
+the ODE function's parameters = 9 function evaluations (4 forward, 1 + 4 in the adjoint).
+``value`` = nnz(A_hat) * func-evals / time  [edges/s], inputs resident in HBM; ``e2e`` = the same metric
+through the public module API with the step's input copied from pinned host memory and the loss read back.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "gcn_ode_rk4_fwd_bwd_edges_per_sec"
+UNIT = "edges/s"
+NFE_PER_STEP = 9  # rk4 on t=[0,1]: 4 forward + (1 + 4) adjoint evaluations of ODEfunc (GCN/models.py:173 counter)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--nodes", type=int, default=10_000_000)
+    ap.add_argument("--avg-degree", type=float, default=20.0)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--locality", type=float, default=0.9)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--method", default="rk4")
+    ap.add_argument("--cpu-sample-nodes", type=int, default=0, help="0 = size automatically (about 20 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "gcn-ode rk4 fwd+bwd, synthetic power-law graph N=%d avg_deg=%g d=%d locality=%g seed=%d" % (
+        a.nodes, a.avg_degree, a.dim, a.locality, a.seed)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference arithmetic on the host cores
+# --------------------------------------------------------------------------------------------------
+
+
+def cpu_reference_step(n, a, threads):
+    """Builds the sample problem and returns a closure running one fwd+bwd step with the reference arithmetic
+    (torch.spmm on the COO tensor + torch.mm + GroupNorm, restated solver) -- oracle/gcn_ref.py."""
+    import torch
+    from graph_odenet_b200 import synth
+    from oracle import gcn_ref
+    torch.set_num_threads(threads)
+    row, col, val = synth.powerlaw_graph(n, avg_degree=a.avg_degree, locality=a.locality, seed=a.seed, device="cpu")
+    nnz = int(val.numel())
+    adj = torch.sparse_coo_tensor(torch.stack([row, col]), val, (n, n))
+    d = a.dim
+    g = torch.Generator().manual_seed(a.seed)
+    bound = 1.0 / d ** 0.5
+    p = {"odefunc.norm1.weight": torch.ones(d), "odefunc.norm1.bias": torch.zeros(d),
+         "odefunc.gc1.weight": (torch.rand(d + 1, d, generator=g) * 2 - 1) * bound,
+         "odefunc.gc1.bias": (torch.rand(d, generator=g) * 2 - 1) * bound}
+    p = {k: v.requires_grad_(True) for k, v in p.items()}
+    x = torch.randn(n, d, generator=g)
+
+    def step():
+        for v in p.values():
+            v.grad = None
+        xx = x.clone().requires_grad_(True)
+        y, f = gcn_ref.ode_block(xx, adj, p, prefix="odefunc.", method=a.method)
+        loss = 0.5 * (y * y).mean()
+        loss.backward()
+        return f.nfe, float(loss)
+
+    return step, nnz
+
+
+def run_cpu_sample(a, steps, warmup, budget_s=20.0):
+    import torch
+    threads = os.cpu_count() or 1
+    n = a.cpu_sample_nodes
+    if n <= 0:
+        # calibrate on a small graph, then size the sample so that (steps + warmup) steps take about budget_s
+        step, nnz = cpu_reference_step(20_000, a, threads)
+        step()
+        t0 = time.perf_counter()
+        step()
+        per_edge = (time.perf_counter() - t0) / nnz
+        n = int(budget_s / max(steps + warmup, 1) / per_edge / a.avg_degree)
+        n = max(20_000, min(n, a.nodes, 2_000_000))
+    step, nnz = cpu_reference_step(n, a, threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    nfe = 0
+    for _ in range(steps):
+        k, _ = step()
+        nfe += k
+    dt = time.perf_counter() - t0
+    value = nnz * nfe / dt
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "same generator at N=%d nnz=%d d=%d, %d timed fwd+bwd steps (%.1f s), torch %s CPU, torch.spmm on COO as the reference"
+                      % (n, nnz, a.dim, steps, dt, torch.__version__),
+            "ms_per_step": dt / max(steps, 1) * 1e3, "func_evals_per_sec": nfe / dt}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = run_cpu_sample(a, max(a.steps, 1), max(a.warmup, 0), budget_s=60.0)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "note": "CPU run on a bounded sample of the workload; edges/s is size-normalised"},
+            "func_evals_per_sec": base["func_evals_per_sec"],
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# ours
+# --------------------------------------------------------------------------------------------------
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    import graph_odenet_b200  # noqa: F401  (fails loudly if libgode.so is missing)
+    from graph_odenet_b200 import _lib, ops, synth
+    from graph_odenet_b200.GCN import models
+
+    if world > 1:
+        from graph_odenet_b200 import parallel
+        return parallel.bench_partitioned(a, world, rank, dev, METRIC, UNIT, NFE_PER_STEP, workload_name(a),
+                                          ClockSampler, peaks)
+
+    n, d = a.nodes, a.dim
+    row, col, val = synth.powerlaw_graph(n, avg_degree=a.avg_degree, locality=a.locality, seed=a.seed, device=dev)
+    nnz = int(val.numel())
+    plan = ops.GraphPlan.from_coo(row, col, val, n, n)
+    del row, col, val
+    torch.cuda.empty_cache()
+    torch.manual_seed(a.seed)
+    blk = models.ODEBlock(models.ODEfunc(d), method=a.method).to(dev)
+    opt = torch.optim.Adam(blk.parameters(), lr=0.01, weight_decay=5e-4)   # GCN/train_res.py:126-127
+    gen = torch.Generator(device=dev).manual_seed(a.seed)
+    x_dev = torch.randn(n, d, device=dev, generator=gen)
+
+    def step(x):
+        opt.zero_grad(set_to_none=True)
+        xx = x.requires_grad_(True)
+        y = blk(xx, plan)
+        loss = 0.5 * (y * y).mean()
+        loss.backward()
+        opt.step()
+        return loss
+
+    blk.nfe = 0
+    for _ in range(max(a.warmup, 3)):
+        step(x_dev.detach())
+    torch.cuda.synchronize()
+    nfe_per_step = blk.nfe // max(a.warmup, 3)
+    assert nfe_per_step == NFE_PER_STEP or a.method != "rk4", nfe_per_step
+
+    # ---- timed region: device-resident inputs ---------------------------------------------------
+    lib = _lib.lib
+    lib.gode_profile_enable(1)
+    launches0 = lib.gode_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(a.steps):
+            loss = step(x_dev.detach())
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / a.steps
+    launches = int(lib.gode_launch_count() - launches0)
+    import ctypes as C
+    prof = {}
+    for name, kind in (("agg_fwd", 0), ("agg_t", 1), ("transform", 2), ("vjp_dense", 3), ("other", 4)):
+        cnt, tot, mx = C.c_int(), C.c_float(), C.c_float()
+        lib.gode_profile_read(kind, C.byref(cnt), C.byref(tot), C.byref(mx))
+        prof[name] = {"launches": cnt.value, "ms_total": tot.value, "ms_avg": tot.value / max(cnt.value, 1)}
+    lib.gode_profile_enable(0)
+    value = nnz * nfe_per_step / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel (the A_hat*S gather with fused epilogue) -----------------
+    peak, peak_src = peaks()
+    b_f = nnz * 8 + (n + 1) * 4 + 2 * n * d * 4          # CSR once + S once + k once
+    agg = prof["agg_fwd"]
+    achieved = b_f / (agg["ms_avg"] / 1e3) / 1e9 if agg["launches"] else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("agg_fwd_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_spmm_vec<32,1> (A_hat*S gather + bias + relu + RK combine)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": traffic, "algorithmic_bytes_per_launch": b_f, "ms_per_launch": agg["ms_avg"],
+                "launches_timed": agg["launches"], "peak_source": peak_src,
+                "step_share": agg["ms_total"] / (ms * a.steps), "kernel_classes_ms": prof}
+
+    # ---- e2e: public API, host buffers ------------------------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        x_host = torch.empty(n, d, dtype=torch.float32, pin_memory=True)
+        x_host.copy_(x_dev)
+        x_stage = torch.empty_like(x_dev)
+
+        def e2e_step():
+            x_stage.copy_(x_host, non_blocking=True)
+            return float(step(x_stage.detach()).item())
+
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e_ms = (time.perf_counter() - t0) / a.steps * 1e3
+        e2e = {"value": nnz * nfe_per_step / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * d * 4,
+               "d2h_bytes_per_step": 4, "ms_per_step": e_ms,
+               "note": "graph plan stays resident across steps as adj.cuda() does in GCN/train_res.py:57"}
+        del x_host, x_stage
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        cpu = run_cpu_sample(a, steps=1, warmup=0, budget_s=20.0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "nnz": nnz, "solver": a.method, "func_evals_per_step": nfe_per_step,
+                       "l2": "inputs larger than L2 (every [N,d] tensor is %.2f GB)" % (n * d * 4 / 1e9),
+                       "optimizer": "Adam on the ODE function's parameters (in the timed region)"},
+            "func_evals_per_sec": nfe_per_step / (ms / 1e3), "final_loss": float(loss.item()),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary()}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+    return run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

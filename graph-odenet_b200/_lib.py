@@ -9,8 +9,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libgode.so")
 
 MAX_STAGES = 8
-HEAVY_ROW = 2048
+HEAVY_ROW = 256
+HEAVY_CHUNK = 256
 PREC_FP32, PREC_TF32 = 0, 1
+PROF_AGG_FWD, PROF_AGG_T, PROF_TRANSFORM, PROF_VJP_DENSE, PROF_OTHER = range(5)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -28,12 +30,13 @@ class SpmmEpilogue(C.Structure):
                 ("mask_src", vp), ("mask_scale", f32), ("gp_out", vp)]
 
 
+class Csr(C.Structure):
+    _fields_ = [("n_rows", i64), ("n_cols", i64), ("rowptr", vp), ("colidx", vp), ("vals", vp),
+                ("heavy_rows", vp), ("heavy_chunk_ptr", vp), ("n_heavy", i32), ("n_chunks", i32)]
+
+
 class GcnOdeFunc(C.Structure):
-    _fields_ = [("n_rows", i64), ("n_cols", i64), ("n_cols_t", i64), ("d", i32), ("groups", i32), ("gn_eps", f32),
-                ("precision", i32),
-                ("rowptr", vp), ("colidx", vp), ("vals", vp),
-                ("rowptr_t", vp), ("colidx_t", vp), ("vals_t", vp),
-                ("heavy", vp), ("n_heavy", i32), ("heavy_t", vp), ("n_heavy_t", i32),
+    _fields_ = [("A", Csr), ("At", Csr), ("d", i32), ("groups", i32), ("gn_eps", f32), ("precision", i32),
                 ("W", vp), ("b", vp), ("gamma", vp), ("beta", vp)]
 
 
@@ -42,12 +45,15 @@ _PROTOS = {
     "gode_last_error": (C.c_char_p, []),
     "gode_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "gode_launch_count": (C.c_ulonglong, []),
+    "gode_profile_enable": (C.c_int, [C.c_int]),
+    "gode_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "gode_csr_from_coo_workspace_bytes": (sz, [i64, i64]),
     "gode_csr_from_coo": (C.c_int, [i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "gode_csr_transpose_workspace_bytes": (sz, [i64, i64, i64]),
     "gode_csr_transpose": (C.c_int, [i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
-    "gode_csr_heavy_rows": (C.c_int, [i64, vp, vp, vp, vp]),
-    "gode_spmm_csr_f32": (C.c_int, [i64, vp, vp, vp, vp, i32, vp, i64, i32, vp, i64, C.POINTER(SpmmEpilogue), vp]),
+    "gode_csr_heavy_rows": (C.c_int, [i64, vp, vp, vp, vp, vp]),
+    "gode_spmm_workspace_bytes": (sz, [C.POINTER(Csr), i32]),
+    "gode_spmm_csr_f32": (C.c_int, [C.POINTER(Csr), vp, i64, i32, vp, i64, C.POINTER(SpmmEpilogue), vp, sz, vp]),
     "gode_gemm_f32": (C.c_int, [i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, f32, vp, i64, i32, i32, vp, sz, vp]),
     "gode_groupnorm_fwd": (C.c_int, [i64, i32, i32, f32, vp, i64, vp, vp, vp, i64, vp]),
     "gode_groupnorm_bwd": (C.c_int, [i64, i32, i32, f32, vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, sz, vp]),
@@ -60,7 +66,8 @@ _PROTOS = {
     "gode_gcn_stage_fwd": (C.c_int, [C.POINTER(GcnOdeFunc), vp, vp, vp, C.POINTER(vp), C.POINTER(f32), i32, f32, vp,
                                      f32, vp, vp, sz, vp]),
     "gode_gcn_stage_vjp": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, f32, vp, vp, vp, vp, sz, vp]),
-    "gode_gcn_vjp_phase1": (C.c_int, [C.POINTER(GcnOdeFunc), vp, vp, f32, vp, vp, vp]),
+    "gode_gcn_vjp_phase1": (C.c_int, [C.POINTER(GcnOdeFunc), vp, vp, f32, vp, vp, vp, C.POINTER(vp), C.POINTER(f32), i32,
+                                      f32, vp, vp, sz, vp]),
     "gode_gcn_vjp_phase2": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, vp, vp, sz, vp]),
 }
 

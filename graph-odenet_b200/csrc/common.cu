@@ -1,6 +1,8 @@
 // libgode: error state, device info.
 #include "common.cuh"
 #include <string.h>
+#include <vector>
+#include <utility>
 
 namespace gode {
 static thread_local char g_err[512] = "";
@@ -11,6 +13,29 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+struct ProfPair { cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfPair> g_prof[GODE_PROF_KINDS];
+static size_t g_prof_used[GODE_PROF_KINDS] = {0};
+
+ProfScope::ProfScope(int kind_, cudaStream_t st_) : kind(kind_), st(st_), slot(nullptr) {
+  if (!g_prof_on || kind < 0 || kind >= GODE_PROF_KINDS) return;
+  std::vector<ProfPair>& v = g_prof[kind];
+  if (g_prof_used[kind] == v.size()) {
+    if (v.size() >= 65536) return;
+    ProfPair p;
+    if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
+    v.push_back(p);
+  }
+  ProfPair* p = &v[g_prof_used[kind]++];
+  slot = p;
+  cudaEventRecord(p->a, st);
+}
+
+ProfScope::~ProfScope() {
+  if (slot) cudaEventRecord(static_cast<ProfPair*>(slot)->b, st);
 }
 
 int sm_count() {
@@ -41,5 +66,30 @@ extern "C" int gode_device_info(int* sm, int* major, int* minor) {
   if (sm) *sm = p.multiProcessorCount;
   if (major) *major = p.major;
   if (minor) *minor = p.minor;
+  return GODE_OK;
+}
+
+extern "C" int gode_profile_enable(int on) {
+  gode::g_prof_on = on != 0;
+  for (int k = 0; k < GODE_PROF_KINDS; ++k) gode::g_prof_used[k] = 0;
+  return GODE_OK;
+}
+
+extern "C" int gode_profile_read(int kind, int* launches, float* total_ms, float* max_ms) {
+  GODE_REQUIRE(kind >= 0 && kind < GODE_PROF_KINDS, "profile_read: bad kind");
+  float tot = 0.f, mx = 0.f;
+  int n = 0;
+  for (size_t i = 0; i < gode::g_prof_used[kind]; ++i) {
+    gode::ProfPair& p = gode::g_prof[kind][i];
+    GODE_CHECK_CUDA(cudaEventSynchronize(p.b));
+    float ms = 0.f;
+    GODE_CHECK_CUDA(cudaEventElapsedTime(&ms, p.a, p.b));
+    tot += ms;
+    if (ms > mx) mx = ms;
+    ++n;
+  }
+  if (launches) *launches = n;
+  if (total_ms) *total_ms = tot;
+  if (max_ms) *max_ms = mx;
   return GODE_OK;
 }

@@ -41,6 +41,15 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 int sm_count();
 
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline leg).
+struct ProfScope {
+  int kind;
+  cudaStream_t st;
+  void* slot;
+  ProfScope(int kind, cudaStream_t st);
+  ~ProfScope();
+};
+
 // bump allocator over a caller-provided workspace
 struct Arena {
   char* base;

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) k_gemm(int64_t M, int64_t N, int64_t K, f
   __shared__ float sA[BK][BM + 4];
   __shared__ float sB[BK][BN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int64_t m0 = blockIdx.y * (int64_t)BM, n0 = blockIdx.x * (int64_t)BN;
+  const int64_t m0 = blockIdx.x * (int64_t)BM, n0 = blockIdx.y * (int64_t)BN;  // M tiles on x (2^31-1 limit)
   const int64_t kbeg = blockIdx.z * k_chunk;
   const int64_t kend = min(K, kbeg + k_chunk);
   float acc[TM][TN];
@@ -101,7 +101,7 @@ template <int BM, int BN>
 static int launch_gemm(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
                        const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int splits, int64_t k_chunk,
                        float* part, const float* rowvec, float rowvec_scale, cudaStream_t st) {
-  dim3 grid(static_cast<unsigned>((N + BN - 1) / BN), static_cast<unsigned>((M + BM - 1) / BM), splits);
+  dim3 grid(static_cast<unsigned>((M + BM - 1) / BM), static_cast<unsigned>((N + BN - 1) / BN), splits);
   if (!ta && !tb) k_gemm<BM, BN, false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, k_chunk, part, rowvec, rowvec_scale);
   else if (!ta && tb) k_gemm<BM, BN, false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, k_chunk, part, rowvec, rowvec_scale);
   else if (ta && !tb) k_gemm<BM, BN, true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, k_chunk, part, rowvec, rowvec_scale);

@@ -3,9 +3,9 @@
 #include "common.cuh"
 
 namespace gode {
-int spmm_dispatch(int64_t n_rows, const int32_t* rowptr, const int32_t* colidx, const float* vals,
-                  const int32_t* heavy_rows, int32_t n_heavy, const float* X, int64_t ldx, int32_t d, float* Y,
-                  int64_t ldy, const gode_spmm_epilogue_t& ep, cudaStream_t st);
+size_t spmm_ws_bytes(const gode_csr_t& A, int d);
+int spmm_dispatch(const gode_csr_t& A, const float* X, int64_t ldx, int32_t d, float* Y, int64_t ldy,
+                  const gode_spmm_epilogue_t& ep, void* ws, size_t ws_bytes, cudaStream_t st);
 int gemm_simt(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B,
               int64_t ldb, float beta, float* C, int64_t ldc, int splits, void* ws, size_t ws_bytes, cudaStream_t st,
               const float* rowvec, float rowvec_scale);

@@ -14,6 +14,8 @@ int transform_tc(const gode_gcn_odefunc_t* f, const float* y, float t, float* S,
 bool transform_tc_supported(const gode_gcn_odefunc_t* f);
 
 struct GcnWs {
+  float* heavy;    // heavy-row partial sums of the SpMMs
+  size_t heavy_bytes;
   float* bufA;
   float* bufB;
   float* bufC;
@@ -25,10 +27,16 @@ struct GcnWs {
 };
 
 static int64_t max_rows(const gode_gcn_odefunc_t* f) {
-  int64_t m = f->n_rows;
-  if (f->n_cols > m) m = f->n_cols;
-  if (f->n_cols_t > m) m = f->n_cols_t;
+  int64_t m = f->A.n_rows;
+  if (f->A.n_cols > m) m = f->A.n_cols;
+  if (f->At.rowptr && f->At.n_cols > m) m = f->At.n_cols;
   return m;
+}
+
+static size_t heavy_bytes_for(const gode_gcn_odefunc_t* f) {
+  size_t a = spmm_ws_bytes(f->A, f->d);
+  size_t b = f->At.rowptr ? spmm_ws_bytes(f->At, f->d) : 0;
+  return a > b ? a : b;
 }
 
 static int splits_for(int64_t k) {
@@ -42,8 +50,8 @@ static int splits_for(int64_t k) {
 static size_t ws_bytes_for(const gode_gcn_odefunc_t* f) {
   const size_t nd = align_up(sizeof(float) * static_cast<size_t>(max_rows(f)) * f->d, 256);
   const size_t red = align_up(gode_colreduce_workspace_bytes(2 * f->d), 256);
-  const size_t sk = align_up(sizeof(float) * static_cast<size_t>(splits_for(f->n_rows)) * f->d * f->d, 256);
-  return 3 * nd + red + sk + 4096;
+  const size_t sk = align_up(sizeof(float) * static_cast<size_t>(splits_for(f->A.n_rows)) * f->d * f->d, 256);
+  return 3 * nd + red + sk + heavy_bytes_for(f) + 8192;
 }
 
 static int carve(const gode_gcn_odefunc_t* f, void* ws, size_t ws_bytes, GcnWs& w) {
@@ -53,12 +61,14 @@ static int carve(const gode_gcn_odefunc_t* f, void* ws, size_t ws_bytes, GcnWs& 
   }
   Arena ar(ws, ws_bytes);
   const size_t nd = static_cast<size_t>(max_rows(f)) * f->d;
+  w.heavy_bytes = heavy_bytes_for(f);
+  w.heavy = w.heavy_bytes ? reinterpret_cast<float*>(ar.take<char>(w.heavy_bytes)) : nullptr;
   w.bufA = ar.take<float>(nd);
   w.bufB = ar.take<float>(nd);
   w.bufC = ar.take<float>(nd);
   w.red_bytes = gode_colreduce_workspace_bytes(2 * f->d);
   w.red = reinterpret_cast<float*>(ar.take<char>(w.red_bytes));
-  w.splitk_bytes = sizeof(float) * static_cast<size_t>(splits_for(f->n_rows)) * f->d * f->d;
+  w.splitk_bytes = sizeof(float) * static_cast<size_t>(splits_for(f->A.n_rows)) * f->d * f->d;
   w.splitk = reinterpret_cast<float*>(ar.take<char>(w.splitk_bytes));
   w.small = ar.take<float>(1024);
   if (!w.small) {
@@ -70,8 +80,8 @@ static int carve(const gode_gcn_odefunc_t* f, void* ws, size_t ws_bytes, GcnWs& 
 
 static int check(const gode_gcn_odefunc_t* f) {
   GODE_REQUIRE(f != nullptr, "gcn: null descriptor");
-  GODE_REQUIRE(f->n_rows >= 0 && f->d > 0 && f->groups > 0 && f->d % f->groups == 0, "gcn: bad shape");
-  GODE_REQUIRE(f->W && f->gamma && f->beta && f->rowptr, "gcn: null parameter pointer");
+  GODE_REQUIRE(f->A.n_rows >= 0 && f->d > 0 && f->groups > 0 && f->d % f->groups == 0, "gcn: bad shape");
+  GODE_REQUIRE(f->W && f->gamma && f->beta && f->A.rowptr, "gcn: null parameter pointer");
   return GODE_OK;
 }
 
@@ -96,11 +106,12 @@ __global__ void k_time_terms(int d, float t, const float* __restrict__ cs, const
 }
 
 static int transform_impl(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, GcnWs& w, cudaStream_t st) {
+  ProfScope prof(GODE_PROF_TRANSFORM, st);
   if (transform_tc_supported(f)) return transform_tc(f, y, t, S, st);
   const int d = f->d;
-  int rc = groupnorm_fwd(f->n_rows, d, f->groups, f->gn_eps, y, d, f->gamma, f->beta, w.bufC, d, st);
+  int rc = groupnorm_fwd(f->A.n_rows, d, f->groups, f->gn_eps, y, d, f->gamma, f->beta, w.bufC, d, st);
   if (rc) return rc;
-  return gemm_simt(0, 0, f->n_rows, d, d, 1.f, w.bufC, d, f->W + d, d, 0.f, S, d, 1, nullptr, 0, st, f->W, t);
+  return gemm_simt(0, 0, f->A.n_rows, d, d, 1.f, w.bufC, d, f->W + d, d, 0.f, S, d, 1, nullptr, 0, st, f->W, t);
 }
 
 }  // namespace gode
@@ -116,7 +127,7 @@ extern "C" int gode_gcn_transform(const gode_gcn_odefunc_t* f, const float* y, f
                                   size_t ws_bytes, void* stream) {
   int rc = check(f);
   if (rc) return rc;
-  GODE_REQUIRE(f->n_rows == 0 || (y && S), "gcn_transform: null pointer");
+  GODE_REQUIRE(f->A.n_rows == 0 || (y && S), "gcn_transform: null pointer");
   GcnWs w;
   rc = carve(f, ws, ws_bytes, w);
   if (rc) return rc;
@@ -132,6 +143,9 @@ extern "C" int gode_gcn_stage_fwd(const gode_gcn_odefunc_t* f, const float* S, f
   GODE_REQUIRE(!S_next || y_next, "gcn_stage_fwd: S_next needs y_next");
   GODE_REQUIRE(!y_next || y0, "gcn_stage_fwd: y_next needs y0");
   cudaStream_t st = as_stream(stream);
+  GcnWs w;
+  rc = carve(f, ws, ws_bytes, w);
+  if (rc) return rc;
   gode_spmm_epilogue_t ep;
   memset(&ep, 0, sizeof(ep));
   ep.bias = f->b;
@@ -146,22 +160,26 @@ extern "C" int gode_gcn_stage_fwd(const gode_gcn_odefunc_t* f, const float* S, f
     ep.coef_self = coef_self;
     ep.ynext = y_next;
   }
-  rc = spmm_dispatch(f->n_rows, f->rowptr, f->colidx, f->vals, f->heavy, f->n_heavy, S, f->d, f->d, k_out, f->d, ep, st);
-  if (rc) return rc;
-  if (S_next) {
-    GcnWs w;
-    rc = carve(f, ws, ws_bytes, w);
-    if (rc) return rc;
-    rc = transform_impl(f, y_next, t_next, S_next, w, st);
+  {
+    ProfScope prof(GODE_PROF_AGG_FWD, st);
+    rc = spmm_dispatch(f->A, S, f->d, f->d, k_out, f->d, ep, w.heavy, w.heavy_bytes, st);
   }
+  if (rc) return rc;
+  if (S_next) rc = transform_impl(f, y_next, t_next, S_next, w, st);
   return rc;
 }
 
 extern "C" int gode_gcn_vjp_phase1(const gode_gcn_odefunc_t* f, const float* S, const float* a, float sign, float* k_y,
-                                   float* gP, void* stream) {
+                                   float* gP, const float* y0, const float* const* kprev_host, const float* coef_host,
+                                   int32_t n_prev, float coef_self, float* y_next, void* ws, size_t ws_bytes,
+                                   void* stream) {
   int rc = check(f);
   if (rc) return rc;
-  GODE_REQUIRE(f->n_rows == 0 || (S && a && gP), "gcn_vjp_phase1: null pointer");
+  GODE_REQUIRE(f->A.n_rows == 0 || (S && a && gP), "gcn_vjp_phase1: null pointer");
+  GcnWs w;
+  rc = carve(f, ws, ws_bytes, w);
+  if (rc) return rc;
+  GODE_REQUIRE(n_prev >= 0 && n_prev <= GODE_MAX_STAGES && (!y_next || y0), "gcn_vjp_phase1: bad RK arguments");
   gode_spmm_epilogue_t ep;
   memset(&ep, 0, sizeof(ep));
   ep.bias = f->b;
@@ -169,21 +187,31 @@ extern "C" int gode_gcn_vjp_phase1(const gode_gcn_odefunc_t* f, const float* S, 
   ep.mask_src = a;
   ep.mask_scale = sign;
   ep.gp_out = gP;
-  return spmm_dispatch(f->n_rows, f->rowptr, f->colidx, f->vals, f->heavy, f->n_heavy, S, f->d, f->d, k_y, f->d, ep,
-                       as_stream(stream));
+  if (y_next) {
+    ep.y0 = y0;
+    ep.ynext = y_next;
+    ep.n_prev = n_prev;
+    ep.coef_self = coef_self;
+    for (int j = 0; j < n_prev; ++j) {
+      ep.kprev[j] = kprev_host[j];
+      ep.coef[j] = coef_host[j];
+    }
+  }
+  ProfScope prof(GODE_PROF_AGG_FWD, as_stream(stream));
+  return spmm_dispatch(f->A, S, f->d, f->d, k_y, f->d, ep, w.heavy, w.heavy_bytes, as_stream(stream));
 }
 
 extern "C" int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, float t, const float* gP, float* k_a,
                                    float* gtheta, void* ws, size_t ws_bytes, void* stream) {
   int rc = check(f);
   if (rc) return rc;
-  GODE_REQUIRE(f->rowptr_t && (f->n_rows == 0 || (y && gP && k_a)) && gtheta, "gcn_vjp_phase2: null pointer");
+  GODE_REQUIRE(f->At.rowptr && (f->A.n_rows == 0 || (y && gP && k_a)) && gtheta, "gcn_vjp_phase2: null pointer");
   GcnWs w;
   rc = carve(f, ws, ws_bytes, w);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   const int d = f->d;
-  const int64_t n = f->n_rows;
+  const int64_t n = f->A.n_rows;
   float* gW = gtheta;
   float* gb = gtheta + static_cast<size_t>(d + 1) * d;
   float* ggamma = gb + d;
@@ -196,8 +224,12 @@ extern "C" int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, 
   // gS = A_hat^T gP
   gode_spmm_epilogue_t ep;
   memset(&ep, 0, sizeof(ep));
-  rc = spmm_dispatch(n, f->rowptr_t, f->colidx_t, f->vals_t, f->heavy_t, f->n_heavy_t, gP, d, d, gS, d, ep, st);
+  {
+    ProfScope prof(GODE_PROF_AGG_T, st);
+    rc = spmm_dispatch(f->At, gP, d, d, gS, d, ep, w.heavy, w.heavy_bytes, st);
+  }
   if (rc) return rc;
+  ProfScope prof_dense(GODE_PROF_VJP_DENSE, st);
   // bias gradient and the two time-column terms
   if ((rc = colsum(n, d, gP, d, gb, w.red, w.red_bytes, st))) return rc;
   if ((rc = colsum(n, d, gS, d, cs, w.red, w.red_bytes, st))) return rc;
@@ -217,12 +249,13 @@ extern "C" int gode_gcn_stage_vjp(const gode_gcn_odefunc_t* f, const float* y, f
                                   void* stream) {
   int rc = check(f);
   if (rc) return rc;
-  GODE_REQUIRE(f->n_cols == f->n_rows && f->n_cols_t == f->n_rows,
+  GODE_REQUIRE(f->A.n_cols == f->A.n_rows && f->At.n_cols == f->A.n_rows,
                "gcn_stage_vjp: partitioned graphs must call phase1 / exchange / phase2");
   GcnWs w;
   rc = carve(f, ws, ws_bytes, w);
   if (rc) return rc;
-  if ((rc = gode_gcn_vjp_phase1(f, S, a, sign, k_y, w.bufA, stream))) return rc;
+  if ((rc = gode_gcn_vjp_phase1(f, S, a, sign, k_y, w.bufA, nullptr, nullptr, nullptr, 0, 0.f, nullptr, ws, ws_bytes, stream)))
+    return rc;
   // phase2 reuses bufA for gz only after the bias column sum has consumed gP
   return gode_gcn_vjp_phase2(f, y, t, w.bufA, k_a, gtheta, ws, ws_bytes, stream);
 }

@@ -233,17 +233,17 @@ extern "C" int gode_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, c
 }
 
 namespace gode {
+// single block, ordered compaction of the heavy rows + exclusive prefix of their chunk counts
+// (hubs are few; one-off plan work)
 __global__ void k_compact_heavy(int64_t n_rows, const int32_t* __restrict__ rowptr, int32_t* __restrict__ out,
-                                int32_t* __restrict__ count) {
-  // single block, ordered compaction (heavy rows are few; one-off plan work)
+                                int32_t* __restrict__ chunk_ptr, int32_t* __restrict__ counts) {
   __shared__ int32_t base;
+  __shared__ int32_t warp_tot[32];
   if (threadIdx.x == 0) base = 0;
   __syncthreads();
   for (int64_t start = 0; start < n_rows; start += blockDim.x) {
     int64_t r = start + threadIdx.x;
     int flag = (r < n_rows && rowptr[r + 1] - rowptr[r] > GODE_HEAVY_ROW) ? 1 : 0;
-    // block-wide exclusive scan via ballot per warp + shared warp totals
-    __shared__ int32_t warp_tot[32];
     unsigned m = __ballot_sync(0xffffffffu, flag);
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int pre = __popc(m & ((1u << lane) - 1));
@@ -260,14 +260,24 @@ __global__ void k_compact_heavy(int64_t n_rows, const int32_t* __restrict__ rowp
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *count = base;
+  if (threadIdx.x == 0) {
+    int32_t acc = 0;
+    for (int i = 0; i < base; ++i) {
+      chunk_ptr[i] = acc;
+      const int32_t len = rowptr[out[i] + 1] - rowptr[out[i]];
+      acc += (len + GODE_HEAVY_CHUNK - 1) / GODE_HEAVY_CHUNK;
+    }
+    chunk_ptr[base] = acc;
+    counts[0] = base;
+    counts[1] = acc;
+  }
 }
 }  // namespace gode
 
-extern "C" int gode_csr_heavy_rows(int64_t n_rows, const int32_t* rowptr, int32_t* heavy_rows, int32_t* n_heavy_out,
-                                   void* stream_) {
-  GODE_REQUIRE(rowptr && heavy_rows && n_heavy_out, "csr_heavy_rows: null pointer");
-  k_compact_heavy<<<1, 1024, 0, as_stream(stream_)>>>(n_rows, rowptr, heavy_rows, n_heavy_out);
+extern "C" int gode_csr_heavy_rows(int64_t n_rows, const int32_t* rowptr, int32_t* heavy_rows, int32_t* heavy_chunk_ptr,
+                                   int32_t* counts_out, void* stream_) {
+  GODE_REQUIRE(rowptr && heavy_rows && heavy_chunk_ptr && counts_out, "csr_heavy_rows: null pointer");
+  k_compact_heavy<<<1, 1024, 0, as_stream(stream_)>>>(n_rows, rowptr, heavy_rows, heavy_chunk_ptr, counts_out);
   GODE_LAUNCH_CHECK();
   return GODE_OK;
 }

@@ -7,19 +7,19 @@
 //   * one sub-warp of LPR lanes per row, each lane owns VPL float4 (128-bit) channel vectors, so a
 //     gathered neighbour row is read with fully coalesced 16-byte loads (d=128: one 512 B row per warp);
 //   * the row's (col,val) pairs are loaded LPR at a time, coalesced and with a streaming hint, and
-//     broadcast with shuffles; neighbour-row loads are issued four at a time before use to keep >= 4
+//     broadcast with shuffles; neighbour-row loads are issued UNR at a time before use to keep >= UNR
 //     128-bit requests per lane in flight;
 //   * CSR arrays, epilogue operands and outputs use ld/st.global.cs (evict-first) so that L2 keeps the
 //     gather operand X, the only tensor with reuse;
-//   * rows longer than GODE_HEAVY_ROW are skipped here and handled by k_spmm_heavy (one CTA per row).
+//   * rows longer than GODE_HEAVY_ROW (power-law hubs) are skipped by the main kernel; they are cut into
+//     chunks of GODE_HEAVY_CHUNK entries, each gathered by its own sub-warp (k_spmm_heavy_partial), and a
+//     finishing kernel adds a row's chunks in chunk order and applies the epilogue (deterministic).
 #include "internal.cuh"
 #include <string.h>
 
 namespace gode {
 
-struct RowCtx {
-  int64_t row;
-};
+constexpr int UNR = 8;  // neighbour rows in flight per lane
 
 template <int VPL>
 __device__ __forceinline__ void epilogue(const gode_spmm_epilogue_t& ep, int64_t row, int col0 /*first float of lane*/,
@@ -80,6 +80,60 @@ __device__ __forceinline__ void fma_row(float4 (&acc)[VPL], float v, const float
   }
 }
 
+// acc += sum_{e in [e0,e1)} vals[e] * X[colidx[e], lane's channels]; all 32 lanes of the warp call this together
+// (sub-warps own different ranges; `maxlen` is the longest range in the warp).
+template <int LPR, int VPL>
+__device__ __forceinline__ void gather_range(float4 (&acc)[VPL], int e0, int e1, int maxlen, int sub, int sl,
+                                             const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                             const float* __restrict__ xl, int64_t ldx) {
+  constexpr int U = UNR < LPR ? UNR : LPR;
+  for (int off = 0; off < maxlen; off += LPR) {
+    const int e = e0 + off + sl;
+    int c = 0;
+    float v = 0.f;
+    if (e < e1) {
+      c = __ldcs(colidx + e);
+      v = __ldcs(vals + e);
+    }
+    const int cnt = min(LPR, e1 - e0 - off);  // may be <= 0 for a finished range
+#pragma unroll
+    for (int j = 0; j < LPR; j += U) {
+      int cj[U];
+      float vj[U];
+#pragma unroll
+      for (int q = 0; q < U; ++q) {
+        cj[q] = __shfl_sync(0xffffffffu, c, sub * LPR + j + q);
+        vj[q] = __shfl_sync(0xffffffffu, v, sub * LPR + j + q);
+      }
+      if (j + U <= cnt) {
+        float4 x[U][VPL];
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+#pragma unroll
+          for (int u = 0; u < VPL; ++u) x[q][u] = ld_ro4(xl + (int64_t)cj[q] * ldx + u * 4);
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+#pragma unroll
+          for (int u = 0; u < VPL; ++u) {
+            acc[u].x += vj[q] * x[q][u].x; acc[u].y += vj[q] * x[q][u].y;
+            acc[u].z += vj[q] * x[q][u].z; acc[u].w += vj[q] * x[q][u].w;
+          }
+      } else if (j < cnt) {
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+          if (j + q < cnt) fma_row<VPL>(acc, vj[q], xl + (int64_t)cj[q] * ldx);
+      }
+    }
+  }
+}
+
+template <int LPR>
+__device__ __forceinline__ int warp_max_over_subs(int v) {
+#pragma unroll
+  for (int o = 16; o >= LPR; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
 template <int LPR, int VPL>
 __global__ void __launch_bounds__(256) k_spmm_vec(int64_t n_rows, const int32_t* __restrict__ rowptr,
                                                   const int32_t* __restrict__ colidx, const float* __restrict__ vals,
@@ -98,117 +152,77 @@ __global__ void __launch_bounds__(256) k_spmm_vec(int64_t n_rows, const int32_t*
   }
   const bool heavy = (e1 - e0) > GODE_HEAVY_ROW;
   if (heavy) e1 = e0;
-  int maxlen = e1 - e0;
-#pragma unroll
-  for (int o = 16; o >= LPR && o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+  const int maxlen = warp_max_over_subs<LPR>(e1 - e0);
   const int col0 = sl * VPL * 4;
-  const float* __restrict__ xl = X + col0;
-
   float4 acc[VPL];
 #pragma unroll
   for (int u = 0; u < VPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  for (int off = 0; off < maxlen; off += LPR) {
-    const int e = e0 + off + sl;
-    int c = 0;
-    float v = 0.f;
-    if (e < e1) {
-      c = __ldcs(colidx + e);
-      v = __ldcs(vals + e);
-    }
-    const int cnt = min(LPR, e1 - e0 - off);  // may be <= 0 for a finished row
-#pragma unroll
-    for (int j = 0; j < LPR; j += 4) {
-      int cj[4];
-      float vj[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int src = sub * LPR + ((j + q) % LPR);
-        cj[q] = __shfl_sync(0xffffffffu, c, src);
-        vj[q] = __shfl_sync(0xffffffffu, v, src);
-      }
-      if (j + 3 < cnt) {
-        float4 x[4][VPL];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int u = 0; u < VPL; ++u) x[q][u] = ld_ro4(xl + (int64_t)cj[q] * ldx + u * 4);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int u = 0; u < VPL; ++u) {
-            acc[u].x += vj[q] * x[q][u].x; acc[u].y += vj[q] * x[q][u].y;
-            acc[u].z += vj[q] * x[q][u].z; acc[u].w += vj[q] * x[q][u].w;
-          }
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (j + q < cnt && (LPR >= 4 || q < LPR)) fma_row<VPL>(acc, vj[q], xl + (int64_t)cj[q] * ldx);
-      }
-    }
-  }
+  gather_range<LPR, VPL>(acc, e0, e1, maxlen, sub, sl, colidx, vals, X + col0, ldx);
   if (valid && !heavy) epilogue<VPL>(ep, row, col0, acc, Y, ldy);
 }
 
-// one CTA per heavy row: NS = 8*RPW "slots" stride over the row's entries, partial sums meet in smem and are
-// added in slot order (deterministic)
+// one sub-warp per chunk of a heavy row -> partial[chunk][d]
 template <int LPR, int VPL>
-__global__ void __launch_bounds__(256) k_spmm_heavy(const int32_t* __restrict__ heavy_rows, const int32_t* __restrict__ rowptr,
-                                                    const int32_t* __restrict__ colidx, const float* __restrict__ vals,
-                                                    const float* __restrict__ X, int64_t ldx, float* __restrict__ Y,
-                                                    int64_t ldy, const gode_spmm_epilogue_t ep) {
+__global__ void __launch_bounds__(256) k_spmm_heavy_partial(int n_heavy, int n_chunks, const int32_t* __restrict__ heavy_rows,
+                                                            const int32_t* __restrict__ chunk_ptr,
+                                                            const int32_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                                            const float* __restrict__ X, int64_t ldx,
+                                                            float* __restrict__ partial) {
   constexpr int RPW = 32 / LPR;
-  constexpr int NS = 8 * RPW;
   constexpr int D = LPR * VPL * 4;
-  extern __shared__ float4 sm4[];  // [NS][D/4]
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, sl = lane % LPR;
-  const int slot = w * RPW + sub;
-  const int64_t row = heavy_rows[blockIdx.x];
-  const int e0 = rowptr[row], e1 = rowptr[row + 1];
+  const int chunk = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+  int e0 = 0, e1 = 0;
+  if (chunk < n_chunks) {
+    int lo = 0, hi = n_heavy - 1;  // last heavy row whose first chunk is <= chunk
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(chunk_ptr + mid) <= chunk) lo = mid; else hi = mid - 1;
+    }
+    const int row = __ldg(heavy_rows + lo);
+    const int r0 = __ldg(rowptr + row), r1 = __ldg(rowptr + row + 1);
+    e0 = r0 + (chunk - __ldg(chunk_ptr + lo)) * GODE_HEAVY_CHUNK;
+    e1 = min(r1, e0 + GODE_HEAVY_CHUNK);
+  }
+  const int maxlen = warp_max_over_subs<LPR>(e1 - e0);
   const int col0 = sl * VPL * 4;
-  const float* __restrict__ xl = X + col0;
   float4 acc[VPL];
 #pragma unroll
   for (int u = 0; u < VPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-  int e = e0 + slot;
-  for (; e + 3 * NS < e1; e += 4 * NS) {
-    int cj[4];
-    float vj[4];
-    float4 x[4][VPL];
+  gather_range<LPR, VPL>(acc, e0, e1, maxlen, sub, sl, colidx, vals, X + col0, ldx);
+  if (chunk < n_chunks) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      cj[q] = __ldcs(colidx + e + q * NS);
-      vj[q] = __ldcs(vals + e + q * NS);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int u = 0; u < VPL; ++u) x[q][u] = ld_ro4(xl + (int64_t)cj[q] * ldx + u * 4);
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int u = 0; u < VPL; ++u) {
-        acc[u].x += vj[q] * x[q][u].x; acc[u].y += vj[q] * x[q][u].y;
-        acc[u].z += vj[q] * x[q][u].z; acc[u].w += vj[q] * x[q][u].w;
-      }
+    for (int u = 0; u < VPL; ++u) *reinterpret_cast<float4*>(partial + (int64_t)chunk * D + col0 + u * 4) = acc[u];
   }
-  for (; e < e1; e += NS) fma_row<VPL>(acc, __ldcs(vals + e), xl + (int64_t)__ldcs(colidx + e) * ldx);
+}
+
+// one sub-warp per heavy row: add its chunks in order, then the row epilogue
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) k_spmm_heavy_finish(int n_heavy, const int32_t* __restrict__ heavy_rows,
+                                                           const int32_t* __restrict__ chunk_ptr,
+                                                           const float* __restrict__ partial, float* __restrict__ Y,
+                                                           int64_t ldy, const gode_spmm_epilogue_t ep) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int D = LPR * VPL * 4;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const int h = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+  if (h >= n_heavy) return;
+  const int c0 = chunk_ptr[h], c1 = chunk_ptr[h + 1];
+  const int col0 = sl * VPL * 4;
+  float4 acc[VPL];
 #pragma unroll
-  for (int u = 0; u < VPL; ++u) sm4[slot * (D / 4) + sl * VPL + u] = acc[u];
-  __syncthreads();
-  if (slot == 0) {
+  for (int u = 0; u < VPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = c0; c < c1; ++c) {
 #pragma unroll
     for (int u = 0; u < VPL; ++u) {
-      float4 t = sm4[sl * VPL + u];
-      for (int s = 1; s < NS; ++s) {
-        float4 o = sm4[s * (D / 4) + sl * VPL + u];
-        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
-      }
-      acc[u] = t;
+      const float4 p = *reinterpret_cast<const float4*>(partial + (int64_t)c * D + col0 + u * 4);
+      acc[u].x += p.x; acc[u].y += p.y; acc[u].z += p.z; acc[u].w += p.w;
     }
-    epilogue<VPL>(ep, row, col0, acc, Y, ldy);
   }
+  epilogue<VPL>(ep, heavy_rows[h], col0, acc, Y, ldy);
 }
 
 // any d (e.g. nclass = 7, QC hidden = 73): one warp per row, lanes stride over channels, scalar loads.
@@ -252,19 +266,22 @@ __global__ void __launch_bounds__(256) k_spmm_generic(int64_t n_rows, const int3
 }
 
 template <int LPR, int VPL>
-static int launch_vec(int64_t n_rows, const int32_t* rowptr, const int32_t* colidx, const float* vals,
-                      const int32_t* heavy_rows, int32_t n_heavy, const float* X, int64_t ldx, float* Y, int64_t ldy,
-                      const gode_spmm_epilogue_t& ep, cudaStream_t st) {
+static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                      const gode_spmm_epilogue_t& ep, float* ws, cudaStream_t st) {
   constexpr int RPW = 32 / LPR;
   constexpr int RPB = 8 * RPW;
-  if (n_heavy > 0) {
-    size_t smem = sizeof(float4) * RPB * LPR * VPL;
-    k_spmm_heavy<LPR, VPL><<<n_heavy, 256, smem, st>>>(heavy_rows, rowptr, colidx, vals, X, ldx, Y, ldy, ep);
+  if (A.n_rows > 0) {
+    unsigned grid = static_cast<unsigned>((A.n_rows + RPB - 1) / RPB);
+    k_spmm_vec<LPR, VPL><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, X, ldx, Y, ldy, ep);
     GODE_LAUNCH_CHECK();
   }
-  if (n_rows > 0) {
-    unsigned grid = static_cast<unsigned>((n_rows + RPB - 1) / RPB);
-    k_spmm_vec<LPR, VPL><<<grid, 256, 0, st>>>(n_rows, rowptr, colidx, vals, X, ldx, Y, ldy, ep);
+  if (A.n_heavy > 0) {
+    unsigned g1 = static_cast<unsigned>((A.n_chunks + RPB - 1) / RPB);
+    k_spmm_heavy_partial<LPR, VPL><<<g1, 256, 0, st>>>(A.n_heavy, A.n_chunks, A.heavy_rows, A.heavy_chunk_ptr, A.rowptr,
+                                                      A.colidx, A.vals, X, ldx, ws);
+    GODE_LAUNCH_CHECK();
+    unsigned g2 = static_cast<unsigned>((A.n_heavy + RPB - 1) / RPB);
+    k_spmm_heavy_finish<LPR, VPL><<<g2, 256, 0, st>>>(A.n_heavy, A.heavy_rows, A.heavy_chunk_ptr, ws, Y, ldy, ep);
     GODE_LAUNCH_CHECK();
   }
   return GODE_OK;
@@ -272,27 +289,38 @@ static int launch_vec(int64_t n_rows, const int32_t* rowptr, const int32_t* coli
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-int spmm_dispatch(int64_t n_rows, const int32_t* rowptr, const int32_t* colidx, const float* vals,
-                  const int32_t* heavy_rows, int32_t n_heavy, const float* X, int64_t ldx, int32_t d, float* Y,
-                  int64_t ldy, const gode_spmm_epilogue_t& ep, cudaStream_t st) {
-  bool vec_ok = (d % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y) && aligned16(ep.bias) &&
+static bool vec_width(int d) { return d == 8 || d == 16 || d == 32 || d == 64 || d == 128 || d == 256; }
+
+size_t spmm_ws_bytes(const gode_csr_t& A, int d) {
+  if (A.n_heavy <= 0 || !vec_width(d)) return 0;
+  return align_up(sizeof(float) * static_cast<size_t>(A.n_chunks) * d, 256);
+}
+
+int spmm_dispatch(const gode_csr_t& A, const float* X, int64_t ldx, int32_t d, float* Y, int64_t ldy,
+                  const gode_spmm_epilogue_t& ep, void* ws, size_t ws_bytes, cudaStream_t st) {
+  bool vec_ok = vec_width(d) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y) && aligned16(ep.bias) &&
                 aligned16(ep.residual) && aligned16(ep.y0) && aligned16(ep.ynext) && aligned16(ep.mask_src) &&
-                aligned16(ep.gp_out);
+                aligned16(ep.gp_out) && aligned16(ws);
   for (int j = 0; j < ep.n_prev; ++j) vec_ok = vec_ok && aligned16(ep.kprev[j]);
+  if (vec_ok && A.n_heavy > 0 && (!ws || ws_bytes < spmm_ws_bytes(A, d) || !A.heavy_rows || !A.heavy_chunk_ptr)) {
+    set_error("spmm: heavy-row workspace missing or too small (%zu < %zu)", ws_bytes, spmm_ws_bytes(A, d));
+    return GODE_EWORKSPACE;
+  }
   if (vec_ok) {
+    float* w = static_cast<float*>(ws);
     switch (d) {
-      case 8: return launch_vec<2, 1>(n_rows, rowptr, colidx, vals, heavy_rows, n_heavy, X, ldx, Y, ldy, ep, st);
-      case 16: return launch_vec<4, 1>(n_rows, rowptr, colidx, vals, heavy_rows, n_heavy, X, ldx, Y, ldy, ep, st);
-      case 32: return launch_vec<8, 1>(n_rows, rowptr, colidx, vals, heavy_rows, n_heavy, X, ldx, Y, ldy, ep, st);
-      case 64: return launch_vec<16, 1>(n_rows, rowptr, colidx, vals, heavy_rows, n_heavy, X, ldx, Y, ldy, ep, st);
-      case 128: return launch_vec<32, 1>(n_rows, rowptr, colidx, vals, heavy_rows, n_heavy, X, ldx, Y, ldy, ep, st);
-      case 256: return launch_vec<32, 2>(n_rows, rowptr, colidx, vals, heavy_rows, n_heavy, X, ldx, Y, ldy, ep, st);
+      case 8: return launch_vec<2, 1>(A, X, ldx, Y, ldy, ep, w, st);
+      case 16: return launch_vec<4, 1>(A, X, ldx, Y, ldy, ep, w, st);
+      case 32: return launch_vec<8, 1>(A, X, ldx, Y, ldy, ep, w, st);
+      case 64: return launch_vec<16, 1>(A, X, ldx, Y, ldy, ep, w, st);
+      case 128: return launch_vec<32, 1>(A, X, ldx, Y, ldy, ep, w, st);
+      case 256: return launch_vec<32, 2>(A, X, ldx, Y, ldy, ep, w, st);
       default: break;
     }
   }
-  if (n_rows > 0) {
-    unsigned grid = static_cast<unsigned>((n_rows + 7) / 8);
-    k_spmm_generic<<<grid, 256, 0, st>>>(n_rows, rowptr, colidx, vals, X, ldx, d, Y, ldy, ep);
+  if (A.n_rows > 0) {
+    unsigned grid = static_cast<unsigned>((A.n_rows + 7) / 8);
+    k_spmm_generic<<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, X, ldx, d, Y, ldy, ep);
     GODE_LAUNCH_CHECK();
   }
   return GODE_OK;
@@ -300,13 +328,16 @@ int spmm_dispatch(int64_t n_rows, const int32_t* rowptr, const int32_t* colidx, 
 
 }  // namespace gode
 
-extern "C" int gode_spmm_csr_f32(int64_t n_rows, const int32_t* rowptr, const int32_t* colidx, const float* vals,
-                                 const int32_t* heavy_rows, int32_t n_heavy, const float* X, int64_t ldx, int32_t d,
-                                 float* Y, int64_t ldy, const gode_spmm_epilogue_t* epi, void* stream) {
+extern "C" size_t gode_spmm_workspace_bytes(const gode_csr_t* A, int32_t d) {
+  if (!A) return 0;
+  return gode::spmm_ws_bytes(*A, d);
+}
+
+extern "C" int gode_spmm_csr_f32(const gode_csr_t* A, const float* X, int64_t ldx, int32_t d, float* Y, int64_t ldy,
+                                 const gode_spmm_epilogue_t* epi, void* ws, size_t ws_bytes, void* stream) {
   using namespace gode;
-  GODE_REQUIRE(n_rows >= 0 && d > 0 && ldx >= d && (Y == nullptr || ldy >= d), "spmm: bad shape");
-  GODE_REQUIRE(rowptr && X, "spmm: null pointer");
-  GODE_REQUIRE(n_heavy == 0 || heavy_rows != nullptr, "spmm: heavy row list missing");
+  GODE_REQUIRE(A && A->n_rows >= 0 && d > 0 && ldx >= d && (Y == nullptr || ldy >= d), "spmm: bad shape");
+  GODE_REQUIRE(A->rowptr && X, "spmm: null pointer");
   gode_spmm_epilogue_t ep;
   if (epi) {
     ep = *epi;
@@ -318,5 +349,6 @@ extern "C" int gode_spmm_csr_f32(int64_t n_rows, const int32_t* rowptr, const in
   GODE_REQUIRE(!ep.gp_out || ep.mask_src, "spmm: gp_out needs mask_src");
   GODE_REQUIRE(Y || ep.ynext || ep.gp_out, "spmm: no output requested");
   if (!Y && ldy < d) ldy = d;  // every epilogue operand shares the leading dimension ldy
-  return spmm_dispatch(n_rows, rowptr, colidx, vals, heavy_rows, n_heavy, X, ldx, d, Y, ldy, ep, as_stream(stream));
+  ProfScope prof(GODE_PROF_OTHER, as_stream(stream));
+  return spmm_dispatch(*A, X, ldx, d, Y, ldy, ep, ws, ws_bytes, as_stream(stream));
 }

@@ -132,15 +132,10 @@ class GcnKernel:
                                                          None if bias is None else bias.detach().contiguous(),
                                                          gamma.detach().contiguous(), beta.detach().contiguous())
         f = _lib.GcnOdeFunc()
-        f.n_rows, f.n_cols, f.n_cols_t = plan.n_rows, plan.n_cols, plan.n_rows
-        f.d, f.groups, f.gn_eps, f.precision = self.d, groups, eps, precision
-        f.rowptr, f.colidx, f.vals = plan.rowptr.data_ptr(), plan.colidx.data_ptr(), plan.vals.data_ptr()
+        f.A = plan.csr(False)
         if plan.rowptr_t is not None:
-            f.rowptr_t, f.colidx_t, f.vals_t = plan.rowptr_t.data_ptr(), plan.colidx_t.data_ptr(), plan.vals_t.data_ptr()
-        f.heavy = plan.heavy.data_ptr() if plan.n_heavy else None
-        f.n_heavy = plan.n_heavy
-        f.heavy_t = plan.heavy_t.data_ptr() if plan.n_heavy_t else None
-        f.n_heavy_t = plan.n_heavy_t
+            f.At = plan.csr(True)
+        f.d, f.groups, f.gn_eps, f.precision = self.d, groups, eps, precision
         f.W, f.gamma, f.beta = self.weight.data_ptr(), self.gamma.data_ptr(), self.beta.data_ptr()
         f.b = self.bias.data_ptr() if self.bias is not None else None
         self.f = f
@@ -171,21 +166,14 @@ class GcnKernel:
                                      self.ws_bytes, ops._stream()), "gode_gcn_stage_fwd")
 
     def vjp_phase1(self, S, a, sign, k_y, gP, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None):
-        """k_y = f(.), gP = sign*a*(k_y>0), fused y_next -- one SpMM launch (gode_spmm_csr_f32 epilogue)."""
+        """k_y = f(.), gP = sign*a*(k_y>0), fused y_next = y0 + sum coefs*kprev + coef_self*k_y -- one SpMM launch."""
         self.nfe += 1
-        p = self.plan
-        ep = _lib.SpmmEpilogue()
-        ep.bias = self.f.b
-        ep.relu = 1
-        ep.mask_src, ep.mask_scale, ep.gp_out = a.data_ptr(), float(sign), gP.data_ptr()
-        if y_next is not None:
-            ep.y0, ep.ynext, ep.n_prev, ep.coef_self = y0.data_ptr(), y_next.data_ptr(), len(kprev), float(coef_self)
-            for j, (k, c) in enumerate(zip(kprev, coefs)):
-                ep.kprev[j] = k.data_ptr()
-                ep.coef[j] = float(c)
-        check(lib.gode_spmm_csr_f32(p.n_rows, ops._p(p.rowptr), ops._p(p.colidx), ops._p(p.vals), ops._p(p.heavy),
-                                    p.n_heavy, ops._p(S), self.d, self.d, ops._p(k_y), self.d, C.byref(ep),
-                                    ops._stream()), "gode_spmm_csr_f32")
+        ws = self._ws()
+        karr = (C.c_void_p * _lib.MAX_STAGES)(*[k.data_ptr() for k in kprev])
+        carr = (C.c_float * _lib.MAX_STAGES)(*[float(c) for c in coefs])
+        check(lib.gode_gcn_vjp_phase1(C.byref(self.f), ops._p(S), ops._p(a), float(sign), ops._p(k_y), ops._p(gP),
+                                      ops._p(y0), karr, carr, len(kprev), float(coef_self), ops._p(y_next),
+                                      ops._p(ws), self.ws_bytes, ops._stream()), "gode_gcn_vjp_phase1")
 
     def vjp_phase2(self, y, t, gP, k_a, gtheta):
         ws = self._ws()

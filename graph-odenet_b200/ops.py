@@ -70,21 +70,40 @@ class GraphPlan:
         self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
         self.nnz = int(colidx.numel())
         self.device = rowptr.device
-        self.heavy, self.n_heavy = self._heavy(rowptr, self.n_rows)
+        self.heavy, self.chunk_ptr, self.n_heavy, self.n_chunks = self._heavy(rowptr, self.n_rows)
         self.rowptr_t = self.colidx_t = self.vals_t = self.perm_t = None
-        self.heavy_t, self.n_heavy_t = None, 0
+        self.heavy_t, self.chunk_ptr_t, self.n_heavy_t, self.n_chunks_t = None, None, 0, 0
         if build_transpose:
             self._build_transpose()
+        self._csr = self._csr_t = None
 
     @staticmethod
     def _heavy(rowptr, n_rows):
+        """Heavy (hub) rows and the chunk table the SpMM splits them by (gode_csr_heavy_rows)."""
         if n_rows == 0:
-            return None, 0
-        out = torch.empty(n_rows, dtype=torch.int32, device=rowptr.device)
-        cnt = torch.zeros(1, dtype=torch.int32, device=rowptr.device)
-        check(lib.gode_csr_heavy_rows(n_rows, _p(rowptr), _p(out), _p(cnt), _stream()), "gode_csr_heavy_rows")
-        n = int(cnt.item())
-        return (out[:n].clone() if n else None), n
+            return None, None, 0, 0
+        rows = torch.empty(n_rows, dtype=torch.int32, device=rowptr.device)
+        cptr = torch.empty(n_rows + 1, dtype=torch.int32, device=rowptr.device)
+        cnt = torch.zeros(2, dtype=torch.int32, device=rowptr.device)
+        check(lib.gode_csr_heavy_rows(n_rows, _p(rowptr), _p(rows), _p(cptr), _p(cnt), _stream()), "gode_csr_heavy_rows")
+        n, nc = [int(v) for v in cnt.tolist()]
+        if n == 0:
+            return None, None, 0, 0
+        return rows[:n].clone(), cptr[:n + 1].clone(), n, nc
+
+    def csr(self, transpose=False):
+        """The ``gode_csr_t`` view of A (or A^T) passed to the kernels."""
+        if transpose:
+            if self._csr_t is None:
+                if self.rowptr_t is None:
+                    raise RuntimeError("this plan was built without its transpose")
+                self._csr_t = _make_csr(self.n_cols, self.n_rows, self.rowptr_t, self.colidx_t, self.vals_t,
+                                        self.heavy_t, self.chunk_ptr_t, self.n_heavy_t, self.n_chunks_t)
+            return self._csr_t
+        if self._csr is None:
+            self._csr = _make_csr(self.n_rows, self.n_cols, self.rowptr, self.colidx, self.vals, self.heavy,
+                                  self.chunk_ptr, self.n_heavy, self.n_chunks)
+        return self._csr
 
     def _build_transpose(self):
         dev = self.device
@@ -98,7 +117,7 @@ class GraphPlan:
         check(lib.gode_csr_transpose(self.n_rows, self.n_cols, nnz, _p(self.rowptr), _p(self.colidx), _p(self.vals),
                                      _p(self.rowptr_t), _p(self.colidx_t), _p(self.vals_t), _p(self.perm_t),
                                      _p(ws), nb, _stream()), "gode_csr_transpose")
-        self.heavy_t, self.n_heavy_t = self._heavy(self.rowptr_t, self.n_cols)
+        self.heavy_t, self.chunk_ptr_t, self.n_heavy_t, self.n_chunks_t = self._heavy(self.rowptr_t, self.n_cols)
         del ws
 
     @classmethod
@@ -141,10 +160,21 @@ class GraphPlan:
         t = object.__new__(GraphPlan)
         t.n_rows, t.n_cols, t.nnz, t.device = self.n_cols, self.n_rows, self.nnz, self.device
         t.rowptr, t.colidx, t.vals = self.rowptr_t, self.colidx_t, self.vals_t
-        t.heavy, t.n_heavy = self.heavy_t, self.n_heavy_t
+        t.heavy, t.chunk_ptr, t.n_heavy, t.n_chunks = self.heavy_t, self.chunk_ptr_t, self.n_heavy_t, self.n_chunks_t
         t.rowptr_t, t.colidx_t, t.vals_t, t.perm_t = self.rowptr, self.colidx, self.vals, None
-        t.heavy_t, t.n_heavy_t = self.heavy, self.n_heavy
+        t.heavy_t, t.chunk_ptr_t, t.n_heavy_t, t.n_chunks_t = self.heavy, self.chunk_ptr, self.n_heavy, self.n_chunks
+        t._csr = t._csr_t = None
         return t
+
+
+def _make_csr(n_rows, n_cols, rowptr, colidx, vals, heavy, chunk_ptr, n_heavy, n_chunks):
+    c = _lib.Csr()
+    c.n_rows, c.n_cols = n_rows, n_cols
+    c.rowptr, c.colidx, c.vals = rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr()
+    c.heavy_rows = heavy.data_ptr() if n_heavy else None
+    c.heavy_chunk_ptr = chunk_ptr.data_ptr() if n_heavy else None
+    c.n_heavy, c.n_chunks = n_heavy, n_chunks
+    return c
 
 
 _plan_cache = {}
@@ -182,17 +212,12 @@ def plan_for(adj):
 def spmm(plan, x, bias=None, relu=False, residual=None, out=None, transpose=False):
     """out = relu?(A x + bias) + residual  via gode_spmm_csr_f32."""
     x = _rowmajor(x, "x")
-    if transpose:
-        rowptr, colidx, vals, heavy, n_heavy, n_rows, n_in = (plan.rowptr_t, plan.colidx_t, plan.vals_t, plan.heavy_t,
-                                                              plan.n_heavy_t, plan.n_cols, plan.n_rows)
-    else:
-        rowptr, colidx, vals, heavy, n_heavy, n_rows, n_in = (plan.rowptr, plan.colidx, plan.vals, plan.heavy,
-                                                              plan.n_heavy, plan.n_rows, plan.n_cols)
-    if x.shape[0] != n_in:
-        raise ValueError("spmm: operand has %d rows, adjacency expects %d" % (x.shape[0], n_in))
+    csr = plan.csr(transpose)
+    if x.shape[0] != csr.n_cols:
+        raise ValueError("spmm: operand has %d rows, adjacency expects %d" % (x.shape[0], csr.n_cols))
     d = x.shape[1]
     if out is None:
-        out = torch.empty(n_rows, d, dtype=torch.float32, device=x.device)
+        out = torch.empty(csr.n_rows, d, dtype=torch.float32, device=x.device)
     ep = _lib.SpmmEpilogue()
     ep.bias = _p(_req(bias, "bias").contiguous()) if bias is not None else None
     ep.relu = 1 if relu else 0
@@ -201,8 +226,10 @@ def spmm(plan, x, bias=None, relu=False, residual=None, out=None, transpose=Fals
         if residual.stride(0) != out.stride(0):
             residual = residual.contiguous()
         ep.residual = _p(residual)
-    check(lib.gode_spmm_csr_f32(n_rows, _p(rowptr), _p(colidx), _p(vals), _p(heavy), n_heavy, _p(x), x.stride(0), d,
-                                _p(out), out.stride(0), C.byref(ep), _stream()), "gode_spmm_csr_f32")
+    nb = lib.gode_spmm_workspace_bytes(C.byref(csr), d)
+    ws = workspace(nb, x.device, "spmm") if nb else None
+    check(lib.gode_spmm_csr_f32(C.byref(csr), _p(x), x.stride(0), d, _p(out), out.stride(0), C.byref(ep), _p(ws), nb,
+                                _stream()), "gode_spmm_csr_f32")
     return out
 
 

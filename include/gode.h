@@ -45,6 +45,18 @@ int gode_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* number of CUDA kernels this library has launched in this process (monotonic) */
 unsigned long long gode_launch_count(void);
 
+/* Optional CUDA-event timing of the library's kernel classes, recorded on the launching stream
+ * (used by bench.py for the roofline of the dominant kernel; off by default, ~2 us per scope when on).
+ * enable(on) clears the records.  read() synchronises on the recorded events. */
+#define GODE_PROF_AGG_FWD 0    /* A_hat * S gather with fused epilogue (the ODE function's SpMM)   */
+#define GODE_PROF_AGG_T 1      /* A_hat^T * gP gather of the VJP                                     */
+#define GODE_PROF_TRANSFORM 2  /* S = [t || GN(y)] W                                                 */
+#define GODE_PROF_VJP_DENSE 3  /* column sums, weight-gradient and input-gradient products, GN bwd   */
+#define GODE_PROF_OTHER 4      /* stand-alone gode_spmm / gode_gemm / rk helpers                     */
+#define GODE_PROF_KINDS 5
+int gode_profile_enable(int on);
+int gode_profile_read(int kind, int* launches, float* total_ms, float* max_ms);
+
 /* ------------------------------------------------------------------------------------------------
  * Graph plan: canonical CSR from the reference's COO.
  * replaces: the implicit COO->CSR conversion inside torch.spmm (GCN/layers.py:33,71) fed by
@@ -68,11 +80,29 @@ int gode_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz,
                        int32_t* rowptr_t, int32_t* colidx_t, float* vals_t, int32_t* perm_t,
                        void* ws, size_t ws_bytes, void* stream);
 
-/* rows with more than GODE_HEAVY_ROW stored entries, ascending; *n_heavy_out is a device int32.
- * The SpMM processes these with one thread block each instead of one warp each. */
-#define GODE_HEAVY_ROW 2048
-int gode_csr_heavy_rows(int64_t n_rows, const int32_t* rowptr, int32_t* heavy_rows, int32_t* n_heavy_out,
-                        void* stream);
+/* A CSR matrix as the kernels consume it.  Rows with more than GODE_HEAVY_ROW stored entries ("heavy" rows:
+ * the hubs of a power-law graph) are listed separately: the SpMM splits each of them into chunks of
+ * GODE_HEAVY_CHUNK entries that are gathered by independent warps and summed in chunk order, so one hub
+ * cannot serialise the kernel.  heavy_chunk_ptr[i] = first chunk of heavy row i (exclusive prefix sum of
+ * ceil(len/GODE_HEAVY_CHUNK)), heavy_chunk_ptr[n_heavy] = n_chunks. */
+#define GODE_HEAVY_ROW 256
+#define GODE_HEAVY_CHUNK 256
+typedef struct {
+  int64_t n_rows;
+  int64_t n_cols;
+  const int32_t* rowptr;            /* [n_rows + 1] */
+  const int32_t* colidx;            /* [nnz] */
+  const float* vals;                /* [nnz] */
+  const int32_t* heavy_rows;        /* [n_heavy] ascending, or NULL */
+  const int32_t* heavy_chunk_ptr;   /* [n_heavy + 1], or NULL */
+  int32_t n_heavy;
+  int32_t n_chunks;
+} gode_csr_t;
+
+/* heavy_rows (capacity n_rows) and heavy_chunk_ptr (capacity n_rows + 1) are filled on the device;
+ * counts_out is a device int32[2] = {n_heavy, n_chunks}. */
+int gode_csr_heavy_rows(int64_t n_rows, const int32_t* rowptr, int32_t* heavy_rows, int32_t* heavy_chunk_ptr,
+                        int32_t* counts_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * CSR SpMM with a fused row epilogue.
@@ -100,10 +130,10 @@ typedef struct {
   float* gp_out;           /* [n_rows, ld] or NULL */
 } gode_spmm_epilogue_t;
 
-int gode_spmm_csr_f32(int64_t n_rows, const int32_t* rowptr, const int32_t* colidx, const float* vals,
-                      const int32_t* heavy_rows, int32_t n_heavy,
-                      const float* X, int64_t ldx, int32_t d, float* Y, int64_t ldy,
-                      const gode_spmm_epilogue_t* epi, void* stream);
+/* ws: n_chunks * d floats of scratch for the heavy-row partial sums (0 bytes when n_heavy == 0) */
+size_t gode_spmm_workspace_bytes(const gode_csr_t* A, int32_t d);
+int gode_spmm_csr_f32(const gode_csr_t* A, const float* X, int64_t ldx, int32_t d, float* Y, int64_t ldy,
+                      const gode_spmm_epilogue_t* epi, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense GEMM  C = alpha * op(A) op(B) + beta * C      (row-major, fp32 in/out)
@@ -159,17 +189,14 @@ int gode_rk_error_sumsq(int64_t n_elems, const float* y0, const float* y1, const
  *   aggregate : k = relu(A_hat * S + b), y_next = y0 + sum c_j k_j, S_next = transform(y_next, t_next)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
-  int64_t n_rows;          /* rows owned (outputs) */
-  int64_t n_cols;          /* rows of the gather operand S (= n_rows, or owned + halo when partitioned) */
-  int64_t n_cols_t;        /* rows of the gather operand of A_hat^T (= n_rows, or owned + halo of the transpose) */
+  gode_csr_t A;            /* A_hat row block: n_rows = rows owned (outputs), n_cols = rows of the gather operand S
+                              (= n_rows, or owned + halo when partitioned) */
+  gode_csr_t At;           /* A_hat^T row block (rows owned; n_cols = owned + halo of the transpose); rowptr may be
+                              NULL when only forward evaluations are needed */
   int32_t d;
   int32_t groups;
   float gn_eps;
   int32_t precision;       /* GODE_PREC_* */
-  const int32_t* rowptr;   const int32_t* colidx;   const float* vals;     /* A_hat   */
-  const int32_t* rowptr_t; const int32_t* colidx_t; const float* vals_t;   /* A_hat^T */
-  const int32_t* heavy;    int32_t n_heavy;
-  const int32_t* heavy_t;  int32_t n_heavy_t;
   const float* W;          /* [d+1, d]; row 0 multiplies the time column */
   const float* b;          /* [d] or NULL */
   const float* gamma;      /* [d] */
@@ -200,10 +227,13 @@ int gode_gcn_stage_vjp(const gode_gcn_odefunc_t* f, const float* y, float t, con
 
 /* The same evaluation in two halves, for the row-partitioned (multi-GPU) path where the rows of gP that
  * other ranks own must be exchanged between them:
- *   phase1: k_y = relu(A_hat S + b);  gP[0:n_rows] = sign * a * (k_y > 0)
+ *   phase1: k_y = relu(A_hat S + b);  gP[0:n_rows] = sign * a * (k_y > 0);  optional fused RK combination
+ *           y_next = y0 + sum_j coef[j] kprev[j] + coef_self k_y (the y-part of the augmented stage state)
  *   phase2: gS = A_hat^T gP (gP has n_cols_t rows);  k_a, gtheta as above (gtheta = this rank's partial sum) */
 int gode_gcn_vjp_phase1(const gode_gcn_odefunc_t* f, const float* S, const float* a, float sign,
-                        float* k_y, float* gP, void* stream);
+                        float* k_y, float* gP,
+                        const float* y0, const float* const* kprev_host, const float* coef_host, int32_t n_prev,
+                        float coef_self, float* y_next, void* ws, size_t ws_bytes, void* stream);
 int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, float t, const float* gP,
                         float* k_a, float* gtheta, void* ws, size_t ws_bytes, void* stream);
 

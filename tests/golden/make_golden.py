@@ -180,11 +180,11 @@ def main():
             G[k + "grad/" + name] = gr.numpy()
 
     torch.manual_seed(7)
-    f2 = gcn.models.ODEfunc2(32, 0.0)
+    f2 = gcn.models.ODEfunc2(128, 0.0)
     f2.set_adj(adj_s)
-    x = rnd(31, NS, 32).requires_grad_(True)
+    x = rnd(31, NS, 128).requires_grad_(True)
     t = torch.tensor(0.61, requires_grad=True)
-    g = rnd(32, NS, 32)
+    g = rnd(32, NS, 128)
     y = f2(t, x)
     grads = torch.autograd.grad(y, (x, t) + tuple(f2.parameters()), g)
     G.update({"odefunc2/out": y.detach().numpy(), "odefunc2/grad_x": grads[0].numpy(),

@@ -84,8 +84,10 @@ def test_csr_synthetic_matches_oracle(dev):
     rp, ci, va = graph_ops.coo_to_csr(n, row.numpy(), col.numpy(), val.numpy())
     assert np.array_equal(plan.rowptr.cpu().numpy(), rp) and np.array_equal(plan.colidx.cpu().numpy(), ci)
     assert np.array_equal(plan.vals.cpu().numpy().view(np.uint32), va.view(np.uint32))
-    heavy = np.flatnonzero(np.diff(rp) > 2048)
-    assert plan.n_heavy == len(heavy) and (plan.n_heavy == 0 or np.array_equal(plan.heavy.cpu().numpy(), heavy))
+    heavy = np.flatnonzero(np.diff(rp) > 256)
+    assert plan.n_heavy == len(heavy) > 0 and np.array_equal(plan.heavy.cpu().numpy(), heavy)
+    chunks = np.concatenate([[0], np.cumsum((np.diff(rp)[heavy] + 255) // 256)])
+    assert np.array_equal(plan.chunk_ptr.cpu().numpy(), chunks) and plan.n_chunks == chunks[-1]
 
 
 # ------------------------------------------------------------------------------------------- kernels
@@ -114,7 +116,7 @@ def test_spmm_heavy_rows_and_ragged(dev):
     cols = np.concatenate([np.arange(1, 6001), rs.randint(0, n, size=len(rows) - 6001), [0]])
     vals = rs.standard_normal(len(rows)).astype(np.float32)
     plan = _plan_from(rows, cols, vals, n, dev)
-    assert plan.n_heavy == 1 and plan.heavy.cpu().tolist() == [0]
+    assert plan.n_heavy == 1 and plan.heavy.cpu().tolist() == [0] and plan.n_chunks == 24
     x = G.rnd(9, n, d)
     adj = torch.sparse_coo_tensor(torch.tensor(np.vstack([rows, cols])), torch.from_numpy(vals), (n, n))
     G.assert_close(ops.spmm(plan, x.to(dev), relu=True), torch.relu(torch.spmm(adj, x)), rtol=1e-5, atol_scale=2e-5,
@@ -152,12 +154,18 @@ def test_groupnorm_matches_oracle(d, dev):
     yg = ops.group_norm(xg, min(32, d), gg, bg, 1e-5)
     yg.backward(g.to(dev))
     if d // min(32, d) == 1:   # one channel per group: output = beta + noise, dx = noise
-        assert float((yg.cpu() - y).abs().max()) < 1e-4
+        # noise scale = |x| * gamma * rsqrt(eps) * 2^-23 ~ 4 * 1.5 * 316 * 1.2e-7 = 2.3e-4 for this randn input
+        assert float((yg.detach().cpu() - y.detach()).abs().max()) < 3e-4
         assert float((xg.grad.cpu() - x.grad).abs().max()) < 1e-2 * float(g.abs().max())
+        # dgamma = sum dy * xhat with xhat == 0: exactly 0 here, accumulated rounding noise in ATen
+        assert float(gg.grad.abs().max()) < 1e-2 and float(gamma.grad.abs().max()) < 1e-2
     else:
-        G.assert_close(yg, y, **TOL, what="y")
-        G.assert_close(xg.grad, x.grad, rtol=1e-4, atol_scale=1e-5, what="dx")
-    G.assert_close(gg.grad, gamma.grad, rtol=1e-4, atol_scale=1e-5, what="dgamma")
+        # two channels per group: pairs with x1 ~ x2 have rstd up to 1/sqrt(eps) = 316, which amplifies the
+        # rounding of (x - mean) in both implementations -> absolute floor 5e-5 of the tensor's scale
+        ft = dict(rtol=1e-5, atol_scale=5e-5) if d // min(32, d) == 2 else TOL
+        G.assert_close(yg, y, **ft, what="y")
+        G.assert_close(xg.grad, x.grad, rtol=1e-4, atol_scale=1e-4 if d // min(32, d) == 2 else 1e-5, what="dx")
+        G.assert_close(gg.grad, gamma.grad, rtol=1e-4, atol_scale=1e-5, what="dgamma")
     G.assert_close(bg.grad, beta.grad, **TOL, what="dbeta")
 
 
@@ -241,14 +249,14 @@ def test_odefunc_golden(d, dev):
 def test_odefunc2_golden(dev):
     models = _pkg()[4]
     g = G.load("gcn_golden")
-    f = models.ODEfunc2(32, 0.0)
+    f = models.ODEfunc2(128, 0.0)
     f.load_state_dict(G.params(g, "odefunc2/p/"))
     f = f.to(dev)
     f.set_adj(G.sub_adj().to(dev))
-    x = G.rnd(31, 512, 32).to(dev).requires_grad_(True)
+    x = G.rnd(31, 512, 128).to(dev).requires_grad_(True)
     t = torch.tensor(0.61, device=dev, requires_grad=True)
     y = f(t, x)
-    grads = torch.autograd.grad(y, (x, t), G.rnd(32, 512, 32).to(dev))
+    grads = torch.autograd.grad(y, (x, t), G.rnd(32, 512, 128).to(dev))
     G.assert_close(y, g["odefunc2/out"], **TOL, what="out")
     G.assert_close(grads[0], g["odefunc2/grad_x"], rtol=1e-4, atol_scale=2e-5, what="grad_x")
     G.assert_close(grads[1], g["odefunc2/grad_t"], rtol=1e-4, atol_scale=2e-5, what="grad_t")
@@ -291,6 +299,10 @@ def test_ode_block_golden(case, dev):
     gtol = dict(rtol=1e-4, atol_scale=5e-5) if d != 16 else dict(rtol=1e-3, atol_scale=2e-3)
     G.assert_close(x.grad, g[k + "grad_x"], **gtol, what="grad_x")
     for name, p in blk.named_parameters():
+        if d == 16 and name == "odefunc.norm1.weight":
+            # one channel per group: dgamma is identically 0 (xhat == 0); ATen reports ~1e-8 of rounding noise
+            assert float(p.grad.abs().max()) < 1e-6 and float(np.abs(g[k + "grad/" + name]).max()) < 1e-6
+            continue
         G.assert_close(p.grad, g[k + "grad/" + name], **gtol, what=name)
 
 
@@ -322,6 +334,9 @@ def test_models_golden(name, dev):
     if "_" in name:
         assert model.nfe == int(g[k + "nfe_b"])
     for pn, p in model.named_parameters():
+        if pn.endswith("odefunc.norm1.weight"):
+            assert float(p.grad.abs().max()) < 1e-6 and float(np.abs(g[k + "grad/" + pn]).max()) < 1e-6
+            continue
         tol = dict(rtol=1e-4, atol_scale=1e-4)
         if "odefunc" in pn or ("ODEGCN3" in name and pn.startswith("gc1")):
             tol = dict(rtol=1e-2, atol_scale=2e-2)   # gradients that pass through the degenerate hidden=16 GroupNorm

@@ -99,7 +99,7 @@ def test_gcn_odefunc2_matches_reference():
     g = G.load("gcn_golden")
     adj = G.sub_adj()
     p = G.params(g, "odefunc2/p/")
-    y = gcn_ref.odefunc2(torch.tensor(0.61), G.rnd(31, 512, 32), p, adj)
+    y = gcn_ref.odefunc2(torch.tensor(0.61), G.rnd(31, 512, 128), p, adj)
     G.assert_close(y, g["odefunc2/out"], **TOL, what="out")
 
 
