@@ -16,6 +16,7 @@
 //     finishing kernel adds a row's chunks in chunk order and applies the epilogue (deterministic).
 #include "internal.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace gode {
 
@@ -287,6 +288,213 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
   return GODE_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Bulk-copy (TMA engine) gather pipeline for wide rows (d = 128 / 256).
+//
+// The register-staged kernel above can keep only UNR neighbour rows per lane in flight, and every warp pays
+// the rowptr -> colidx -> gather dependency chain once per row: measured 1.1 ms for 1M rows / 20M entries
+// (13 % of the HBM roofline) -- latency-bound, not bandwidth-bound.  Here every lane issues ONE
+// cp.async.bulk (global -> shared, a whole 512 B / 1 KB neighbour row, completion counted on an mbarrier),
+// so a warp has up to 2 x 32 rows in flight without holding a register for them; the (col,val) pairs of the
+// batch after next are prefetched into registers while the next batch's rows are in flight and the current
+// batch is consumed from shared memory.  One warp walks a tile of R consecutive rows; batches never cross a
+// row, so the accumulator is a register float4 per lane and the fused epilogue is unchanged.
+//   smem per warp: 2 buffers x 32 slots x d x 4 B (32 KB at d=128)  ->  NW warps per CTA, one CTA per SM.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct Batch {
+  int lr;     // local row (or chunk) index in the warp's tile
+  int off;    // offset of the batch in its row
+  int e;      // first entry
+  int cnt;    // entries in the batch (0 for an empty row)
+  bool last;  // final batch of its row
+  bool valid;
+};
+
+constexpr int BULK_NW = 6;   // warps per CTA
+constexpr int BULK_R = 16;   // rows (or heavy-row chunks) per warp
+
+// CHUNKS = false: rows r0.. of the matrix (heavy rows skipped), epilogue per row.
+// CHUNKS = true : chunks of the heavy rows, partial sums to `partial`.
+template <int VPL, bool CHUNKS>
+__global__ void __launch_bounds__(BULK_NW * 32, 1)
+k_spmm_bulk(int64_t n_units, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+            const float* __restrict__ vals, const int32_t* __restrict__ heavy_rows, const int32_t* __restrict__ chunk_ptr,
+            int n_heavy, const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
+            float* __restrict__ partial, const gode_spmm_epilogue_t ep) {
+  constexpr int D = 32 * VPL * 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 2 * 32 * D;          // [2][32][D]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)BULK_NW * 2 * 32 * D * 4) + warp * 2;
+  if (lane == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int64_t u0 = (blockIdx.x * (int64_t)BULK_NW + warp) * BULK_R;
+  const int nu = static_cast<int>(min((int64_t)BULK_R, n_units - u0));
+  if (nu <= 0) return;
+
+  // lane i < nu holds [rs, re) = entry range of local unit i, and whether its epilogue must be skipped
+  int rs = 0, re = 0;
+  bool skip = false;
+  if (lane < nu) {
+    if (!CHUNKS) {
+      rs = __ldg(rowptr + u0 + lane);
+      re = __ldg(rowptr + u0 + lane + 1);
+      if (re - rs > GODE_HEAVY_ROW) { skip = true; re = rs; }
+    } else {
+      const int chunk = static_cast<int>(u0) + lane;
+      int lo = 0, hi = n_heavy - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(chunk_ptr + mid) <= chunk) lo = mid; else hi = mid - 1;
+      }
+      const int row = __ldg(heavy_rows + lo);
+      const int r0 = __ldg(rowptr + row), r1 = __ldg(rowptr + row + 1);
+      rs = r0 + (chunk - __ldg(chunk_ptr + lo)) * GODE_HEAVY_CHUNK;
+      re = min(r1, rs + GODE_HEAVY_CHUNK);
+    }
+  }
+
+  auto make = [&](int lr, int off) {
+    Batch b;
+    b.lr = lr; b.off = off; b.valid = lr < nu;
+    const int src = b.valid ? lr : 0;
+    const int s = __shfl_sync(0xffffffffu, rs, src), e = __shfl_sync(0xffffffffu, re, src);
+    b.e = s + off;
+    const int rem = e - s - off;
+    b.cnt = b.valid ? max(0, min(32, rem)) : 0;
+    b.last = rem <= 32;
+    return b;
+  };
+  auto advance = [&](const Batch& b) {
+    if (!b.valid) return b;
+    return b.last ? make(b.lr + 1, 0) : make(b.lr, b.off + 32);
+  };
+  auto load_cv = [&](const Batch& b, int& c, float& v) {
+    c = 0; v = 0.f;
+    if (lane < b.cnt) {
+      c = __ldcs(colidx + b.e + lane);
+      v = __ldcs(vals + b.e + lane);
+    }
+  };
+  auto issue = [&](const Batch& b, int c, int buf) {
+    if (b.cnt <= 0) return;
+    if (lane == 0) mbar_expect_tx(&bars[buf], static_cast<uint32_t>(b.cnt) * D * 4u);
+    __syncwarp();
+    if (lane < b.cnt) bulk_g2s(ring + ((size_t)buf * 32 + lane) * D, X + (int64_t)c * ldx, D * 4u, &bars[buf]);
+  };
+
+  Batch b0 = make(0, 0), b1 = advance(b0), b2 = advance(b1);
+  int c0, c1, c2 = 0;
+  float v0, v1, v2 = 0.f;
+  load_cv(b0, c0, v0);
+  issue(b0, c0, 0);
+  load_cv(b1, c1, v1);
+  uint32_t phase[2] = {0u, 0u};
+  float4 acc[VPL];
+#pragma unroll
+  for (int u = 0; u < VPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int col0 = lane * VPL * 4;
+
+  for (int k = 0; b0.valid; ++k) {
+    const int buf = k & 1;
+    if (b1.valid) issue(b1, c1, buf ^ 1);
+    if (b2.valid) load_cv(b2, c2, v2);
+    if (b0.cnt > 0) {
+      mbar_wait(&bars[buf], phase[buf]);
+      phase[buf] ^= 1u;
+      const float* rb = ring + (size_t)buf * 32 * D + col0;
+#pragma unroll 8
+      for (int j = 0; j < b0.cnt; ++j) {
+        const float vj = __shfl_sync(0xffffffffu, v0, j);
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) {
+          const float4 x = *reinterpret_cast<const float4*>(rb + (size_t)j * D + u * 4);
+          acc[u].x += vj * x.x; acc[u].y += vj * x.y; acc[u].z += vj * x.z; acc[u].w += vj * x.w;
+        }
+      }
+    }
+    if (b0.last) {
+      if (CHUNKS) {
+#pragma unroll
+        for (int u = 0; u < VPL; ++u)
+          *reinterpret_cast<float4*>(partial + (u0 + b0.lr) * D + col0 + u * 4) = acc[u];
+      } else {
+        const bool sk = __shfl_sync(0xffffffffu, skip ? 1 : 0, b0.lr) != 0;
+        if (!sk) epilogue<VPL>(ep, u0 + b0.lr, col0, acc, Y, ldy);
+      }
+#pragma unroll
+      for (int u = 0; u < VPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    b0 = b1; b1 = b2; b2 = advance(b2);
+    c0 = c1; v0 = v1; c1 = c2; v1 = v2;
+  }
+}
+
+template <int VPL>
+static int launch_bulk(const gode_csr_t& A, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                       const gode_spmm_epilogue_t& ep, float* ws, cudaStream_t st) {
+  constexpr int D = 32 * VPL * 4;
+  constexpr size_t smem = (size_t)BULK_NW * 2 * 32 * D * 4 + BULK_NW * 2 * 8;
+  static bool configured = false;
+  if (!configured) {
+    GODE_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_bulk<VPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GODE_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_bulk<VPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  constexpr int UPB = BULK_NW * BULK_R;  // units per block
+  if (A.n_rows > 0) {
+    unsigned grid = static_cast<unsigned>((A.n_rows + UPB - 1) / UPB);
+    k_spmm_bulk<VPL, false><<<grid, BULK_NW * 32, smem, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, nullptr, nullptr, 0, X, ldx,
+                                                              Y, ldy, nullptr, ep);
+    GODE_LAUNCH_CHECK();
+  }
+  if (A.n_heavy > 0) {
+    unsigned g1 = static_cast<unsigned>((A.n_chunks + UPB - 1) / UPB);
+    k_spmm_bulk<VPL, true><<<g1, BULK_NW * 32, smem, st>>>(A.n_chunks, A.rowptr, A.colidx, A.vals, A.heavy_rows,
+                                                           A.heavy_chunk_ptr, A.n_heavy, X, ldx, nullptr, 0, ws, ep);
+    GODE_LAUNCH_CHECK();
+    constexpr int RPB = 8;
+    unsigned g2 = static_cast<unsigned>((A.n_heavy + RPB - 1) / RPB);
+    k_spmm_heavy_finish<32, VPL><<<g2, 256, 0, st>>>(A.n_heavy, A.heavy_rows, A.heavy_chunk_ptr, ws, Y, ldy, ep);
+    GODE_LAUNCH_CHECK();
+  }
+  return GODE_OK;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static bool vec_width(int d) { return d == 8 || d == 16 || d == 32 || d == 64 || d == 128 || d == 256; }
@@ -308,6 +516,12 @@ int spmm_dispatch(const gode_csr_t& A, const float* X, int64_t ldx, int32_t d, f
   }
   if (vec_ok) {
     float* w = static_cast<float*>(ws);
+    static const int use_bulk = [] {
+      const char* e = getenv("GODE_SPMM_BULK");
+      return e ? atoi(e) : 1;
+    }();
+    if (use_bulk && d == 128) return launch_bulk<1>(A, X, ldx, Y, ldy, ep, w, st);
+    if (use_bulk && d == 256 && false) return launch_bulk<2>(A, X, ldx, Y, ldy, ep, w, st);
     switch (d) {
       case 8: return launch_vec<2, 1>(A, X, ldx, Y, ldy, ep, w, st);
       case 16: return launch_vec<4, 1>(A, X, ldx, Y, ldy, ep, w, st);
