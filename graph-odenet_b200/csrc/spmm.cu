@@ -343,7 +343,11 @@ constexpr int BULK_R = 16;   // rows (or heavy-row chunks) per warp
 
 // CHUNKS = false: rows r0.. of the matrix (heavy rows skipped), epilogue per row.
 // CHUNKS = true : chunks of the heavy rows, partial sums to `partial`.
-template <int VPL, bool CHUNKS>
+// ASYNC = 0: one cp.async.bulk (TMA engine) per neighbour row, issued by one lane, mbarrier completion.
+// ASYNC = 1: one warp-wide cp.async (LDGSTS, 16 B per lane) per neighbour row, commit/wait groups.
+// Measured (N=1M, 20M entries, d=128): the TMA engine sustains only about one 512 B request per ~55 cycles
+// per SM (2.6 TB/s chip-wide), so per-row bulk copies lose to LDGSTS; both are kept for the record.
+template <int VPL, bool CHUNKS, int ASYNC>
 __global__ void __launch_bounds__(BULK_NW * 32, 1)
 k_spmm_bulk(int64_t n_units, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
             const float* __restrict__ vals, const int32_t* __restrict__ heavy_rows, const int32_t* __restrict__ chunk_ptr,
@@ -410,10 +414,25 @@ k_spmm_bulk(int64_t n_units, const int32_t* __restrict__ rowptr, const int32_t* 
     }
   };
   auto issue = [&](const Batch& b, int c, int buf) {
-    if (b.cnt <= 0) return;
-    if (lane == 0) mbar_expect_tx(&bars[buf], static_cast<uint32_t>(b.cnt) * D * 4u);
-    __syncwarp();
-    if (lane < b.cnt) bulk_g2s(ring + ((size_t)buf * 32 + lane) * D, X + (int64_t)c * ldx, D * 4u, &bars[buf]);
+    if (ASYNC == 0) {
+      if (b.cnt <= 0) return;
+      if (lane == 0) mbar_expect_tx(&bars[buf], static_cast<uint32_t>(b.cnt) * D * 4u);
+      __syncwarp();
+      if (lane < b.cnt) bulk_g2s(ring + ((size_t)buf * 32 + lane) * D, X + (int64_t)c * ldx, D * 4u, &bars[buf]);
+    } else {
+      const uint32_t dst0 = smem_u32(ring + (size_t)buf * 32 * D + lane * VPL * 4);
+      const float* src0 = X + lane * VPL * 4;
+#pragma unroll 4
+      for (int j = 0; j < b.cnt; ++j) {
+        const int cj = __shfl_sync(0xffffffffu, c, j);
+#pragma unroll
+        for (int u = 0; u < VPL; ++u)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(j * D + u * 4) * 4u),
+                       "l"(src0 + (int64_t)cj * ldx + u * 4)
+                       : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");   // one group per batch, empty batches included
+    }
   };
 
   Batch b0 = make(0, 0), b1 = advance(b0), b2 = advance(b1);
@@ -432,16 +451,25 @@ k_spmm_bulk(int64_t n_units, const int32_t* __restrict__ rowptr, const int32_t* 
     const int buf = k & 1;
     if (b1.valid) issue(b1, c1, buf ^ 1);
     if (b2.valid) load_cv(b2, c2, v2);
+    if (ASYNC == 1) {
+      // groups are committed in batch order; all but the newest (b1's) must have landed
+      if (b1.valid) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+    }
     if (b0.cnt > 0) {
-      mbar_wait(&bars[buf], phase[buf]);
-      phase[buf] ^= 1u;
+      if (ASYNC == 0) {
+        mbar_wait(&bars[buf], phase[buf]);
+        phase[buf] ^= 1u;
+      }
       const float* rb = ring + (size_t)buf * 32 * D + col0;
+      constexpr int USTRIDE = 4;
 #pragma unroll 8
       for (int j = 0; j < b0.cnt; ++j) {
         const float vj = __shfl_sync(0xffffffffu, v0, j);
 #pragma unroll
         for (int u = 0; u < VPL; ++u) {
-          const float4 x = *reinterpret_cast<const float4*>(rb + (size_t)j * D + u * 4);
+          const float4 x = *reinterpret_cast<const float4*>(rb + (size_t)j * D + u * USTRIDE);
           acc[u].x += vj * x.x; acc[u].y += vj * x.y; acc[u].z += vj * x.z; acc[u].w += vj * x.w;
         }
       }
@@ -464,27 +492,27 @@ k_spmm_bulk(int64_t n_units, const int32_t* __restrict__ rowptr, const int32_t* 
   }
 }
 
-template <int VPL>
+template <int VPL, int ASYNC>
 static int launch_bulk(const gode_csr_t& A, const float* X, int64_t ldx, float* Y, int64_t ldy,
                        const gode_spmm_epilogue_t& ep, float* ws, cudaStream_t st) {
   constexpr int D = 32 * VPL * 4;
   constexpr size_t smem = (size_t)BULK_NW * 2 * 32 * D * 4 + BULK_NW * 2 * 8;
   static bool configured = false;
   if (!configured) {
-    GODE_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_bulk<VPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GODE_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_bulk<VPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GODE_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_bulk<VPL, false, ASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GODE_CHECK_CUDA(cudaFuncSetAttribute(k_spmm_bulk<VPL, true, ASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   constexpr int UPB = BULK_NW * BULK_R;  // units per block
   if (A.n_rows > 0) {
     unsigned grid = static_cast<unsigned>((A.n_rows + UPB - 1) / UPB);
-    k_spmm_bulk<VPL, false><<<grid, BULK_NW * 32, smem, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, nullptr, nullptr, 0, X, ldx,
+    k_spmm_bulk<VPL, false, ASYNC><<<grid, BULK_NW * 32, smem, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, nullptr, nullptr, 0, X, ldx,
                                                               Y, ldy, nullptr, ep);
     GODE_LAUNCH_CHECK();
   }
   if (A.n_heavy > 0) {
     unsigned g1 = static_cast<unsigned>((A.n_chunks + UPB - 1) / UPB);
-    k_spmm_bulk<VPL, true><<<g1, BULK_NW * 32, smem, st>>>(A.n_chunks, A.rowptr, A.colidx, A.vals, A.heavy_rows,
+    k_spmm_bulk<VPL, true, ASYNC><<<g1, BULK_NW * 32, smem, st>>>(A.n_chunks, A.rowptr, A.colidx, A.vals, A.heavy_rows,
                                                            A.heavy_chunk_ptr, A.n_heavy, X, ldx, nullptr, 0, ws, ep);
     GODE_LAUNCH_CHECK();
     constexpr int RPB = 8;
@@ -518,10 +546,10 @@ int spmm_dispatch(const gode_csr_t& A, const float* X, int64_t ldx, int32_t d, f
     float* w = static_cast<float*>(ws);
     static const int use_bulk = [] {
       const char* e = getenv("GODE_SPMM_BULK");
-      return e ? atoi(e) : 1;
+      return e ? atoi(e) : 1;   // 0: register-staged, 1: LDGSTS pipeline, 2: TMA bulk-copy pipeline
     }();
-    if (use_bulk && d == 128) return launch_bulk<1>(A, X, ldx, Y, ldy, ep, w, st);
-    if (use_bulk && d == 256 && false) return launch_bulk<2>(A, X, ldx, Y, ldy, ep, w, st);
+    if (use_bulk == 1 && d == 128) return launch_bulk<1, 1>(A, X, ldx, Y, ldy, ep, w, st);
+    if (use_bulk == 2 && d == 128) return launch_bulk<1, 0>(A, X, ldx, Y, ldy, ep, w, st);
     switch (d) {
       case 8: return launch_vec<2, 1>(A, X, ldx, Y, ldy, ep, w, st);
       case 16: return launch_vec<4, 1>(A, X, ldx, Y, ldy, ep, w, st);

@@ -48,14 +48,14 @@ def dense_features(ds):
     return torch.from_numpy(np.asarray(m.todense(), dtype=np.float32))
 
 
-def assert_close(a, b, rtol=1e-5, atol_scale=1e-5, what=""):
-    """|a-b| <= rtol*|b| + atol_scale*max|b| elementwise (fp32 parity bar, tolerance stated at call site)."""
+def assert_close(a, b, rtol=1e-5, atol_scale=1e-5, what="", atol_abs=0.0):
+    """|a-b| <= rtol*|b| + atol_scale*max|b| + atol_abs elementwise (fp32 parity bar, stated at the call site)."""
     a = torch.as_tensor(a).detach().cpu().double()
     b = torch.as_tensor(b).detach().cpu().double()
     assert a.shape == b.shape, (what, a.shape, b.shape)
     scale = float(b.abs().max()) if b.numel() else 0.0
     err = (a - b).abs()
-    tol = rtol * b.abs() + atol_scale * scale
+    tol = rtol * b.abs() + atol_scale * scale + atol_abs
     bad = err > tol
     if bool(bad.any()):
         i = int(torch.argmax(err - tol))
