@@ -31,7 +31,7 @@ class SpmmEpilogue(C.Structure):
 
 
 class Csr(C.Structure):
-    _fields_ = [("n_rows", i64), ("n_cols", i64), ("rowptr", vp), ("colidx", vp), ("vals", vp),
+    _fields_ = [("n_rows", i64), ("n_cols", i64), ("rowptr", vp), ("colidx", vp), ("vals", vp), ("row_vals", vp),
                 ("heavy_rows", vp), ("heavy_chunk_ptr", vp), ("n_heavy", i32), ("n_chunks", i32)]
 
 
@@ -52,6 +52,7 @@ _PROTOS = {
     "gode_csr_transpose_workspace_bytes": (sz, [i64, i64, i64]),
     "gode_csr_transpose": (C.c_int, [i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "gode_csr_heavy_rows": (C.c_int, [i64, vp, vp, vp, vp, vp]),
+    "gode_csr_row_values": (C.c_int, [i64, vp, vp, vp, vp, vp]),
     "gode_spmm_workspace_bytes": (sz, [C.POINTER(Csr), i32]),
     "gode_spmm_csr_f32": (C.c_int, [C.POINTER(Csr), vp, i64, i32, vp, i64, C.POINTER(SpmmEpilogue), vp, sz, vp]),
     "gode_gemm_f32": (C.c_int, [i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, f32, vp, i64, i32, i32, vp, sz, vp]),

@@ -10,8 +10,14 @@
 
 namespace gode {
 
-int transform_tc(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, cudaStream_t st);  // transform_tc.cu
+// transform_tc.cu (tcgen05 kernels)
+int transform_tc(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, cudaStream_t st);
 bool transform_tc_supported(const gode_gcn_odefunc_t* f);
+int input_grad_tc(const gode_gcn_odefunc_t* f, const float* gS, float* gz, cudaStream_t st);
+bool wgrad_tc_supported(const gode_gcn_odefunc_t* f);
+size_t wgrad_tc_ws_bytes(const gode_gcn_odefunc_t* f);
+int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, const float* cs, float* gW1, float* ws,
+             size_t ws_bytes, cudaStream_t st);
 
 struct GcnWs {
   float* heavy;    // heavy-row partial sums of the SpMMs
@@ -47,10 +53,16 @@ static int splits_for(int64_t k) {
   return static_cast<int>(s);
 }
 
+static size_t splitk_bytes_for(const gode_gcn_odefunc_t* f) {
+  size_t a = sizeof(float) * static_cast<size_t>(splits_for(f->A.n_rows)) * f->d * f->d;
+  size_t b = wgrad_tc_supported(f) ? wgrad_tc_ws_bytes(f) : 0;
+  return a > b ? a : b;
+}
+
 static size_t ws_bytes_for(const gode_gcn_odefunc_t* f) {
   const size_t nd = align_up(sizeof(float) * static_cast<size_t>(max_rows(f)) * f->d, 256);
   const size_t red = align_up(gode_colreduce_workspace_bytes(2 * f->d), 256);
-  const size_t sk = align_up(sizeof(float) * static_cast<size_t>(splits_for(f->A.n_rows)) * f->d * f->d, 256);
+  const size_t sk = align_up(splitk_bytes_for(f), 256);
   return 3 * nd + red + sk + heavy_bytes_for(f) + 8192;
 }
 
@@ -68,7 +80,7 @@ static int carve(const gode_gcn_odefunc_t* f, void* ws, size_t ws_bytes, GcnWs& 
   w.bufC = ar.take<float>(nd);
   w.red_bytes = gode_colreduce_workspace_bytes(2 * f->d);
   w.red = reinterpret_cast<float*>(ar.take<char>(w.red_bytes));
-  w.splitk_bytes = sizeof(float) * static_cast<size_t>(splits_for(f->A.n_rows)) * f->d * f->d;
+  w.splitk_bytes = splitk_bytes_for(f);
   w.splitk = reinterpret_cast<float*>(ar.take<char>(w.splitk_bytes));
   w.small = ar.take<float>(1024);
   if (!w.small) {
@@ -236,11 +248,19 @@ extern "C" int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, 
   k_time_terms<<<1, 128, 0, st>>>(d, t, cs, f->W, gW, gt);
   GODE_LAUNCH_CHECK();
   // gW[1:,:] = z^T gS
-  if ((rc = groupnorm_fwd(n, d, f->groups, f->gn_eps, y, d, f->gamma, f->beta, z, d, st))) return rc;
-  if ((rc = gemm_simt(1, 0, d, d, n, 1.f, z, d, gS, d, 0.f, gW + d, d, splits_for(n), w.splitk, w.splitk_bytes, st, nullptr, 0.f)))
-    return rc;
+  if (wgrad_tc_supported(f)) {
+    if ((rc = wgrad_tc(f, y, gS, cs, gW + d, w.splitk, w.splitk_bytes, st))) return rc;
+  } else {
+    if ((rc = groupnorm_fwd(n, d, f->groups, f->gn_eps, y, d, f->gamma, f->beta, z, d, st))) return rc;
+    if ((rc = gemm_simt(1, 0, d, d, n, 1.f, z, d, gS, d, 0.f, gW + d, d, splits_for(n), w.splitk, w.splitk_bytes, st, nullptr, 0.f)))
+      return rc;
+  }
   // gz = gS W[1:,:]^T ; GroupNorm backward
-  if ((rc = gemm_simt(0, 1, n, d, d, 1.f, gS, d, f->W + d, d, 0.f, gz, d, 1, nullptr, 0, st, nullptr, 0.f))) return rc;
+  if (transform_tc_supported(f)) {
+    if ((rc = input_grad_tc(f, gS, gz, st))) return rc;
+  } else if ((rc = gemm_simt(0, 1, n, d, d, 1.f, gS, d, f->W + d, d, 0.f, gz, d, 1, nullptr, 0, st, nullptr, 0.f))) {
+    return rc;
+  }
   return groupnorm_bwd(n, d, f->groups, f->gn_eps, y, d, f->gamma, gz, d, k_a, d, ggamma, gbeta, w.red, w.red_bytes, st);
 }
 

@@ -105,6 +105,8 @@ __global__ void k_heavy_flags(int64_t n_rows, const int32_t* __restrict__ rowptr
   flag[r] = (rowptr[r + 1] - rowptr[r] > GODE_HEAVY_ROW) ? 1 : 0;
 }
 
+__global__ void k_set_one(int32_t* p) { *p = 1; }
+
 __global__ void k_flag_bad(const int* bad, int64_t* nnz_out) {
   if (*bad && nnz_out) *nnz_out = -1;
 }
@@ -279,5 +281,34 @@ extern "C" int gode_csr_heavy_rows(int64_t n_rows, const int32_t* rowptr, int32_
   GODE_REQUIRE(rowptr && heavy_rows && heavy_chunk_ptr && counts_out, "csr_heavy_rows: null pointer");
   k_compact_heavy<<<1, 1024, 0, as_stream(stream_)>>>(n_rows, rowptr, heavy_rows, heavy_chunk_ptr, counts_out);
   GODE_LAUNCH_CHECK();
+  return GODE_OK;
+}
+
+namespace gode {
+__global__ void k_row_values(int64_t n_rows, const int32_t* __restrict__ rowptr, const float* __restrict__ vals,
+                             float* __restrict__ out, int32_t* __restrict__ is_const) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int e0 = rowptr[row], e1 = rowptr[row + 1];
+  const float v0 = e1 > e0 ? vals[e0] : 0.f;
+  bool same = true;
+  for (int e = e0 + lane; e < e1; e += 32) same = same && (__float_as_uint(vals[e]) == __float_as_uint(v0));
+  if (!__all_sync(0xffffffffu, same) && lane == 0) *is_const = 0;
+  if (lane == 0) out[row] = v0;
+}
+}  // namespace gode
+
+extern "C" int gode_csr_row_values(int64_t n_rows, const int32_t* rowptr, const float* vals, float* row_vals_out,
+                                   int32_t* is_const_out, void* stream_) {
+  GODE_REQUIRE(rowptr && row_vals_out && is_const_out && (n_rows == 0 || vals), "csr_row_values: null pointer");
+  cudaStream_t st = as_stream(stream_);
+  GODE_CHECK_CUDA(cudaMemsetAsync(is_const_out, 0, sizeof(int32_t), st));
+  k_set_one<<<1, 1, 0, st>>>(is_const_out);
+  GODE_LAUNCH_CHECK();
+  if (n_rows > 0) {
+    k_row_values<<<static_cast<unsigned>((n_rows + 7) / 8), 256, 0, st>>>(n_rows, rowptr, vals, row_vals_out, is_const_out);
+    GODE_LAUNCH_CHECK();
+  }
   return GODE_OK;
 }

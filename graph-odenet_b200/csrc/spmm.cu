@@ -83,11 +83,11 @@ __device__ __forceinline__ void fma_row(float4 (&acc)[VPL], float v, const float
 
 // acc += sum_{e in [e0,e1)} vals[e] * X[colidx[e], lane's channels]; all 32 lanes of the warp call this together
 // (sub-warps own different ranges; `maxlen` is the longest range in the warp).
-template <int LPR, int VPL>
+template <int LPR, int VPL, int UN = UNR>
 __device__ __forceinline__ void gather_range(float4 (&acc)[VPL], int e0, int e1, int maxlen, int sub, int sl,
                                              const int32_t* __restrict__ colidx, const float* __restrict__ vals,
                                              const float* __restrict__ xl, int64_t ldx) {
-  constexpr int U = UNR < LPR ? UNR : LPR;
+  constexpr int U = UN < LPR ? UN : LPR;
   for (int off = 0; off < maxlen; off += LPR) {
     const int e = e0 + off + sl;
     int c = 0;
@@ -160,6 +160,185 @@ __global__ void __launch_bounds__(256) k_spmm_vec(int64_t n_rows, const int32_t*
   for (int u = 0; u < VPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
   gather_range<LPR, VPL>(acc, e0, e1, maxlen, sub, sl, colidx, vals, X + col0, ldx);
   if (valid && !heavy) epilogue<VPL>(ep, row, col0, acc, Y, ldy);
+}
+
+
+// L1-locality variant: ONE 1024-thread CTA per SM walks a contiguous tile of TILE_ROWS rows, so the neighbour
+// rows its 32 warps gather (in a locality-ordered graph: a band around the tile) stay resident in that SM's L1
+// and are served at L1 bandwidth (128 B/clk/SM) instead of L2 bandwidth (~42 B/clk/SM).
+constexpr int TILE_WARPS = 32;
+constexpr int TILE_ROUNDS = 4;   // rows per sub-warp
+
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(TILE_WARPS * 32, 1) k_spmm_tile(int64_t n_rows, const int32_t* __restrict__ rowptr,
+                                                                 const int32_t* __restrict__ colidx,
+                                                                 const float* __restrict__ vals, const float* __restrict__ X,
+                                                                 int64_t ldx, float* __restrict__ Y, int64_t ldy,
+                                                                 const gode_spmm_epilogue_t ep) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int ROWS_PER_ROUND = TILE_WARPS * RPW;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const int col0 = sl * VPL * 4;
+  const int64_t tile0 = blockIdx.x * (int64_t)(ROWS_PER_ROUND * TILE_ROUNDS);
+#pragma unroll 1
+  for (int r = 0; r < TILE_ROUNDS; ++r) {
+    const int64_t row = tile0 + (int64_t)r * ROWS_PER_ROUND + w * RPW + sub;
+    const bool valid = row < n_rows;
+    int e0 = 0, e1 = 0;
+    if (valid) {
+      e0 = __ldg(rowptr + row);
+      e1 = __ldg(rowptr + row + 1);
+    }
+    const bool heavy = (e1 - e0) > GODE_HEAVY_ROW;
+    if (heavy) e1 = e0;
+    const int maxlen = warp_max_over_subs<LPR>(e1 - e0);
+    float4 acc[VPL];
+#pragma unroll
+    for (int u = 0; u < VPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_range<LPR, VPL, 4>(acc, e0, e1, maxlen, sub, sl, colidx, vals, X + col0, ldx);
+    if (valid && !heavy) epilogue<VPL>(ep, row, col0, acc, Y, ldy);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Persistent-warp gather (default).  ncu on the one-row-per-warp kernel above (N=2M, 39M entries, d=128):
+// 26 % of the stall samples sit on the rowptr -> (col,val) dependency chain at the head of every row and the
+// L1 data pipe is 60 % busy (a 512 B row costs 4 wavefronts, each broadcast shuffle one more).  Here
+//   * a fixed grid of warps strides over the rows; the (col,val) batch of the NEXT row and the rowptr pair of
+//     the row after it are already in flight while the current row's neighbour rows are gathered;
+//   * there is a single predicated code path (no slow tail): U loads are always issued back to back;
+//   * ROWVAL: when the matrix is row-constant (gode_csr_t.row_vals, the reference's D^-1(A+I)) the values
+//     stream and its broadcast shuffle disappear: acc = row_val * sum_e X[col_e].
+// ------------------------------------------------------------------------------------------------
+template <int LPR, int VPL, int U, bool ROWVAL>
+__device__ __forceinline__ void consume_batch(float4 (&acc)[VPL], int c, float v, int cnt, int maxcnt, int sub,
+                                              const float* __restrict__ xl, int64_t ldx) {
+  constexpr int UU = U < LPR ? U : LPR;
+#pragma unroll
+  for (int j = 0; j < LPR; j += UU) {
+    if (j >= maxcnt) break;  // warp-uniform
+    int cj[UU];
+    float vj[UU];
+#pragma unroll
+    for (int q = 0; q < UU; ++q) {
+      cj[q] = __shfl_sync(0xffffffffu, c, sub * LPR + j + q);
+      vj[q] = ROWVAL ? 1.f : __shfl_sync(0xffffffffu, v, sub * LPR + j + q);
+    }
+    float4 x[UU][VPL];
+#pragma unroll
+    for (int q = 0; q < UU; ++q) {
+      const bool on = j + q < cnt;
+#pragma unroll
+      for (int u = 0; u < VPL; ++u) {
+        x[q][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) x[q][u] = ld_ro4(xl + (int64_t)cj[q] * ldx + u * 4);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < UU; ++q)
+#pragma unroll
+      for (int u = 0; u < VPL; ++u) {
+        if (ROWVAL) {
+          acc[u].x += x[q][u].x; acc[u].y += x[q][u].y; acc[u].z += x[q][u].z; acc[u].w += x[q][u].w;
+        } else {
+          acc[u].x += vj[q] * x[q][u].x; acc[u].y += vj[q] * x[q][u].y;
+          acc[u].z += vj[q] * x[q][u].z; acc[u].w += vj[q] * x[q][u].w;
+        }
+      }
+  }
+}
+
+template <int LPR, int VPL, int U, int MINB, bool ROWVAL>
+__global__ void __launch_bounds__(256, MINB) k_spmm_pw(int64_t n_rows, const int32_t* __restrict__ rowptr,
+                                                       const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                                       const float* __restrict__ row_vals, const float* __restrict__ X,
+                                                       int64_t ldx, float* __restrict__ Y, int64_t ldy,
+                                                       const gode_spmm_epilogue_t ep) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const int col0 = sl * VPL * 4;
+  const float* __restrict__ xl = X + col0;
+  const int64_t n_units = (n_rows + RPW - 1) / RPW;
+  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int64_t unit = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (unit >= n_units) return;
+
+  auto load_ptr = [&](int64_t u, int& e0, int& e1, float& rv, bool& heavy) {
+    const int64_t r = u * RPW + sub;
+    e0 = 0; e1 = 0; rv = 0.f; heavy = false;
+    if (u < n_units && r < n_rows) {
+      e0 = __ldg(rowptr + r);
+      e1 = __ldg(rowptr + r + 1);
+      if (ROWVAL) rv = __ldg(row_vals + r);
+    }
+  };
+  auto load_cv = [&](int e0, int e1, int off, int& c, float& v) {
+    c = 0; v = 0.f;
+    const int e = e0 + off + sl;
+    if (e < e1) {
+      c = __ldcs(colidx + e);
+      if (!ROWVAL) v = __ldcs(vals + e);
+    }
+  };
+
+  // pipeline registers: current row (e0,e1,rv,c,v), next row (pointers + first batch), row after next (pointers)
+  int e0, e1, e0n, e1n, e0nn, e1nn, c, cn;
+  float rv, rvn, rvnn, v, vn;
+  bool hv, hvn, hvnn;
+  load_ptr(unit, e0, e1, rv, hv);
+  load_ptr(unit + stride, e0n, e1n, rvn, hvn);
+  if (e1 - e0 > GODE_HEAVY_ROW) { hv = true; e1 = e0; }
+  load_cv(e0, e1, 0, c, v);
+
+  for (; unit < n_units; unit += stride) {
+    // prefetch: next row's first batch, and the pointers of the row after next
+    if (e1n - e0n > GODE_HEAVY_ROW) { hvn = true; e1n = e0n; }
+    load_cv(e0n, e1n, 0, cn, vn);
+    load_ptr(unit + 2 * stride, e0nn, e1nn, rvnn, hvnn);
+
+    float4 acc[VPL];
+#pragma unroll
+    for (int u = 0; u < VPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int len = e1 - e0;
+    const int maxlen = warp_max_over_subs<LPR>(len);
+    consume_batch<LPR, VPL, U, ROWVAL>(acc, c, v, min(len, LPR), min(maxlen, LPR), sub, xl, ldx);
+    for (int off = LPR; off < maxlen; off += LPR) {   // rows longer than one batch (uncommon)
+      load_cv(e0, e1, off, c, v);
+      consume_batch<LPR, VPL, U, ROWVAL>(acc, c, v, min(len - off, LPR), min(maxlen - off, LPR), sub, xl, ldx);
+    }
+    const int64_t row = unit * RPW + sub;
+    if (row < n_rows && !hv) {
+      if (ROWVAL) {
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) { acc[u].x *= rv; acc[u].y *= rv; acc[u].z *= rv; acc[u].w *= rv; }
+      }
+      epilogue<VPL>(ep, row, col0, acc, Y, ldy);
+    }
+    e0 = e0n; e1 = e1n; rv = rvn; hv = hvn; c = cn; v = vn;
+    e0n = e0nn; e1n = e1nn; rvn = rvnn; hvn = hvnn;
+  }
+}
+
+template <int LPR, int VPL, int U, int MINB>
+static int launch_pw(const gode_csr_t& A, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                     const gode_spmm_epilogue_t& ep, cudaStream_t st) {
+  constexpr int RPW = 32 / LPR;
+  const int64_t n_units = (A.n_rows + RPW - 1) / RPW;
+  int64_t blocks = (n_units + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * MINB;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) return GODE_OK;
+  if (A.row_vals)
+    k_spmm_pw<LPR, VPL, U, MINB, true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals,
+                                                                                       A.row_vals, X, ldx, Y, ldy, ep);
+  else
+    k_spmm_pw<LPR, VPL, U, MINB, false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals,
+                                                                                        nullptr, X, ldx, Y, ldy, ep);
+  GODE_LAUNCH_CHECK();
+  return GODE_OK;
 }
 
 // one sub-warp per chunk of a heavy row -> partial[chunk][d]
@@ -271,7 +450,20 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
                       const gode_spmm_epilogue_t& ep, float* ws, cudaStream_t st) {
   constexpr int RPW = 32 / LPR;
   constexpr int RPB = 8 * RPW;
-  if (A.n_rows > 0) {
+  static const int variant = [] {
+    const char* e = getenv("GODE_SPMM_VARIANT");
+    return e ? atoi(e) : 5;   // 5/4: persistent warps (U=8 x 3 CTAs/SM | U=4 x 4 CTAs/SM), 0: one row per sub-warp,
+                              // 3: one 1024-thread CTA per SM on a row tile
+  }();
+  if (A.n_rows > 0 && (variant == 5 || variant == 4)) {
+    int rc = variant == 5 ? launch_pw<LPR, VPL, 8, 3>(A, X, ldx, Y, ldy, ep, st) : launch_pw<LPR, VPL, 4, 4>(A, X, ldx, Y, ldy, ep, st);
+    if (rc) return rc;
+  } else if (A.n_rows > 0 && variant == 3) {
+    constexpr int TR = TILE_WARPS * RPW * TILE_ROUNDS;
+    unsigned grid = static_cast<unsigned>((A.n_rows + TR - 1) / TR);
+    k_spmm_tile<LPR, VPL><<<grid, TILE_WARPS * 32, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, X, ldx, Y, ldy, ep);
+    GODE_LAUNCH_CHECK();
+  } else if (A.n_rows > 0) {
     unsigned grid = static_cast<unsigned>((A.n_rows + RPB - 1) / RPB);
     k_spmm_vec<LPR, VPL><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, X, ldx, Y, ldy, ep);
     GODE_LAUNCH_CHECK();
@@ -546,7 +738,7 @@ int spmm_dispatch(const gode_csr_t& A, const float* X, int64_t ldx, int32_t d, f
     float* w = static_cast<float*>(ws);
     static const int use_bulk = [] {
       const char* e = getenv("GODE_SPMM_BULK");
-      return e ? atoi(e) : 1;   // 0: register-staged, 1: LDGSTS pipeline, 2: TMA bulk-copy pipeline
+      return e ? atoi(e) : 0;   // 0: register-staged (default), 1: LDGSTS pipeline, 2: TMA bulk-copy pipeline
     }();
     if (use_bulk == 1 && d == 128) return launch_bulk<1, 1>(A, X, ldx, Y, ldy, ep, w, st);
     if (use_bulk == 2 && d == 128) return launch_bulk<1, 0>(A, X, ldx, Y, ldy, ep, w, st);

@@ -1,15 +1,540 @@
-// libgode: tensor-core (tcgen05) path of the dense transform S = [t || GroupNorm(y)] W.
-// Placeholder in this commit: reports "unsupported" so odefunc.cu takes the SIMT path.
+// libgode: tensor-core (tcgen05 / TMEM) kernels for the d x d products of the GCN ODE function.
+//
+// Reference call sites: torch.mm(input, weight) inside FixedGraphConvolution.forward (GCN/layers.py:70) applied to
+// [t || GroupNorm(x)] (GCN/models.py:175-178), and the two products its autograd issues (dS W^T and z^T dS).
+//
+// fp32 result on the 5th-generation tensor cores: every fp32 operand is split x = hi + lo with hi = tf32(x)
+// (cvt.rna) and lo = x - hi, and three kind::tf32 MMAs accumulate hi*hi + lo*hi + hi*lo in TMEM (the dropped
+// lo*lo term is 2^-22 relative).  GODE_PREC_TF32 issues the hi*hi pass only.
+//
+// k_rows_tc  (M = 128 rows per tile, N = K = D):     Out[r,:] = A[r,:] * B + rowvec
+//     MODE 0  transform : A = xhat(y) (GroupNorm statistics computed on load, affine folded into B),
+//                         B = diag(gamma) W[1:,:], rowvec = t W[0,:] + beta^T W[1:,:]            -> S
+//     MODE 1  input grad: A = dS, B = W[1:,:]^T                                                    -> dz
+//   One persistent CTA per SM.  B (hi and lo) stays resident in shared memory in the UMMA canonical
+//   K-major no-swizzle layout; the A tile is staged half of K at a time (registers -> shared, converted and
+//   split on the way) while the next half is already in flight from HBM; one elected thread issues the MMAs;
+//   the accumulator is read back with tcgen05.ld, staged through shared memory and stored as full 512 B rows.
+//
+// k_wgrad_tc (M = N = D channels, K = rows):         P = xhat(y)^T * dS   (accumulated over all rows of a CTA)
+//   Both operands are row-major [rows, D] tiles used as MN-major UMMA operands -- the same physical layout.
+//
+// Shared-memory layout of an [R rows, C channels] fp32 tile (bytes):
+//     off(r, c) = (r / 8) * (C * 32) + (c / 4) * 128 + (r % 8) * 16 + (c % 4) * 4
+//   = 8-row x 16-byte core matrices; as a K-major operand (rows = M/N, channels = K): LBO = 128, SBO = C*32;
+//   as an MN-major operand (channels = M/N, rows = K): SBO = 128, LBO = C*32.
 #include "internal.cuh"
+#include <stdlib.h>
 
 namespace gode {
-bool transform_tc_supported(const gode_gcn_odefunc_t* f) {
-  (void)f;
-  return false;
+
+namespace tc {
+
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
+  // | base_offset=0 | lbo_mode=0 | layout_type=SWIZZLE_NONE(0) [61,64)
+  return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo >> 4) << 16) |
+         (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46);
 }
+
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+  // InstrDescriptor: c_format=F32 (1<<4) | a_format=TF32 (2<<7) | b_format=TF32 (2<<10) | a_major<<15 | b_major<<16
+  // | (N>>3)<<17 | (M>>4)<<24
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TC_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TC_DONE;\n"
+      "bra TC_WAIT;\n"
+      "TC_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns: thread t of warp w reads TMEM lane 32*(w%4)+t
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
+  hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
+  lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
+}
+
+// GroupNorm statistics of one 16-byte chunk (4 channels): CPG = 4 -> one group, CPG = 2 -> two groups; no affine
+template <int CPG>
+__device__ __forceinline__ float4 normalize4(float4 x, float eps) {
+  if (CPG == 4) {
+    const float mean = (x.x + x.y + x.z + x.w) * 0.25f;
+    const float a = x.x - mean, b = x.y - mean, c = x.z - mean, d = x.w - mean;
+    const float rstd = 1.0f / sqrtf((a * a + b * b + c * c + d * d) * 0.25f + eps);
+    return make_float4(a * rstd, b * rstd, c * rstd, d * rstd);
+  } else if (CPG == 2) {
+    const float m0 = (x.x + x.y) * 0.5f, m1 = (x.z + x.w) * 0.5f;
+    const float a = x.x - m0, b = x.y - m0, c = x.z - m1, d = x.w - m1;
+    const float r0 = 1.0f / sqrtf((a * a + b * b) * 0.5f + eps), r1 = 1.0f / sqrtf((c * c + d * d) * 0.5f + eps);
+    return make_float4(a * r0, b * r0, c * r1, d * r1);
+  }
+  return x;
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------
+// Out[r, :] = A[r, :] * B + rowvec,  rows tiled by 128
+// ------------------------------------------------------------------------------------------------
+template <int D, int CPG, int MODE>
+__global__ void __launch_bounds__(tc::THREADS, 1)
+k_rows_tc(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, const float* __restrict__ W /*[D+1, D]*/,
+          const float* __restrict__ gamma, const float* __restrict__ beta, float t, float eps, int passes) {
+  using namespace tc;
+  constexpr int KH = D / 2;                 // channels per staged half of K
+  constexpr int NI = (16 * (KH / 16)) / 8;  // warp-instructions (8 rows x 4 chunks) per warp per half tile
+  constexpr uint32_t RSB = D * 32;          // 8-row-group stride of the B tile (full K)
+  constexpr uint32_t RSA = KH * 32;         // 8-row-group stride of an A half tile
+  constexpr uint32_t B_BYTES = D * D * 4;
+  constexpr uint32_t A_BYTES = 128 * KH * 4;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sBhi = smem;
+  unsigned char* sBlo = smem + B_BYTES;
+  unsigned char* sAhi = smem + 2 * B_BYTES;
+  unsigned char* sAlo = sAhi + A_BYTES;               // sAhi..sAlo+A_BYTES doubles as the epilogue staging buffer
+  float* sRow = reinterpret_cast<float*>(sAlo + A_BYTES);   // [D] rowvec
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sRow + D);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n_tiles = (n_rows + 127) / 128;
+  if ((int64_t)blockIdx.x >= n_tiles) return;
+
+  // ---- one-time setup: barrier, TMEM, B operand, row vector -----------------------------------
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, D);
+  const float* W1 = W + D;   // rows 1..D of the [D+1, D] weight
+  for (int n = tid; n < D; n += THREADS) {
+    float r = 0.f;
+    if (MODE == 0) {
+      r = t * __ldg(W + n);
+      for (int k = 0; k < D; ++k) r = fmaf(__ldg(beta + k), __ldg(W1 + (int64_t)k * D + n), r);
+    }
+    sRow[n] = r;
+  }
+  // B[n][k]: MODE 0 -> gamma[k] * W1[k][n] ; MODE 1 -> W1[n][k].  lane -> (n%8, 4 k-chunks); conflict-free stores.
+  for (int g = warp; g < (D / 8) * (D / 16); g += THREADS / 32) {
+    const int ng = g / (D / 16), cg = g % (D / 16);
+    const int n = ng * 8 + (lane & 7), kc = cg * 4 + (lane >> 3);
+    float4 b;
+    if (MODE == 0) {
+      const int k = kc * 4;
+      b.x = __ldg(gamma + k) * __ldg(W1 + (int64_t)k * D + n);
+      b.y = __ldg(gamma + k + 1) * __ldg(W1 + (int64_t)(k + 1) * D + n);
+      b.z = __ldg(gamma + k + 2) * __ldg(W1 + (int64_t)(k + 2) * D + n);
+      b.w = __ldg(gamma + k + 3) * __ldg(W1 + (int64_t)(k + 3) * D + n);
+    } else {
+      b = __ldg(reinterpret_cast<const float4*>(W1 + (int64_t)n * D + kc * 4));
+    }
+    float4 hi, lo;
+    split4(b, hi, lo);
+    const uint32_t off = ng * RSB + kc * 128 + (lane & 7) * 16;
+    *reinterpret_cast<float4*>(sBhi + off) = hi;
+    *reinterpret_cast<float4*>(sBlo + off) = lo;
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+  constexpr uint32_t IDESC = make_idesc(128, D, false, false);
+  const uint32_t aHi = smem_u32(sAhi), aLo = smem_u32(sAlo), bHi = smem_u32(sBhi), bLo = smem_u32(sBlo);
+
+  // ---- software pipeline over (tile, half) stages ------------------------------------------------
+  float4 raw[NI];
+  auto load_raw = [&](int64_t tile, int half) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int g = warp * NI + i;
+      const int rg = g / (KH / 16), cg = g % (KH / 16);
+      const int64_t row = tile * 128 + rg * 8 + (lane & 7);
+      const int kc = cg * 4 + (lane >> 3);
+      raw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < n_rows) raw[i] = __ldcs(reinterpret_cast<const float4*>(X + row * D + half * KH + kc * 4));
+    }
+  };
+  auto store_half = [&]() {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int g = warp * NI + i;
+      const int rg = g / (KH / 16), cg = g % (KH / 16);
+      const int kc = cg * 4 + (lane >> 3);
+      float4 hi, lo;
+      split4(normalize4<CPG>(raw[i], eps), hi, lo);
+      const uint32_t off = rg * RSA + kc * 128 + (lane & 7) * 16;
+      *reinterpret_cast<float4*>(sAhi + off) = hi;
+      *reinterpret_cast<float4*>(sAlo + off) = lo;
+    }
+  };
+
+  uint32_t parity = 0;
+  int64_t tile = blockIdx.x;
+  load_raw(tile, 0);
+  bool pending = false;   // an MMA batch has been committed and not yet waited for
+  for (; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      if (pending) {   // the A buffer is still being read by the previous half's MMAs
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        pending = false;
+      }
+      store_half();
+      // next stage's loads fly while this half is multiplied
+      if (half == 0) load_raw(tile, 1);
+      else if (tile + gridDim.x < n_tiles) load_raw(tile + gridDim.x, 0);
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < KH / 8; ++s) {
+          const uint32_t ks = half * (KH / 8) + s;
+          const uint64_t da_hi = make_desc(aHi + s * 256, 128, RSA), da_lo = make_desc(aLo + s * 256, 128, RSA);
+          const uint64_t db_hi = make_desc(bHi + ks * 256, 128, RSB), db_lo = make_desc(bLo + ks * 256, 128, RSB);
+          mma_tf32(tmem_d, da_hi, db_hi, IDESC, (half | s) != 0 ? 1u : 0u);
+          if (passes == 3) {
+            mma_tf32(tmem_d, da_lo, db_hi, IDESC, 1u);
+            mma_tf32(tmem_d, da_hi, db_lo, IDESC, 1u);
+          }
+        }
+        mma_commit(bar);
+      }
+      pending = true;
+    }
+    // ---- epilogue: TMEM -> registers -> (+rowvec) -> staging smem -> 512 B row stores ------------
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    pending = false;
+    tc_fence_after();
+    {
+      constexpr int CH = D / 4;            // 16-byte chunks per output row
+      constexpr int HC = D / 2;            // columns handled by one warp (two warps share a TMEM lane quarter)
+      const int q = warp & 3, hc = warp >> 2;
+      const int row = q * 32 + lane;
+      float* stage = reinterpret_cast<float*>(sAhi);
+#pragma unroll
+      for (int cb = 0; cb < HC; cb += 32) {
+        float v[32];
+        tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + hc * HC + cb, v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int col = hc * HC + cb + j;
+          const int chunk = (col >> 2) ^ (row & (CH - 1));
+          float4 o = make_float4(v[j] + sRow[col], v[j + 1] + sRow[col + 1], v[j + 2] + sRow[col + 2], v[j + 3] + sRow[col + 3]);
+          *reinterpret_cast<float4*>(stage + row * D + chunk * 4) = o;
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+      // each warp writes whole rows: lane -> 16-byte chunk(s) of the row
+      for (int r = warp; r < 128; r += THREADS / 32) {
+        const int64_t grow = tile * 128 + r;
+        if (grow >= n_rows) break;
+#pragma unroll
+        for (int c = lane; c < CH; c += 32) {
+          const float4 o = *reinterpret_cast<const float4*>(stage + r * D + ((c ^ (r & (CH - 1))) * 4));
+          __stcs(reinterpret_cast<float4*>(Out + grow * D + c * 4), o);
+        }
+      }
+      __syncthreads();   // staging buffer is the A buffer of the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, D);
+}
+
+static bool tc_enabled() {
+  static const int on = [] {
+    const char* e = getenv("GODE_TC");
+    return e ? atoi(e) : 1;
+  }();
+  return on != 0;
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ------------------------------------------------------------------------------------------------
+// P[i, o] = sum_r xhat(y)[r, i] * dS[r, o]      (weight gradient before the GroupNorm affine is re-applied)
+// ------------------------------------------------------------------------------------------------
+template <int D, int CPG>
+__global__ void __launch_bounds__(tc::THREADS, 1)
+k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restrict__ G, float* __restrict__ partial /*[grid][D][D]*/,
+           float eps, int passes) {
+  using namespace tc;
+  static_assert(D == 128, "the accumulator uses all 128 TMEM lanes");
+  constexpr int RC = 32;                       // rows (= K) per staged chunk
+  constexpr uint32_t RS = D * 32;              // stride between 8-row groups
+  constexpr uint32_t MAT = RC * D * 4;         // bytes of one [RC, D] operand tile
+  constexpr int NI = ((RC / 8) * (D / 16)) / (THREADS / 32);   // warp-instructions per warp per operand
+  extern __shared__ __align__(1024) unsigned char smem[];
+  // stage b: [A_hi | A_lo | B_hi | B_lo] at smem + b * 4 * MAT
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * 4 * MAT);   // [0],[1]: stage free; [2]: all done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n_chunks = (n_rows + RC - 1) / RC;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, D);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+  constexpr uint32_t IDESC = make_idesc(D, D, true, true);
+
+  float4 ra[NI], rb[NI];
+  auto load_raw = [&](int64_t chunk) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int g = warp * NI + i;
+      const int rg = g / (D / 16), cg = g % (D / 16);
+      const int64_t row = chunk * RC + rg * 8 + (lane & 7);
+      const int kc = cg * 4 + (lane >> 3);
+      ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[i] = ra[i];
+      if (row < n_rows) {
+        ra[i] = __ldcs(reinterpret_cast<const float4*>(Yin + row * D + kc * 4));
+        rb[i] = __ldcs(reinterpret_cast<const float4*>(G + row * D + kc * 4));
+      }
+    }
+  };
+  auto store_stage = [&](int b, int64_t chunk) {
+    unsigned char* base = smem + (size_t)b * 4 * MAT;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int g = warp * NI + i;
+      const int rg = g / (D / 16), cg = g % (D / 16);
+      const int kc = cg * 4 + (lane >> 3);
+      const int64_t row = chunk * RC + rg * 8 + (lane & 7);
+      float4 xa = normalize4<CPG>(ra[i], eps);
+      if (row >= n_rows) xa = make_float4(0.f, 0.f, 0.f, 0.f);   // xhat of a padding row is not zero by itself
+      float4 hi, lo;
+      const uint32_t off = rg * RS + kc * 128 + (lane & 7) * 16;
+      split4(xa, hi, lo);
+      *reinterpret_cast<float4*>(base + off) = hi;
+      *reinterpret_cast<float4*>(base + MAT + off) = lo;
+      split4(rb[i], hi, lo);
+      *reinterpret_cast<float4*>(base + 2 * MAT + off) = hi;
+      *reinterpret_cast<float4*>(base + 3 * MAT + off) = lo;
+    }
+  };
+
+  uint32_t parity[2] = {0u, 0u};
+  int it = 0;
+  int64_t chunk = blockIdx.x;
+  if (chunk < n_chunks) load_raw(chunk);
+  for (; chunk < n_chunks; chunk += gridDim.x, ++it) {
+    const int b = it & 1;
+    if (it >= 2) {   // the MMAs that read this stage two iterations ago must have retired
+      mbar_wait(&bars[b], parity[b]);
+      parity[b] ^= 1u;
+    }
+    store_stage(b, chunk);
+    if (chunk + gridDim.x < n_chunks) load_raw(chunk + gridDim.x);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t base = smem_u32(smem + (size_t)b * 4 * MAT);
+#pragma unroll
+      for (int s = 0; s < RC / 8; ++s) {
+        // MN-major operands: SBO = 128 (next 4 channels), LBO = RS (next 8 rows of K)
+        const uint64_t a_hi = make_desc(base + s * RS, RS, 128), a_lo = make_desc(base + MAT + s * RS, RS, 128);
+        const uint64_t b_hi = make_desc(base + 2 * MAT + s * RS, RS, 128), b_lo = make_desc(base + 3 * MAT + s * RS, RS, 128);
+        mma_tf32(tmem_d, a_hi, b_hi, IDESC, (it | s) != 0 ? 1u : 0u);
+        if (passes == 3) {
+          mma_tf32(tmem_d, a_lo, b_hi, IDESC, 1u);
+          mma_tf32(tmem_d, a_hi, b_lo, IDESC, 1u);
+        }
+      }
+      mma_commit(&bars[b]);
+    }
+  }
+  if (tid == 0) mma_commit(&bars[2]);   // arrives when every MMA issued above has completed
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+  {
+    const int q = warp & 3, hc = warp >> 2;
+    const int row = q * 32 + lane;   // channel i
+    float* out = partial + (size_t)blockIdx.x * D * D + (size_t)row * D;
+#pragma unroll
+    for (int cb = 0; cb < D / 2; cb += 32) {
+      float v[32];
+      if (it > 0) {
+        tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + hc * (D / 2) + cb, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(out + hc * (D / 2) + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, D);
+}
+
+// gW1[i][o] = gamma[i] * sum_b partial[b][i][o] + beta[i] * cs[o]
+__global__ void k_wgrad_finish(int nblk, int d, const float* __restrict__ partial, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ cs, float* __restrict__ gW1) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= d * d) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * d * d + idx];
+  const int i = idx / d, o = idx % d;
+  gW1[idx] = gamma[i] * s + beta[i] * cs[o];
+}
+
+bool wgrad_tc_supported(const gode_gcn_odefunc_t* f) { return tc_enabled() && f->d == 128 && f->groups == 32; }
+
+size_t wgrad_tc_ws_bytes(const gode_gcn_odefunc_t* f) { return sizeof(float) * (size_t)sm_count() * f->d * f->d; }
+
+// gW1 = z^T dS with z = GroupNorm(y);  cs = column sums of dS (already computed by the caller)
+int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, const float* cs, float* gW1, float* ws,
+             size_t ws_bytes, cudaStream_t st) {
+  constexpr int D = 128;
+  GODE_REQUIRE(al16(y) && al16(gS) && al16(ws), "wgrad_tc: operands must be 16-byte aligned");
+  const int64_t n_chunks = (f->A.n_rows + 31) / 32;
+  int grid = static_cast<int>(n_chunks < sm_count() ? n_chunks : sm_count());
+  if (grid < 1) grid = 1;
+  if (ws_bytes < sizeof(float) * (size_t)grid * D * D) {
+    set_error("wgrad_tc: workspace too small");
+    return GODE_EWORKSPACE;
+  }
+  constexpr size_t smem = 2 * 4 * (size_t)32 * D * 4 + 64;
+  static bool configured = false;
+  if (!configured) {
+    GODE_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_tc<D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int passes = f->precision == GODE_PREC_TF32 ? 1 : 3;
+  k_wgrad_tc<D, 4><<<grid, tc::THREADS, smem, st>>>(f->A.n_rows, y, gS, ws, f->gn_eps, passes);
+  GODE_LAUNCH_CHECK();
+  k_wgrad_finish<<<(D * D + 255) / 256, 256, 0, st>>>(grid, D, ws, f->gamma, f->beta, cs, gW1);
+  GODE_LAUNCH_CHECK();
+  return GODE_OK;
+}
+
+template <int D, int CPG, int MODE>
+static int launch_rows_tc(int64_t n_rows, const float* X, float* Out, const float* W, const float* gamma, const float* beta,
+                          float t, float eps, int passes, cudaStream_t st) {
+  constexpr size_t smem = 2 * (size_t)D * D * 4 + 2 * (size_t)128 * (D / 2) * 4 + D * 4 + 64;
+  static bool configured = false;
+  if (!configured) {
+    GODE_CHECK_CUDA(cudaFuncSetAttribute(k_rows_tc<D, CPG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int64_t n_tiles = (n_rows + 127) / 128;
+  if (n_tiles == 0) return GODE_OK;
+  const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
+  k_rows_tc<D, CPG, MODE><<<grid, tc::THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes);
+  GODE_LAUNCH_CHECK();
+  return GODE_OK;
+}
+
+bool transform_tc_supported(const gode_gcn_odefunc_t* f) {
+  if (!tc_enabled()) return false;
+  const int cpg = f->d / f->groups;
+  return (f->d == 128 && cpg == 4) || (f->d == 64 && cpg == 2);
+}
+
 int transform_tc(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, cudaStream_t st) {
-  (void)f; (void)y; (void)t; (void)S; (void)st;
-  set_error("transform_tc: not built");
+  GODE_REQUIRE(al16(y) && al16(S), "transform_tc: operands must be 16-byte aligned");
+  const int passes = f->precision == GODE_PREC_TF32 ? 1 : 3;
+  if (f->d == 128) return launch_rows_tc<128, 4, 0>(f->A.n_rows, y, S, f->W, f->gamma, f->beta, t, f->gn_eps, passes, st);
+  if (f->d == 64) return launch_rows_tc<64, 2, 0>(f->A.n_rows, y, S, f->W, f->gamma, f->beta, t, f->gn_eps, passes, st);
+  set_error("transform_tc: unsupported width %d", f->d);
   return GODE_EINVAL;
 }
+
+// dz = dS * W[1:,:]^T
+int input_grad_tc(const gode_gcn_odefunc_t* f, const float* gS, float* gz, cudaStream_t st) {
+  GODE_REQUIRE(al16(gS) && al16(gz), "input_grad_tc: operands must be 16-byte aligned");
+  const int passes = f->precision == GODE_PREC_TF32 ? 1 : 3;
+  if (f->d == 128) return launch_rows_tc<128, 0, 1>(f->A.n_rows, gS, gz, f->W, f->gamma, f->beta, 0.f, f->gn_eps, passes, st);
+  if (f->d == 64) return launch_rows_tc<64, 0, 1>(f->A.n_rows, gS, gz, f->W, f->gamma, f->beta, 0.f, f->gn_eps, passes, st);
+  set_error("input_grad_tc: unsupported width %d", f->d);
+  return GODE_EINVAL;
+}
+
 }  // namespace gode

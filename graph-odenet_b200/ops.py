@@ -71,6 +71,8 @@ class GraphPlan:
         self.nnz = int(colidx.numel())
         self.device = rowptr.device
         self.heavy, self.chunk_ptr, self.n_heavy, self.n_chunks = self._heavy(rowptr, self.n_rows)
+        self.row_vals = self._row_values(rowptr, vals, self.n_rows)
+        self.row_vals_t = None
         self.rowptr_t = self.colidx_t = self.vals_t = self.perm_t = None
         self.heavy_t, self.chunk_ptr_t, self.n_heavy_t, self.n_chunks_t = None, None, 0, 0
         if build_transpose:
@@ -91,6 +93,16 @@ class GraphPlan:
             return None, None, 0, 0
         return rows[:n].clone(), cptr[:n + 1].clone(), n, nc
 
+    @staticmethod
+    def _row_values(rowptr, vals, n_rows):
+        """Per-row common value if the matrix is row-constant (D^-1 (A+I) is), else None (gode_csr_row_values)."""
+        if n_rows == 0 or vals.numel() == 0:
+            return None
+        out = torch.empty(n_rows, dtype=torch.float32, device=rowptr.device)
+        flag = torch.zeros(1, dtype=torch.int32, device=rowptr.device)
+        check(lib.gode_csr_row_values(n_rows, _p(rowptr), _p(vals), _p(out), _p(flag), _stream()), "gode_csr_row_values")
+        return out if int(flag.item()) == 1 else None
+
     def csr(self, transpose=False):
         """The ``gode_csr_t`` view of A (or A^T) passed to the kernels."""
         if transpose:
@@ -98,11 +110,11 @@ class GraphPlan:
                 if self.rowptr_t is None:
                     raise RuntimeError("this plan was built without its transpose")
                 self._csr_t = _make_csr(self.n_cols, self.n_rows, self.rowptr_t, self.colidx_t, self.vals_t,
-                                        self.heavy_t, self.chunk_ptr_t, self.n_heavy_t, self.n_chunks_t)
+                                        self.heavy_t, self.chunk_ptr_t, self.n_heavy_t, self.n_chunks_t, self.row_vals_t)
             return self._csr_t
         if self._csr is None:
             self._csr = _make_csr(self.n_rows, self.n_cols, self.rowptr, self.colidx, self.vals, self.heavy,
-                                  self.chunk_ptr, self.n_heavy, self.n_chunks)
+                                  self.chunk_ptr, self.n_heavy, self.n_chunks, self.row_vals)
         return self._csr
 
     def _build_transpose(self):
@@ -118,6 +130,7 @@ class GraphPlan:
                                      _p(self.rowptr_t), _p(self.colidx_t), _p(self.vals_t), _p(self.perm_t),
                                      _p(ws), nb, _stream()), "gode_csr_transpose")
         self.heavy_t, self.chunk_ptr_t, self.n_heavy_t, self.n_chunks_t = self._heavy(self.rowptr_t, self.n_cols)
+        self.row_vals_t = self._row_values(self.rowptr_t, self.vals_t, self.n_cols)
         del ws
 
     @classmethod
@@ -163,14 +176,16 @@ class GraphPlan:
         t.heavy, t.chunk_ptr, t.n_heavy, t.n_chunks = self.heavy_t, self.chunk_ptr_t, self.n_heavy_t, self.n_chunks_t
         t.rowptr_t, t.colidx_t, t.vals_t, t.perm_t = self.rowptr, self.colidx, self.vals, None
         t.heavy_t, t.chunk_ptr_t, t.n_heavy_t, t.n_chunks_t = self.heavy, self.chunk_ptr, self.n_heavy, self.n_chunks
+        t.row_vals, t.row_vals_t = self.row_vals_t, self.row_vals
         t._csr = t._csr_t = None
         return t
 
 
-def _make_csr(n_rows, n_cols, rowptr, colidx, vals, heavy, chunk_ptr, n_heavy, n_chunks):
+def _make_csr(n_rows, n_cols, rowptr, colidx, vals, heavy, chunk_ptr, n_heavy, n_chunks, row_vals=None):
     c = _lib.Csr()
     c.n_rows, c.n_cols = n_rows, n_cols
     c.rowptr, c.colidx, c.vals = rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr()
+    c.row_vals = row_vals.data_ptr() if row_vals is not None else None
     c.heavy_rows = heavy.data_ptr() if n_heavy else None
     c.heavy_chunk_ptr = chunk_ptr.data_ptr() if n_heavy else None
     c.n_heavy, c.n_chunks = n_heavy, n_chunks

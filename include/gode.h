@@ -93,11 +93,19 @@ typedef struct {
   const int32_t* rowptr;            /* [n_rows + 1] */
   const int32_t* colidx;            /* [nnz] */
   const float* vals;                /* [nnz] */
+  const float* row_vals;            /* [n_rows] or NULL.  When every stored entry of a row carries the same value
+                                       (the reference's D^-1 (A+I), GCN/utils.py:186,205-212: 1/(deg+1)), the SpMM
+                                       gathers with colidx only and scales the row sum once (gode_csr_row_values). */
   const int32_t* heavy_rows;        /* [n_heavy] ascending, or NULL */
   const int32_t* heavy_chunk_ptr;   /* [n_heavy + 1], or NULL */
   int32_t n_heavy;
   int32_t n_chunks;
 } gode_csr_t;
+
+/* row_vals_out[r] = the common value of row r's entries (0 for an empty row); *is_const_out (device int32) = 1
+ * iff every row's entries are bit-identical -- only then may row_vals_out be used as gode_csr_t.row_vals. */
+int gode_csr_row_values(int64_t n_rows, const int32_t* rowptr, const float* vals, float* row_vals_out,
+                        int32_t* is_const_out, void* stream);
 
 /* heavy_rows (capacity n_rows) and heavy_chunk_ptr (capacity n_rows + 1) are filled on the device;
  * counts_out is a device int32[2] = {n_heavy, n_chunks}. */
