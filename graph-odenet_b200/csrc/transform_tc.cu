@@ -335,9 +335,14 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
            float eps, int passes) {
   using namespace tc;
   static_assert(D == 128, "the accumulator uses all 128 TMEM lanes");
+  // Both operands are [rows, D] row-major in HBM but the reduction runs over rows, so they are transposed on the
+  // way into shared memory and used as ordinary K-major operands: element (channel i, row r) of a staged tile at
+  //     (i/8)*SBO + (r/4)*LBO + (i%8)*16 + (r%4)*4,   LBO = 144, SBO = 1184
+  // (core matrices stay 128 B contiguous; the 16 B / 32 B skews make the 4-byte transposing stores of a warp hit 32
+  // distinct banks).
   constexpr int RC = 32;                       // rows (= K) per staged chunk
-  constexpr uint32_t RS = D * 32;              // stride between 8-row groups
-  constexpr uint32_t MAT = RC * D * 4;         // bytes of one [RC, D] operand tile
+  constexpr uint32_t LBO = 144, SBO = 1184;
+  constexpr uint32_t MAT = (D / 8) * SBO;      // bytes of one staged operand tile
   constexpr int NI = ((RC / 8) * (D / 16)) / (THREADS / 32);   // warp-instructions per warp per operand
   extern __shared__ __align__(1024) unsigned char smem[];
   // stage b: [A_hi | A_lo | B_hi | B_lo] at smem + b * 4 * MAT
@@ -357,7 +362,7 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
-  constexpr uint32_t IDESC = make_idesc(D, D, true, true);
+  constexpr uint32_t IDESC = make_idesc(D, D, false, false);
 
   float4 ra[NI], rb[NI];
   auto load_raw = [&](int64_t chunk) {
@@ -375,6 +380,15 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
       }
     }
   };
+  auto put = [&](unsigned char* tile, int r, int c0, const float4& v) {   // 4 channels of one row, transposed
+    const uint32_t base = (r >> 2) * LBO + (r & 3) * 4;
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = c0 + j;
+      *reinterpret_cast<float*>(tile + (i >> 3) * SBO + (i & 7) * 16 + base) = vv[j];
+    }
+  };
   auto store_stage = [&](int b, int64_t chunk) {
     unsigned char* base = smem + (size_t)b * 4 * MAT;
 #pragma unroll
@@ -382,17 +396,16 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
       const int g = warp * NI + i;
       const int rg = g / (D / 16), cg = g % (D / 16);
       const int kc = cg * 4 + (lane >> 3);
-      const int64_t row = chunk * RC + rg * 8 + (lane & 7);
+      const int r = rg * 8 + (lane & 7);
       float4 xa = normalize4<CPG>(ra[i], eps);
-      if (row >= n_rows) xa = make_float4(0.f, 0.f, 0.f, 0.f);   // xhat of a padding row is not zero by itself
+      if (chunk * RC + r >= n_rows) xa = make_float4(0.f, 0.f, 0.f, 0.f);   // xhat of a padding row is not zero by itself
       float4 hi, lo;
-      const uint32_t off = rg * RS + kc * 128 + (lane & 7) * 16;
       split4(xa, hi, lo);
-      *reinterpret_cast<float4*>(base + off) = hi;
-      *reinterpret_cast<float4*>(base + MAT + off) = lo;
+      put(base, r, kc * 4, hi);
+      put(base + MAT, r, kc * 4, lo);
       split4(rb[i], hi, lo);
-      *reinterpret_cast<float4*>(base + 2 * MAT + off) = hi;
-      *reinterpret_cast<float4*>(base + 3 * MAT + off) = lo;
+      put(base + 2 * MAT, r, kc * 4, hi);
+      put(base + 3 * MAT, r, kc * 4, lo);
     }
   };
 
@@ -416,9 +429,9 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
       const uint32_t base = smem_u32(smem + (size_t)b * 4 * MAT);
 #pragma unroll
       for (int s = 0; s < RC / 8; ++s) {
-        // MN-major operands: SBO = 128 (next 4 channels), LBO = RS (next 8 rows of K)
-        const uint64_t a_hi = make_desc(base + s * RS, RS, 128), a_lo = make_desc(base + MAT + s * RS, RS, 128);
-        const uint64_t b_hi = make_desc(base + 2 * MAT + s * RS, RS, 128), b_lo = make_desc(base + 3 * MAT + s * RS, RS, 128);
+        const uint32_t ko = s * 2 * LBO;   // 8 rows of K = two 16-byte chunks
+        const uint64_t a_hi = make_desc(base + ko, LBO, SBO), a_lo = make_desc(base + MAT + ko, LBO, SBO);
+        const uint64_t b_hi = make_desc(base + 2 * MAT + ko, LBO, SBO), b_lo = make_desc(base + 3 * MAT + ko, LBO, SBO);
         mma_tf32(tmem_d, a_hi, b_hi, IDESC, (it | s) != 0 ? 1u : 0u);
         if (passes == 3) {
           mma_tf32(tmem_d, a_lo, b_hi, IDESC, 1u);
@@ -481,7 +494,7 @@ int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, const
     set_error("wgrad_tc: workspace too small");
     return GODE_EWORKSPACE;
   }
-  constexpr size_t smem = 2 * 4 * (size_t)32 * D * 4 + 64;
+  constexpr size_t smem = 2 * 4 * (size_t)(D / 8) * 1184 + 64;
   static bool configured = false;
   if (!configured) {
     GODE_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_tc<D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
