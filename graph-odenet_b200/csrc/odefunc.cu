@@ -15,6 +15,7 @@ int transform_tc(const gode_gcn_odefunc_t* f, const float* y, float t, float* S,
 bool transform_tc_supported(const gode_gcn_odefunc_t* f);
 int input_grad_tc(const gode_gcn_odefunc_t* f, const float* gS, float* gz, cudaStream_t st);
 bool wgrad_tc_supported(const gode_gcn_odefunc_t* f);
+bool input_grad_tc_supported(const gode_gcn_odefunc_t* f);
 size_t wgrad_tc_ws_bytes(const gode_gcn_odefunc_t* f);
 int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, const float* cs, float* gW1, float* ws,
              size_t ws_bytes, cudaStream_t st);
@@ -256,7 +257,7 @@ extern "C" int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, 
       return rc;
   }
   // gz = gS W[1:,:]^T ; GroupNorm backward
-  if (transform_tc_supported(f)) {
+  if (input_grad_tc_supported(f)) {
     if ((rc = input_grad_tc(f, gS, gz, st))) return rc;
   } else if ((rc = gemm_simt(0, 1, n, d, d, 1.f, gS, d, f->W + d, d, 0.f, gz, d, 1, nullptr, 0, st, nullptr, 0.f))) {
     return rc;

@@ -316,13 +316,15 @@ k_rows_tc(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
   if (warp == 0) tmem_dealloc(tmem_d, D);
 }
 
-static bool tc_enabled() {
-  static const int on = [] {
+// GODE_TC: bit 0 = transform, bit 1 = input gradient, bit 2 = weight gradient on tcgen05 (default all)
+static int tc_mask() {
+  static const int m = [] {
     const char* e = getenv("GODE_TC");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 7;
   }();
-  return on != 0;
+  return m;
 }
+static bool tc_enabled() { return tc_mask() != 0; }
 
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -478,7 +480,7 @@ __global__ void k_wgrad_finish(int nblk, int d, const float* __restrict__ partia
   gW1[idx] = gamma[i] * s + beta[i] * cs[o];
 }
 
-bool wgrad_tc_supported(const gode_gcn_odefunc_t* f) { return tc_enabled() && f->d == 128 && f->groups == 32; }
+bool wgrad_tc_supported(const gode_gcn_odefunc_t* f) { return (tc_mask() & 4) && f->d == 128 && f->groups == 32; }
 
 size_t wgrad_tc_ws_bytes(const gode_gcn_odefunc_t* f) { return sizeof(float) * (size_t)sm_count() * f->d * f->d; }
 
@@ -525,11 +527,12 @@ static int launch_rows_tc(int64_t n_rows, const float* X, float* Out, const floa
   return GODE_OK;
 }
 
-bool transform_tc_supported(const gode_gcn_odefunc_t* f) {
-  if (!tc_enabled()) return false;
+static bool rows_tc_shape(const gode_gcn_odefunc_t* f) {
   const int cpg = f->d / f->groups;
   return (f->d == 128 && cpg == 4) || (f->d == 64 && cpg == 2);
 }
+bool transform_tc_supported(const gode_gcn_odefunc_t* f) { return (tc_mask() & 1) && rows_tc_shape(f); }
+bool input_grad_tc_supported(const gode_gcn_odefunc_t* f) { return (tc_mask() & 2) && rows_tc_shape(f); }
 
 int transform_tc(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, cudaStream_t st) {
   GODE_REQUIRE(al16(y) && al16(S), "transform_tc: operands must be 16-byte aligned");

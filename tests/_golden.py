@@ -61,3 +61,13 @@ def assert_close(a, b, rtol=1e-5, atol_scale=1e-5, what="", atol_abs=0.0):
         i = int(torch.argmax(err - tol))
         raise AssertionError("%s: max err %.3e (scale %.3e) at flat %d: got %.8e want %.8e; %d/%d bad" % (
             what, float(err.max()), scale, i, float(a.reshape(-1)[i]), float(b.reshape(-1)[i]), int(bad.sum()), bad.numel()))
+
+
+def assert_close_l2(a, b, tol, what=""):
+    """||a-b||_F <= tol * ||b||_F.  Used where single entries are legitimately unstable (gradients of ReLU networks:
+    a pre-activation within rounding distance of zero flips its mask; see tools/sensitivity.py)."""
+    a = torch.as_tensor(a).detach().cpu().double()
+    b = torch.as_tensor(b).detach().cpu().double()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = float((a - b).norm() / (b.norm() + 1e-300))
+    assert err <= tol, "%s: relative L2 error %.3e > %.1e" % (what, err, tol)

@@ -8,9 +8,11 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
+    sys.argv = [sys.argv[0], sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4]]
     import graph_odenet_b200  # noqa: F401
     from graph_odenet_b200 import odeint, ops, synth
-    n, d = 50_000, 128
+    n, d = int(sys.argv[3]), 128
+    scale = float(sys.argv[4])
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     row, col, val = synth.powerlaw_graph(n, avg_degree=12, seed=0, device=dev)
@@ -21,7 +23,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     beta = torch.rand(d, device=dev) - 0.5
     kern = odeint.GcnKernel(plan, W, b, gamma, beta, 32)
     y = torch.randn(n, d, device=dev)
-    a = torch.randn(n, d, device=dev)
+    a = torch.randn(n, d, device=dev) * scale
     S, ky, ka, gP = kern.new(), kern.new(), kern.new(), kern.new()
     kern.transform(y, 0.3, S)
     gth = torch.empty(kern.n_theta, device=dev)
@@ -32,12 +34,14 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     sys.exit(0)
 
 outs = {}
+N, SC = sys.argv[1], sys.argv[2]
 for tcv in ("0", "1"):
     f = "/tmp/tc_check_%s.pt" % tcv
     env = dict(os.environ, GODE_TC=tcv)
-    subprocess.run([sys.executable, __file__, "child", f], check=True, env=env)
+    subprocess.run([sys.executable, __file__, "child", f, N, SC], check=True, env=env)
     outs[tcv] = torch.load(f)
 d = 128
+print("n", N, "scale", SC)
 for k in ("S", "ky", "ka"):
     a, b = outs["0"][k].double(), outs["1"][k].double()
     print("%-4s max|simt|=%.3e  max abs diff=%.3e  rel=%.3e" % (k, a.abs().max(), (a - b).abs().max(), (a - b).abs().max() / a.abs().max()))
