@@ -215,15 +215,20 @@ def run_ours(a):
     from graph_odenet_b200 import _lib, ops, synth
     from graph_odenet_b200.GCN import models
 
-    if world > 1:
-        from graph_odenet_b200 import parallel
-        return parallel.bench_partitioned(a, world, rank, dev, METRIC, UNIT, NFE_PER_STEP, workload_name(a),
-                                          ClockSampler, peaks)
-
     n, d = a.nodes, a.dim
     row, col, val = synth.powerlaw_graph(n, avg_degree=a.avg_degree, locality=a.locality, seed=a.seed, device=dev)
-    nnz = int(val.numel())
-    plan = ops.GraphPlan.from_coo(row, col, val, n, n)
+    nnz = int(val.numel())                       # global stored entries of A_hat: the metric's "edges"
+    halo_info = None
+    if world > 1:
+        # contiguous row blocks of A_hat / A_hat^T, halo exchange of the gather operand per evaluation
+        from graph_odenet_b200 import parallel
+        plan = parallel.PartitionedPlan.build(row, col, val, n, rank, world)
+        lo, hi = plan.lo, plan.hi
+        halo_info = {"rows_owned": plan.n_rows, "halo_rows_fwd": plan.halo.n_halo, "halo_rows_bwd": plan.halo_t.n_halo,
+                     "nvlink_bytes_per_step_rank0": plan.halo_bytes_per_step(d, 4, 5) if a.method == "rk4" else None}
+    else:
+        plan = ops.GraphPlan.from_coo(row, col, val, n, n)
+        lo, hi = 0, n
     del row, col, val
     torch.cuda.empty_cache()
     torch.manual_seed(a.seed)
@@ -231,20 +236,31 @@ def run_ours(a):
     opt = torch.optim.Adam(blk.parameters(), lr=0.01, weight_decay=5e-4)   # GCN/train_res.py:126-127
     gen = torch.Generator(device=dev).manual_seed(a.seed)
     x_dev = torch.randn(n, d, device=dev, generator=gen)
+    if world > 1:
+        x_dev = x_dev[lo:hi].clone()             # every rank draws the same [N, d] and keeps its rows
+        torch.cuda.empty_cache()
+    n_loc = hi - lo
+    inv_count = 1.0 / (float(n) * d)
 
     def step(x):
         opt.zero_grad(set_to_none=True)
         xx = x.requires_grad_(True)
         y = blk(xx, plan)
-        loss = 0.5 * (y * y).mean()
-        loss.backward()
+        loss = 0.5 * (y * y).sum() * inv_count   # this rank's share of 0.5*mean(y^2) over the whole graph
+        loss.backward()                          # parameter gradients are summed over ranks inside the adjoint
         opt.step()
         return loss
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
 
     blk.nfe = 0
     for _ in range(max(a.warmup, 3)):
         step(x_dev.detach())
-    torch.cuda.synchronize()
+    sync()
     nfe_per_step = blk.nfe // max(a.warmup, 3)
     assert nfe_per_step == NFE_PER_STEP or a.method != "rk4", nfe_per_step
 
@@ -254,13 +270,22 @@ def run_ours(a):
     launches0 = lib.gode_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
-        torch.cuda.synchronize()
+        sync()
         ev0.record()
         for _ in range(a.steps):
             loss = step(x_dev.detach())
         ev1.record()
-        torch.cuda.synchronize()
+        sync()
     ms = ev0.elapsed_time(ev1) / a.steps
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms = max_over_ranks(ms)
     launches = int(lib.gode_launch_count() - launches0)
     import ctypes as C
     prof = {}
@@ -273,7 +298,10 @@ def run_ours(a):
 
     # ---- roofline of the dominant kernel (the A_hat*S gather with fused epilogue) -----------------
     peak, peak_src = peaks()
-    b_f = nnz * 8 + (n + 1) * 4 + 2 * n * d * 4          # CSR once + S once + k once
+    if world == 1:
+        b_f = nnz * 8 + (n + 1) * 4 + 2 * n * d * 4      # CSR once + S once + k once
+    else:                                                # this rank's block: CSR + S (owned + halo rows) + k
+        b_f = plan.A.nnz * 8 + (n_loc + 1) * 4 + (n_loc + plan.halo.n_halo) * d * 4 + n_loc * d * 4
     agg = prof["agg_fwd"]
     achieved = b_f / (agg["ms_avg"] / 1e3) / 1e9 if agg["launches"] else None
     traffic = None
@@ -283,7 +311,8 @@ def run_ours(a):
             traffic = json.load(open(tpath)).get("agg_fwd_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_spmm_vec<32,1> (A_hat*S gather + bias + relu + RK combine)",
+    roofline = {"bound": "hbm", "kernel": "k_spmm_vec<32,1> (A_hat*S gather + bias + relu + RK combine)%s" % (
+                    "" if world == 1 else " on rank 0's row block"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "algorithmic_bytes_per_launch": b_f, "ms_per_launch": agg["ms_avg"],
                 "launches_timed": agg["launches"], "peak_source": peak_src,
@@ -292,7 +321,7 @@ def run_ours(a):
     # ---- e2e: public API, host buffers ------------------------------------------------------------
     e2e = None
     if not a.no_e2e:
-        x_host = torch.empty(n, d, dtype=torch.float32, pin_memory=True)
+        x_host = torch.empty(n_loc, d, dtype=torch.float32, pin_memory=True)
         x_host.copy_(x_dev)
         x_stage = torch.empty_like(x_dev)
 
@@ -301,31 +330,42 @@ def run_ours(a):
             return float(step(x_stage.detach()).item())
 
         e2e_step()
-        torch.cuda.synchronize()
+        sync()
         t0 = time.perf_counter()
         for _ in range(a.steps):
             e2e_step()
-        torch.cuda.synchronize()
-        e_ms = (time.perf_counter() - t0) / a.steps * 1e3
+        sync()
+        e_ms = max_over_ranks((time.perf_counter() - t0) / a.steps * 1e3)
         e2e = {"value": nnz * nfe_per_step / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * d * 4,
-               "d2h_bytes_per_step": 4, "ms_per_step": e_ms,
-               "note": "graph plan stays resident across steps as adj.cuda() does in GCN/train_res.py:57"}
+               "d2h_bytes_per_step": 4 * world, "ms_per_step": e_ms,
+               "note": "graph plan stays resident across steps as adj.cuda() does in GCN/train_res.py:57; bytes are "
+                       "summed over ranks (each rank copies its own rows)"}
         del x_host, x_stage
 
     cpu = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:
         cpu = run_cpu_sample(a, steps=1, warmup=0, budget_s=20.0)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3),
+    loss_total = loss.detach().clone()
+    if world > 1:
+        dist.all_reduce(loss_total)
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(a), "nnz": nnz, "solver": a.method, "func_evals_per_step": nfe_per_step,
                        "l2": "inputs larger than L2 (every [N,d] tensor is %.2f GB)" % (n * d * 4 / 1e9),
-                       "optimizer": "Adam on the ODE function's parameters (in the timed region)"},
-            "func_evals_per_sec": nfe_per_step / (ms / 1e3), "final_loss": float(loss.item()),
+                       "optimizer": "Adam on the ODE function's parameters (in the timed region)",
+                       "partition": None if world == 1 else dict(halo_info, scheme="contiguous row blocks, all-to-all-v "
+                                                                  "halo exchange of the gather operand per evaluation")},
+            "func_evals_per_sec": nfe_per_step / (ms / 1e3), "final_loss": float(loss_total.item()),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary()}
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

@@ -49,7 +49,7 @@ class ODEfunc(nn.Module):
     def _gode_fused(self):
         """Graph plan if the fused libgode ODE-function kernels apply to this function, else None."""
         adj = self.gc1.adj
-        if isinstance(adj, ops.GraphPlan):
+        if isinstance(adj, ops.GraphPlan) or hasattr(adj, "make_kernel"):   # single-device or row-partitioned plan
             return adj
         if torch.is_tensor(adj) and adj.is_cuda and adj.dim() == 2 and adj.shape[0] == adj.shape[1] and adj.shape[0] > 1:
             return ops.plan_for(adj)

@@ -70,6 +70,7 @@ _PROTOS = {
     "gode_gcn_vjp_phase1": (C.c_int, [C.POINTER(GcnOdeFunc), vp, vp, f32, vp, vp, vp, C.POINTER(vp), C.POINTER(f32), i32,
                                       f32, vp, vp, sz, vp]),
     "gode_gcn_vjp_phase2": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, vp, vp, sz, vp]),
+    "gode_gather_rows": (C.c_int, [i64, vp, i32, vp, i64, vp, i64, vp]),
 }
 
 EXPORTS = tuple(_PROTOS)

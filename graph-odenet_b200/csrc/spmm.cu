@@ -452,8 +452,12 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
   constexpr int RPB = 8 * RPW;
   static const int variant = [] {
     const char* e = getenv("GODE_SPMM_VARIANT");
-    return e ? atoi(e) : 5;   // 5/4: persistent warps (U=8 x 3 CTAs/SM | U=4 x 4 CTAs/SM), 0: one row per sub-warp,
-                              // 3: one 1024-thread CTA per SM on a row tile
+    // 0 (default): one row per sub-warp, CTAs dispatched in row order -- the hardware scheduler keeps the rows in
+    //    flight inside a narrow id window, which is what lets L2 hold the gather band of a locality-ordered graph.
+    // 5/4: persistent warps (U=8 x 3 CTAs/SM | U=4 x 4 CTAs/SM): faster at N <= 2M, but the warps drift apart on a
+    //    power-law graph (ncu at N=10M: L2 hit rate 26 %, 52 GB of DRAM reads per launch -> DRAM-bound, 7 % slower).
+    // 3: one 1024-thread CTA per SM on a row tile.
+    return e ? atoi(e) : 0;
   }();
   if (A.n_rows > 0 && (variant == 5 || variant == 4)) {
     int rc = variant == 5 ? launch_pw<LPR, VPL, 8, 3>(A, X, ldx, Y, ldy, ep, st) : launch_pw<LPR, VPL, 4, 4>(A, X, ldx, Y, ldy, ep, st);

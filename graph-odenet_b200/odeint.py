@@ -149,6 +149,28 @@ class GcnKernel:
     def new(self):
         return torch.empty(self.n, self.d, dtype=torch.float32, device=self.dev)
 
+    # Hooks the row-partitioned kernel (parallel.PartitionedGcnKernel) overrides: operand buffers of the two
+    # gathers carry a halo tail there, and reductions over all nodes / all ranks need a collective.
+    def new_S(self):
+        """Buffer for a support S (operand of the A_hat gather)."""
+        return self.new()
+
+    def new_gP(self):
+        """Buffer for gP (operand of the A_hat^T gather)."""
+        return self.new()
+
+    def numel_global(self):
+        """Number of state elements over the whole graph (denominator of the RMS norms)."""
+        return self.n * self.d
+
+    def scalar(self, dev_scalar):
+        """Host value of a device scalar that is a sum over nodes."""
+        return float(dev_scalar.item())
+
+    def reduce_small(self, t):
+        """In-place sum over ranks of a small tensor of per-rank partial sums (a_theta, a_t)."""
+        return t
+
     def transform(self, y, t, out):
         ws = self._ws()
         check(lib.gode_gcn_transform(C.byref(self.f), ops._p(y), float(t), ops._p(out), ops._p(ws), self.ws_bytes,
@@ -203,7 +225,7 @@ def gcn_solve_forward(kern, y0, t0, t1, method="dopri5", step_size=None, rtol=1e
     if method in FIXED_METHODS:
         grid = _grid(t0, t1, step_size)
         y = y0
-        S = kern.transform(y, grid[0], kern.new())
+        S = kern.transform(y, grid[0], kern.new_S())
         for g0, g1 in zip(grid[:-1], grid[1:]):
             dt = F32(g1 - g0)
             last_step = g1 == grid[-1]
@@ -228,7 +250,7 @@ def _gcn_fixed_step(kern, tab, t0, dt, y0, S0, want_S):
         store = (not last) and _needed_later(tab, i)
         k_i = kern.new() if store else None
         y_next = kern.new() if last else scratch_y[i & 1]
-        S_next = kern.new() if (not last or want_S) else None
+        S_next = kern.new_S() if (not last or want_S) else None
         kern.stage_fwd(S, k_i, y0, kprev, cprev, coefs[i], y_next, t_n, S_next)
         ks.append(k_i)
         S = S_next
@@ -242,19 +264,19 @@ def _msr(kern, y0, y1, ks, coefs, rtol, atol):
 
 
 def _gcn_dopri5(kern, tab, y0, t0, t1, rtol, atol, stats):
-    n_el = y0.numel()
-    S = kern.transform(y0, t0, kern.new())
+    n_el = kern.numel_global()
+    S = kern.transform(y0, t0, kern.new_S())
     f0 = kern.new()
     kern.stage_fwd(S, f0)
     # Hairer initial step: norms are RMS of x / (atol + rtol*|y0|)
-    d0 = float(np.sqrt(ops.rk_error_sumsq(y0, y0, [y0], [1.0], rtol, atol).item() / n_el))
-    d1 = float(np.sqrt(ops.rk_error_sumsq(y0, y0, [f0], [1.0], rtol, atol).item() / n_el))
+    d0 = float(np.sqrt(kern.scalar(ops.rk_error_sumsq(y0, y0, [y0], [1.0], rtol, atol)) / n_el))
+    d1 = float(np.sqrt(kern.scalar(ops.rk_error_sumsq(y0, y0, [f0], [1.0], rtol, atol)) / n_el))
     h0 = F32(1e-6) if (d0 < 1e-5 or d1 < 1e-5) else F32(0.01 * d0 / d1)
-    y_probe, S_probe, f_probe = kern.new(), kern.new(), kern.new()
+    y_probe, S_probe, f_probe = kern.new(), kern.new_S(), kern.new()
     ops.rk_combine(y0, [f0], [h0], out=y_probe)
     kern.transform(y_probe, F32(t0 + h0), S_probe)
     kern.stage_fwd(S_probe, f_probe)
-    d2 = float(np.sqrt(ops.rk_error_sumsq(y0, y0, [f_probe, f0], [1.0, -1.0], rtol, atol).item() / n_el)) / float(h0)
+    d2 = float(np.sqrt(kern.scalar(ops.rk_error_sumsq(y0, y0, [f_probe, f0], [1.0, -1.0], rtol, atol)) / n_el)) / float(h0)
     if d1 <= 1e-15 and d2 <= 1e-15:
         h1 = max(F32(1e-6), F32(h0 * F32(1e-3)))
     else:
@@ -265,7 +287,7 @@ def _gcn_dopri5(kern, tab, y0, t0, t1, rtol, atol, stats):
     t = t0
     y, f = y0, f0
     ks = [f] + [kern.new() for _ in range(6)]
-    Yb, Sb = [kern.new(), kern.new()], [kern.new(), kern.new()]
+    Yb, Sb = [kern.new(), kern.new()], [kern.new_S(), kern.new_S()]
     last = None  # (t_lo, t_hi, y_lo, y_hi, ks, dt) of the accepted step that crossed t1
     while t1 > t:
         if not (F32(t + dt) > t):
@@ -289,7 +311,7 @@ def _gcn_dopri5(kern, tab, y0, t0, t1, rtol, atol, stats):
                 kern.stage_fwd(S_i, ks[i], y, kprev, cprev, coefs[i], y_next, t_n, S_n)
             S_i = S_n
         kern.stage_fwd(S_i, ks[6])  # k_6 = f(t + dt, y1): FSAL derivative of the next step
-        msr = float(_msr(kern, y, y1, ks, [F32(dt * F32(c)) for c in tab.c_err], rtol, atol).item()) / n_el
+        msr = kern.scalar(_msr(kern, y, y1, ks, [F32(dt * F32(c)) for c in tab.c_err], rtol, atol)) / n_el
         accept = msr <= 1.0
         dt_next = _optimal_step(dt, msr)
         if stats is not None:
@@ -322,12 +344,13 @@ def gcn_solve_adjoint(kern, y1, g1, t0, t1, method="dopri5", step_size=None, rto
     P = kern.n_theta
     dev = kern.dev
     # a_t(t1) = - <f(t1, y1), g>   (torchdiffeq evaluates func once here: counted in nfe)
-    S = kern.transform(y1, t1, kern.new())
+    S = kern.transform(y1, t1, kern.new_S())
     f1 = kern.new()
     kern.stage_fwd(S, f1)
     # the dot product only feeds a_t, which nothing reads for fixed-step methods (the evaluation itself is
     # kept: the reference's nfe_b counts it)
-    a_t = -(f1 * g1).sum() if method not in FIXED_METHODS else torch.zeros((), dtype=torch.float32, device=dev)
+    a_t = (kern.reduce_small(-(f1 * g1).sum().reshape(1)).reshape(()) if method not in FIXED_METHODS
+           else torch.zeros((), dtype=torch.float32, device=dev))
     del f1
     a_theta = torch.zeros(P, dtype=torch.float32, device=dev)
     if method in FIXED_METHODS:
@@ -339,6 +362,7 @@ def gcn_solve_adjoint(kern, y1, g1, t0, t1, method="dopri5", step_size=None, rto
             a_theta += dth
             if stats is not None:
                 stats["accepted"] = stats.get("accepted", 0) + 1
+        kern.reduce_small(a_theta)
         a_t = a_t + a_theta[P - 1]
         return a, a_theta[:P - 1], a_t
     return _gcn_aug_dopri5(kern, tab, y1, g1, a_t, F32(t1), F32(t0), S, rtol, atol, stats)
@@ -350,7 +374,7 @@ def _gcn_aug_fixed_step(kern, tab, t0, h, y0, a0, S0, want_S):
     P = kern.n_theta
     ky, ka = [], []
     gth = torch.empty(s, P, dtype=torch.float32, device=kern.dev)
-    gP = kern.new()
+    gP = kern.new_gP()
     Ybuf, Abuf = [kern.new(), kern.new()], [kern.new(), kern.new()]
     Y_i, A_i, S_i = y0, a0, S0
     y_out = a_out = S_out = None
@@ -373,7 +397,7 @@ def _gcn_aug_fixed_step(kern, tab, t0, h, y0, a0, S0, want_S):
         kap, cap = _nz(ka, coefs)
         ops.rk_combine(a0, kap, cap, out=A_n)
         if (not last) or want_S:
-            S_n = kern.transform(Y_n, t_n, kern.new() if S_i is S0 else S_i)
+            S_n = kern.transform(Y_n, t_n, kern.new_S() if S_i is S0 else S_i)
         else:
             S_n = None
         Y_i, A_i, S_i = Y_n, A_n, S_n
@@ -402,14 +426,14 @@ def _gcn_aug_dopri5(kern, tab, y1, g1, a_t1, t_start, t_end, S, rtol, atol, stat
     """
     P = kern.n_theta
     dev = kern.dev
-    n_el = y1.numel()
+    n_el = kern.numel_global()
     new = kern.new
     theta0 = torch.zeros(P - 1, dtype=torch.float32, device=dev)   # a_theta(t1)
     at0 = a_t1.reshape(1).to(torch.float32)
-    gP = new()
+    gP = kern.new_gP()
 
     def rms_big(x, ref):
-        return float(np.sqrt(ops.rk_error_sumsq(ref, ref, [x], [1.0], rtol, atol).item() / n_el))
+        return float(np.sqrt(kern.scalar(ops.rk_error_sumsq(ref, ref, [x], [1.0], rtol, atol)) / n_el))
 
     def rms_small(x, ref):
         return float(torch.sqrt(((x / (atol + rtol * ref.abs())) ** 2).mean()).item())
@@ -418,20 +442,22 @@ def _gcn_aug_dopri5(kern, tab, y1, g1, a_t1, t_start, t_end, S, rtol, atol, stat
     ky0, ka0 = new(), new()
     g0 = torch.empty(P, dtype=torch.float32, device=dev)
     _gcn_aug_eval(kern, S, y1, g1, t_start, ky0, ka0, g0, gP)
+    kern.reduce_small(g0)
     d0 = max(rms_big(y1, y1), rms_big(g1, g1), rms_small(at0, at0), rms_small(theta0, theta0))
     d1 = max(rms_big(ky0, y1), rms_big(ka0, g1), rms_small(g0[P - 1:], at0), rms_small(g0[:P - 1], theta0))
     # torchdiffeq works on the mirrored problem: its f0 is -F and its step is positive; norms are identical
     h0 = F32(1e-6) if (d0 < 1e-5 or d1 < 1e-5) else F32(0.01 * d0 / d1)
-    yp, ap, Sp, kyp, kap = new(), new(), new(), new(), new()
+    yp, ap, Sp, kyp, kap = new(), new(), kern.new_S(), new(), new()
     gp_ = torch.empty(P, dtype=torch.float32, device=dev)
     ops.rk_combine(y1, [ky0], [-h0], out=yp)
     ops.rk_combine(g1, [ka0], [-h0], out=ap)
     kern.transform(yp, F32(t_start - h0), Sp)
     # (a_t, a_theta do not enter F, so the probe state only needs y and a_y)
     _gcn_aug_eval(kern, Sp, yp, ap, F32(t_start - h0), kyp, kap, gp_, gP)
+    kern.reduce_small(gp_)
     d2 = max(
-        float(np.sqrt(ops.rk_error_sumsq(y1, y1, [kyp, ky0], [1.0, -1.0], rtol, atol).item() / n_el)),
-        float(np.sqrt(ops.rk_error_sumsq(g1, g1, [kap, ka0], [1.0, -1.0], rtol, atol).item() / n_el)),
+        float(np.sqrt(kern.scalar(ops.rk_error_sumsq(y1, y1, [kyp, ky0], [1.0, -1.0], rtol, atol)) / n_el)),
+        float(np.sqrt(kern.scalar(ops.rk_error_sumsq(g1, g1, [kap, ka0], [1.0, -1.0], rtol, atol)) / n_el)),
         rms_small(gp_[P - 1:] - g0[P - 1:], at0), rms_small(gp_[:P - 1] - g0[:P - 1], theta0)) / float(h0)
     if d1 <= 1e-15 and d2 <= 1e-15:
         h1 = max(F32(1e-6), F32(h0 * F32(1e-3)))
@@ -446,7 +472,7 @@ def _gcn_aug_dopri5(kern, tab, y1, g1, a_t1, t_start, t_end, S, rtol, atol, stat
     ka = [ka0] + [new() for _ in range(6)]
     gth = torch.empty(7, P, dtype=torch.float32, device=dev)
     gth[0] = g0
-    Yb, Ab, Ss = [new(), new()], [new(), new()], new()
+    Yb, Ab, Ss = [new(), new()], [new(), new()], kern.new_S()
     last = None
     while t > t_end:
         if not (F32(t - dt) < t):
@@ -472,14 +498,15 @@ def _gcn_aug_dopri5(kern, tab, y1, g1, a_t1, t_start, t_end, S, rtol, atol, stat
             kern.transform(Y_n, t_n, Ss)
             S_i, Y_i, A_i = Ss, Y_n, A_n
         _gcn_aug_eval(kern, Ss, y_new, a_new, F32(t + h), ky[6], ka[6], gth[6], gP)
+        kern.reduce_small(gth[1:])     # row 0 is carried over from the previous step (FSAL), already summed
         cerr = [F32(h * F32(c)) for c in tab.c_err]
         wb = torch.tensor([float(F32(h * F32(b))) for b in tab.b], dtype=torch.float32, device=dev)
         we = torch.tensor([float(c) for c in cerr], dtype=torch.float32, device=dev)
         small_new = (wb[:, None] * gth).sum(0)
         small_err = (we[:, None] * gth).sum(0)
         th_new, at_new = th + small_new[:P - 1], at + small_new[P - 1:]
-        msr = max(float(_msr(kern, y, y_new, ky, cerr, rtol, atol).item()) / n_el,
-                  float(_msr(kern, a, a_new, ka, cerr, rtol, atol).item()) / n_el,
+        msr = max(kern.scalar(_msr(kern, y, y_new, ky, cerr, rtol, atol)) / n_el,
+                  kern.scalar(_msr(kern, a, a_new, ka, cerr, rtol, atol)) / n_el,
                   _small_msr(small_err[P - 1:], at, at_new, rtol, atol),
                   _small_msr(small_err[:P - 1], th, th_new, rtol, atol))
         accept = msr <= 1.0
@@ -512,14 +539,20 @@ def _gcn_aug_dopri5(kern, tab, y1, g1, a_t1, t_start, t_end, S, rtol, atol, stat
     return a_out, th_out, at_out
 
 
+def _make_kernel(plan, *args):
+    """GcnKernel for a single-device plan; the plan's own kernel class for a row-partitioned one."""
+    factory = getattr(plan, "make_kernel", None)
+    return factory(*args) if factory is not None else GcnKernel(plan, *args)
+
+
 class _GcnAdjointFn(torch.autograd.Function):
     """autograd node for the fused GCN ODE block: forward solve without a tape, adjoint solve in backward."""
 
     @staticmethod
     def forward(ctx, y0, weight, bias, gamma, beta, funcmod, plan, t0, t1, rtol, atol, method, step_size, stats):
         y0 = ops._rowmajor(y0, "y0")
-        kern = GcnKernel(plan, weight, bias, gamma, beta, funcmod.norm1.num_groups, funcmod.norm1.eps,
-                         getattr(funcmod, "precision", _lib.PREC_FP32))
+        kern = _make_kernel(plan, weight, bias, gamma, beta, funcmod.norm1.num_groups, funcmod.norm1.eps,
+                            getattr(funcmod, "precision", _lib.PREC_FP32))
         y1 = gcn_solve_forward(kern, y0, t0, t1, method, step_size, rtol, atol,
                                None if stats is None else stats.setdefault("forward", {}))
         funcmod.nfe += kern.nfe
@@ -533,8 +566,8 @@ class _GcnAdjointFn(torch.autograd.Function):
         y1, weight, bias, gamma, beta = ctx.saved_tensors
         t0, t1, rtol, atol, method, step_size = ctx.cfg
         fm = ctx.funcmod
-        kern = GcnKernel(ctx.plan, weight, bias, gamma, beta, fm.norm1.num_groups, fm.norm1.eps,
-                         getattr(fm, "precision", _lib.PREC_FP32))
+        kern = _make_kernel(ctx.plan, weight, bias, gamma, beta, fm.norm1.num_groups, fm.norm1.eps,
+                            getattr(fm, "precision", _lib.PREC_FP32))
         g = ops._rowmajor(g, "grad").contiguous()
         a, th, _ = gcn_solve_adjoint(kern, y1, g, t0, t1, method, step_size, rtol, atol,
                                      None if ctx.stats is None else ctx.stats.setdefault("backward", {}))

@@ -245,6 +245,15 @@ int gode_gcn_vjp_phase1(const gode_gcn_odefunc_t* f, const float* S, const float
 int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, float t, const float* gP,
                         float* k_a, float* gtheta, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Halo pack for the row-partitioned (multi-GPU) path: dst[i, :] = src[idx[i], :].
+ * The reference is single-device; this packs the rows of the SpMM operand of
+ * torch.spmm(adj, support) (GCN/layers.py:71) that peer ranks reference, ordered by destination rank,
+ * for the NCCL all-to-all-v issued by the host code (graph-odenet_b200/parallel.py).
+ * ---------------------------------------------------------------------------------------------- */
+int gode_gather_rows(int64_t n_idx, const int32_t* idx, int32_t d, const float* src, int64_t lds,
+                     float* dst, int64_t ldd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

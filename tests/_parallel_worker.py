@@ -1,0 +1,78 @@
+"""torchrun worker for tests/test_gpu_parallel.py: the row-partitioned GCN-ODE block on WORLD_SIZE GPUs must
+reproduce the single-GPU block (same graph, same parameters) -- forward state, input gradient, parameter
+gradients, and for dopri5 the accepted/rejected step counts."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    method = sys.argv[1] if len(sys.argv) > 1 else "rk4"
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
+    d = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    import graph_odenet_b200  # noqa: F401
+    from graph_odenet_b200 import ops, parallel, synth
+    from graph_odenet_b200.GCN import models
+
+    row, col, val = synth.powerlaw_graph(n, avg_degree=12, locality=0.6, window=512, seed=5, device=dev)
+    torch.manual_seed(7)
+    blk = models.ODEBlock(models.ODEfunc(d), method=method).to(dev)
+    with torch.no_grad():
+        blk.odefunc.norm1.weight.uniform_(0.5, 1.5)
+        blk.odefunc.norm1.bias.uniform_(-0.5, 0.5)
+    g = torch.Generator(device=dev).manual_seed(9)
+    x_all = 0.5 * torch.randn(n, d, device=dev, generator=g)
+    g_all = torch.randn(n, d, device=dev, generator=g) / n
+
+    def run(plan, x, gy):
+        for p in blk.parameters():
+            p.grad = None
+        stats = {}
+        blk.stats = stats
+        xx = x.clone().requires_grad_(True)
+        blk.nfe = 0
+        y = blk(xx, plan)
+        y.backward(gy)
+        return y.detach(), xx.grad.detach(), [p.grad.detach().clone() for p in blk.parameters()], blk.nfe, stats
+
+    pplan = parallel.PartitionedPlan.build(row, col, val, n, rank, world)
+    lo, hi = pplan.lo, pplan.hi
+    y_p, gx_p, gp_p, nfe_p, st_p = run(pplan, x_all[lo:hi], g_all[lo:hi].contiguous())
+    # gather the row blocks on every rank
+    sizes = [pplan.bounds[r + 1] - pplan.bounds[r] for r in range(world)]
+    ys = [torch.empty(s, d, device=dev) for s in sizes]
+    gxs = [torch.empty(s, d, device=dev) for s in sizes]
+    dist.all_gather(ys, y_p.contiguous())
+    dist.all_gather(gxs, gx_p.contiguous())
+    ok = True
+    if rank == 0:
+        plan = ops.GraphPlan.from_coo(row, col, val, n, n)
+        y_1, gx_1, gp_1, nfe_1, st_1 = run(plan, x_all, g_all)
+
+        def rel(a, b):
+            return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+        errs = {"y": rel(torch.cat(ys), y_1), "gx": rel(torch.cat(gxs), gx_1)}
+        for (name, _), a, b in zip(blk.named_parameters(), gp_p, gp_1):
+            errs["g_" + name] = rel(a, b)
+        print("world=%d method=%s nfe %d/%d errs %s stats %s / %s" % (world, method, nfe_p, nfe_1, errs, st_p, st_1), flush=True)
+        ok = nfe_p == nfe_1 and all(v < 2e-5 for v in errs.values())
+        if method == "dopri5":
+            ok = ok and st_p == st_1
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
