@@ -1,4 +1,4 @@
-"""GCN models with the reference's names, constructor signatures, ``forward(x, adj)`` and ``state_dict``
+"""GCN models with the reference's names, constructor signatures, ``forward(x, *adj)`` and ``state_dict``
 keys (GCN/models.py:8-600), running on libgode kernels.
 
 The reference file spells out ~20 near-identical classes; here one ``_Stack`` describes a model as
@@ -100,8 +100,8 @@ class ODEBlock(nn.Module):
         self.method, self.options = method, options
         self.stats = None
 
-    def forward(self, x, adj):
-        self.odefunc.set_adj(adj)
+    def forward(self, x, *adj):
+        self.odefunc.set_adj(*adj)
         # integration_time stays on the host: the solver keeps time in float32 scalars, so there is no
         # device round trip per forward (the reference's .type_as(x) moves it to the GPU and reads it back)
         return _solver.odeint_adjoint_final(self.odefunc, x, self.integration_time, rtol=self.tol, atol=self.tol,
@@ -122,6 +122,12 @@ class ODEBlock(nn.Module):
 
 
 class _NfeMixin:
+    """``nfe`` plumbing + the layer family a model is built from (GCN here; GAT/models.py rebinds these)."""
+
+    _conv = GraphConvolution
+    _odefunc = None     # bound below, after ODEfunc / ODEfunc2 are defined
+    _odefunc2 = None
+
     @property
     def nfe(self):
         blocks = [m for m in self.modules() if isinstance(m, ODEBlock)]
@@ -134,38 +140,42 @@ class _NfeMixin:
                 m.nfe = value
 
 
+_NfeMixin._odefunc = ODEfunc
+_NfeMixin._odefunc2 = ODEfunc2
+
+
 def _drop(x, p, training):
     return F.dropout(x, p, training=training)
 
 
-class GCN(nn.Module):
+class GCN(nn.Module, _NfeMixin):
     """gc1 -> relu -> dropout -> gc2 -> log_softmax  (GCN/models.py:8-21)."""
 
     def __init__(self, nfeat, nhid, nclass, dropout):
         super().__init__()
-        self.gc1 = GraphConvolution(nfeat, nhid)
-        self.gc2 = GraphConvolution(nhid, nclass)
+        self.gc1 = self._conv(nfeat, nhid)
+        self.gc2 = self._conv(nhid, nclass)
         self.dropout = dropout
 
-    def forward(self, x, adj):
-        x = _drop(self.gc1(x, adj, relu=True), self.dropout, self.training)
-        return F.log_softmax(self.gc2(x, adj), dim=1)
+    def forward(self, x, *adj):
+        x = _drop(self.gc1(x, *adj, relu=True), self.dropout, self.training)
+        return F.log_softmax(self.gc2(x, *adj), dim=1)
 
 
-class RGCN2(nn.Module):
+class RGCN2(nn.Module, _NfeMixin):
     """GCN/models.py:23-40: residual on the output layer, first nclass columns are the logits."""
 
     def __init__(self, nfeat, nhid, nclass, dropout):
         super().__init__()
         if nhid < nclass:
             raise ValueError("nhid must be equal or larger than nclass")
-        self.gc1 = GraphConvolution(nfeat, nhid)
-        self.gc2 = GraphConvolution(nhid, nhid)
+        self.gc1 = self._conv(nfeat, nhid)
+        self.gc2 = self._conv(nhid, nhid)
         self.nclass, self.dropout = nclass, dropout
 
-    def forward(self, x, adj):
-        x = _drop(self.gc1(x, adj, relu=True), self.dropout, self.training)
-        x = self.gc2(x, adj) + x
+    def forward(self, x, *adj):
+        x = _drop(self.gc1(x, *adj, relu=True), self.dropout, self.training)
+        x = self.gc2(x, *adj) + x
         return F.log_softmax(x[:, :self.nclass], dim=1)
 
 
@@ -176,12 +186,12 @@ class ODEGCN2(nn.Module, _NfeMixin):
         super().__init__()
         if nhid < nclass:
             raise ValueError("nhid must be equal or larger than nclass")
-        self.gc1 = GraphConvolution(nfeat, nhid)
-        self.gc2 = ODEBlock(ODEfunc(nhid))
+        self.gc1 = self._conv(nfeat, nhid)
+        self.gc2 = ODEBlock(self._odefunc(nhid))
         self.nclass, self.dropout = nclass, dropout
 
-    def forward(self, x, adj):
-        x = self.gc2(self.gc1(x, adj, relu=True), adj)
+    def forward(self, x, *adj):
+        x = self.gc2(self.gc1(x, *adj, relu=True), *adj)
         return F.log_softmax(x[:, :self.nclass], dim=1)
 
 
@@ -195,27 +205,27 @@ class _Three(nn.Module, _NfeMixin):
 
     def __init__(self, nfeat, nhid, nclass, dropout):
         super().__init__()
-        self.gc1 = GraphConvolution(nfeat, nhid)
+        self.gc1 = self._conv(nfeat, nhid)
         if self.in_norm:
             self.norm1 = _norm(nhid)
-        self.gc2 = ODEBlock(ODEfunc(nhid)) if self.ode else GraphConvolution(nhid, nhid)
+        self.gc2 = ODEBlock(self._odefunc(nhid)) if self.ode else self._conv(nhid, nhid)
         if self.mid_norm:
             self.norm2 = _norm(nhid)
-        self.gc3 = GraphConvolution(nhid, nclass)
+        self.gc3 = self._conv(nhid, nclass)
         self.dropout = dropout
 
-    def forward(self, x, adj):
-        x = self.gc1(x, adj, relu=True)
+    def forward(self, x, *adj):
+        x = self.gc1(x, *adj, relu=True)
         x = self.norm1(x) if self.in_norm else _drop(x, self.dropout, self.training)
         if self.ode:
-            x = self.gc2(x, adj)
+            x = self.gc2(x, *adj)
         else:
             r = x
-            x = self.gc2(x, adj, relu=True)
+            x = self.gc2(x, *adj, relu=True)
             x = self.norm2(x) if self.mid_norm else _drop(x, self.dropout, self.training)
             if self.residual:
                 x = x + r
-        return F.log_softmax(self.gc3(x, adj), dim=1)
+        return F.log_softmax(self.gc3(x, *adj), dim=1)
 
 
 class GCN3(_Three):               # GCN/models.py:66-81
@@ -262,8 +272,8 @@ class _Deep(nn.Module, _NfeMixin):
         if nlayers < self._min(self.residue_layers):
             raise ValueError(self._too_few_msg(self.residue_layers))
         self.n_layers = nlayers
-        self.gcs = nn.ModuleList([GraphConvolution(nfeat, nhid)] + self._middle(nhid, nlayers, dropout)
-                                 + [GraphConvolution(nhid, nclass)])
+        self.gcs = nn.ModuleList([self._conv(nfeat, nhid)] + self._middle(nhid, nlayers, dropout)
+                                 + [self._conv(nhid, nclass)])
         if self.use_norm:
             self.norms = nn.ModuleList([_norm(nhid) for _ in range(nlayers - 2)])
         self.dropout = dropout
@@ -275,26 +285,26 @@ class _Deep(nn.Module, _NfeMixin):
         return self.too_few
 
     def _middle(self, nhid, nlayers, dropout):
-        return [GraphConvolution(nhid, nhid) for _ in range(nlayers - 2)]
+        return [self._conv(nhid, nhid) for _ in range(nlayers - 2)]
 
-    def forward(self, x, adj):
-        x = _drop(self.gcs[0](x, adj, relu=True), self.dropout, self.training)
+    def forward(self, x, *adj):
+        x = _drop(self.gcs[0](x, *adj, relu=True), self.dropout, self.training)
         countdown, r = 1, None
         for i, gc in enumerate(self.gcs[1:-1]):
             if isinstance(gc, ODEBlock):
-                x = gc(x, adj)
+                x = gc(x, *adj)
                 continue
             if self.residue_layers:
                 countdown -= 1
                 if countdown == 0:
                     r, countdown = x, self.residue_layers
-            x = gc(x, adj, relu=True)
+            x = gc(x, *adj, relu=True)
             x = self.norms[i](x) if self.use_norm else _drop(x, self.dropout, self.training)
             if self.residue_layers and countdown == 1:
                 x = x + r
         if self.residue_layers and countdown > 1:
             x = x + r
-        return F.log_softmax(self.gcs[-1](x, adj), dim=1)
+        return F.log_softmax(self.gcs[-1](x, *adj), dim=1)
 
 
 class GCNK(_Deep):                # GCN/models.py:255-278
@@ -342,7 +352,7 @@ class ODEK1(_Deep):               # GCN/models.py:524-548
     too_few = RESK1.too_few
 
     def _middle(self, nhid, nlayers, dropout):
-        return [ODEBlock(ODEfunc(nhid)) for _ in range(nlayers - 2)]
+        return [ODEBlock(self._odefunc(nhid)) for _ in range(nlayers - 2)]
 
 
 class ODEK2(_Deep):               # GCN/models.py:578-600
@@ -351,7 +361,24 @@ class ODEK2(_Deep):               # GCN/models.py:578-600
 
     def _middle(self, nhid, nlayers, dropout):
         # the reference passes `dropout` as the block's tolerance (models.py:587); kept for parity
-        blocks = [ODEBlock(ODEfunc2(nhid, dropout), dropout) for _ in range((nlayers - 2) // 2)]
+        blocks = [ODEBlock(self._odefunc2(nhid, dropout), dropout) for _ in range((nlayers - 2) // 2)]
         if nlayers % 2 == 1:
-            blocks.append(ODEBlock(ODEfunc(nhid)))
+            blocks.append(ODEBlock(self._odefunc(nhid)))
         return blocks
+
+
+MODEL_NAMES = ("GCN", "RGCN2", "ODEGCN2", "GCN3", "GCN3norm", "RGCN3", "RGCN3norm", "RGCN3fullnorm", "ODEGCN3",
+               "ODEGCN3fullnorm", "GCNK", "GCNKnorm", "RESK1", "RESK2", "RESK", "RESK1norm", "RESK2norm", "RESKnorm",
+               "ODEK1", "ODEK2")
+
+
+def rebind_family(namespace, conv, odefunc, odefunc2):
+    """Define every model class of this file in ``namespace`` on another layer family (used by GAT/models.py,
+    whose reference file is this one with ``adj`` replaced by ``src, tgt, Mtgt`` -- GAT/models.py:16-600)."""
+    made = {}
+    for name in MODEL_NAMES:
+        made[name] = type(name, (globals()[name],), {"_conv": conv, "_odefunc": odefunc, "_odefunc2": odefunc2,
+                                                     "__module__": namespace.get("__name__", __name__),
+                                                     "__doc__": globals()[name].__doc__})
+    namespace.update(made)
+    return made

@@ -35,6 +35,11 @@ class Csr(C.Structure):
                 ("heavy_rows", vp), ("heavy_chunk_ptr", vp), ("n_heavy", i32), ("n_chunks", i32)]
 
 
+class GatGraph(C.Structure):
+    _fields_ = [("n_nodes", i64), ("n_edges", i64), ("tptr", vp), ("t_src", vp), ("t_tgt", vp), ("sptr", vp),
+                ("s_tgt", vp), ("s_pos", vp)]
+
+
 class GcnOdeFunc(C.Structure):
     _fields_ = [("A", Csr), ("At", Csr), ("d", i32), ("groups", i32), ("gn_eps", f32), ("precision", i32),
                 ("W", vp), ("b", vp), ("gamma", vp), ("beta", vp)]
@@ -56,10 +61,12 @@ _PROTOS = {
     "gode_spmm_workspace_bytes": (sz, [C.POINTER(Csr), i32]),
     "gode_spmm_csr_f32": (C.c_int, [C.POINTER(Csr), vp, i64, i32, vp, i64, C.POINTER(SpmmEpilogue), vp, sz, vp]),
     "gode_gemm_f32": (C.c_int, [i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, f32, vp, i64, i32, i32, vp, sz, vp]),
+    "gode_linear_f32": (C.c_int, [i32, i64, i64, i64, vp, i64, vp, i64, vp, i32, vp, i64, vp]),
     "gode_groupnorm_fwd": (C.c_int, [i64, i32, i32, f32, vp, i64, vp, vp, vp, i64, vp]),
     "gode_groupnorm_bwd": (C.c_int, [i64, i32, i32, f32, vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, sz, vp]),
     "gode_colreduce_workspace_bytes": (sz, [i32]),
     "gode_colsum_f32": (C.c_int, [i64, i32, vp, i64, vp, vp, sz, vp]),
+    "gode_relu_bwd": (C.c_int, [i64, vp, vp, vp, vp]),
     "gode_rk_combine": (C.c_int, [i64, vp, C.POINTER(vp), C.POINTER(f32), i32, vp, vp]),
     "gode_rk_error_sumsq": (C.c_int, [i64, vp, vp, C.POINTER(vp), C.POINTER(f32), i32, f32, f32, vp, vp, sz, vp]),
     "gode_gcn_workspace_bytes": (sz, [C.POINTER(GcnOdeFunc)]),
@@ -71,6 +78,11 @@ _PROTOS = {
                                       f32, vp, vp, sz, vp]),
     "gode_gcn_vjp_phase2": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, vp, vp, sz, vp]),
     "gode_gather_rows": (C.c_int, [i64, vp, i32, vp, i64, vp, i64, vp]),
+    "gode_edge_matvec": (C.c_int, [i64, i32, vp, vp, vp, i64, vp, vp]),
+    "gode_edge_matvec_bwd": (C.c_int, [i64, i32, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp]),
+    "gode_gat_fwd": (C.c_int, [C.POINTER(GatGraph), i32, i32, vp, i64, f32, vp, i64, vp, vp, vp, vp]),
+    "gode_gat_bwd_workspace_bytes": (sz, [i64, i32]),
+    "gode_gat_bwd": (C.c_int, [C.POINTER(GatGraph), i32, i32, vp, i64, vp, i64, vp, vp, vp, i64, vp, vp, sz, vp]),
 }
 
 EXPORTS = tuple(_PROTOS)

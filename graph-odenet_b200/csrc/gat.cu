@@ -1,0 +1,321 @@
+// libgode: GAT attention aggregation -- segmented softmax / scatter over the edge list, forward and backward.
+//
+// Reference: GAT/layers.py:31-58 (GraphConvolution.forward) and :95-122 (FixedGraphConvolution.forward):
+//     h = [x[src] || x[tgt]]                     [E, 2i]
+//     y = relu(f(h));  a = w(h)                  f: Linear(2i -> o), w: Linear(2i -> 1)
+//     a_exp = exp(a - max_over_ALL_edges(a))     (a global shift, NOT a per-target one)
+//     out = (Mtgt (y * a_exp)) / (Mtgt a_exp + eps)          Mtgt[n, e] = 1 iff tgt[e] == n
+//
+// Restructuring (algebraically identical, rounding differs at the 1e-7 level):
+//   * a Linear on a concatenation is a sum of two Linears, so the host first projects the NODES once,
+//         P = x * [Wf_src^T | Wf_tgt^T | ww_src^T | ww_tgt^T]        [N, 2C + 2H]   (one GEMM, gode_gemm_f32)
+//     with the biases folded into the target halves; then per edge  z_e = Ps[src] + Pt[tgt],  a_e = as[src] + at[tgt].
+//     The [E, 2i] gather + cat + edge-level GEMM of the reference is never materialised (F up to 3703 on the
+//     input layer: 2F*E*4 bytes = 138 MB per call on Citeseer become an N x 2C projection).
+//   * the incidence products are segmented sums: edges are grouped by target (CSR of Mtgt), one thread owns one
+//     (node, head) pair and walks its segment in edge order -- no atomics, deterministic, same summation order as
+//     the reference's row-sorted COO product.
+//   * heads: H independent reference heads batched in the channel dimension (C = H * oh channels; head h owns
+//     channels [h*oh, (h+1)*oh)), each with its own global max.  H = 1 is the reference layer.
+//
+// Layout of P (row-major, leading dimension ldp >= 2C + 2H): [0,C) Ps | [C,2C) Pt | [2C,2C+H) as | [2C+H,2C+2H) at.
+//
+// Backward (given g = dL/dout), with w_e = exp(a_e - amax), y_e = relu(z_e), gn = g / den:
+//     d z_e   = w_e * gn[tgt] * (z_e > 0)
+//     d w_e   = sum_c y_e[c] gn[tgt, c]  -  sum_c out[tgt, c] gn[tgt, c]            (per head)
+//     d a_e   = d w_e * w_e ;  d amax = - sum_e d a_e  -> added to the arg-max edge (torch.max's backward)
+//     dPt[n]  = sum_{e: tgt=n} d z_e,  dat[n] = sum d a_e        (target pass, registers)
+//     dPs[s]  = sum_{e: src=s} d z_e,  das[s] = sum d a_e        (source pass over the by-source grouping)
+// The host then finishes with two GEMMs (dx = dP W^T, dW = x^T dP).
+#include "internal.cuh"
+
+namespace gode {
+
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ float key_max(unsigned long long k) { return ord2f(static_cast<unsigned int>(k >> 32)); }
+__device__ __forceinline__ unsigned int key_pos(unsigned long long k) { return 0xffffffffu - static_cast<unsigned int>(k); }
+
+// amax_key[h] = max over edges of (ordered(a_e), first position on ties); edges in by-target order
+__global__ void __launch_bounds__(256) k_gat_amax(int64_t n_edges, int H, const int32_t* __restrict__ t_src,
+                                                  const int32_t* __restrict__ t_tgt, const float* __restrict__ P,
+                                                  int64_t ldp, int C, unsigned long long* __restrict__ amax_key,
+                                                  int* __restrict__ nan_flag) {
+  __shared__ unsigned long long sm[8];
+  for (int h = 0; h < H; ++h) {
+    unsigned long long best = 0ull;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
+      const float a = __ldg(P + (int64_t)__ldg(t_src + e) * ldp + 2 * C + h) + __ldg(P + (int64_t)__ldg(t_tgt + e) * ldp + 2 * C + H + h);
+      if (a != a) *nan_flag = 1;
+      const unsigned long long k = (static_cast<unsigned long long>(f2ord(a)) << 32) | (0xffffffffu - static_cast<unsigned int>(e));
+      best = k > best ? k : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < (blockDim.x >> 5); ++i) best = sm[i] > best ? sm[i] : best;
+      if (best) atomicMax(amax_key + h, best);
+    }
+    __syncthreads();
+  }
+}
+
+// one thread per (node, head); CH >= oh channels held in registers
+template <int CH>
+__global__ void __launch_bounds__(128) k_gat_fwd(int64_t n_nodes, int H, int oh, const int32_t* __restrict__ tptr,
+                                                 const int32_t* __restrict__ t_src, const float* __restrict__ P, int64_t ldp,
+                                                 float eps, const unsigned long long* __restrict__ amax_key,
+                                                 float* __restrict__ out, int64_t ldo, float* __restrict__ den_out,
+                                                 int* __restrict__ nan_flag) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gid >= n_nodes * H) return;
+  const int64_t n = gid / H;
+  const int h = static_cast<int>(gid - n * H);
+  const int C = H * oh;
+  const float amax = key_max(amax_key[h]);
+  const float* pn = P + n * ldp;
+  const float at = __ldg(pn + 2 * C + H + h);
+  float pt[CH], num[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) {
+    pt[j] = j < oh ? __ldg(pn + C + h * oh + j) : 0.f;
+    num[j] = 0.f;
+  }
+  float den = 0.f;
+  const int e0 = __ldg(tptr + n), e1 = __ldg(tptr + n + 1);
+  for (int e = e0; e < e1; ++e) {
+    const float* ps = P + (int64_t)__ldg(t_src + e) * ldp;
+    const float w = expf(__ldg(ps + 2 * C + h) + at - amax);
+    den += w;
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (j < oh) num[j] += fmaxf(__ldg(ps + h * oh + j) + pt[j], 0.f) * w;
+  }
+  den += eps;
+  den_out[n * H + h] = den;
+  bool bad = den != den;
+#pragma unroll
+  for (int j = 0; j < CH; ++j)
+    if (j < oh) {
+      const float o = num[j] / den;
+      bad = bad || (o != o);
+      out[n * ldo + h * oh + j] = o;
+    }
+  if (bad) *nan_flag = 1;
+}
+
+// target pass of the backward: dPt, dat (registers), per-edge d a_e (by-target order) for the source pass
+template <int CH>
+__global__ void __launch_bounds__(128) k_gat_bwd_tgt(int64_t n_nodes, int H, int oh, const int32_t* __restrict__ tptr,
+                                                     const int32_t* __restrict__ t_src, const float* __restrict__ P,
+                                                     int64_t ldp, const unsigned long long* __restrict__ amax_key,
+                                                     const float* __restrict__ out, int64_t ldo,
+                                                     const float* __restrict__ den, const float* __restrict__ g, int64_t ldg,
+                                                     float* __restrict__ dP, float* __restrict__ dA) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gid >= n_nodes * H) return;
+  const int64_t n = gid / H;
+  const int h = static_cast<int>(gid - n * H);
+  const int C = H * oh;
+  const float amax = key_max(amax_key[h]);
+  const float* pn = P + n * ldp;
+  const float at = __ldg(pn + 2 * C + H + h);
+  const float inv = 1.f / den[n * H + h];
+  float pt[CH], gn[CH], dpt[CH];
+  float go = 0.f;
+#pragma unroll
+  for (int j = 0; j < CH; ++j) {
+    pt[j] = 0.f; gn[j] = 0.f; dpt[j] = 0.f;
+    if (j < oh) {
+      pt[j] = __ldg(pn + C + h * oh + j);
+      gn[j] = __ldg(g + n * ldg + h * oh + j) * inv;
+      go += gn[j] * __ldg(out + n * ldo + h * oh + j);
+    }
+  }
+  float dat = 0.f;
+  const int e0 = __ldg(tptr + n), e1 = __ldg(tptr + n + 1);
+  for (int e = e0; e < e1; ++e) {
+    const float* ps = P + (int64_t)__ldg(t_src + e) * ldp;
+    const float w = expf(__ldg(ps + 2 * C + h) + at - amax);
+    float dw = -go;
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (j < oh) {
+        const float z = __ldg(ps + h * oh + j) + pt[j];
+        if (z > 0.f) {
+          dw += z * gn[j];
+          dpt[j] += w * gn[j];
+        }
+      }
+    const float da = dw * w;
+    dat += da;
+    dA[(int64_t)e * H + h] = da;
+  }
+  float* dpn = dP + n * ldp;
+#pragma unroll
+  for (int j = 0; j < CH; ++j)
+    if (j < oh) dpn[C + h * oh + j] = dpt[j];
+  dpn[2 * C + H + h] = dat;
+}
+
+// source pass: dPs, das over the by-source grouping (s_tgt = target of the edge, s_pos = its by-target position)
+template <int CH>
+__global__ void __launch_bounds__(128) k_gat_bwd_src(int64_t n_nodes, int H, int oh, const int32_t* __restrict__ sptr,
+                                                     const int32_t* __restrict__ s_tgt, const int32_t* __restrict__ s_pos,
+                                                     const float* __restrict__ P, int64_t ldp,
+                                                     const unsigned long long* __restrict__ amax_key,
+                                                     const float* __restrict__ den, const float* __restrict__ g, int64_t ldg,
+                                                     const float* __restrict__ dA, float* __restrict__ dP) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gid >= n_nodes * H) return;
+  const int64_t s = gid / H;
+  const int h = static_cast<int>(gid - s * H);
+  const int C = H * oh;
+  const float amax = key_max(amax_key[h]);
+  const float* psn = P + s * ldp;
+  const float as = __ldg(psn + 2 * C + h);
+  float ps[CH], dps[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) {
+    ps[j] = j < oh ? __ldg(psn + h * oh + j) : 0.f;
+    dps[j] = 0.f;
+  }
+  float das = 0.f;
+  const int e0 = __ldg(sptr + s), e1 = __ldg(sptr + s + 1);
+  for (int e = e0; e < e1; ++e) {
+    const int64_t n = __ldg(s_tgt + e);
+    const float* pt = P + n * ldp;
+    const float w = expf(as + __ldg(pt + 2 * C + H + h) - amax) / __ldg(den + n * H + h);
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (j < oh) {
+        const float z = ps[j] + __ldg(pt + C + h * oh + j);
+        if (z > 0.f) dps[j] += w * __ldg(g + n * ldg + h * oh + j);
+      }
+    das += __ldg(dA + (int64_t)__ldg(s_pos + e) * H + h);
+  }
+  float* dpn = dP + s * ldp;
+#pragma unroll
+  for (int j = 0; j < CH; ++j)
+    if (j < oh) dpn[h * oh + j] = dps[j];
+  dpn[2 * C + h] = das;
+}
+
+// d amax[h] = -sum_e dA[e, h]  goes to the arg-max edge: das[src*] and dat[tgt*]
+__global__ void k_gat_bwd_max(int H, int C, const unsigned long long* __restrict__ amax_key, const float* __restrict__ dA_colsum,
+                              const int32_t* __restrict__ t_src, const int32_t* __restrict__ t_tgt, float* __restrict__ dP,
+                              int64_t ldp) {
+  const int h = threadIdx.x;
+  if (h >= H) return;
+  const unsigned long long k = amax_key[h];
+  if (!k) return;
+  const unsigned int pos = key_pos(k);
+  const float d = -dA_colsum[h];
+  // distinct heads touch distinct columns; src* != tgt* rows or distinct columns (2C+h vs 2C+H+h): no race
+  dP[(int64_t)t_src[pos] * ldp + 2 * C + h] += d;
+  dP[(int64_t)t_tgt[pos] * ldp + 2 * C + H + h] += d;
+}
+
+template <int CH>
+static int gat_fwd_t(const gode_gat_graph_t* G, int H, int oh, const float* P, int64_t ldp, float eps, float* out, int64_t ldo,
+                     float* den, unsigned long long* amax_key, int* nan_flag, cudaStream_t st) {
+  const int64_t work = G->n_nodes * H;
+  k_gat_fwd<CH><<<static_cast<unsigned>((work + 127) / 128), 128, 0, st>>>(G->n_nodes, H, oh, G->tptr, G->t_src, P, ldp, eps,
+                                                                          amax_key, out, ldo, den, nan_flag);
+  GODE_LAUNCH_CHECK();
+  return GODE_OK;
+}
+
+template <int CH>
+static int gat_bwd_t(const gode_gat_graph_t* G, int H, int oh, const float* P, int64_t ldp, const float* out, int64_t ldo,
+                     const float* den, const unsigned long long* amax_key, const float* g, int64_t ldg, float* dP, float* dA,
+                     cudaStream_t st) {
+  const int64_t work = G->n_nodes * H;
+  const unsigned grid = static_cast<unsigned>((work + 127) / 128);
+  k_gat_bwd_tgt<CH><<<grid, 128, 0, st>>>(G->n_nodes, H, oh, G->tptr, G->t_src, P, ldp, amax_key, out, ldo, den, g, ldg, dP, dA);
+  GODE_LAUNCH_CHECK();
+  k_gat_bwd_src<CH><<<grid, 128, 0, st>>>(G->n_nodes, H, oh, G->sptr, G->s_tgt, G->s_pos, P, ldp, amax_key, den, g, ldg, dA, dP);
+  GODE_LAUNCH_CHECK();
+  return GODE_OK;
+}
+
+}  // namespace gode
+
+using namespace gode;
+
+static int gat_check(const gode_gat_graph_t* G, int H, int oh, int64_t ldp) {
+  GODE_REQUIRE(G && G->n_nodes >= 0 && G->n_edges >= 0, "gat: bad graph");
+  GODE_REQUIRE(H >= 1 && H <= 64 && oh >= 1 && oh <= 64, "gat: heads must be in [1,64] and channels per head in [1,64]");
+  GODE_REQUIRE(ldp >= 2LL * H * oh + 2 * H, "gat: ldp too small for [Ps | Pt | as | at]");
+  GODE_REQUIRE(G->n_nodes == 0 || (G->tptr && G->sptr), "gat: null segment pointers");
+  GODE_REQUIRE(G->n_edges == 0 || (G->t_src && G->t_tgt && G->s_tgt && G->s_pos), "gat: null edge arrays");
+  return GODE_OK;
+}
+
+extern "C" size_t gode_gat_bwd_workspace_bytes(int64_t n_edges, int32_t heads) {
+  return align_up(sizeof(float) * static_cast<size_t>(n_edges > 0 ? n_edges : 1) * heads, 256) + align_up(sizeof(float) * 64, 256) +
+         gode_colreduce_workspace_bytes(heads);
+}
+
+extern "C" int gode_gat_fwd(const gode_gat_graph_t* G, int32_t heads, int32_t oh, const float* P, int64_t ldp, float eps,
+                            float* out, int64_t ldo, float* den, unsigned long long* amax_key, int32_t* nan_flag,
+                            void* stream) {
+  int rc = gat_check(G, heads, oh, ldp);
+  if (rc) return rc;
+  GODE_REQUIRE(ldo >= heads * oh && amax_key && nan_flag && (G->n_nodes == 0 || (P && out && den)), "gat_fwd: bad argument");
+  cudaStream_t st = as_stream(stream);
+  GODE_CHECK_CUDA(cudaMemsetAsync(amax_key, 0, sizeof(unsigned long long) * heads, st));
+  if (G->n_nodes == 0) return GODE_OK;
+  if (G->n_edges > 0) {
+    int64_t blocks = (G->n_edges + 255) / 256;
+    const int64_t cap = 4LL * sm_count();
+    if (blocks > cap) blocks = cap;
+    k_gat_amax<<<static_cast<unsigned>(blocks), 256, 0, st>>>(G->n_edges, heads, G->t_src, G->t_tgt, P, ldp, heads * oh, amax_key,
+                                                              nan_flag);
+    GODE_LAUNCH_CHECK();
+  }
+  if (oh <= 8) return gat_fwd_t<8>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, st);
+  if (oh <= 16) return gat_fwd_t<16>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, st);
+  if (oh <= 32) return gat_fwd_t<32>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, st);
+  return gat_fwd_t<64>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, st);
+}
+
+extern "C" int gode_gat_bwd(const gode_gat_graph_t* G, int32_t heads, int32_t oh, const float* P, int64_t ldp, const float* out,
+                            int64_t ldo, const float* den, const unsigned long long* amax_key, const float* gout, int64_t ldg,
+                            float* dP, void* ws, size_t ws_bytes, void* stream) {
+  int rc = gat_check(G, heads, oh, ldp);
+  if (rc) return rc;
+  GODE_REQUIRE(amax_key && (G->n_nodes == 0 || (P && out && den && gout && dP)), "gat_bwd: null pointer");
+  if (!ws || ws_bytes < gode_gat_bwd_workspace_bytes(G->n_edges, heads)) {
+    set_error("gat_bwd: workspace too small");
+    return GODE_EWORKSPACE;
+  }
+  if (G->n_nodes == 0) return GODE_OK;
+  cudaStream_t st = as_stream(stream);
+  Arena ar(ws, ws_bytes);
+  float* dA = ar.take<float>(static_cast<size_t>(G->n_edges > 0 ? G->n_edges : 1) * heads);
+  float* dsum = ar.take<float>(64);
+  const size_t red_bytes = gode_colreduce_workspace_bytes(heads);
+  float* red = reinterpret_cast<float*>(ar.take<char>(red_bytes));
+  if (oh <= 8) rc = gat_bwd_t<8>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, st);
+  else if (oh <= 16) rc = gat_bwd_t<16>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, st);
+  else if (oh <= 32) rc = gat_bwd_t<32>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, st);
+  else rc = gat_bwd_t<64>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, st);
+  if (rc) return rc;
+  if (G->n_edges > 0) {
+    if ((rc = colsum(G->n_edges, heads, dA, heads, dsum, red, red_bytes, st))) return rc;
+    k_gat_bwd_max<<<1, 64, 0, st>>>(heads, heads * oh, amax_key, dsum, G->t_src, G->t_tgt, dP, ldp);
+    GODE_LAUNCH_CHECK();
+  }
+  return GODE_OK;
+}

@@ -23,7 +23,7 @@ template <int BM, int BN, bool TA, bool TB>
 __global__ void __launch_bounds__(256) k_gemm(int64_t M, int64_t N, int64_t K, float alpha, const float* __restrict__ A,
                                               int64_t lda, const float* __restrict__ B, int64_t ldb, float beta,
                                               float* __restrict__ C, int64_t ldc, int64_t k_chunk, float* __restrict__ part,
-                                              const float* __restrict__ rowvec, float rowvec_scale) {
+                                              const float* __restrict__ rowvec, float rowvec_scale, int relu) {
   constexpr int BK = 8, TM = BM / 16, TN = BN / 16;
   __shared__ float sA[BK][BM + 4];
   __shared__ float sB[BK][BN + 4];
@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(256) k_gemm(int64_t M, int64_t N, int64_t K, f
       } else {
         float prev = beta != 0.f ? beta * C[m * ldc + n] : 0.f;
         if (rowvec) prev += rowvec_scale * __ldg(rowvec + n);
-        C[m * ldc + n] = alpha * acc[i][j] + prev;
+        const float v = alpha * acc[i][j] + prev;
+        C[m * ldc + n] = relu ? fmaxf(v, 0.f) : v;
       }
     }
   }
@@ -100,21 +101,21 @@ __global__ void k_reduce_splits(int64_t M, int64_t N, int splits, const float* _
 template <int BM, int BN>
 static int launch_gemm(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
                        const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int splits, int64_t k_chunk,
-                       float* part, const float* rowvec, float rowvec_scale, cudaStream_t st) {
+                       float* part, const float* rowvec, float rowvec_scale, int relu, cudaStream_t st) {
   dim3 grid(static_cast<unsigned>((M + BM - 1) / BM), static_cast<unsigned>((N + BN - 1) / BN), splits);
-  if (!ta && !tb) k_gemm<BM, BN, false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, k_chunk, part, rowvec, rowvec_scale);
-  else if (!ta && tb) k_gemm<BM, BN, false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, k_chunk, part, rowvec, rowvec_scale);
-  else if (ta && !tb) k_gemm<BM, BN, true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, k_chunk, part, rowvec, rowvec_scale);
-  else k_gemm<BM, BN, true, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, k_chunk, part, rowvec, rowvec_scale);
+  if (!ta && !tb) k_gemm<BM, BN, false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, k_chunk, part, rowvec, rowvec_scale, relu);
+  else if (!ta && tb) k_gemm<BM, BN, false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, k_chunk, part, rowvec, rowvec_scale, relu);
+  else if (ta && !tb) k_gemm<BM, BN, true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, k_chunk, part, rowvec, rowvec_scale, relu);
+  else k_gemm<BM, BN, true, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, k_chunk, part, rowvec, rowvec_scale, relu);
   GODE_LAUNCH_CHECK();
   return GODE_OK;
 }
 
 int gemm_simt(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B,
               int64_t ldb, float beta, float* C, int64_t ldc, int splits, void* ws, size_t ws_bytes, cudaStream_t st,
-              const float* rowvec, float rowvec_scale) {
+              const float* rowvec, float rowvec_scale, int relu) {
   if (M == 0 || N == 0) return GODE_OK;
-  if (rowvec && splits > 1) {
+  if ((rowvec || relu) && splits > 1) {
     set_error("gemm: rowvec epilogue is not available with split-K");
     return GODE_EINVAL;
   }
@@ -133,11 +134,11 @@ int gemm_simt(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, cons
   }
   int rc;
   if (M >= 128 && N >= 128)
-    rc = launch_gemm<128, 128>(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splits, k_chunk, part, rowvec, rowvec_scale, st);
+    rc = launch_gemm<128, 128>(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splits, k_chunk, part, rowvec, rowvec_scale, relu, st);
   else if (N <= 32)
-    rc = launch_gemm<128, 32>(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splits, k_chunk, part, rowvec, rowvec_scale, st);
+    rc = launch_gemm<128, 32>(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splits, k_chunk, part, rowvec, rowvec_scale, relu, st);
   else
-    rc = launch_gemm<64, 64>(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splits, k_chunk, part, rowvec, rowvec_scale, st);
+    rc = launch_gemm<64, 64>(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splits, k_chunk, part, rowvec, rowvec_scale, relu, st);
   if (rc != GODE_OK) return rc;
   if (part) {
     k_reduce_splits<<<static_cast<unsigned>((M * N + 255) / 256), 256, 0, st>>>(M, N, splits, part, beta, C, ldc);
@@ -157,4 +158,15 @@ extern "C" int gode_gemm_f32(int32_t transA, int32_t transB, int64_t M, int64_t 
   GODE_REQUIRE((M == 0 || N == 0) || (A && B && C) || K == 0, "gemm: null pointer");
   GODE_REQUIRE(ldc >= N, "gemm: ldc < N");
   return gemm_simt(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, splits, ws, ws_bytes, as_stream(stream), nullptr, 0.f);
+}
+
+// C = act(A B + bias): nn.Linear / MyLinear with the bias (and ReLU) applied in the GEMM epilogue
+extern "C" int gode_linear_f32(int32_t transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                               int64_t ldb, const float* bias, int32_t relu, float* C, int64_t ldc, void* stream) {
+  using namespace gode;
+  GODE_REQUIRE(M >= 0 && N >= 0 && K >= 0, "linear: negative size");
+  GODE_REQUIRE((M == 0 || N == 0) || (A && B && C) || K == 0, "linear: null pointer");
+  GODE_REQUIRE(ldc >= N, "linear: ldc < N");
+  return gemm_simt(0, transB, M, N, K, 1.f, A, lda, B, ldb, 0.f, C, ldc, 1, nullptr, 0, as_stream(stream), bias, 1.f,
+                   relu ? 1 : 0);
 }

@@ -8,7 +8,7 @@ int spmm_dispatch(const gode_csr_t& A, const float* X, int64_t ldx, int32_t d, f
                   const gode_spmm_epilogue_t& ep, void* ws, size_t ws_bytes, cudaStream_t st);
 int gemm_simt(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B,
               int64_t ldb, float beta, float* C, int64_t ldc, int splits, void* ws, size_t ws_bytes, cudaStream_t st,
-              const float* rowvec, float rowvec_scale);
+              const float* rowvec, float rowvec_scale, int relu = 0);
 int colsum(int64_t n, int d, const float* x, int64_t ldx, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 int groupnorm_fwd(int64_t n, int d, int groups, float eps, const float* x, int64_t ldx, const float* gamma,
                   const float* beta, float* y, int64_t ldy, cudaStream_t st);

@@ -418,3 +418,23 @@ extern "C" int gode_rk_error_sumsq(int64_t n_elems, const float* y0, const float
   GODE_LAUNCH_CHECK();
   return reduce_partials(grid, 1, static_cast<float*>(ws), sumsq_out, st);
 }
+
+// res = g * (out > 0): backward of a fused ReLU epilogue (F.relu in GCN/models.py:76-80, MLP hidden layers QC/layers.py:55)
+namespace gode {
+__global__ void __launch_bounds__(256) k_relu_bwd(int64_t n, const float* __restrict__ g, const float* __restrict__ out,
+                                                  float* __restrict__ res) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    res[i] = __ldcs(out + i) > 0.f ? __ldcs(g + i) : 0.f;
+}
+}  // namespace gode
+
+extern "C" int gode_relu_bwd(int64_t n_elems, const float* g, const float* out, float* res, void* stream) {
+  GODE_REQUIRE(n_elems >= 0 && (n_elems == 0 || (g && out && res)), "relu_bwd: bad argument");
+  if (n_elems == 0) return GODE_OK;
+  int64_t blocks = (n_elems + 255) / 256;
+  const int64_t cap = 8LL * sm_count();
+  if (blocks > cap) blocks = cap;
+  k_relu_bwd<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(n_elems, g, out, res);
+  GODE_LAUNCH_CHECK();
+  return GODE_OK;
+}

@@ -352,7 +352,7 @@ class GraphConvFn(torch.autograd.Function):
         x, w, out = ctx.saved_tensors
         g = _rowmajor(g, "grad")
         if ctx.relu:
-            g = g * (out > 0).to(g.dtype)
+            g = relu_mask(g, out)
         gb = colsum(g) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         gs = spmm(ctx.plan, g, transpose=True)                       # A^T g
         gx = gemm(gs, w, trans_b=True) if ctx.needs_input_grad[0] else None
@@ -384,3 +384,268 @@ def graph_conv(x, adj, weight, bias, relu=False):
 
 def group_norm(x, groups, gamma, beta, eps=1e-5):
     return GroupNormFn.apply(x, gamma, beta, groups, eps)
+
+
+# --------------------------------------------------------------------------------------------------
+# Linear with fused bias / ReLU (GAT projections, QC MyLinear / MLP)
+# --------------------------------------------------------------------------------------------------
+
+
+def linear(x, weight, bias=None, relu=False, weight_is_out_in=False, out=None):
+    """``act(x @ W + b)`` via gode_linear_f32.  ``weight`` is [in, out] (QC MyLinear) or, with
+    ``weight_is_out_in``, [out, in] (nn.Linear)."""
+    x = _rowmajor(x, "x")
+    w = _rowmajor(weight, "weight")
+    K = x.shape[1]
+    N = w.shape[0] if weight_is_out_in else w.shape[1]
+    if (w.shape[1] if weight_is_out_in else w.shape[0]) != K:
+        raise ValueError("linear: inner dimensions differ")
+    if out is None:
+        out = torch.empty(x.shape[0], N, dtype=torch.float32, device=x.device)
+    b = _req(bias, "bias").contiguous() if bias is not None else None
+    check(lib.gode_linear_f32(int(weight_is_out_in), x.shape[0], N, K, _p(x), x.stride(0), _p(w), w.stride(0), _p(b),
+                              int(relu), _p(out), out.stride(0), _stream()), "gode_linear_f32")
+    return out
+
+
+class LinearFn(torch.autograd.Function):
+    """x @ W + b (+ ReLU) with W stored [in, out] -- QC/layers.py:26-30 (MyLinear) and the MLP's hidden ReLU (:55)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        x = _rowmajor(x, "x")
+        w = _rowmajor(weight, "weight")
+        out = linear(x, w, bias, relu)
+        ctx.relu, ctx.has_bias = relu, bias is not None
+        ctx.save_for_backward(x, w, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, out = ctx.saved_tensors
+        g = _rowmajor(g, "grad")
+        if ctx.relu:
+            g = relu_mask(g, out)
+        gx = gemm(g, w, trans_b=True) if ctx.needs_input_grad[0] else None
+        gw = gemm(x, g, trans_a=True, splits=_splits_for(x.shape[0], x.shape[1], g.shape[1])) if ctx.needs_input_grad[1] else None
+        gb = colsum(g) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb, None
+
+
+def relu_mask(g, out):
+    """g * (out > 0) via gode_rk_combine-free path: one libgode elementwise kernel (gode_relu_bwd)."""
+    g = g.contiguous()
+    res = torch.empty_like(g)
+    check(lib.gode_relu_bwd(g.numel(), _p(g), _p(out.contiguous()), _p(res), _stream()), "gode_relu_bwd")
+    return res
+
+
+# --------------------------------------------------------------------------------------------------
+# GAT: edge groupings + attention aggregation (gode_gat_fwd / gode_gat_bwd)
+# --------------------------------------------------------------------------------------------------
+
+
+class GatGraph:
+    """Edges grouped by target and by source (built once per edge list; replaces the N x E incidence ``Mtgt``
+    of GAT/utils.py:194-196 -- the grouping by target *is* its CSR)."""
+
+    def __init__(self, src, tgt, n_nodes):
+        if not (src.is_cuda and tgt.is_cuda):
+            raise TypeError("GAT edge lists must live on a CUDA device; graph-odenet_b200 has no CPU path")
+        dev = src.device
+        E = int(src.numel())
+        self.n_nodes, self.n_edges, self.device = int(n_nodes), E, dev
+        src64, tgt64 = src.to(torch.int64).contiguous(), tgt.to(torch.int64).contiguous()
+        if E and (int(src64.min()) < 0 or int(tgt64.min()) < 0 or int(src64.max()) >= n_nodes or int(tgt64.max()) >= n_nodes):
+            raise IndexError("edge endpoint out of range for %d nodes" % n_nodes)
+        eid = torch.arange(E, device=dev, dtype=torch.int64)
+        ones = torch.ones(E, dtype=torch.float32, device=dev)
+        # CSR of Mtgt (rows = targets, columns = edge ids): gode_csr_from_coo keeps edge order inside a segment
+        pt = GraphPlan.from_coo(tgt64, eid, ones, n_nodes, max(E, 1), build_transpose=False)
+        ps = GraphPlan.from_coo(src64, eid, ones, n_nodes, max(E, 1), build_transpose=False)
+        t_eid = pt.colidx[:E].to(torch.int64)
+        s_eid = ps.colidx[:E].to(torch.int64)
+        self.tptr, self.sptr = pt.rowptr, ps.rowptr
+        self.t_src = src64[t_eid].to(torch.int32)
+        self.t_tgt = tgt64[t_eid].to(torch.int32)
+        self.s_tgt = tgt64[s_eid].to(torch.int32)
+        pos = torch.empty(E, dtype=torch.int64, device=dev)
+        pos[t_eid] = eid
+        self.s_pos = pos[s_eid].to(torch.int32)
+        g = _lib.GatGraph()
+        g.n_nodes, g.n_edges = self.n_nodes, E
+        g.tptr, g.t_src, g.t_tgt = self.tptr.data_ptr(), self.t_src.data_ptr(), self.t_tgt.data_ptr()
+        g.sptr, g.s_tgt, g.s_pos = self.sptr.data_ptr(), self.s_tgt.data_ptr(), self.s_pos.data_ptr()
+        self.c = g
+        self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+
+
+_gat_cache = {}
+
+
+def gat_graph_for(src, tgt, n_nodes):
+    if isinstance(src, GatGraph):
+        return src
+    key = (src.data_ptr(), tgt.data_ptr(), int(src.numel()), int(n_nodes), src.device.index)
+    hit = _gat_cache.get(key)
+    if hit is not None and hit[0]() is src:
+        return hit[1]
+    g = GatGraph(src, tgt, n_nodes)
+    _gat_cache[key] = (weakref.ref(src), g)
+    if len(_gat_cache) > 64:
+        for k in [k for k, v in _gat_cache.items() if v[0]() is None]:
+            _gat_cache.pop(k, None)
+    return g
+
+
+class GatConvFn(torch.autograd.Function):
+    """GAT/layers.py:40-58 on libgode: node projection GEMM -> gode_gat_fwd; backward gode_gat_bwd -> two GEMMs.
+
+    ``f_weight`` [H*oh, 2i], ``f_bias`` [H*oh], ``w_weight`` [H, 2i], ``w_bias`` [H] (H = 1: the reference layer).
+    """
+
+    @staticmethod
+    def forward(ctx, x, f_weight, f_bias, w_weight, w_bias, graph, heads, eps):
+        x = _rowmajor(x, "x")
+        i = x.shape[1]
+        C_, H = f_weight.shape[0], heads
+        oh = C_ // H
+        ldp = 2 * C_ + 2 * H
+        # W_cat [i, ldp] = [Wf_src^T | Wf_tgt^T | ww_src^T | ww_tgt^T]; biases ride on the target halves
+        wcat = torch.cat([f_weight[:, :i].t(), f_weight[:, i:].t(), w_weight[:, :i].t(), w_weight[:, i:].t()], 1).contiguous()
+        zc, zh = torch.zeros(C_, device=x.device), torch.zeros(H, device=x.device)
+        bcat = torch.cat([zc, f_bias if f_bias is not None else zc, zh, w_bias if w_bias is not None else zh])
+        P = linear(x, wcat, bcat)
+        out = torch.empty(graph.n_nodes, C_, dtype=torch.float32, device=x.device)
+        den = torch.empty(graph.n_nodes, H, dtype=torch.float32, device=x.device)
+        amax = torch.empty(H, dtype=torch.int64, device=x.device)
+        check(lib.gode_gat_fwd(C.byref(graph.c), H, oh, _p(P), ldp, float(eps), _p(out), out.stride(0), _p(den), _p(amax),
+                               _p(graph.nan_flag), _stream()), "gode_gat_fwd")
+        ctx.graph, ctx.H, ctx.oh, ctx.i = graph, H, oh, i
+        ctx.has_bias = (f_bias is not None, w_bias is not None)
+        ctx.save_for_backward(x, wcat, P, out, den, amax)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wcat, P, out, den, amax = ctx.saved_tensors
+        graph, H, oh, i = ctx.graph, ctx.H, ctx.oh, ctx.i
+        C_ = H * oh
+        ldp = 2 * C_ + 2 * H
+        g = _rowmajor(g, "grad").contiguous()
+        dP = torch.empty_like(P)
+        nb = lib.gode_gat_bwd_workspace_bytes(graph.n_edges, H)
+        ws = workspace(nb, x.device, "gat")
+        check(lib.gode_gat_bwd(C.byref(graph.c), H, oh, _p(P), ldp, _p(out), out.stride(0), _p(den), _p(amax), _p(g),
+                               g.stride(0), _p(dP), _p(ws), nb, _stream()), "gode_gat_bwd")
+        gx = gemm(dP, wcat, trans_b=True) if ctx.needs_input_grad[0] else None
+        gfw = gfb = gww = gwb = None
+        if any(ctx.needs_input_grad[1:5]):
+            dw = gemm(x, dP, trans_a=True, splits=_splits_for(x.shape[0], i, ldp))       # [i, ldp]
+            gfw = torch.cat([dw[:, :C_].t(), dw[:, C_:2 * C_].t()], 1)
+            gww = torch.cat([dw[:, 2 * C_:2 * C_ + H].t(), dw[:, 2 * C_ + H:].t()], 1)
+            db = colsum(dP)
+            gfb = db[C_:2 * C_] if ctx.has_bias[0] else None
+            gwb = db[2 * C_ + H:] if ctx.has_bias[1] else None
+        return gx, gfw, gfb, gww, gwb, None, None, None
+
+
+def gat_conv(x, src, tgt, f_weight, f_bias, w_weight, w_bias, heads=1, eps=1e-6, check_nan=True):
+    graph = gat_graph_for(src, tgt, x.shape[0])
+    out = GatConvFn.apply(x, f_weight, f_bias, w_weight, w_bias, graph, heads, eps)
+    if check_nan:
+        # the reference asserts on NaNs six times per call (GAT/layers.py:46-56); one device flag, one read
+        assert int(graph.nan_flag.item()) == 0, "NaN in GAT attention"
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# segmented sums through a plan (scatter_add readout, one-hot incidence products) and QC edge messages
+# --------------------------------------------------------------------------------------------------
+
+
+class PlanMatmulFn(torch.autograd.Function):
+    """``A @ x`` for a planned sparse A (forward gode_spmm_csr_f32, backward the same kernel on A^T)."""
+
+    @staticmethod
+    def forward(ctx, x, plan, bias):
+        ctx.plan, ctx.has_bias = plan, bias is not None
+        return spmm(plan, x, bias=bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _rowmajor(g, "grad")
+        gx = spmm(ctx.plan, g, transpose=True) if ctx.needs_input_grad[0] else None
+        gb = colsum(g) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, None, gb
+
+
+def index_plan(index, n_rows):
+    """Plan of the one-hot matrix M[index[j], j] = 1 (``scatter_add(x, index)`` == ``M @ x``), cached per index tensor."""
+    key = ("idx", index.data_ptr(), int(index.numel()), int(n_rows), index.device.index)
+    hit = _plan_cache.get(key)
+    if hit is not None and hit[0]() is index:
+        return hit[1]
+    if not index.is_cuda:
+        raise TypeError("index must live on a CUDA device; graph-odenet_b200 has no CPU path")
+    j = torch.arange(index.numel(), device=index.device, dtype=torch.int64)
+    plan = GraphPlan.from_coo(index.to(torch.int64), j, torch.ones(index.numel(), dtype=torch.float32, device=index.device),
+                              int(n_rows), int(index.numel()))
+    _plan_cache[key] = (weakref.ref(index), plan)
+    return plan
+
+
+def scatter_add_rows(x, index, n_rows):
+    """``torch_scatter.scatter_add(x, index, dim=0, dim_size=n_rows)`` (QC/layer_models.py:121, QC/torch_scatter.py)
+    as a deterministic segmented sum."""
+    return PlanMatmulFn.apply(x, index_plan(index, n_rows), None)
+
+
+def incidence_plan(Etgt, n_nodes=None):
+    """Plan of the reference's ``Etgt`` (dense one-hot [N, E], QC/datasets/utils.py:214; also accepted: sparse COO,
+    or the target index vector [E] with ``n_nodes``)."""
+    if isinstance(Etgt, GraphPlan):
+        return Etgt
+    if Etgt.dim() == 1:
+        return index_plan(Etgt, n_nodes)
+    return plan_for(Etgt)
+
+
+class EdgeMessageFn(torch.autograd.Function):
+    """out = Etgt @ (edge_data[e] @ s[Esrc[e]])_e (+ bias)  -- QC/layers.py:143-147, QC/mpnn.py:27-29."""
+
+    @staticmethod
+    def forward(ctx, s, edge_data, esrc, plan_t, bias):
+        s = _rowmajor(s, "support")
+        ed = _req(edge_data, "edge_data").contiguous()
+        E, f = ed.shape[0], ed.shape[1]
+        if ed.dim() != 3 or ed.shape[2] != f or s.shape[1] != f:
+            raise ValueError("edge_data must be [E, f, f] with f = support width")
+        esrc32 = esrc.to(torch.int32).contiguous()
+        msg = torch.empty(E, f, dtype=torch.float32, device=s.device)
+        check(lib.gode_edge_matvec(E, f, _p(ed), _p(esrc32), _p(s), s.stride(0), _p(msg), _stream()), "gode_edge_matvec")
+        out = spmm(plan_t, msg, bias=bias)
+        ctx.plan_t, ctx.has_bias, ctx.n = plan_t, bias is not None, s.shape[0]
+        ctx.save_for_backward(s, ed, esrc32, esrc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        s, ed, esrc32, esrc = ctx.saved_tensors
+        g = _rowmajor(g, "grad")
+        E, f = ed.shape[0], ed.shape[1]
+        dm = spmm(ctx.plan_t, g, transpose=True)                    # Etgt^T g : [E, f]
+        ds_msg = torch.empty(E, f, dtype=torch.float32, device=g.device)
+        d_ed = torch.empty_like(ed) if ctx.needs_input_grad[1] else None
+        check(lib.gode_edge_matvec_bwd(E, f, _p(ed), _p(esrc32), None, _p(s), s.stride(0), _p(dm), dm.stride(0),
+                                       _p(ds_msg), _p(d_ed), _stream()), "gode_edge_matvec_bwd")
+        ds = spmm(index_plan(esrc, ctx.n), ds_msg) if ctx.needs_input_grad[0] else None
+        gb = colsum(g) if (ctx.has_bias and ctx.needs_input_grad[4]) else None
+        return ds, d_ed, None, None, gb
+
+
+def edge_message(s, edge_data, esrc, Etgt, bias=None):
+    plan_t = incidence_plan(Etgt, s.shape[0])
+    if plan_t.n_rows != s.shape[0] or plan_t.n_cols < edge_data.shape[0]:
+        raise ValueError("Etgt must be [N, E]")
+    return EdgeMessageFn.apply(s, edge_data, esrc, plan_t, bias)

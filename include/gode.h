@@ -154,6 +154,14 @@ int gode_gemm_f32(int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t 
                   float* C, int64_t ldc, int32_t precision, int32_t splits, void* ws, size_t ws_bytes,
                   void* stream);
 
+/* C = act(A op(B) + bias)  -- a Linear layer with bias (and ReLU) in the GEMM epilogue.
+ * replaces: nn.Linear f(h), w(h) (GAT/layers.py:20-21,44-45, as node projections: see gode_gat_fwd);
+ *           MyLinear / MLP (QC/layers.py:26-30, 49-57: mm + bias, relu between layers).
+ * transB = 0: B is [K, N] (MyLinear's weight layout); transB = 1: B is [N, K] (nn.Linear's). bias [N] or NULL. */
+int gode_linear_f32(int32_t transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                    const float* B, int64_t ldb, const float* bias, int32_t relu, float* C, int64_t ldc,
+                    void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Row-wise GroupNorm on [n, d] (groups of d/groups contiguous channels per row).
  * replaces: nn.GroupNorm(min(32,d), d) -- GCN/models.py:165,175 (ATen formula
@@ -171,6 +179,10 @@ size_t gode_colreduce_workspace_bytes(int32_t width);
 /* out[c] = sum_r x[r, c]   (bias gradients; GCN/layers.py:35 autograd) */
 int gode_colsum_f32(int64_t n, int32_t d, const float* x, int64_t ldx, float* out,
                     void* ws, size_t ws_bytes, void* stream);
+
+/* res = g * (out > 0): backward of a ReLU fused into a producing kernel's epilogue
+ * (autograd of F.relu, GCN/models.py:76-80; MLP hidden layers QC/layers.py:55). */
+int gode_relu_bwd(int64_t n_elems, const float* g, const float* out, float* res, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Runge-Kutta helpers (torchdiffeq rk_common / dopri5, restated in oracle/odeint.py).
@@ -244,6 +256,58 @@ int gode_gcn_vjp_phase1(const gode_gcn_odefunc_t* f, const float* S, const float
                         float coef_self, float* y_next, void* ws, size_t ws_bytes, void* stream);
 int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, float t, const float* gP,
                         float* k_a, float* gtheta, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GAT attention aggregation (segmented softmax / scatter over the edge list).
+ * replaces: GAT/layers.py:40-58 and :103-120 -- x[src], x[tgt], cat, relu(f(h)), w(h), torch.max(a, 0), exp,
+ *           the two torch.spmm(Mtgt, .) incidence products and the division.
+ * The caller projects the nodes once (gode_gemm_f32):  P[N, ldp] = [Ps (C) | Pt (C) | as (H) | at (H)],
+ *   Ps = x Wf[:, :i]^T, Pt = x Wf[:, i:]^T + bf, as = x ww[:, :i]^T, at = x ww[:, i:]^T + bw   (C = heads*oh),
+ * so that z_e = Ps[src_e] + Pt[tgt_e] = f(h_e) and a_e = as[src_e] + at[tgt_e] = w(h_e).
+ *   out[n, c] = sum_{e: tgt_e = n} relu(z_e[c]) exp(a_e - amax_h) / (sum_{e: tgt_e = n} exp(a_e - amax_h) + eps)
+ * with amax_h the maximum of a_e over ALL edges (the reference's global shift), per head h = c / oh.
+ * heads > 1 is the builder extension "H independent reference heads, concatenated" (SURVEY 8a).
+ * Edges are grouped by target (tptr / t_src / t_tgt: CSR of Mtgt, edge order kept inside a segment) and by
+ * source (sptr / s_tgt / s_pos; s_pos = position of the edge in the by-target order) -- built once per graph.
+ * fwd saves den[N, heads] (denominators incl. eps) and amax_key[heads] (max value and arg-max edge, packed).
+ * nan_flag (device int32) is set to 1 if any a_e or output is NaN (the reference asserts on those,
+ * GAT/layers.py:46-56); it is never cleared by the library.
+ * bwd writes dP[N, ldp] (columns [0, 2C+2H) are written, padding is left alone); the caller finishes with
+ * dx = dP W^T and dW = x^T dP.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t n_nodes;
+  int64_t n_edges;
+  const int32_t* tptr;   /* [n_nodes + 1] segments by target */
+  const int32_t* t_src;  /* [n_edges] source node of each edge, by-target order */
+  const int32_t* t_tgt;  /* [n_edges] target node of each edge, by-target order */
+  const int32_t* sptr;   /* [n_nodes + 1] segments by source */
+  const int32_t* s_tgt;  /* [n_edges] target node of each edge, by-source order */
+  const int32_t* s_pos;  /* [n_edges] by-target position of each edge, by-source order */
+} gode_gat_graph_t;
+
+int gode_gat_fwd(const gode_gat_graph_t* g, int32_t heads, int32_t oh, const float* P, int64_t ldp, float eps,
+                 float* out, int64_t ldo, float* den, unsigned long long* amax_key, int32_t* nan_flag, void* stream);
+size_t gode_gat_bwd_workspace_bytes(int64_t n_edges, int32_t heads);
+int gode_gat_bwd(const gode_gat_graph_t* g, int32_t heads, int32_t oh, const float* P, int64_t ldp,
+                 const float* out, int64_t ldo, const float* den, const unsigned long long* amax_key,
+                 const float* gout, int64_t ldg, float* dP, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * QC edge-conditioned messages: the per-edge mat-vec.
+ * replaces: index_select(support, 0, Esrc) + torch.bmm(edge_data, .) -- QC/layers.py:143-144, QC/mpnn.py:27-28.
+ *   msg[e, r] = sum_c edge_data[e, r, c] * s[esrc[e], c]        edge_data [E, f, f] contiguous, f <= 128
+ * The reference's dense one-hot product torch.spmm(Etgt, edge_msg) (QC/layers.py:145) is the segmented sum
+ * gode_spmm_csr_f32 over msg with the CSR of Etgt (rows = targets, columns = edge ids, values 1).
+ * bwd (dm_e = gout[etgt[e]], or gout[e] when etgt is NULL):
+ *                              ds_msg[e, c] = sum_r edge_data[e, r, c] * dm_e[r]   (scatter by esrc afterwards)
+ *                              d_edge_data[e, r, c] = dm_e[r] * s[esrc[e], c]       (skipped when NULL)
+ * ---------------------------------------------------------------------------------------------- */
+int gode_edge_matvec(int64_t n_edges, int32_t f, const float* edge_data, const int32_t* esrc,
+                     const float* s, int64_t lds, float* msg, void* stream);
+int gode_edge_matvec_bwd(int64_t n_edges, int32_t f, const float* edge_data, const int32_t* esrc,
+                         const int32_t* etgt, const float* s, int64_t lds, const float* gout, int64_t ldg,
+                         float* ds_msg, float* d_edge_data, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Halo pack for the row-partitioned (multi-GPU) path: dst[i, :] = src[idx[i], :].

@@ -1,0 +1,182 @@
+"""GPU parity of the GAT path (gode_gat_fwd / gode_gat_bwd behind graph-odenet_b200/GAT) against the golden
+fixtures produced by the unmodified reference (GAT/layers.py, GAT/models.py) and against the CPU oracle.
+
+Bar: fp32, 1e-5 relative (+1e-5 of the tensor's max magnitude as the absolute floor)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gat_ref, odeint as oracle_odeint
+from tests import _golden as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _pkg():
+    import graph_odenet_b200  # noqa: F401
+    from graph_odenet_b200 import ops
+    from graph_odenet_b200.GAT import layers, models
+    return ops, layers, models
+
+
+def _cora_edges():
+    c = G.load("planetoid_cora")
+    return (torch.from_numpy(c["gat_src"].astype(np.int64)), torch.from_numpy(c["gat_tgt"].astype(np.int64)), int(c["n"]))
+
+
+def test_gat_layer_golden():
+    ops, layers, _ = _pkg()
+    g = G.load("gat_golden")
+    src, tgt, n = _cora_edges()
+    lay = layers.GraphConvolution(16, 8).to(DEV)
+    lay.load_state_dict({k: v for k, v in G.params(g, "gc/p/").items()})
+    x = G.rnd(61, n, 16).to(DEV).requires_grad_(True)
+    y = lay(x, src.to(DEV), tgt.to(DEV), None)
+    y.backward(G.rnd(62, n, 8).to(DEV))
+    G.assert_close(y, g["gc/out"], rtol=1e-5, atol_scale=1e-5, what="out")
+    G.assert_close(x.grad, g["gc/grad_x"], rtol=1e-5, atol_scale=1e-5, what="grad_x")
+    for k, p in lay.named_parameters():
+        G.assert_close(p.grad, g["gc/grad/" + k], rtol=1e-5, atol_scale=1e-5, what=k)
+    # nodes without incoming edges output exactly 0 (679 of them on Cora)
+    indeg = torch.bincount(tgt, minlength=n)
+    assert int((indeg == 0).sum()) == 679
+    assert float(y[(indeg == 0).to(DEV)].abs().max()) == 0.0
+
+
+def test_gat_odefunc_golden():
+    _, _, models = _pkg()
+    g = G.load("gat_golden")
+    src, tgt, n = _cora_edges()
+    f = models.ODEfunc(16).to(DEV)
+    f.load_state_dict(G.params(g, "odefunc/p/"))
+    f.set_adj(src.to(DEV), tgt.to(DEV), None)
+    x = G.rnd(63, n, 16).to(DEV).requires_grad_(True)
+    t = torch.tensor(0.25, device=DEV, requires_grad=True)
+    y = f(t, x)
+    grads = torch.autograd.grad(y, (x, t) + tuple(f.parameters()), G.rnd(64, n, 16).to(DEV))
+    G.assert_close(y, g["odefunc/out"], rtol=1e-5, atol_scale=1e-5, what="out")
+    G.assert_close(grads[0], g["odefunc/grad_x"], rtol=1e-5, atol_scale=1e-5, what="grad_x")
+    G.assert_close(grads[1], g["odefunc/grad_t"], rtol=1e-4, atol_abs=1e-6, what="grad_t")
+    for (k, _), gr in zip(f.named_parameters(), grads[2:]):
+        # hidden=16 GroupNorm is degenerate: its gamma gradient is a sum of rounding noise
+        tol = dict(rtol=1e-5, atol_scale=1e-5) if "norm1.weight" not in k else dict(rtol=1e-3, atol_scale=1e-3, atol_abs=1e-6)
+        G.assert_close(gr, g["odefunc/grad/" + k], what=k, **tol)
+    assert f.nfe == 1
+
+
+def _random_edges(n, e, seed, isolated=5):
+    rs = np.random.RandomState(seed)
+    src = rs.randint(0, n, e)
+    tgt = rs.randint(isolated, n, e)            # nodes [0, isolated) have no incoming edge
+    tgt[: e // 8] = n - 1                       # one hub with many incoming edges
+    src[-3:] = src[-6:-3]
+    tgt[-3:] = tgt[-6:-3]                       # duplicate edges are separate terms of the sums
+    return torch.from_numpy(src.astype(np.int64)), torch.from_numpy(tgt.astype(np.int64))
+
+
+@pytest.mark.parametrize("i,o,heads", [(16, 7, 1), (9, 16, 1), (33, 16, 8), (12, 3, 2), (20, 64, 1)])
+def test_gat_matches_oracle(i, o, heads):
+    """Single- and multi-head layers against the oracle (H independent reference heads, concatenated)."""
+    ops, layers, _ = _pkg()
+    n, e = 700, 5000
+    src, tgt = _random_edges(n, e, seed=i + o)
+    torch.manual_seed(i * 100 + o)
+    lay = layers.GraphConvolution(i, o, heads=heads)
+    with torch.no_grad():
+        lay.f.bias.uniform_(-0.3, 0.3)
+        lay.w.bias.uniform_(-0.3, 0.3)
+    x = torch.randn(n, i)
+    gy = torch.randn(n, o * heads)
+    # oracle: per-head reference layers
+    pc = {k: v.detach().clone().requires_grad_(True) for k, v in lay.state_dict().items()}
+    xo = x.clone().requires_grad_(True)
+    hs = [(pc["f.weight"][h * o:(h + 1) * o], pc["f.bias"][h * o:(h + 1) * o], pc["w.weight"][h:h + 1], pc["w.bias"][h:h + 1])
+          for h in range(heads)]
+    yo = gat_ref.gat_multihead(xo, src, tgt, hs)
+    yo.backward(gy)
+    lay = lay.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    y = lay(xg, src.to(DEV), tgt.to(DEV), None)
+    y.backward(gy.to(DEV))
+    G.assert_close(y, yo, rtol=1e-5, atol_scale=1e-5, what="out")
+    G.assert_close(xg.grad, xo.grad, rtol=1e-5, atol_scale=1e-5, what="grad_x")
+    for k, p in lay.named_parameters():
+        G.assert_close(p.grad, pc[k].grad, rtol=1e-5, atol_scale=2e-5, what=k)
+
+
+def test_gat_empty_and_degenerate():
+    ops, layers, _ = _pkg()
+    lay = layers.GraphConvolution(4, 8).to(DEV)
+    x = torch.randn(10, 4, device=DEV, requires_grad=True)
+    e0 = torch.empty(0, dtype=torch.int64, device=DEV)
+    y = lay(x, e0, e0, None)                      # no edges: every node outputs 0 / (0 + eps) = 0
+    assert y.shape == (10, 8) and float(y.abs().max()) == 0.0
+    y.sum().backward()
+    assert float(x.grad.abs().max()) == 0.0
+    with pytest.raises(IndexError):
+        lay(x, torch.tensor([0, 11], device=DEV), torch.tensor([1, 2], device=DEV), None)
+    with pytest.raises(TypeError):
+        lay(x, torch.tensor([0]), torch.tensor([1]), None)      # CPU edge list: no CPU path
+    xn = x.detach().clone()
+    xn[3, 0] = float("nan")
+    with pytest.raises(AssertionError):           # the reference asserts on NaNs (GAT/layers.py:46-56)
+        lay(xn, torch.tensor([3, 1], device=DEV), torch.tensor([1, 2], device=DEV), None)
+
+
+def test_gat_ode_block_rk4_matches_oracle():
+    """GAT-ODE block, fixed-step rk4, step for step against the restated solver driving the oracle function."""
+    _, _, models = _pkg()
+    n, e, d = 400, 2500, 16
+    src, tgt = _random_edges(n, e, seed=3)
+    torch.manual_seed(5)
+    blk = models.ODEBlock(models.ODEfunc(d), method="rk4", options={"step_size": 0.5})
+    with torch.no_grad():
+        blk.odefunc.norm1.weight.uniform_(0.5, 1.5)
+        blk.odefunc.norm1.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(n, d)
+    gy = torch.randn(n, d)
+    pc = {k: v.detach().clone().requires_grad_(True) for k, v in blk.odefunc.state_dict().items()}
+
+    class F_(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(v) for v in pc.values()])
+            self.nfe = 0
+
+        def forward(self, t, y):
+            self.nfe += 1
+            return gat_ref.gat_odefunc(t, y, dict(zip(pc.keys(), self.ps)), src, tgt)
+
+    fo = F_()
+    xo = x.clone().requires_grad_(True)
+    yo = oracle_odeint.odeint_adjoint(fo, xo, torch.tensor([0.0, 1.0]), rtol=1e-5, atol=1e-5, method="rk4",
+                                      options={"step_size": 0.5})[1]
+    yo.backward(gy)
+    blk = blk.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    blk.nfe = 0
+    y = blk(xg, src.to(DEV), tgt.to(DEV), None)
+    nfe_f = blk.nfe
+    y.backward(gy.to(DEV))
+    assert nfe_f == 8 and blk.nfe == fo.nfe
+    G.assert_close(y, yo, rtol=1e-5, atol_scale=1e-5, what="y(1)")
+    G.assert_close_l2(xg.grad, xo.grad, 1e-4, what="grad_x")
+    for (k, p), po in zip(blk.odefunc.named_parameters(), fo.ps):
+        G.assert_close_l2(p.grad, po.grad, 1e-4, what=k)
+
+
+def test_gat_model_surface():
+    _, layers, models = _pkg()
+    m = models.ODEGCN3(nfeat=12, nhid=16, nclass=3, dropout=0.0)
+    assert list(m.state_dict())[:4] == ["gc1.f.weight", "gc1.f.bias", "gc1.w.weight", "gc1.w.bias"]
+    assert m.gc2.odefunc.gc1.f.weight.shape == (16, 34)
+    with pytest.raises(ValueError):
+        models.RESK1(12, 16, 3, 0.5, nlayers=2)
+    n, e = 300, 1500
+    src, tgt = _random_edges(n, e, seed=9)
+    m = models.RGCN3(12, 16, 3, 0.0).to(DEV)
+    out = m(torch.randn(n, 12, device=DEV), src.to(DEV), tgt.to(DEV), None)
+    assert out.shape == (n, 3) and torch.isfinite(out).all()
+    out.sum().backward()
+    assert all(p.grad is not None for p in m.parameters())
