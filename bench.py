@@ -205,9 +205,11 @@ def run_ours(a):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sys.path.insert(0, ROOT)
+        import graph_odenet_b200  # noqa: F401
+        from graph_odenet_b200 import parallel as _par
+        _par.init_process_group(torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
 

@@ -27,7 +27,7 @@ vp, i64, i32, f32, sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
 class SpmmEpilogue(C.Structure):
     _fields_ = [("bias", vp), ("relu", i32), ("residual", vp), ("y0", vp), ("kprev", vp * MAX_STAGES),
                 ("coef", f32 * MAX_STAGES), ("n_prev", i32), ("coef_self", f32), ("ynext", vp),
-                ("mask_src", vp), ("mask_scale", f32), ("gp_out", vp)]
+                ("mask_src", vp), ("mask_scale", f32), ("gp_out", vp), ("acc_in", vp)]
 
 
 class Csr(C.Structure):
@@ -42,7 +42,7 @@ class GatGraph(C.Structure):
 
 class GcnOdeFunc(C.Structure):
     _fields_ = [("A", Csr), ("At", Csr), ("d", i32), ("groups", i32), ("gn_eps", f32), ("precision", i32),
-                ("W", vp), ("b", vp), ("gamma", vp), ("beta", vp)]
+                ("W", vp), ("b", vp), ("gamma", vp), ("beta", vp), ("gather_row_offset", i64), ("partial_in", vp)]
 
 
 _PROTOS = {

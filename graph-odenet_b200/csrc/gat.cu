@@ -264,7 +264,7 @@ static int gat_check(const gode_gat_graph_t* G, int H, int oh, int64_t ldp) {
 
 extern "C" size_t gode_gat_bwd_workspace_bytes(int64_t n_edges, int32_t heads) {
   return align_up(sizeof(float) * static_cast<size_t>(n_edges > 0 ? n_edges : 1) * heads, 256) + align_up(sizeof(float) * 64, 256) +
-         gode_colreduce_workspace_bytes(heads);
+         align_up(gode_colreduce_workspace_bytes(heads), 256);
 }
 
 extern "C" int gode_gat_fwd(const gode_gat_graph_t* G, int32_t heads, int32_t oh, const float* P, int64_t ldp, float eps,

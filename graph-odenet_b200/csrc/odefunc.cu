@@ -34,10 +34,8 @@ struct GcnWs {
 };
 
 static int64_t max_rows(const gode_gcn_odefunc_t* f) {
-  int64_t m = f->A.n_rows;
-  if (f->A.n_cols > m) m = f->A.n_cols;
-  if (f->At.rowptr && f->At.n_cols > m) m = f->At.n_cols;
-  return m;
+  // scratch tensors are [n_rows, d]; the gather operands (which may be longer: owned + halo rows) are the caller's
+  return f->A.n_rows;
 }
 
 static size_t heavy_bytes_for(const gode_gcn_odefunc_t* f) {
@@ -175,7 +173,8 @@ extern "C" int gode_gcn_stage_fwd(const gode_gcn_odefunc_t* f, const float* S, f
   }
   {
     ProfScope prof(GODE_PROF_AGG_FWD, st);
-    rc = spmm_dispatch(f->A, S, f->d, f->d, k_out, f->d, ep, w.heavy, w.heavy_bytes, st);
+    ep.acc_in = f->partial_in;
+    rc = spmm_dispatch(f->A, S + f->gather_row_offset * f->d, f->d, f->d, k_out, f->d, ep, w.heavy, w.heavy_bytes, st);
   }
   if (rc) return rc;
   if (S_next) rc = transform_impl(f, y_next, t_next, S_next, w, st);
@@ -210,8 +209,10 @@ extern "C" int gode_gcn_vjp_phase1(const gode_gcn_odefunc_t* f, const float* S, 
       ep.coef[j] = coef_host[j];
     }
   }
+  ep.acc_in = f->partial_in;
   ProfScope prof(GODE_PROF_AGG_FWD, as_stream(stream));
-  return spmm_dispatch(f->A, S, f->d, f->d, k_y, f->d, ep, w.heavy, w.heavy_bytes, as_stream(stream));
+  return spmm_dispatch(f->A, S + f->gather_row_offset * f->d, f->d, f->d, k_y, f->d, ep, w.heavy, w.heavy_bytes,
+                       as_stream(stream));
 }
 
 extern "C" int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, float t, const float* gP, float* k_a,
@@ -239,7 +240,8 @@ extern "C" int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, 
   memset(&ep, 0, sizeof(ep));
   {
     ProfScope prof(GODE_PROF_AGG_T, st);
-    rc = spmm_dispatch(f->At, gP, d, d, gS, d, ep, w.heavy, w.heavy_bytes, st);
+    ep.acc_in = f->partial_in;
+    rc = spmm_dispatch(f->At, gP + f->gather_row_offset * d, d, d, gS, d, ep, w.heavy, w.heavy_bytes, st);
   }
   if (rc) return rc;
   ProfScope prof_dense(GODE_PROF_VJP_DENSE, st);
@@ -270,7 +272,7 @@ extern "C" int gode_gcn_stage_vjp(const gode_gcn_odefunc_t* f, const float* y, f
                                   void* stream) {
   int rc = check(f);
   if (rc) return rc;
-  GODE_REQUIRE(f->A.n_cols == f->A.n_rows && f->At.n_cols == f->A.n_rows,
+  GODE_REQUIRE(f->A.n_cols == f->A.n_rows && f->At.n_cols == f->A.n_rows && f->gather_row_offset == 0 && !f->partial_in,
                "gcn_stage_vjp: partitioned graphs must call phase1 / exchange / phase2");
   GcnWs w;
   rc = carve(f, ws, ws_bytes, w);

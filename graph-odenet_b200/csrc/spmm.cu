@@ -29,6 +29,10 @@ __device__ __forceinline__ void epilogue(const gode_spmm_epilogue_t& ep, int64_t
   for (int u = 0; u < VPL; ++u) {
     const int c = col0 + u * 4;
     float4 v = acc[u];
+    if (ep.acc_in) {
+      float4 p = ld_stream4(ep.acc_in + row * ldy + c);
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
     if (ep.bias) {
       float4 b = ld_ro4(ep.bias + c);
       v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -430,6 +434,7 @@ __global__ void __launch_bounds__(256) k_spmm_generic(int64_t n_rows, const int3
       const int c = c0 + q * 32 + lane;
       if (c >= d) continue;
       float v = acc[q];
+      if (ep.acc_in) v += ep.acc_in[row * ldy + c];
       if (ep.bias) v += ep.bias[c];
       if (ep.relu) v = fmaxf(v, 0.f);
       const int64_t o = row * ldy + c;
@@ -732,7 +737,7 @@ int spmm_dispatch(const gode_csr_t& A, const float* X, int64_t ldx, int32_t d, f
                   const gode_spmm_epilogue_t& ep, void* ws, size_t ws_bytes, cudaStream_t st) {
   bool vec_ok = vec_width(d) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y) && aligned16(ep.bias) &&
                 aligned16(ep.residual) && aligned16(ep.y0) && aligned16(ep.ynext) && aligned16(ep.mask_src) &&
-                aligned16(ep.gp_out) && aligned16(ws);
+                aligned16(ep.gp_out) && aligned16(ep.acc_in) && aligned16(ws);
   for (int j = 0; j < ep.n_prev; ++j) vec_ok = vec_ok && aligned16(ep.kprev[j]);
   if (vec_ok && A.n_heavy > 0 && (!ws || ws_bytes < spmm_ws_bytes(A, d) || !A.heavy_rows || !A.heavy_chunk_ptr)) {
     set_error("spmm: heavy-row workspace missing or too small (%zu < %zu)", ws_bytes, spmm_ws_bytes(A, d));

@@ -389,6 +389,13 @@ def _gcn_aug_fixed_step(kern, tab, t0, h, y0, a0, S0, want_S):
         Y_n = kern.new() if last else Ybuf[i & 1]
         kyp, cyp = _nz(ky[:i], coefs[:i])
         kern.vjp_phase1(S_i, A_i, -1.0, ky_i, gP, y0, kyp, cyp, coefs[i], Y_n)
+        # The next stage's support only needs Y_n, which phase 1 has just produced: issue its transform BEFORE
+        # phase 2, so that on the row-partitioned path both halo exchanges (gP, then S_n) are in flight underneath
+        # the transform and phase 2's dense chain instead of being exposed (S_i is free: only phase 1 reads it).
+        if (not last) or want_S:
+            S_n = kern.transform(Y_n, t_n, kern.new_S() if S_i is S0 else S_i)
+        else:
+            S_n = None
         ka_i = kern.new()
         kern.vjp_phase2(Y_i, t_i, gP, ka_i, gth[i])
         ky.append(ky_i)
@@ -396,10 +403,6 @@ def _gcn_aug_fixed_step(kern, tab, t0, h, y0, a0, S0, want_S):
         A_n = kern.new() if last else Abuf[i & 1]
         kap, cap = _nz(ka, coefs)
         ops.rk_combine(a0, kap, cap, out=A_n)
-        if (not last) or want_S:
-            S_n = kern.transform(Y_n, t_n, kern.new_S() if S_i is S0 else S_i)
-        else:
-            S_n = None
         Y_i, A_i, S_i = Y_n, A_n, S_n
         y_out, a_out, S_out = Y_n, A_n, S_n
     w = torch.tensor([float(F32(h * F32(b))) for b in tab.b], dtype=torch.float32, device=kern.dev)
@@ -489,13 +492,14 @@ def _gcn_aug_dopri5(kern, tab, y1, g1, a_t1, t_start, t_end, S, rtol, atol, stat
             A_n = a_new if i == 5 else Ab[i & 1]
             if i == 0:
                 ops.rk_combine(y, [ky[0]], [coefs[0]], out=Y_n)
+                kern.transform(Y_n, t_n, Ss)
             else:
                 kyp_, cyp_ = _nz(ky[:i], coefs[:i])
                 kern.vjp_phase1(S_i, A_i, -1.0, ky[i], gP, y, kyp_, cyp_, coefs[i], Y_n)
+                kern.transform(Y_n, t_n, Ss)      # before phase 2: see _gcn_aug_fixed_step (S_i is Ss or S, both consumed)
                 kern.vjp_phase2(Y_i, t_i, gP, ka[i], gth[i])
             kap_, cap_ = _nz(ka[:i + 1], coefs)
             ops.rk_combine(a, kap_, cap_, out=A_n)
-            kern.transform(Y_n, t_n, Ss)
             S_i, Y_i, A_i = Ss, Y_n, A_n
         _gcn_aug_eval(kern, Ss, y_new, a_new, F32(t + h), ky[6], ka[6], gth[6], gP)
         kern.reduce_small(gth[1:])     # row 0 is carried over from the previous step (FSAL), already summed

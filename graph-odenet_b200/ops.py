@@ -622,6 +622,11 @@ class EdgeMessageFn(torch.autograd.Function):
         if ed.dim() != 3 or ed.shape[2] != f or s.shape[1] != f:
             raise ValueError("edge_data must be [E, f, f] with f = support width")
         esrc32 = esrc.to(torch.int32).contiguous()
+        if E == 0:      # no edges: the aggregate is the bias alone
+            out = torch.zeros(s.shape[0], f, dtype=torch.float32, device=s.device)
+            ctx.plan_t, ctx.has_bias, ctx.n = plan_t, bias is not None, s.shape[0]
+            ctx.save_for_backward(s, ed, esrc32, esrc)
+            return out if bias is None else out + bias
         msg = torch.empty(E, f, dtype=torch.float32, device=s.device)
         check(lib.gode_edge_matvec(E, f, _p(ed), _p(esrc32), _p(s), s.stride(0), _p(msg), _stream()), "gode_edge_matvec")
         out = spmm(plan_t, msg, bias=bias)
@@ -634,6 +639,9 @@ class EdgeMessageFn(torch.autograd.Function):
         s, ed, esrc32, esrc = ctx.saved_tensors
         g = _rowmajor(g, "grad")
         E, f = ed.shape[0], ed.shape[1]
+        if E == 0:
+            return (torch.zeros_like(s), torch.zeros_like(ed), None, None,
+                    colsum(g) if (ctx.has_bias and ctx.needs_input_grad[4]) else None)
         dm = spmm(ctx.plan_t, g, transpose=True)                    # Etgt^T g : [E, f]
         ds_msg = torch.empty(E, f, dtype=torch.float32, device=g.device)
         d_ed = torch.empty_like(ed) if ctx.needs_input_grad[1] else None

@@ -27,6 +27,20 @@ from . import ops
 from ._lib import lib, check
 
 
+def init_process_group(device, backend="nccl"):
+    """One process per GPU (RANK / WORLD_SIZE / MASTER_* from the launcher).  The NCCL stream is created with high
+    priority so that a halo exchange issued underneath a gather or a dense kernel is scheduled as soon as SM
+    resources free up instead of behind the compute kernel's remaining CTAs."""
+    import os
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    kw = {}
+    if backend == "nccl":
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        kw = dict(pg_options=opts, device_id=device)
+    dist.init_process_group(backend, **kw)
+
+
 def partition_bounds(n, world):
     """Row bounds [b_0=0, ..., b_world=n] of the contiguous 1-D partition (sizes differ by at most one)."""
     return [(n * r) // world for r in range(world + 1)]
@@ -120,10 +134,29 @@ def global_cols(c_local, halo, lo, n_own):
     return torch.where(own, c_local + lo, halo[(c_local - n_own).clamp_(min=0)])
 
 
-class PartitionedPlan:
-    """This rank's row block of A_hat and of A_hat^T with their halo plans (what ``GcnKernel`` needs from a plan)."""
+def split_block(r, c_local, v, n_own):
+    """Column split of a renumbered block: (owned-column entries, halo-column entries with columns re-based to 0)."""
+    own = c_local < n_own
+    halo = ~own
+    return (r[own], c_local[own], v[own]), (r[halo], c_local[halo] - n_own, v[halo])
 
-    def __init__(self, n, bounds, rank, A, At, halo, halo_t, nnz_global, group=None):
+
+class PartitionedPlan:
+    """This rank's row block of A_hat and of A_hat^T with their halo plans (what ``GcnKernel`` needs from a plan).
+
+    ``mode`` (argument, else ``GODE_HALO_MODE``, else "async" when world > 1):
+      "sync"   every exchange is issued and awaited on the compute stream;
+      "async"  exchanges run on a high-priority side stream and are awaited by the kernel that gathers from the
+               buffer -- the adjoint issues the next stage's transform before phase 2 (odeint._gcn_aug_fixed_step), so
+               both of its exchanges hide under the transform and the dense VJP chain; the 4 forward exchanges of an
+               rk4 step have no independent work to hide under and stay exposed;
+      "split"  "async" plus a column split of each block -- ``A_own`` [n_own, n_own] and ``A_halo`` [n_own, n_halo] --
+               so a gather runs in two passes: owned columns while the halo is in flight, then halo columns with the
+               first pass as ``partial_in``.  Measured at 2 GPUs (N = 10 M): the second pass over all rows costs more
+               (+33 ms/step) than the exchange it hides; kept for graphs with a small boundary.
+    """
+
+    def __init__(self, n, bounds, rank, A, At, halo, halo_t, nnz_global, group=None, split=None, mode="sync"):
         self.n_global, self.bounds, self.rank, self.group = n, bounds, rank, group
         self.world = len(bounds) - 1
         self.lo, self.hi = bounds[rank], bounds[rank + 1]
@@ -133,36 +166,76 @@ class PartitionedPlan:
         self.nnz_global = nnz_global
         self.rowptr_t = At.rowptr            # "has a transpose" marker GcnKernel looks at
         self.device = A.device
+        self.split = split                   # None, or dict(A_own, A_halo, At_own, At_halo)
+        self.mode = mode
+        self.comm_stream = (torch.cuda.Stream(device=self.device, priority=-1)
+                            if (mode != "sync" and A.device.type == "cuda") else None)
 
     @classmethod
-    def build(cls, row, col, val, n, rank=None, world=None, group=None, bounds=None):
+    def build(cls, row, col, val, n, rank=None, world=None, group=None, bounds=None, mode=None):
         """``row, col, val``: the COO of A_hat (int64, int64, fp32) -- at least every entry whose row or column
         this rank owns; the full COO is fine."""
         if rank is None:
             rank = dist.get_rank(group) if dist.is_initialized() else 0
         if world is None:
             world = dist.get_world_size(group) if dist.is_initialized() else 1
+        import os
+        mode = mode or os.environ.get("GODE_HALO_MODE") or ("async" if world > 1 else "sync")
+        if mode not in ("sync", "async", "split"):
+            raise ValueError("halo mode must be sync, async or split")
+        if world == 1:
+            mode = "sync"
+        overlap = mode == "split"
         bounds = bounds or partition_bounds(n, world)
         n_own = bounds[rank + 1] - bounds[rank]
+        split = {} if overlap else None
         r, c, v, halo = local_block(row, col, val, bounds, rank)
         A = ops.GraphPlan.from_coo(r, c, v, n_own, n_own + int(halo.numel()), build_transpose=False)
+        if overlap:
+            own, hal = split_block(r, c, v, n_own)
+            split["A_own"] = ops.GraphPlan.from_coo(*own, n_own, n_own, build_transpose=False)
+            split["A_halo"] = ops.GraphPlan.from_coo(*hal, n_own, max(int(halo.numel()), 1), build_transpose=False)
+            del own, hal
         del r, c, v
         r, c, v, halo_t = local_block(row, col, val, bounds, rank, transpose=True)
         At = ops.GraphPlan.from_coo(r, c, v, n_own, n_own + int(halo_t.numel()), build_transpose=False)
+        if overlap:
+            own, hal = split_block(r, c, v, n_own)
+            split["At_own"] = ops.GraphPlan.from_coo(*own, n_own, n_own, build_transpose=False)
+            split["At_halo"] = ops.GraphPlan.from_coo(*hal, n_own, max(int(halo_t.numel()), 1), build_transpose=False)
+            del own, hal
         del r, c, v
         return cls(n, bounds, rank, A, At, HaloPlan(halo, bounds, rank, group), HaloPlan(halo_t, bounds, rank, group),
-                   int(val.numel()), group)
+                   int(val.numel()), group, split, mode)
 
     def csr(self, transpose=False):
         return (self.At if transpose else self.A).csr(False)
 
     def make_kernel(self, *args):
         from .odeint import GcnKernel
+        from . import _lib
 
         plan = self
 
         class PartitionedGcnKernel(GcnKernel):
-            """GcnKernel on a row block: halo exchanges after every producer of a gather operand."""
+            """GcnKernel on a row block: halo exchanges after every producer of a gather operand; with a split plan
+            the exchange runs on a side stream underneath the owned-column pass of the next gather."""
+
+            def __init__(self, *a):
+                super().__init__(*a)
+                self.pending = {}            # data_ptr of an operand buffer -> event of its in-flight halo exchange
+                self.partial = None
+                if plan.split is not None:
+                    # descriptor for the second (halo-column) pass: same parameters, halo blocks, operand offset
+                    h = _lib.GcnOdeFunc()
+                    C.memmove(C.byref(h), C.byref(self.f), C.sizeof(h))
+                    h.A = plan.split["A_halo"].csr(False)
+                    h.At = plan.split["At_halo"].csr(False)
+                    h.gather_row_offset = plan.n_rows
+                    self.f_halo = h
+                    self.csr_own = plan.split["A_own"].csr(False)
+                    self.csr_own_t = plan.split["At_own"].csr(False)
+                    self.ws_bytes = max(self.ws_bytes, lib.gode_gcn_workspace_bytes(C.byref(h)))
 
             def new_S(self):
                 return torch.empty(plan.n_rows + plan.halo.n_halo, self.d, dtype=torch.float32, device=self.dev)
@@ -188,20 +261,87 @@ class PartitionedPlan:
                         t.copy_(c)
                 return t
 
+            # ---- halo exchange, synchronous or on the side stream ------------------------------------------------
+            def _exchange(self, halo, buf):
+                if plan.mode == "sync" or plan.world == 1:
+                    halo.exchange(buf)
+                    return
+                main = torch.cuda.current_stream()
+                ready = torch.cuda.Event()
+                ready.record(main)
+                cs = plan.comm_stream
+                cs.wait_event(ready)
+                buf.record_stream(cs)        # the allocator must not recycle the buffer under the side stream
+                with torch.cuda.stream(cs):
+                    halo.exchange(buf)
+                    done = torch.cuda.Event()
+                    done.record(cs)
+                self.pending[buf.data_ptr()] = done
+
+            def _wait(self, buf):
+                ev = self.pending.pop(buf.data_ptr(), None)
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
+
+            def _own_pass(self, csr, X):
+                """partial = (owned-column block) @ X[:n_own]  -- runs while X's halo tail is still arriving."""
+                if self.partial is None:
+                    self.partial = self.new()
+                nb = lib.gode_spmm_workspace_bytes(C.byref(csr), self.d)
+                ws = ops.workspace(nb, self.dev, "spmm") if nb else None
+                check(lib.gode_spmm_csr_f32(C.byref(csr), ops._p(X), self.d, self.d, ops._p(self.partial), self.d, None,
+                                            ops._p(ws), nb, ops._stream()), "gode_spmm_csr_f32")
+                return self.partial
+
             def transform(self, y, t, out):
                 super().transform(y, t, out)
-                plan.halo.exchange(out)
+                self._exchange(plan.halo, out)
                 return out
 
             def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0,
                           S_next=None):
-                super().stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next)
+                if plan.split is None:
+                    self._wait(S)
+                    super().stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next)
+                else:
+                    part = self._own_pass(self.csr_own, S)
+                    self._wait(S)
+                    self.f_halo.partial_in = part.data_ptr()
+                    full, self.f = self.f, self.f_halo
+                    try:
+                        super().stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next)
+                    finally:
+                        self.f = full
                 if S_next is not None:
-                    plan.halo.exchange(S_next)
+                    self._exchange(plan.halo, S_next)
 
             def vjp_phase1(self, S, a, sign, k_y, gP, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None):
-                super().vjp_phase1(S, a, sign, k_y, gP, y0, kprev, coefs, coef_self, y_next)
-                plan.halo_t.exchange(gP)
+                if plan.split is None:
+                    self._wait(S)
+                    super().vjp_phase1(S, a, sign, k_y, gP, y0, kprev, coefs, coef_self, y_next)
+                else:
+                    part = self._own_pass(self.csr_own, S)
+                    self._wait(S)
+                    self.f_halo.partial_in = part.data_ptr()
+                    full, self.f = self.f, self.f_halo
+                    try:
+                        super().vjp_phase1(S, a, sign, k_y, gP, y0, kprev, coefs, coef_self, y_next)
+                    finally:
+                        self.f = full
+                self._exchange(plan.halo_t, gP)
+
+            def vjp_phase2(self, y, t, gP, k_a, gtheta):
+                if plan.split is None:
+                    self._wait(gP)
+                    return super().vjp_phase2(y, t, gP, k_a, gtheta)
+                part = self._own_pass(self.csr_own_t, gP)
+                self._wait(gP)
+                self.f_halo.partial_in = part.data_ptr()
+                full, self.f = self.f, self.f_halo
+                try:
+                    super().vjp_phase2(y, t, gP, k_a, gtheta)
+                finally:
+                    self.f = full
 
         return PartitionedGcnKernel(self, *args)
 

@@ -116,7 +116,7 @@ int gode_csr_heavy_rows(int64_t n_rows, const int32_t* rowptr, int32_t* heavy_ro
  * CSR SpMM with a fused row epilogue.
  * replaces: torch.spmm(adj, support) (+ bias, + F.relu, + residual) -- GCN/layers.py:33-35,71-73,
  *           GCN/models.py:76-80,110-116,178.
- *   acc   = sum_e vals[e] * X[colidx[e], :]
+ *   acc   = sum_e vals[e] * X[colidx[e], :]   (+ acc_in, if given)
  *   v     = acc + bias (if bias)          ; v = max(v,0) (if relu)
  *   Y     = v + residual (if residual)    (Y may be NULL)
  *   fused Runge-Kutta stage combination (torchdiffeq rk_common._runge_kutta_step, restated in
@@ -136,6 +136,9 @@ typedef struct {
   const float* mask_src;   /* adjoint state a, or NULL */
   float mask_scale;
   float* gp_out;           /* [n_rows, ld] or NULL */
+  const float* acc_in;     /* [n_rows, ld] or NULL: partial sums added to acc before the bias (the product with
+                              another column block of the same rows -- the row-partitioned path gathers the owned
+                              columns while the halo is in flight, then the halo columns with acc_in) */
 } gode_spmm_epilogue_t;
 
 /* ws: n_chunks * d floats of scratch for the heavy-row partial sums (0 bytes when n_heavy == 0) */
@@ -221,6 +224,12 @@ typedef struct {
   const float* b;          /* [d] or NULL */
   const float* gamma;      /* [d] */
   const float* beta;       /* [d] */
+  /* Split gathers of the row-partitioned path (both 0 / NULL otherwise): the gather operand of A (S) and of At (gP)
+   * is read from row `gather_row_offset` on (column indices are relative to it) and `partial_in` [n_rows, d] is
+   * added to the gathered sums before the epilogue.  Everything else (transform output, column sums of gP, ...)
+   * still addresses the buffers from row 0. */
+  int64_t gather_row_offset;
+  const float* partial_in;
 } gode_gcn_odefunc_t;
 
 size_t gode_gcn_workspace_bytes(const gode_gcn_odefunc_t* f);

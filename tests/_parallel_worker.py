@@ -15,12 +15,13 @@ def main():
     method = sys.argv[1] if len(sys.argv) > 1 else "rk4"
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
     d = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+    smooth = (sys.argv[4] == "smooth") if len(sys.argv) > 4 else False
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
     import graph_odenet_b200  # noqa: F401
     from graph_odenet_b200 import ops, parallel, synth
+    parallel.init_process_group(dev)
     from graph_odenet_b200.GCN import models
 
     row, col, val = synth.powerlaw_graph(n, avg_degree=12, locality=0.6, window=512, seed=5, device=dev)
@@ -29,6 +30,10 @@ def main():
     with torch.no_grad():
         blk.odefunc.norm1.weight.uniform_(0.5, 1.5)
         blk.odefunc.norm1.bias.uniform_(-0.5, 0.5)
+        if smooth:
+            # every pre-activation far above zero: ReLU never switches, the function is smooth, and differently ordered
+            # fp32 sums must agree to rounding (1e-5); the default regime has mask flips (tools/sensitivity.py)
+            blk.odefunc.gc1.bias.fill_(6.0)
     g = torch.Generator(device=dev).manual_seed(9)
     x_all = 0.5 * torch.randn(n, d, device=dev, generator=g)
     g_all = torch.randn(n, d, device=dev, generator=g) / n
@@ -65,7 +70,15 @@ def main():
         for (name, _), a, b in zip(blk.named_parameters(), gp_p, gp_1):
             errs["g_" + name] = rel(a, b)
         print("world=%d method=%s nfe %d/%d errs %s stats %s / %s" % (world, method, nfe_p, nfe_1, errs, st_p, st_1), flush=True)
-        ok = nfe_p == nfe_1 and all(v < 2e-5 for v in errs.values())
+        # y: 1e-6 relative L2.  Gradients: 1e-5 in the smooth regime; with active ReLUs a 1e-7 difference in a
+        # pre-activation flips mask elements and moves the summed gradients by 1e-4..1e-3 (measured: tools/sensitivity.py)
+        gtol = 1e-5 if smooth else 5e-3
+        if method == "dopri5":
+            # the adaptive controller turns rounding-level differences of the error norm into slightly different step
+            # sizes, i.e. O(rtol) = 1e-5 differences of the solution and 1e-4 of the adjoint gradients, with identical
+            # accepted / rejected step counts (asserted below)
+            gtol = max(gtol, 2e-3)
+        ok = nfe_p == nfe_1 and errs["y"] < 1e-6 and all(v < gtol for v in errs.values())
         if method == "dopri5":
             ok = ok and st_p == st_1
     flag = torch.tensor([1 if ok else 0], device=dev)

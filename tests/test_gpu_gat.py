@@ -37,7 +37,10 @@ def test_gat_layer_golden():
     G.assert_close(y, g["gc/out"], rtol=1e-5, atol_scale=1e-5, what="out")
     G.assert_close(x.grad, g["gc/grad_x"], rtol=1e-5, atol_scale=1e-5, what="grad_x")
     for k, p in lay.named_parameters():
-        G.assert_close(p.grad, g["gc/grad/" + k], rtol=1e-5, atol_scale=1e-5, what=k)
+        # w.bias shifts every a_e equally and a - max(a) is shift-invariant: its gradient is mathematically 0 (the
+        # reference's autograd gets an exact 0 by summing and negating the same numbers); here two differently
+        # ordered fp32 sums cancel to ~1e-6 of the summed magnitudes -> absolute floor
+        G.assert_close(p.grad, g["gc/grad/" + k], rtol=1e-5, atol_scale=1e-5, what=k, atol_abs=1e-5 if k == "w.bias" else 0.0)
     # nodes without incoming edges output exactly 0 (679 of them on Cora)
     indeg = torch.bincount(tgt, minlength=n)
     assert int((indeg == 0).sum()) == 679
@@ -55,12 +58,20 @@ def test_gat_odefunc_golden():
     t = torch.tensor(0.25, device=DEV, requires_grad=True)
     y = f(t, x)
     grads = torch.autograd.grad(y, (x, t) + tuple(f.parameters()), G.rnd(64, n, 16).to(DEV))
-    G.assert_close(y, g["odefunc/out"], rtol=1e-5, atol_scale=1e-5, what="out")
-    G.assert_close(grads[0], g["odefunc/grad_x"], rtol=1e-5, atol_scale=1e-5, what="grad_x")
-    G.assert_close(grads[1], g["odefunc/grad_t"], rtol=1e-4, atol_abs=1e-6, what="grad_t")
+    # hidden=16: GroupNorm(16 groups of ONE channel) outputs beta + rounding noise, so the layer's input is
+    # noise-level sensitive to how x*(gamma*rstd) + (beta - mean*gamma*rstd) is rounded: absolute tolerances here, as in
+    # tests/test_gpu_gcn.py::test_odefunc_golden[16]; the non-degenerate widths are held to 1e-5 in test_gat_matches_oracle
+    assert float((y.detach().cpu() - torch.from_numpy(g["odefunc/out"])).abs().max()) < 1e-4
+    assert float((grads[0].cpu() - torch.from_numpy(g["odefunc/grad_x"])).abs().max()) < 2e-2
+    G.assert_close(grads[1], g["odefunc/grad_t"], rtol=1e-3, atol_abs=1e-5, what="grad_t")
     for (k, _), gr in zip(f.named_parameters(), grads[2:]):
-        # hidden=16 GroupNorm is degenerate: its gamma gradient is a sum of rounding noise
-        tol = dict(rtol=1e-5, atol_scale=1e-5) if "norm1.weight" not in k else dict(rtol=1e-3, atol_scale=1e-3, atol_abs=1e-6)
+        if "norm1.weight" in k:
+            continue                                           # sum of rounding noise (x - mean == 0 exactly)
+        tol = dict(rtol=1e-4, atol_scale=1e-4)
+        if k.endswith("w.bias"):
+            tol = dict(rtol=1e-5, atol_scale=1e-5, atol_abs=1e-5)      # mathematically zero, see test_gat_layer_golden
+        if k.endswith("w.weight"):
+            tol = dict(rtol=1e-5, atol_scale=1e-5, atol_abs=1e-6)      # input rows are all ~beta: the reference value is 6e-9 of noise
         G.assert_close(gr, g["odefunc/grad/" + k], what=k, **tol)
     assert f.nfe == 1
 
@@ -102,7 +113,7 @@ def test_gat_matches_oracle(i, o, heads):
     G.assert_close(y, yo, rtol=1e-5, atol_scale=1e-5, what="out")
     G.assert_close(xg.grad, xo.grad, rtol=1e-5, atol_scale=1e-5, what="grad_x")
     for k, p in lay.named_parameters():
-        G.assert_close(p.grad, pc[k].grad, rtol=1e-5, atol_scale=2e-5, what=k)
+        G.assert_close(p.grad, pc[k].grad, rtol=1e-5, atol_scale=2e-5, what=k, atol_abs=1e-5 if k == "w.bias" else 0.0)
 
 
 def test_gat_empty_and_degenerate():
@@ -125,28 +136,35 @@ def test_gat_empty_and_degenerate():
 
 
 def test_gat_ode_block_rk4_matches_oracle():
-    """GAT-ODE block, fixed-step rk4, step for step against the restated solver driving the oracle function."""
+    """GAT-ODE block (8 heads x 16, the config-3 shape), fixed-step rk4, step for step against the restated solver
+    driving the oracle function (H independent reference heads, concatenated)."""
     _, _, models = _pkg()
-    n, e, d = 400, 2500, 16
+    n, e, d, H = 400, 2500, 128, 8   # 32 GroupNorm groups of 4 channels (1- and 2-channel groups are degenerate)
+    oh = d // H
     src, tgt = _random_edges(n, e, seed=3)
     torch.manual_seed(5)
-    blk = models.ODEBlock(models.ODEfunc(d), method="rk4", options={"step_size": 0.5})
+    blk = models.ODEBlock(models.ODEfunc(d, heads=H), method="rk4", options={"step_size": 0.5})
     with torch.no_grad():
         blk.odefunc.norm1.weight.uniform_(0.5, 1.5)
         blk.odefunc.norm1.bias.uniform_(-0.5, 0.5)
     x = torch.randn(n, d)
     gy = torch.randn(n, d)
-    pc = {k: v.detach().clone().requires_grad_(True) for k, v in blk.odefunc.state_dict().items()}
+    pc = {k: v.detach().clone() for k, v in blk.odefunc.state_dict().items()}
 
     class F_(torch.nn.Module):
         def __init__(self):
             super().__init__()
-            self.ps = torch.nn.ParameterList([torch.nn.Parameter(v) for v in pc.values()])
+            self.ps = torch.nn.ParameterDict({k.replace(".", "_"): torch.nn.Parameter(v) for k, v in pc.items()})
             self.nfe = 0
 
         def forward(self, t, y):
             self.nfe += 1
-            return gat_ref.gat_odefunc(t, y, dict(zip(pc.keys(), self.ps)), src, tgt)
+            p = self.ps
+            yn = torch.nn.functional.group_norm(y, 32, p["norm1_weight"], p["norm1_bias"], 1e-5)
+            ttx = torch.cat([torch.ones_like(yn[:, :1]) * t, yn], 1)
+            heads = [(p["gc1_f_weight"][h * oh:(h + 1) * oh], p["gc1_f_bias"][h * oh:(h + 1) * oh],
+                      p["gc1_w_weight"][h:h + 1], p["gc1_w_bias"][h:h + 1]) for h in range(H)]
+            return torch.relu(gat_ref.gat_multihead(ttx, src, tgt, heads))
 
     fo = F_()
     xo = x.clone().requires_grad_(True)
@@ -162,8 +180,10 @@ def test_gat_ode_block_rk4_matches_oracle():
     assert nfe_f == 8 and blk.nfe == fo.nfe
     G.assert_close(y, yo, rtol=1e-5, atol_scale=1e-5, what="y(1)")
     G.assert_close_l2(xg.grad, xo.grad, 1e-4, what="grad_x")
-    for (k, p), po in zip(blk.odefunc.named_parameters(), fo.ps):
-        G.assert_close_l2(p.grad, po.grad, 1e-4, what=k)
+    for k, p in blk.odefunc.named_parameters():
+        if k.endswith("w.bias"):
+            continue                                   # mathematically zero (shift invariance of a - max a)
+        G.assert_close_l2(p.grad, fo.ps[k.replace(".", "_")].grad, 1e-4, what=k)
 
 
 def test_gat_model_surface():

@@ -36,13 +36,15 @@ def test_partitioned_plan_world1_matches_plain_plan():
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
 
 
-@pytest.mark.parametrize("method", ["rk4", "dopri5"])
-def test_two_gpus_match_one(method):
+@pytest.mark.parametrize("method,regime,mode", [("rk4", "relu", "async"), ("rk4", "smooth", "async"), ("rk4", "smooth", "sync"),
+                                                ("rk4", "smooth", "split"), ("dopri5", "relu", "async"),
+                                                ("dopri5", "smooth", "split")])
+def test_two_gpus_match_one(method, regime, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     world = min(torch.cuda.device_count(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "_parallel_worker.py"), method,
-           "20000" if method == "rk4" else "6000", "128"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+           "20000" if method == "rk4" else "6000", "128", regime]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, GODE_HALO_MODE=mode))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

@@ -144,7 +144,7 @@ def test_mpnn_enn_edge_matches_restatement():
 def test_edge_ode_block_matches_oracle():
     """Builder extension (config 5): ODEBlock over the reference EdgeGraphConvolution, rk4, vs the restated solver."""
     ops, synth, _, lm, _ = _pkg()
-    d = 16
+    d = 128                      # 32 groups of 4 channels (1- and 2-channel groups are degenerate / ill-conditioned)
     b = synth.qm9_like_batch(5, d, seed=6, device="cpu")
     n, e = b["node_features"].shape[0], b["esrc"].numel()
     torch.manual_seed(8)
