@@ -299,16 +299,44 @@ def run_ours(a):
     value = nnz * nfe_per_step / (ms / 1e3)
 
     # ---- roofline of the dominant kernel (the A_hat*S gather with fused epilogue) -----------------
+    # Algorithmic bytes of one launch = CSR once + one [N,d] stream per operand the launch must read or write:
+    # S, k_i (when a later stage needs it), y0, the k_j with a non-zero coefficient in the stage combination, y_next,
+    # and in the adjoint the state a and gP.  Averaged over the launches of a step (DESIGN.md 3.1).  The compulsory-only
+    # figure of SURVEY 8d (CSR + S + k, no Runge-Kutta operands) is reported next to it.
     peak, peak_src = peaks()
-    if world == 1:
-        b_f = nnz * 8 + (n + 1) * 4 + 2 * n * d * 4      # CSR once + S once + k once
-    else:                                                # this rank's block: CSR + S (owned + halo rows) + k
-        b_f = plan.A.nnz * 8 + (n_loc + 1) * 4 + (n_loc + plan.halo.n_halo) * d * 4 + n_loc * d * 4
+    from graph_odenet_b200 import odeint as _od
+    n_rows_loc = n_loc
+    n_gather = n_loc + (plan.halo.n_halo if world > 1 else 0)
+    nnz_loc = plan.A.nnz if world > 1 else nnz
+    csr_bytes = nnz_loc * 8 + (n_rows_loc + 1) * 4
+    row_stream = n_rows_loc * d * 4
+    b_compulsory = csr_bytes + n_gather * d * 4 + row_stream
+
+    def launch_streams(method):
+        """[N,d] streams (besides S) of every agg_fwd launch of one fwd+bwd step on grid [0,1]."""
+        tab = _od.TABLEAUS[method]
+        out = []
+        for aug in (False, True):
+            if aug:
+                out.append(1)                                        # f(t1): writes k only
+            for i in range(tab.s):
+                last = i == tab.s - 1
+                row = tab.b if last else tab.a[i + 1]
+                n_prev = sum(1 for c in row[:i] if c != 0)
+                store = (not last) and _od._needed_later(tab, i)
+                out.append((1 if store else 0) + 1 + n_prev + 1 + (2 if aug else 0))   # k_i, y0, k_j.., y_next, (a, gP)
+        return out
+
+    if a.method in _od.FIXED_METHODS:
+        ls = launch_streams(a.method)
+        b_f = sum(csr_bytes + n_gather * d * 4 + k * row_stream for k in ls) / len(ls)
+    else:
+        b_f = b_compulsory
     agg = prof["agg_fwd"]
     achieved = b_f / (agg["ms_avg"] / 1e3) / 1e9 if agg["launches"] else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1 and n == 10_000_000 and d == 128:
         try:
             traffic = json.load(open(tpath)).get("agg_fwd_dram_bytes_per_launch")
         except Exception:
@@ -318,6 +346,11 @@ def run_ours(a):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "algorithmic_bytes_per_launch": b_f, "ms_per_launch": agg["ms_avg"],
                 "launches_timed": agg["launches"], "peak_source": peak_src,
+                "compulsory_only": {"bytes_per_launch": b_compulsory,
+                                    "frac": (b_compulsory / (agg["ms_avg"] / 1e3) / 1e9 / peak) if agg["launches"] else None,
+                                    "note": "SURVEY 8d model: CSR + S + k only, Runge-Kutta operands not counted"},
+                "note": "ncu (profiles/r01_spmm_10m.md): the gather is bound by L2->SM throughput (78 GB of sectors per "
+                        "launch at 71 % of the fabric cap), not by HBM",
                 "step_share": agg["ms_total"] / (ms * a.steps), "kernel_classes_ms": prof}
 
     # ---- e2e: public API, host buffers ------------------------------------------------------------

@@ -50,6 +50,7 @@ _PROTOS = {
     "gode_last_error": (C.c_char_p, []),
     "gode_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "gode_launch_count": (C.c_ulonglong, []),
+    "gode_reserve_sms": (C.c_int, [C.c_int]),
     "gode_profile_enable": (C.c_int, [C.c_int]),
     "gode_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "gode_csr_from_coo_workspace_bytes": (sz, [i64, i64]),

@@ -50,7 +50,21 @@ int sm_count() {
   }
   return cached;
 }
+static int g_reserved_sms = 0;
+int persistent_ctas() {
+  const int n = sm_count() - g_reserved_sms;
+  return n < 1 ? 1 : n;
+}
 }  // namespace gode
+
+extern "C" int gode_reserve_sms(int n) {
+  if (n < 0 || n >= gode::sm_count()) {
+    gode::set_error("reserve_sms: %d is outside [0, %d)", n, gode::sm_count());
+    return GODE_EINVAL;
+  }
+  gode::g_reserved_sms = n;
+  return GODE_OK;
+}
 
 extern "C" int gode_version(void) { return 100; }
 

@@ -40,6 +40,7 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int sm_count();
+int persistent_ctas();   // sm_count() minus the SMs left free for a concurrent collective (gode_reserve_sms)
 
 // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline leg).
 struct ProfScope {

@@ -490,7 +490,7 @@ int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, const
   constexpr int D = 128;
   GODE_REQUIRE(al16(y) && al16(gS) && al16(ws), "wgrad_tc: operands must be 16-byte aligned");
   const int64_t n_chunks = (f->A.n_rows + 31) / 32;
-  int grid = static_cast<int>(n_chunks < sm_count() ? n_chunks : sm_count());
+  int grid = static_cast<int>(n_chunks < persistent_ctas() ? n_chunks : persistent_ctas());
   if (grid < 1) grid = 1;
   if (ws_bytes < sizeof(float) * (size_t)grid * D * D) {
     set_error("wgrad_tc: workspace too small");
@@ -521,7 +521,7 @@ static int launch_rows_tc(int64_t n_rows, const float* X, float* Out, const floa
   }
   const int64_t n_tiles = (n_rows + 127) / 128;
   if (n_tiles == 0) return GODE_OK;
-  const int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
+  const int grid = static_cast<int>(n_tiles < persistent_ctas() ? n_tiles : persistent_ctas());
   k_rows_tc<D, CPG, MODE><<<grid, tc::THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes);
   GODE_LAUNCH_CHECK();
   return GODE_OK;

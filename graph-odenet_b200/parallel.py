@@ -170,6 +170,13 @@ class PartitionedPlan:
         self.mode = mode
         self.comm_stream = (torch.cuda.Stream(device=self.device, priority=-1)
                             if (mode != "sync" and A.device.type == "cuda") else None)
+        if self.comm_stream is not None:
+            # the exchange of gP is issued right before the (persistent, one CTA per SM) transform kernel: without free
+            # SMs the NCCL kernel only starts when that kernel ends (torch.profiler timeline, profiles/r01_halo_overlap.md).
+            # Measured at 2 GPUs: reserving 20 SMs raises the overlapped NCCL time from 6.2 to 10.6 ms per step but slows
+            # the persistent kernels and NCCL itself by more (162.8 vs 159.2 ms per step) -> default 0, knob kept.
+            import os
+            check(lib.gode_reserve_sms(int(os.environ.get("GODE_RESERVE_SMS", "0"))), "gode_reserve_sms")
 
     @classmethod
     def build(cls, row, col, val, n, rank=None, world=None, group=None, bounds=None, mode=None):

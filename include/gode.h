@@ -45,6 +45,11 @@ int gode_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* number of CUDA kernels this library has launched in this process (monotonic) */
 unsigned long long gode_launch_count(void);
 
+/* Leave n SMs free of the library's persistent (one-CTA-per-SM) kernels, so that a collective issued on another
+ * stream (the NCCL halo exchange of the row-partitioned path) can start underneath them instead of queueing behind
+ * them: a persistent tcgen05 kernel holds ~200 KB of shared memory on every SM for its whole duration.  Default 0. */
+int gode_reserve_sms(int n);
+
 /* Optional CUDA-event timing of the library's kernel classes, recorded on the launching stream
  * (used by bench.py for the roofline of the dominant kernel; off by default, ~2 us per scope when on).
  * enable(on) clears the records.  read() synchronises on the recorded events. */
