@@ -1,0 +1,154 @@
+"""The reference's ``train_res.py`` experiment driver (GCN/train_res.py:1-158, GAT/train_res.py) on libgode.
+
+Same flags, same per-epoch / per-run print format, same ``nfe_f`` / ``nfe_b`` accounting (``model.nfe`` read around
+``backward()``), Adam(lr 0.01, weight decay 5e-4), seed 42.  Added flags (defaults reproduce the reference):
+``--method`` / ``--step_size`` / ``--tol`` for the ODE block, ``--data-root`` (the reference reads ``./data``),
+``--npz`` (a saved loader output).  ``GCN/train_res.py`` and ``GAT/train_res.py`` call ``main(family)``.
+"""
+from __future__ import annotations
+
+import argparse
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+import torch.optim as optim
+
+from . import utils
+
+MODEL_CHOICES = ["gcn2", "gcn3", "gcn3norm", "res3", "ode3", "res3norm", "res3fullnorm", "ode3norm"]
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument("--no-cuda", action="store_true", default=False, help="Disables CUDA training (unsupported: no CPU path).")
+    p.add_argument("--fastmode", action="store_true", default=False, help="Validate during training pass.")
+    p.add_argument("--seed", type=int, default=42, help="Random seed.")
+    p.add_argument("--epochs", type=int, default=200, help="Number of epochs to train.")
+    p.add_argument("--runs", type=int, default=1, help="Number of times to train and evaluate the model.")
+    p.add_argument("--lr", type=float, default=0.01, help="Initial learning rate.")
+    p.add_argument("--weight_decay", type=float, default=5e-4, help="Weight decay (L2 loss on parameters).")
+    p.add_argument("--hidden", type=int, default=16, help="Number of hidden units.")
+    p.add_argument("--dropout", type=float, default=0.5, help="Dropout rate (1 - keep probability).")
+    p.add_argument("--dataset", choices=["cora", "citeseer", "pubmed"], default="cora", help="Which dataset to use")
+    p.add_argument("--model", choices=MODEL_CHOICES, default="res3", help="Which model to train")
+    # builder extensions
+    p.add_argument("--method", default=None, choices=[None, "dopri5", "rk4", "euler", "midpoint"], help="ODE solver (default dopri5)")
+    p.add_argument("--step_size", type=float, default=None, help="fixed-step size (default: one step over [0,1])")
+    p.add_argument("--tol", type=float, default=1e-5, help="rtol = atol of the ODE block")
+    p.add_argument("--data-root", default=None, help="directory holding ind.<dataset>.* (default $GODE_DATA or ./data)")
+    p.add_argument("--npz", default=None, help="loader output saved as .npz (tests/golden/planetoid_<ds>.npz)")
+    return p
+
+
+def model_table(models):
+    # GCN/train_res.py:39 (gcn3norm silently maps to GCN3 there; kept)
+    return {"GCN3": models.GCN3, "GCN3NORM": models.GCN3, "RES3": models.RGCN3, "ODE3": models.ODEGCN3,
+            "RES3NORM": models.RGCN3norm, "RES3FULLNORM": models.RGCN3fullnorm, "ODE3NORM": models.ODEGCN3fullnorm}
+
+
+def main(family="GCN", argv=None, out=print):
+    args = build_parser().parse_args(argv)
+    if args.no_cuda or not torch.cuda.is_available():
+        raise RuntimeError("graph-odenet_b200 has no CPU path: a CUDA device is required")
+    if family == "GAT":
+        from .GAT import models
+    else:
+        from .GCN import models
+    table = model_table(models)
+    if args.model.upper() not in table:
+        raise KeyError(args.model.upper())         # as the reference does for "gcn2"
+    Model = table[args.model.upper()]
+    if args.runs == 1:
+        np.random.seed(args.seed)
+        torch.manual_seed(args.seed)
+        torch.cuda.manual_seed(args.seed)
+
+    if args.npz:
+        data = utils.load_npz(args.npz, family)
+    elif family == "GAT":
+        data = utils.load_data_gat(args.dataset, args.data_root)
+    else:
+        data = utils.load_data_new(args.dataset, args.data_root)
+    data = tuple(t.cuda() for t in data)
+    graph, (features, labels, idx_train, idx_val, idx_test) = data[:-5], data[-5:]
+    is_ode = "ode" in args.model
+
+    def configure(model):
+        for m in model.modules():
+            if isinstance(m, models.ODEBlock):
+                m.tol = args.tol
+                m.method = args.method
+                m.options = {"step_size": args.step_size} if args.step_size else None
+        return model
+
+    def train(model, optimizer, epoch):
+        model.nfe = 0
+        t = time.time()
+        model.train()
+        optimizer.zero_grad()
+        output = model(features, *graph)
+        nfe_forward = nfe_backward = 0
+        if is_ode:
+            nfe_forward = model.nfe
+            model.nfe = 0
+        loss_train = F.nll_loss(output[idx_train], labels[idx_train])
+        acc_train = utils.accuracy(output[idx_train], labels[idx_train])
+        loss_train.backward()
+        optimizer.step()
+        if is_ode:
+            nfe_backward = model.nfe
+            model.nfe = 0
+        if not args.fastmode:
+            model.eval()
+            with torch.no_grad():
+                output = model(features, *graph)
+        loss_val = F.nll_loss(output[idx_val], labels[idx_val])
+        acc_val = utils.accuracy(output[idx_val], labels[idx_val])
+        if args.runs == 1:
+            out("Epoch: {:04d}".format(epoch + 1), "loss_train: {:.4f}".format(loss_train.item()),
+                "acc_train: {:.4f}".format(acc_train.item()), "loss_val: {:.4f}".format(loss_val.item()),
+                "acc_val: {:.4f}".format(acc_val.item()), "time: {:.4f}s".format(time.time() - t),
+                "" if not is_ode else "nfe_f: {}".format(nfe_forward), "" if not is_ode else "nfe_b: {}".format(nfe_backward))
+        return loss_train.item(), nfe_forward, nfe_backward
+
+    def test(model):
+        model.eval()
+        with torch.no_grad():
+            output = model(features, *graph)
+        loss_test = F.nll_loss(output[idx_test], labels[idx_test])
+        acc_test = utils.accuracy(output[idx_test], labels[idx_test])
+        if args.runs == 1:
+            out("Test set results:", "loss= {:.4f}".format(loss_test.item()), "accuracy= {:.4f}".format(acc_test.item()))
+        return loss_test.item(), acc_test.item()
+
+    total_loss = total_acc = total_time = 0.0
+    history = []
+    model = None
+    runs = args.runs
+    for run in range(args.runs):
+        model = configure(Model(nfeat=features.shape[1], nhid=args.hidden, nclass=labels.max().item() + 1,
+                                dropout=args.dropout)).cuda()
+        optimizer = optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay)
+        try:
+            t0 = time.time()
+            for epoch in range(args.epochs):
+                history.append(train(model, optimizer, epoch))
+            run_time = time.time() - t0
+            run_loss, run_acc = test(model)
+            if args.runs > 1:
+                out("Run #{run} Test -- time: {time}s acc: {acc:.2f}%".format(run=run, time=run_time, acc=100 * run_acc), flush=True)
+        except KeyboardInterrupt:
+            runs = run
+            break
+        total_loss += run_loss
+        total_acc += run_acc
+        total_time += run_time
+    runs = max(runs, 1)
+    total_loss, total_acc, total_time = total_loss / runs, total_acc / runs, total_time / runs
+    out('Optimization on dataset "{dataset}" Finished!'.format(dataset=args.dataset))
+    out("#Parameters: {param_count}".format(param_count=utils.count_params(model)))
+    out("Average time elapsed: {:.4f}s".format(total_time))
+    out("Test set results:", "avg loss= {:.4f}".format(total_loss), "avg accuracy= {:.4f}".format(total_acc))
+    return {"loss": total_loss, "acc": total_acc, "time": total_time, "history": history}
