@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--method", default="rk4")
     ap.add_argument("--cpu-sample-nodes", type=int, default=0, help="0 = size automatically (about 20 s)")
+    ap.add_argument("--halo-mode", default=None, help="N>1: sync | async | split (NCCL) | p2p | p2p-async (peer memory); "
+                                                      "default: GODE_HALO_MODE or the library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -224,10 +226,10 @@ def run_ours(a):
     if world > 1:
         # contiguous row blocks of A_hat / A_hat^T, halo exchange of the gather operand per evaluation
         from graph_odenet_b200 import parallel
-        plan = parallel.PartitionedPlan.build(row, col, val, n, rank, world)
+        plan = parallel.PartitionedPlan.build(row, col, val, n, rank, world, mode=a.halo_mode)
         lo, hi = plan.lo, plan.hi
-        halo_info = {"rows_owned": plan.n_rows, "halo_rows_fwd": plan.halo.n_halo, "halo_rows_bwd": plan.halo_t.n_halo,
-                     "nvlink_bytes_per_step_rank0": plan.halo_bytes_per_step(d, 4, 5) if a.method == "rk4" else None}
+        halo_info = {"halo_mode": plan.mode, "rows_owned": plan.n_rows, "halo_rows_fwd": plan.halo.n_halo, "halo_rows_bwd": plan.halo_t.n_halo,
+                     "nvlink_bytes_per_step_rank0": plan.halo_bytes_per_step(d, 4, 4) if a.method == "rk4" else None}
     else:
         plan = ops.GraphPlan.from_coo(row, col, val, n, n)
         lo, hi = 0, n
@@ -279,6 +281,8 @@ def run_ours(a):
         ev1.record()
         sync()
     ms = ev0.elapsed_time(ev1) / a.steps
+    if world > 1:
+        plan.check_peers()                       # a timed-out device-side wait on a peer's flag invalidates the run
 
     def max_over_ranks(v):
         if world == 1:
@@ -394,8 +398,12 @@ def run_ours(a):
             "config": {"workload": workload_name(a), "nnz": nnz, "solver": a.method, "func_evals_per_step": nfe_per_step,
                        "l2": "inputs larger than L2 (every [N,d] tensor is %.2f GB)" % (n * d * 4 / 1e9),
                        "optimizer": "Adam on the ODE function's parameters (in the timed region)",
-                       "partition": None if world == 1 else dict(halo_info, scheme="contiguous row blocks, all-to-all-v "
-                                                                  "halo exchange of the gather operand per evaluation")},
+                       "partition": None if world == 1 else dict(halo_info, scheme="contiguous row blocks; halo exchange "
+                                                                  "of the gather operand per evaluation (" + (
+                                                                      "libgode kernel storing rows into the peers' halo "
+                                                                      "tails over NVLink peer memory"
+                                                                      if plan.mode.startswith("p2p") else
+                                                                      "pack + NCCL all-to-all-v") + ")")},
             "func_evals_per_sec": nfe_per_step / (ms / 1e3), "final_loss": float(loss_total.item()),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary()}
     print(json.dumps(line), flush=True)

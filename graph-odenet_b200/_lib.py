@@ -13,6 +13,7 @@ HEAVY_ROW = 256
 HEAVY_CHUNK = 256
 PREC_FP32, PREC_TF32 = 0, 1
 PROF_AGG_FWD, PROF_AGG_T, PROF_TRANSFORM, PROF_VJP_DENSE, PROF_OTHER = range(5)
+MAX_PEERS, PEER_HANDLE_BYTES, PEER_HEADER_BYTES, PEER_TIMEOUT = 16, 64, 4096, 1
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -43,6 +44,10 @@ class GatGraph(C.Structure):
 class GcnOdeFunc(C.Structure):
     _fields_ = [("A", Csr), ("At", Csr), ("d", i32), ("groups", i32), ("gn_eps", f32), ("precision", i32),
                 ("W", vp), ("b", vp), ("gamma", vp), ("beta", vp), ("gather_row_offset", i64), ("partial_in", vp)]
+
+
+class PeerGroup(C.Structure):
+    _fields_ = [("world", i32), ("rank", i32), ("base", vp * MAX_PEERS)]
 
 
 _PROTOS = {
@@ -79,6 +84,14 @@ _PROTOS = {
                                       f32, vp, vp, sz, vp]),
     "gode_gcn_vjp_phase2": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, vp, vp, sz, vp]),
     "gode_gather_rows": (C.c_int, [i64, vp, i32, vp, i64, vp, i64, vp]),
+    "gode_peer_alloc": (C.c_int, [sz, C.POINTER(vp)]),
+    "gode_peer_free": (C.c_int, [vp]),
+    "gode_peer_export": (C.c_int, [vp, vp]),
+    "gode_peer_open": (C.c_int, [vp, C.POINTER(vp)]),
+    "gode_peer_close": (C.c_int, [vp]),
+    "gode_halo_push": (C.c_int, [C.POINTER(PeerGroup), C.c_uint32, vp, vp, vp, i64, i32, vp, i64, i64, i32, vp]),
+    "gode_peer_wait": (C.c_int, [C.POINTER(PeerGroup), C.c_uint32, C.c_uint64, vp]),
+    "gode_peer_status": (C.c_int, [C.POINTER(PeerGroup), C.POINTER(i32), vp]),
     "gode_edge_matvec": (C.c_int, [i64, i32, vp, vp, vp, i64, vp, vp]),
     "gode_edge_matvec_bwd": (C.c_int, [i64, i32, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp]),
     "gode_gat_fwd": (C.c_int, [C.POINTER(GatGraph), i32, i32, vp, i64, f32, vp, i64, vp, vp, vp, vp]),

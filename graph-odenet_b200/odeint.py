@@ -374,7 +374,9 @@ def _gcn_aug_fixed_step(kern, tab, t0, h, y0, a0, S0, want_S):
     P = kern.n_theta
     ky, ka = [], []
     gth = torch.empty(s, P, dtype=torch.float32, device=kern.dev)
-    gP = kern.new_gP()
+    # two gP buffers in turn: with the peer-memory exchange a push of stage i+1's gP must not land in the buffer a
+    # peer's phase 2 of stage i may still be gathering from (peer.py)
+    gPs = [kern.new_gP(), kern.new_gP()]
     Ybuf, Abuf = [kern.new(), kern.new()], [kern.new(), kern.new()]
     Y_i, A_i, S_i = y0, a0, S0
     y_out = a_out = S_out = None
@@ -388,12 +390,13 @@ def _gcn_aug_fixed_step(kern, tab, t0, h, y0, a0, S0, want_S):
         ky_i = kern.new() if store else None
         Y_n = kern.new() if last else Ybuf[i & 1]
         kyp, cyp = _nz(ky[:i], coefs[:i])
+        gP = gPs[i & 1]
         kern.vjp_phase1(S_i, A_i, -1.0, ky_i, gP, y0, kyp, cyp, coefs[i], Y_n)
         # The next stage's support only needs Y_n, which phase 1 has just produced: issue its transform BEFORE
         # phase 2, so that on the row-partitioned path both halo exchanges (gP, then S_n) are in flight underneath
-        # the transform and phase 2's dense chain instead of being exposed (S_i is free: only phase 1 reads it).
+        # the transform and phase 2's dense chain instead of being exposed.
         if (not last) or want_S:
-            S_n = kern.transform(Y_n, t_n, kern.new_S() if S_i is S0 else S_i)
+            S_n = kern.transform(Y_n, t_n, kern.new_S())
         else:
             S_n = None
         ka_i = kern.new()

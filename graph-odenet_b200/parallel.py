@@ -41,6 +41,9 @@ def init_process_group(device, backend="nccl"):
     dist.init_process_group(backend, **kw)
 
 
+MODES = ("sync", "async", "split", "p2p", "p2p-async")
+
+
 def partition_bounds(n, world):
     """Row bounds [b_0=0, ..., b_world=n] of the contiguous 1-D partition (sizes differ by at most one)."""
     return [(n * r) // world for r in range(world + 1)]
@@ -141,6 +144,146 @@ def split_block(r, c_local, v, n_own):
     return (r[own], c_local[own], v[own]), (r[halo], c_local[halo] - n_own, v[halo])
 
 
+class HaloKernelMixin:
+    """GcnKernel on a row block: a halo exchange after every producer of a gather operand, awaited by the kernel that
+    gathers from the buffer.  Mixed in front of odeint.GcnKernel (``plan.make_kernel``); kept free of CUDA calls of its
+    own so that tests/test_peer_protocol_cpu.py can replay the solver's control flow over a recording base class."""
+
+    def __init__(self, plan, *a):
+        super().__init__(plan, *a)
+        self.pending = {}            # data_ptr of an operand buffer -> event / epoch of its in-flight halo exchange
+        self.partial = None
+        self.peer = plan.peer_for(self.d)
+        if plan.split is not None:
+            from . import _lib
+            # descriptor for the second (halo-column) pass: same parameters, halo blocks, operand offset
+            h = _lib.GcnOdeFunc()
+            C.memmove(C.byref(h), C.byref(self.f), C.sizeof(h))
+            h.A = plan.split["A_halo"].csr(False)
+            h.At = plan.split["At_halo"].csr(False)
+            h.gather_row_offset = plan.n_rows
+            self.f_halo = h
+            self.csr_own = plan.split["A_own"].csr(False)
+            self.csr_own_t = plan.split["At_own"].csr(False)
+            self.ws_bytes = max(self.ws_bytes, lib.gode_gcn_workspace_bytes(C.byref(h)))
+
+    def new_S(self):
+        plan = self.plan
+        if self.peer is not None:
+            return self.peer.new(plan.n_rows + plan.halo.n_halo)
+        return torch.empty(plan.n_rows + plan.halo.n_halo, self.d, dtype=torch.float32, device=self.dev)
+
+    def new_gP(self):
+        plan = self.plan
+        if self.peer is not None:
+            return self.peer.new(plan.n_rows + plan.halo_t.n_halo)
+        return torch.empty(plan.n_rows + plan.halo_t.n_halo, self.d, dtype=torch.float32, device=self.dev)
+
+    def numel_global(self):
+        return self.plan.n_global * self.d
+
+    def scalar(self, dev_scalar):
+        if self.plan.world > 1:
+            dist.all_reduce(dev_scalar, group=self.plan.group)
+        return float(dev_scalar.item())
+
+    def reduce_small(self, t):
+        if self.plan.world > 1:
+            if t.is_contiguous():
+                dist.all_reduce(t, group=self.plan.group)
+            else:
+                c = t.contiguous()
+                dist.all_reduce(c, group=self.plan.group)
+                t.copy_(c)
+        return t
+
+    # ---- halo exchange: peer-memory push, or NCCL (synchronous / on the side stream) ------------------------------
+    def _exchange(self, halo, buf):
+        plan = self.plan
+        if self.peer is not None:
+            self.pending[buf.data_ptr()] = self.peer.push(halo, buf)
+            return
+        if plan.mode == "sync" or plan.world == 1:
+            halo.exchange(buf)
+            return
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        cs = plan.comm_stream
+        cs.wait_event(ready)
+        buf.record_stream(cs)        # the allocator must not recycle the buffer under the side stream
+        with torch.cuda.stream(cs):
+            halo.exchange(buf)
+            done = torch.cuda.Event()
+            done.record(cs)
+        self.pending[buf.data_ptr()] = done
+
+    def _wait(self, buf):
+        ev = self.pending.pop(buf.data_ptr(), None)
+        if self.peer is not None:
+            if ev is not None:
+                self.peer.wait(ev)       # ev is the exchange's epoch
+            self.peer.note_read(buf)     # a gather from buf is about to be enqueued
+            return
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def _own_pass(self, csr, X):
+        """partial = (owned-column block) @ X[:n_own]  -- runs while X's halo tail is still arriving."""
+        if self.partial is None:
+            self.partial = self.new()
+        nb = lib.gode_spmm_workspace_bytes(C.byref(csr), self.d)
+        ws = ops.workspace(nb, self.dev, "spmm") if nb else None
+        check(lib.gode_spmm_csr_f32(C.byref(csr), ops._p(X), self.d, self.d, ops._p(self.partial), self.d, None,
+                                    ops._p(ws), nb, ops._stream()), "gode_spmm_csr_f32")
+        return self.partial
+
+    def _with_halo_pass(self, part, call):
+        self.f_halo.partial_in = part.data_ptr()
+        full, self.f = self.f, self.f_halo
+        try:
+            return call()
+        finally:
+            self.f = full
+
+    def transform(self, y, t, out):
+        super().transform(y, t, out)
+        self._exchange(self.plan.halo, out)
+        return out
+
+    def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0, S_next=None):
+        run = lambda: super(HaloKernelMixin, self).stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next)
+        if self.plan.split is None:
+            self._wait(S)
+            run()
+        else:
+            part = self._own_pass(self.csr_own, S)
+            self._wait(S)
+            self._with_halo_pass(part, run)
+        if S_next is not None:
+            self._exchange(self.plan.halo, S_next)
+
+    def vjp_phase1(self, S, a, sign, k_y, gP, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None):
+        run = lambda: super(HaloKernelMixin, self).vjp_phase1(S, a, sign, k_y, gP, y0, kprev, coefs, coef_self, y_next)
+        if self.plan.split is None:
+            self._wait(S)
+            run()
+        else:
+            part = self._own_pass(self.csr_own, S)
+            self._wait(S)
+            self._with_halo_pass(part, run)
+        self._exchange(self.plan.halo_t, gP)
+
+    def vjp_phase2(self, y, t, gP, k_a, gtheta):
+        run = lambda: super(HaloKernelMixin, self).vjp_phase2(y, t, gP, k_a, gtheta)
+        if self.plan.split is None:
+            self._wait(gP)
+            return run()
+        part = self._own_pass(self.csr_own_t, gP)
+        self._wait(gP)
+        return self._with_halo_pass(part, run)
+
+
 class PartitionedPlan:
     """This rank's row block of A_hat and of A_hat^T with their halo plans (what ``GcnKernel`` needs from a plan).
 
@@ -150,6 +293,11 @@ class PartitionedPlan:
                buffer -- the adjoint issues the next stage's transform before phase 2 (odeint._gcn_aug_fixed_step), so
                both of its exchanges hide under the transform and the dense VJP chain; the 4 forward exchanges of an
                rk4 step have no independent work to hide under and stay exposed;
+      "p2p"    no NCCL and no send buffer on the data path: one libgode kernel stores the rows a peer references straight
+               into that peer's halo tail over NVLink peer mappings and publishes an epoch flag; the gather waits for the
+               peers' flags on the device (peer.py, csrc/peer.cu).  Operand buffers come from a cudaIpc-shared arena;
+      "p2p-async"  the same with the push on the high-priority side stream, so it runs underneath independent kernels
+               exactly as "async" does for the NCCL exchange;
       "split"  "async" plus a column split of each block -- ``A_own`` [n_own, n_own] and ``A_halo`` [n_own, n_halo] --
                so a gather runs in two passes: owned columns while the halo is in flight, then halo columns with the
                first pass as ``partial_in``.  Measured at 2 GPUs (N = 10 M): the second pass over all rows costs more
@@ -169,7 +317,8 @@ class PartitionedPlan:
         self.split = split                   # None, or dict(A_own, A_halo, At_own, At_halo)
         self.mode = mode
         self.comm_stream = (torch.cuda.Stream(device=self.device, priority=-1)
-                            if (mode != "sync" and A.device.type == "cuda") else None)
+                            if (mode not in ("sync", "p2p") and A.device.type == "cuda") else None)
+        self._peer = {}                      # feature width -> peer.PeerHalo (modes "p2p", "p2p-async")
         if self.comm_stream is not None:
             # the exchange of gP is issued right before the (persistent, one CTA per SM) transform kernel: without free
             # SMs the NCCL kernel only starts when that kernel ends (torch.profiler timeline, profiles/r01_halo_overlap.md).
@@ -188,8 +337,8 @@ class PartitionedPlan:
             world = dist.get_world_size(group) if dist.is_initialized() else 1
         import os
         mode = mode or os.environ.get("GODE_HALO_MODE") or ("async" if world > 1 else "sync")
-        if mode not in ("sync", "async", "split"):
-            raise ValueError("halo mode must be sync, async or split")
+        if mode not in MODES:
+            raise ValueError("halo mode must be one of %s" % (MODES,))
         if world == 1:
             mode = "sync"
         overlap = mode == "split"
@@ -218,142 +367,30 @@ class PartitionedPlan:
     def csr(self, transpose=False):
         return (self.At if transpose else self.A).csr(False)
 
+    def peer_for(self, d):
+        """The peer-memory arena / exchange state for feature width ``d`` (collective on first use)."""
+        if not self.mode.startswith("p2p") or self.world == 1:
+            return None
+        ph = self._peer.get(d)
+        if ph is None:
+            from . import peer
+            ph = self._peer[d] = peer.PeerHalo(self, d, push_stream=self.comm_stream if self.mode == "p2p-async" else None)
+        return ph
+
+    def check_peers(self):
+        """Raises if a device-side wait of the peer-memory exchange timed out (synchronises the stream)."""
+        for ph in self._peer.values():
+            ph.check()
+
     def make_kernel(self, *args):
         from .odeint import GcnKernel
-        from . import _lib
-
-        plan = self
-
-        class PartitionedGcnKernel(GcnKernel):
-            """GcnKernel on a row block: halo exchanges after every producer of a gather operand; with a split plan
-            the exchange runs on a side stream underneath the owned-column pass of the next gather."""
-
-            def __init__(self, *a):
-                super().__init__(*a)
-                self.pending = {}            # data_ptr of an operand buffer -> event of its in-flight halo exchange
-                self.partial = None
-                if plan.split is not None:
-                    # descriptor for the second (halo-column) pass: same parameters, halo blocks, operand offset
-                    h = _lib.GcnOdeFunc()
-                    C.memmove(C.byref(h), C.byref(self.f), C.sizeof(h))
-                    h.A = plan.split["A_halo"].csr(False)
-                    h.At = plan.split["At_halo"].csr(False)
-                    h.gather_row_offset = plan.n_rows
-                    self.f_halo = h
-                    self.csr_own = plan.split["A_own"].csr(False)
-                    self.csr_own_t = plan.split["At_own"].csr(False)
-                    self.ws_bytes = max(self.ws_bytes, lib.gode_gcn_workspace_bytes(C.byref(h)))
-
-            def new_S(self):
-                return torch.empty(plan.n_rows + plan.halo.n_halo, self.d, dtype=torch.float32, device=self.dev)
-
-            def new_gP(self):
-                return torch.empty(plan.n_rows + plan.halo_t.n_halo, self.d, dtype=torch.float32, device=self.dev)
-
-            def numel_global(self):
-                return plan.n_global * self.d
-
-            def scalar(self, dev_scalar):
-                if plan.world > 1:
-                    dist.all_reduce(dev_scalar, group=plan.group)
-                return float(dev_scalar.item())
-
-            def reduce_small(self, t):
-                if plan.world > 1:
-                    if t.is_contiguous():
-                        dist.all_reduce(t, group=plan.group)
-                    else:
-                        c = t.contiguous()
-                        dist.all_reduce(c, group=plan.group)
-                        t.copy_(c)
-                return t
-
-            # ---- halo exchange, synchronous or on the side stream ------------------------------------------------
-            def _exchange(self, halo, buf):
-                if plan.mode == "sync" or plan.world == 1:
-                    halo.exchange(buf)
-                    return
-                main = torch.cuda.current_stream()
-                ready = torch.cuda.Event()
-                ready.record(main)
-                cs = plan.comm_stream
-                cs.wait_event(ready)
-                buf.record_stream(cs)        # the allocator must not recycle the buffer under the side stream
-                with torch.cuda.stream(cs):
-                    halo.exchange(buf)
-                    done = torch.cuda.Event()
-                    done.record(cs)
-                self.pending[buf.data_ptr()] = done
-
-            def _wait(self, buf):
-                ev = self.pending.pop(buf.data_ptr(), None)
-                if ev is not None:
-                    torch.cuda.current_stream().wait_event(ev)
-
-            def _own_pass(self, csr, X):
-                """partial = (owned-column block) @ X[:n_own]  -- runs while X's halo tail is still arriving."""
-                if self.partial is None:
-                    self.partial = self.new()
-                nb = lib.gode_spmm_workspace_bytes(C.byref(csr), self.d)
-                ws = ops.workspace(nb, self.dev, "spmm") if nb else None
-                check(lib.gode_spmm_csr_f32(C.byref(csr), ops._p(X), self.d, self.d, ops._p(self.partial), self.d, None,
-                                            ops._p(ws), nb, ops._stream()), "gode_spmm_csr_f32")
-                return self.partial
-
-            def transform(self, y, t, out):
-                super().transform(y, t, out)
-                self._exchange(plan.halo, out)
-                return out
-
-            def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0,
-                          S_next=None):
-                if plan.split is None:
-                    self._wait(S)
-                    super().stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next)
-                else:
-                    part = self._own_pass(self.csr_own, S)
-                    self._wait(S)
-                    self.f_halo.partial_in = part.data_ptr()
-                    full, self.f = self.f, self.f_halo
-                    try:
-                        super().stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next)
-                    finally:
-                        self.f = full
-                if S_next is not None:
-                    self._exchange(plan.halo, S_next)
-
-            def vjp_phase1(self, S, a, sign, k_y, gP, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None):
-                if plan.split is None:
-                    self._wait(S)
-                    super().vjp_phase1(S, a, sign, k_y, gP, y0, kprev, coefs, coef_self, y_next)
-                else:
-                    part = self._own_pass(self.csr_own, S)
-                    self._wait(S)
-                    self.f_halo.partial_in = part.data_ptr()
-                    full, self.f = self.f, self.f_halo
-                    try:
-                        super().vjp_phase1(S, a, sign, k_y, gP, y0, kprev, coefs, coef_self, y_next)
-                    finally:
-                        self.f = full
-                self._exchange(plan.halo_t, gP)
-
-            def vjp_phase2(self, y, t, gP, k_a, gtheta):
-                if plan.split is None:
-                    self._wait(gP)
-                    return super().vjp_phase2(y, t, gP, k_a, gtheta)
-                part = self._own_pass(self.csr_own_t, gP)
-                self._wait(gP)
-                self.f_halo.partial_in = part.data_ptr()
-                full, self.f = self.f, self.f_halo
-                try:
-                    super().vjp_phase2(y, t, gP, k_a, gtheta)
-                finally:
-                    self.f = full
-
-        return PartitionedGcnKernel(self, *args)
+        cls = type("PartitionedGcnKernel", (HaloKernelMixin, GcnKernel), {})
+        return cls(self, *args)
 
     def halo_bytes_per_step(self, d, n_fwd_evals, n_aug_evals):
-        """Bytes this rank moves over NVLink (sent + received) in one fwd+bwd step."""
+        """Bytes this rank moves over NVLink (sent + received) in one fixed-step fwd+bwd step: one support exchange per
+        forward evaluation and per augmented evaluation, one gP exchange per augmented evaluation (``n_aug_evals`` counts
+        the VJP evaluations; the evaluation of f(t1) that opens the adjoint shares its support with the first of them)."""
         s = self.halo.bytes_per_exchange(d)
         g = self.halo_t.bytes_per_exchange(d)
         return (n_fwd_evals + n_aug_evals) * s + n_aug_evals * g

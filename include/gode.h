@@ -332,6 +332,47 @@ int gode_edge_matvec_bwd(int64_t n_edges, int32_t f, const float* edge_data, con
 int gode_gather_rows(int64_t n_idx, const int32_t* idx, int32_t d, const float* src, int64_t lds,
                      float* dst, int64_t ldd, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Halo exchange over NVLink peer memory (csrc/peer.cu): one kernel reads the rows peers reference from the
+ * local operand and stores them straight into the halo tails of the peers' operand buffers, then publishes
+ * an epoch flag; the consumer waits for every peer's flag.  Replaces gode_gather_rows + NCCL all-to-all-v for
+ * the same step of the row-partitioned torch.spmm(adj, support) (GCN/layers.py:71).
+ *
+ * Every rank owns one arena (gode_peer_alloc: cudaMalloc, first GODE_PEER_HEADER_BYTES zeroed and reserved:
+ * uint32 flags[GODE_MAX_PEERS] at offset 0, CTA counter at GODE_PEER_COUNTER_OFFSET, status word at
+ * GODE_PEER_STATUS_OFFSET).  Operand buffers are carved from the arena at the SAME offsets on every rank.
+ * gode_peer_export / gode_peer_open move the 64-byte cudaIpc handle between processes (the host code ships the
+ * bytes, e.g. with torch.distributed.all_gather_object).  base[rank] is the local arena, base[p] the mapping of
+ * peer p's arena.  Epochs are the exchange counter (1, 2, ...; wrap-safe), identical on every rank.
+ * gode_halo_push: send_idx[send_ptr[p] .. send_ptr[p+1]) are the local rows peer p needs (host array send_ptr of
+ * world+1 entries); they land at rows dst_row[p] + k of the buffer at byte offset buf_offset of p's arena (leading
+ * dimension ldd floats).  No host synchronisation.  gode_peer_wait spins on the device until every peer has
+ * published `epoch`, at most timeout_ns; on time-out the status word becomes GODE_PEER_TIMEOUT (read it with
+ * gode_peer_status, which synchronises the stream).
+ * ---------------------------------------------------------------------------------------------- */
+#define GODE_MAX_PEERS 16
+#define GODE_PEER_HANDLE_BYTES 64
+#define GODE_PEER_HEADER_BYTES 4096
+#define GODE_PEER_COUNTER_OFFSET 128
+#define GODE_PEER_STATUS_OFFSET 192
+#define GODE_PEER_TIMEOUT 1
+
+typedef struct {
+  int32_t world, rank;
+  void* base[GODE_MAX_PEERS];
+} gode_peer_group_t;
+
+int gode_peer_alloc(size_t bytes, void** out);
+int gode_peer_free(void* p);
+int gode_peer_export(const void* p, void* handle64);
+int gode_peer_open(const void* handle64, void** out);
+int gode_peer_close(void* p);
+int gode_halo_push(const gode_peer_group_t* g, uint32_t epoch, const int32_t* send_idx, const int64_t* send_ptr,
+                   const int64_t* dst_row, int64_t buf_offset, int32_t d, const float* src, int64_t lds,
+                   int64_t ldd, int32_t max_ctas, void* stream);
+int gode_peer_wait(const gode_peer_group_t* g, uint32_t epoch, uint64_t timeout_ns, void* stream);
+int gode_peer_status(const gode_peer_group_t* g, int32_t* status_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

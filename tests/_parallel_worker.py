@@ -51,7 +51,10 @@ def main():
 
     pplan = parallel.PartitionedPlan.build(row, col, val, n, rank, world)
     lo, hi = pplan.lo, pplan.hi
-    y_p, gx_p, gp_p, nfe_p, st_p = run(pplan, x_all[lo:hi], g_all[lo:hi].contiguous())
+    # several steps over the same plan: the peer-memory modes recycle arena slots and epochs across steps
+    for _ in range(3 if pplan.mode.startswith("p2p") else 1):
+        y_p, gx_p, gp_p, nfe_p, st_p = run(pplan, x_all[lo:hi], g_all[lo:hi].contiguous())
+    pplan.check_peers()      # raises if a device-side wait on a peer's flag timed out
     # gather the row blocks on every rank
     sizes = [pplan.bounds[r + 1] - pplan.bounds[r] for r in range(world)]
     ys = [torch.empty(s, d, device=dev) for s in sizes]
@@ -69,7 +72,7 @@ def main():
         errs = {"y": rel(torch.cat(ys), y_1), "gx": rel(torch.cat(gxs), gx_1)}
         for (name, _), a, b in zip(blk.named_parameters(), gp_p, gp_1):
             errs["g_" + name] = rel(a, b)
-        print("world=%d method=%s nfe %d/%d errs %s stats %s / %s" % (world, method, nfe_p, nfe_1, errs, st_p, st_1), flush=True)
+        print("world=%d mode=%s method=%s nfe %d/%d errs %s stats %s / %s" % (world, pplan.mode, method, nfe_p, nfe_1, errs, st_p, st_1), flush=True)
         # y: 1e-6 relative L2.  Gradients: 1e-5 in the smooth regime; with active ReLUs a 1e-7 difference in a
         # pre-activation flips mask elements and moves the summed gradients by 1e-4..1e-3 (measured: tools/sensitivity.py)
         gtol = 1e-5 if smooth else 5e-3

@@ -38,7 +38,9 @@ def test_partitioned_plan_world1_matches_plain_plan():
 
 @pytest.mark.parametrize("method,regime,mode", [("rk4", "relu", "async"), ("rk4", "smooth", "async"), ("rk4", "smooth", "sync"),
                                                 ("rk4", "smooth", "split"), ("dopri5", "relu", "async"),
-                                                ("dopri5", "smooth", "split")])
+                                                ("dopri5", "smooth", "split"), ("rk4", "smooth", "p2p"),
+                                                ("rk4", "relu", "p2p-async"), ("rk4", "smooth", "p2p-async"),
+                                                ("dopri5", "smooth", "p2p"), ("dopri5", "relu", "p2p-async")])
 def test_two_gpus_match_one(method, regime, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")

@@ -1,0 +1,249 @@
+"""CPU: the peer-memory halo exchange protocol (graph-odenet_b200/peer.py) replayed in a randomised multi-rank simulator.
+
+The solver's real control flow (odeint.gcn_solve_forward / gcn_solve_adjoint over parallel.HaloKernelMixin) is run over
+a recording kernel, which yields the per-rank program of gathers, pushes, flag waits and cross-stream events.  Every rank
+executes the same program (SPMD); the simulator interleaves the ranks' streams at random and checks the two properties
+the CUDA path relies on:
+
+  * a gather sees, from begin to end, exactly the version of every peer's halo segment that the program order says
+    it should (no stale tail, no tail overwritten early by a faster peer);
+  * the epoch flag a rank publishes to a peer never decreases.
+
+A deliberately broken protocol (hazard rule disabled) must be caught by the same simulator.
+"""
+import random
+import types
+
+import pytest
+import torch
+
+from graph_odenet_b200 import odeint, ops, parallel, peer
+
+
+class FakeBuf:
+    def __init__(self, owner, slot):
+        self.owner, self.slot, self.version = owner, slot, 0
+
+    def data_ptr(self):
+        return 1000 + self.slot
+
+    def __del__(self):
+        self.owner.pool.release(self.slot)
+
+
+class RecProtocol(peer.ExchangeProtocol):
+    def __init__(self, n_slots, side, prog):
+        super().__init__(n_slots)
+        self.side, self.prog, self.n_ev, self.n_empty = side, prog, 0, 0
+
+    def new(self, rows):
+        return FakeBuf(self, self.pool.acquire())
+
+    def _slot(self, buf):
+        return buf.slot
+
+    def _emit_push(self, epoch, halo, buf, slot):
+        if buf is not None:
+            buf.version = epoch
+        else:
+            self.n_empty += 1
+        self.prog.append(("side" if self.side else "main", "push", epoch, slot))
+
+    def _emit_wait(self, epoch):
+        self.prog.append(("main", "wait", epoch))
+
+    def _emit_side_after_main(self):
+        self.n_ev += 1
+        self.prog.append(("main", "record", "m%d" % self.n_ev))
+        self.prog.append(("side", "waitev", "m%d" % self.n_ev))
+
+    def _emit_done(self, epoch):
+        self.prog.append(("side", "record", "done%d" % epoch))
+
+    def _emit_wait_done(self, epoch):
+        self.prog.append(("main", "waitev", "done%d" % epoch))
+
+
+class BrokenProtocol(RecProtocol):
+    """No write-after-read rule: what a naive push would do."""
+
+    def push(self, halo, buf):
+        self.track.read_at.pop(self._slot(buf), None)
+        return super().push(halo, buf)
+
+
+class RecBase:
+    """Stands in for odeint.GcnKernel: records the gathers instead of launching them."""
+
+    def __init__(self, plan, prog):
+        self.plan, self.prog = plan, prog
+        self.d, self.n, self.dev, self.nfe = 4, plan.n_rows, torch.device("cpu"), 0
+        self.n_theta = (self.d + 1) * self.d + 3 * self.d + 1
+
+    def new(self):
+        return torch.zeros(1)
+
+    def _gather(self, buf):
+        self.prog.append(("main", "gather_begin", buf.slot, buf.version))
+        self.prog.append(("main", "gather_end", buf.slot, buf.version))
+
+    def transform(self, y, t, out):
+        return out
+
+    def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0, S_next=None):
+        self.nfe += 1
+        self._gather(S)
+
+    def vjp_phase1(self, S, a, sign, k_y, gP, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None):
+        self.nfe += 1
+        self._gather(S)
+
+    def vjp_phase2(self, y, t, gP, k_a, gtheta):
+        gtheta.zero_()
+        self._gather(gP)
+
+
+class RecKernel(parallel.HaloKernelMixin, RecBase):
+    def reduce_small(self, t):
+        return t
+
+
+def record_program(proto_cls, side, method, step_size, n_steps, n_slots=8):
+    prog = []
+    proto = proto_cls(n_slots, side, prog)
+    plan = types.SimpleNamespace(mode="p2p-async" if side else "p2p", world=4, split=None, n_rows=10, n_global=40,
+                                 halo=types.SimpleNamespace(n_halo=3), halo_t=types.SimpleNamespace(n_halo=3),
+                                 group=None, comm_stream=None, peer_for=lambda d: proto)
+    for _ in range(n_steps):
+        kf = RecKernel(plan, prog)
+        y1 = odeint.gcn_solve_forward(kf, torch.zeros(1), 0.0, 1.0, method, step_size)
+        kb = RecKernel(plan, prog)
+        odeint.gcn_solve_adjoint(kb, y1, torch.zeros(1), 0.0, 1.0, method, step_size)
+        del kf, kb
+    return prog, proto
+
+
+def simulate(prog, world, rng, max_ops=10 ** 7):
+    """Random interleaving of ``world`` ranks running ``prog``; returns a description of the first violation or None."""
+    streams = {"main": [op[1:] for op in prog if op[0] == "main"], "side": [op[1:] for op in prog if op[0] == "side"]}
+    pc = {(r, s): 0 for r in range(world) for s in streams}
+    flags = [[0] * world for _ in range(world)]            # flags[r][p]: latest epoch p published to r
+    ver = [dict() for _ in range(world)]                   # ver[r][(slot, p)]: version of p's segment in r's slot
+    active = [dict() for _ in range(world)]                # active[r][slot]: expected version of the running gather
+    events = [set() for _ in range(world)]
+    live = list(pc)
+    for _ in range(max_ops):
+        if not live:
+            return None
+        rng.shuffle(live)
+        progressed = False
+        for key in live:
+            r, s = key
+            q = streams[s]
+            if pc[key] >= len(q):
+                live.remove(key)
+                progressed = True
+                break
+            op = q[pc[key]]
+            kind = op[0]
+            if kind == "wait":
+                if any(flags[r][p] < op[1] for p in range(world) if p != r):
+                    continue
+            elif kind == "waitev":
+                if op[1] not in events[r]:
+                    continue
+            elif kind == "record":
+                events[r].add(op[1])
+            elif kind == "push":
+                epoch, slot = op[1], op[2]
+                for p in range(world):
+                    if p == r:
+                        continue
+                    if slot is not None:
+                        if slot in active[p]:
+                            return "rank %d pushed epoch %d into slot %d while rank %d gathers version %d" % (
+                                r, epoch, slot, p, active[p][slot])
+                        ver[p][(slot, r)] = epoch
+                    if flags[p][r] > epoch:
+                        return "flag of rank %d at rank %d went back from %d to %d" % (r, p, flags[p][r], epoch)
+                    flags[p][r] = epoch
+            elif kind in ("gather_begin", "gather_end"):
+                slot, want = op[1], op[2]
+                for p in range(world):
+                    if p != r and ver[r].get((slot, p), 0) != want:
+                        return "rank %d %s slot %d: segment of rank %d has version %d, program order says %d" % (
+                            r, kind, slot, p, ver[r].get((slot, p), 0), want)
+                if kind == "gather_begin":
+                    active[r][slot] = want
+                else:
+                    active[r].pop(slot, None)
+            pc[key] += 1
+            progressed = True
+            break
+        if not progressed:
+            return "deadlock at " + str({k: pc[k] for k in live})
+    return "simulation did not finish"
+
+
+@pytest.fixture(autouse=True)
+def _no_cuda_combine(monkeypatch):
+    monkeypatch.setattr(ops, "rk_combine", lambda y0, ks, cs, out=None: out)
+
+
+@pytest.mark.parametrize("side", [False, True])
+@pytest.mark.parametrize("method,step_size", [("rk4", None), ("rk4", 0.25), ("midpoint", 0.5), ("euler", 0.5)])
+def test_protocol_is_safe_under_random_interleaving(side, method, step_size):
+    prog, proto = record_program(RecProtocol, side, method, step_size, n_steps=3)
+    assert any(op[1] == "push" for op in prog)
+    rng = random.Random(1234)
+    for world in (2, 4):
+        for _ in range(40):
+            assert simulate(prog, world, rng) is None
+
+
+def test_rk4_steady_state_needs_no_empty_exchange():
+    """With the solver's buffer rotation (two gP buffers, fresh S per stage, round-robin slots) the hazard rule never
+    has to insert an empty exchange: 12 exchanges per rk4 fwd+bwd step on grid [0, 1] (4 + 4 supports -- the adjoint's
+    first stage reuses the support of f(t1) -- and 4 masked adjoints), as PartitionedPlan.halo_bytes_per_step counts."""
+    for side in (False, True):
+        prog, proto = record_program(RecProtocol, side, "rk4", None, n_steps=4)
+        assert proto.n_empty == 0
+        assert proto.track.issued == 4 * 12
+
+
+def _single_buffer_program(proto_cls, side, rounds=6):
+    prog = []
+    proto = proto_cls(2, side, prog)
+    buf = proto.new(1)
+    for _ in range(rounds):
+        e = proto.push(object(), buf)
+        proto.wait(e)
+        proto.note_read(buf)
+        prog.append(("main", "gather_begin", buf.slot, buf.version))
+        prog.append(("main", "gather_end", buf.slot, buf.version))
+    return prog, proto
+
+
+@pytest.mark.parametrize("side", [False, True])
+def test_single_buffer_reuse_is_fenced(side):
+    prog, proto = _single_buffer_program(RecProtocol, side)
+    assert proto.n_empty > 0                     # the rule had to act
+    rng = random.Random(7)
+    for _ in range(100):
+        assert simulate(prog, 3, rng) is None
+
+
+def test_simulator_catches_a_protocol_without_the_rule():
+    prog, _ = _single_buffer_program(BrokenProtocol, False)
+    rng = random.Random(7)
+    assert any(simulate(prog, 3, rng) is not None for _ in range(100))
+
+
+def test_slot_pool_round_robin_and_exhaustion():
+    pool = peer.SlotPool(3)
+    assert [pool.acquire() for _ in range(3)] == [0, 1, 2]
+    with pytest.raises(RuntimeError):
+        pool.acquire()
+    pool.release(1)
+    pool.release(0)
+    assert pool.acquire() == 0 and pool.acquire() == 1     # cursor wrapped past slot 2
