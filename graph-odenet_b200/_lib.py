@@ -9,11 +9,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libgode.so")
 
 MAX_STAGES = 8
+MAX_PEERS, PEER_HANDLE_BYTES, PEER_HEADER_BYTES, PEER_TIMEOUT = 16, 64, 4096, 1
 HEAVY_ROW = 256
 HEAVY_CHUNK = 256
 PREC_FP32, PREC_TF32 = 0, 1
 PROF_AGG_FWD, PROF_AGG_T, PROF_TRANSFORM, PROF_VJP_DENSE, PROF_OTHER = range(5)
-MAX_PEERS, PEER_HANDLE_BYTES, PEER_HEADER_BYTES, PEER_TIMEOUT = 16, 64, 4096, 1
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -25,10 +25,14 @@ lib = C.CDLL(LIB_PATH)
 vp, i64, i32, f32, sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
 
 
+class PushRoute(C.Structure):
+    _fields_ = [("ptr", vp), ("ent", vp), ("base", vp * MAX_PEERS)]
+
+
 class SpmmEpilogue(C.Structure):
     _fields_ = [("bias", vp), ("relu", i32), ("residual", vp), ("y0", vp), ("kprev", vp * MAX_STAGES),
                 ("coef", f32 * MAX_STAGES), ("n_prev", i32), ("coef_self", f32), ("ynext", vp),
-                ("mask_src", vp), ("mask_scale", f32), ("gp_out", vp), ("acc_in", vp)]
+                ("mask_src", vp), ("mask_scale", f32), ("gp_out", vp), ("acc_in", vp), ("push", PushRoute)]
 
 
 class Csr(C.Structure):
@@ -43,7 +47,8 @@ class GatGraph(C.Structure):
 
 class GcnOdeFunc(C.Structure):
     _fields_ = [("A", Csr), ("At", Csr), ("d", i32), ("groups", i32), ("gn_eps", f32), ("precision", i32),
-                ("W", vp), ("b", vp), ("gamma", vp), ("beta", vp), ("gather_row_offset", i64), ("partial_in", vp)]
+                ("W", vp), ("b", vp), ("gamma", vp), ("beta", vp), ("gather_row_offset", i64), ("partial_in", vp),
+                ("push_S", PushRoute), ("push_gP", PushRoute)]
 
 
 class PeerGroup(C.Structure):
@@ -76,6 +81,7 @@ _PROTOS = {
     "gode_rk_combine": (C.c_int, [i64, vp, C.POINTER(vp), C.POINTER(f32), i32, vp, vp]),
     "gode_rk_error_sumsq": (C.c_int, [i64, vp, vp, C.POINTER(vp), C.POINTER(f32), i32, f32, f32, vp, vp, sz, vp]),
     "gode_gcn_workspace_bytes": (sz, [C.POINTER(GcnOdeFunc)]),
+    "gode_gcn_push_fusable": (C.c_int, [C.POINTER(GcnOdeFunc)]),
     "gode_gcn_transform": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, sz, vp]),
     "gode_gcn_stage_fwd": (C.c_int, [C.POINTER(GcnOdeFunc), vp, vp, vp, C.POINTER(vp), C.POINTER(f32), i32, f32, vp,
                                      f32, vp, vp, sz, vp]),
@@ -83,6 +89,8 @@ _PROTOS = {
     "gode_gcn_vjp_phase1": (C.c_int, [C.POINTER(GcnOdeFunc), vp, vp, f32, vp, vp, vp, C.POINTER(vp), C.POINTER(f32), i32,
                                       f32, vp, vp, sz, vp]),
     "gode_gcn_vjp_phase2": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, vp, vp, sz, vp]),
+    "gode_gcn_vjp_phase2_rk": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(f32), i32,
+                                         f32, vp, vp, sz, vp]),
     "gode_gather_rows": (C.c_int, [i64, vp, i32, vp, i64, vp, i64, vp]),
     "gode_peer_alloc": (C.c_int, [sz, C.POINTER(vp)]),
     "gode_peer_free": (C.c_int, [vp]),

@@ -17,7 +17,7 @@ int input_grad_tc(const gode_gcn_odefunc_t* f, const float* gS, float* gz, cudaS
 bool wgrad_tc_supported(const gode_gcn_odefunc_t* f);
 bool input_grad_tc_supported(const gode_gcn_odefunc_t* f);
 size_t wgrad_tc_ws_bytes(const gode_gcn_odefunc_t* f);
-int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, const float* cs, float* gW1, float* ws,
+int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, float* cs, float* gW1, float* ws,
              size_t ws_bytes, cudaStream_t st);
 
 struct GcnWs {
@@ -119,6 +119,7 @@ __global__ void k_time_terms(int d, float t, const float* __restrict__ cs, const
 static int transform_impl(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, GcnWs& w, cudaStream_t st) {
   ProfScope prof(GODE_PROF_TRANSFORM, st);
   if (transform_tc_supported(f)) return transform_tc(f, y, t, S, st);
+  GODE_REQUIRE(!f->push_S.ptr, "gcn_transform: a fused halo push needs the tensor-core transform (gode_gcn_push_fusable)");
   const int d = f->d;
   int rc = groupnorm_fwd(f->A.n_rows, d, f->groups, f->gn_eps, y, d, f->gamma, f->beta, w.bufC, d, st);
   if (rc) return rc;
@@ -132,6 +133,11 @@ using namespace gode;
 extern "C" size_t gode_gcn_workspace_bytes(const gode_gcn_odefunc_t* f) {
   if (!f || f->d <= 0) return 0;
   return ws_bytes_for(f);
+}
+
+extern "C" int gode_gcn_push_fusable(const gode_gcn_odefunc_t* f) {
+  if (!f || f->d <= 0 || f->groups <= 0) return 0;
+  return transform_tc_supported(f) ? 1 : 0;   // the vectorised gather kernels cover every width the transform does
 }
 
 extern "C" int gode_gcn_transform(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, void* ws,
@@ -199,6 +205,7 @@ extern "C" int gode_gcn_vjp_phase1(const gode_gcn_odefunc_t* f, const float* S, 
   ep.mask_src = a;
   ep.mask_scale = sign;
   ep.gp_out = gP;
+  ep.push = f->push_gP;
   if (y_next) {
     ep.y0 = y0;
     ep.ynext = y_next;
@@ -215,11 +222,14 @@ extern "C" int gode_gcn_vjp_phase1(const gode_gcn_odefunc_t* f, const float* S, 
                        as_stream(stream));
 }
 
-extern "C" int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, float t, const float* gP, float* k_a,
-                                   float* gtheta, void* ws, size_t ws_bytes, void* stream) {
+extern "C" int gode_gcn_vjp_phase2_rk(const gode_gcn_odefunc_t* f, const float* y, float t, const float* gP, float* k_a,
+                                      float* gtheta, const float* a0, const float* const* kprev_host,
+                                      const float* coef_host, int32_t n_prev, float coef_self, float* a_next, void* ws,
+                                      size_t ws_bytes, void* stream) {
   int rc = check(f);
   if (rc) return rc;
-  GODE_REQUIRE(f->At.rowptr && (f->A.n_rows == 0 || (y && gP && k_a)) && gtheta, "gcn_vjp_phase2: null pointer");
+  GODE_REQUIRE(f->At.rowptr && (f->A.n_rows == 0 || (y && gP && (k_a || a_next))) && gtheta, "gcn_vjp_phase2: null pointer");
+  GODE_REQUIRE(n_prev >= 0 && n_prev <= GODE_MAX_STAGES && (!a_next || a0), "gcn_vjp_phase2: bad RK arguments");
   GcnWs w;
   rc = carve(f, ws, ws_bytes, w);
   if (rc) return rc;
@@ -245,26 +255,34 @@ extern "C" int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, 
   }
   if (rc) return rc;
   ProfScope prof_dense(GODE_PROF_VJP_DENSE, st);
-  // bias gradient and the two time-column terms
+  // bias gradient
   if ((rc = colsum(n, d, gP, d, gb, w.red, w.red_bytes, st))) return rc;
-  if ((rc = colsum(n, d, gS, d, cs, w.red, w.red_bytes, st))) return rc;
-  k_time_terms<<<1, 128, 0, st>>>(d, t, cs, f->W, gW, gt);
-  GODE_LAUNCH_CHECK();
-  // gW[1:,:] = z^T gS
+  // gW[1:,:] = z^T gS, and cs = column sums of gS (tensor-core path: same pass over gS)
   if (wgrad_tc_supported(f)) {
     if ((rc = wgrad_tc(f, y, gS, cs, gW + d, w.splitk, w.splitk_bytes, st))) return rc;
   } else {
+    if ((rc = colsum(n, d, gS, d, cs, w.red, w.red_bytes, st))) return rc;
     if ((rc = groupnorm_fwd(n, d, f->groups, f->gn_eps, y, d, f->gamma, f->beta, z, d, st))) return rc;
     if ((rc = gemm_simt(1, 0, d, d, n, 1.f, z, d, gS, d, 0.f, gW + d, d, splits_for(n), w.splitk, w.splitk_bytes, st, nullptr, 0.f)))
       return rc;
   }
-  // gz = gS W[1:,:]^T ; GroupNorm backward
+  // the two time-column terms: gW[0,:] = t cs, gt = <cs, W[0,:]>
+  k_time_terms<<<1, 128, 0, st>>>(d, t, cs, f->W, gW, gt);
+  GODE_LAUNCH_CHECK();
+  // gz = gS W[1:,:]^T ; GroupNorm backward with the adjoint state's Runge-Kutta combination in its tail
   if (input_grad_tc_supported(f)) {
     if ((rc = input_grad_tc(f, gS, gz, st))) return rc;
   } else if ((rc = gemm_simt(0, 1, n, d, d, 1.f, gS, d, f->W + d, d, 0.f, gz, d, 1, nullptr, 0, st, nullptr, 0.f))) {
     return rc;
   }
-  return groupnorm_bwd(n, d, f->groups, f->gn_eps, y, d, f->gamma, gz, d, k_a, d, ggamma, gbeta, w.red, w.red_bytes, st);
+  return groupnorm_bwd_rk(n, d, f->groups, f->gn_eps, y, d, f->gamma, gz, d, k_a, d, ggamma, gbeta, w.red, w.red_bytes, st,
+                          a0, kprev_host, coef_host, n_prev, coef_self, a_next);
+}
+
+extern "C" int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, float t, const float* gP, float* k_a,
+                                   float* gtheta, void* ws, size_t ws_bytes, void* stream) {
+  GODE_REQUIRE(k_a != nullptr || (f && f->A.n_rows == 0), "gcn_vjp_phase2: null pointer");
+  return gode_gcn_vjp_phase2_rk(f, y, t, gP, k_a, gtheta, nullptr, nullptr, nullptr, 0, 0.f, nullptr, ws, ws_bytes, stream);
 }
 
 extern "C" int gode_gcn_stage_vjp(const gode_gcn_odefunc_t* f, const float* y, float t, const float* S, const float* a,

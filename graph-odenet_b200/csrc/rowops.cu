@@ -126,13 +126,28 @@ __global__ void __launch_bounds__(256) k_gn_fwd(int64_t n, int groups, float eps
   }
 }
 
+struct KList {
+  const float* k[GODE_MAX_STAGES];
+  float c[GODE_MAX_STAGES];
+  int n;
+};
+
+// Runge-Kutta combination fused behind the GroupNorm backward (the adjoint state of the next augmented stage):
+//   anext = a0 + sum_j c[j] k[j] + c_self * dx       (dx itself is stored only when a later stage reads it)
+struct RkTail {
+  const float* a0;
+  KList kl;
+  float c_self;
+  float* anext;
+};
+
 // backward: dx and per-block partial sums of dgamma / dbeta.  blockDim.x is a multiple of `groups`, so a
 // thread keeps the same group (and its CPG channels) for every row it visits.
 template <int CPG>
 __global__ void __launch_bounds__(256) k_gn_bwd(int64_t n, int groups, float eps, const float* __restrict__ x, int64_t ldx,
                                                 const float* __restrict__ gamma, const float* __restrict__ dy,
                                                 int64_t lddy, float* __restrict__ dx, int64_t lddx,
-                                                float* __restrict__ part /*[gridDim][2*d]*/, bool vec) {
+                                                float* __restrict__ part /*[gridDim][2*d]*/, bool vec, RkTail rk) {
   extern __shared__ float sm[];  // [blockDim][2*CPG]
   const int64_t total = n * groups;
   const int g = threadIdx.x % groups;
@@ -166,7 +181,22 @@ __global__ void __launch_bounds__(256) k_gn_bwd(int64_t n, int groups, float eps
     m2 *= (1.0f / CPG);
 #pragma unroll
     for (int c = 0; c < CPG; ++c) o[c] = rstd * (u[c] - m1 - v[c] * m2);
-    store_grp<CPG>(dx + r * lddx + g * CPG, o, vec);
+    if (dx) store_grp<CPG>(dx + r * lddx + g * CPG, o, vec);
+    if (rk.anext) {   // contiguous [n, d] operands (ld = d)
+      const int64_t off = r * (int64_t)(groups * CPG) + g * CPG;
+      float acc[CPG], w[CPG];
+      load_grp<CPG>(rk.a0 + off, acc, vec);
+#pragma unroll
+      for (int c = 0; c < CPG; ++c) acc[c] += rk.c_self * o[c];
+#pragma unroll
+      for (int j = 0; j < GODE_MAX_STAGES; ++j)
+        if (j < rk.kl.n) {
+          load_grp<CPG>(rk.kl.k[j] + off, w, vec);
+#pragma unroll
+          for (int c = 0; c < CPG; ++c) acc[c] += rk.kl.c[j] * w[c];
+        }
+      store_grp<CPG>(rk.anext + off, acc, vec);
+    }
   }
 #pragma unroll
   for (int c = 0; c < CPG; ++c) {
@@ -192,12 +222,6 @@ __global__ void __launch_bounds__(256) k_gn_bwd(int64_t n, int groups, float eps
 // ------------------------------------------------------------------------------------------------
 // Runge-Kutta combination and error norm
 // ------------------------------------------------------------------------------------------------
-struct KList {
-  const float* k[GODE_MAX_STAGES];
-  float c[GODE_MAX_STAGES];
-  int n;
-};
-
 __global__ void __launch_bounds__(256) k_rk_combine4(int64_t n4, const float* __restrict__ y0, KList kl, float* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -279,8 +303,13 @@ static int gn_fwd_t(int64_t n, int groups, float eps, const float* x, int64_t ld
 
 template <int CPG>
 static int gn_bwd_t(int64_t n, int groups, float eps, const float* x, int64_t ldx, const float* gamma, const float* dy,
-                    int64_t lddy, float* dx, int64_t lddx, float* dgamma, float* dbeta, float* part, cudaStream_t st) {
-  const bool vec = al16(x) && al16(dy) && al16(dx) && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0;
+                    int64_t lddy, float* dx, int64_t lddx, float* dgamma, float* dbeta, float* part, cudaStream_t st,
+                    const RkTail& rk) {
+  bool vec = al16(x) && al16(dy) && al16(dx) && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0;
+  if (rk.anext) {
+    vec = vec && al16(rk.a0) && al16(rk.anext) && (groups * CPG) % 4 == 0;
+    for (int j = 0; j < rk.kl.n; ++j) vec = vec && al16(rk.kl.k[j]);
+  }
   const int d = groups * CPG;
   const int tpb = (256 / groups) * groups;
   int64_t total = n * groups;
@@ -289,7 +318,7 @@ static int gn_bwd_t(int64_t n, int groups, float eps, const float* x, int64_t ld
   if (cap > kMaxBlocks) cap = kMaxBlocks;
   int grid = static_cast<int>(want < cap ? want : cap);
   if (grid < 1) grid = 1;
-  k_gn_bwd<CPG><<<grid, tpb, sizeof(float) * tpb * 2 * CPG, st>>>(n, groups, eps, x, ldx, gamma, dy, lddy, dx, lddx, part, vec);
+  k_gn_bwd<CPG><<<grid, tpb, sizeof(float) * tpb * 2 * CPG, st>>>(n, groups, eps, x, ldx, gamma, dy, lddy, dx, lddx, part, vec, rk);
   GODE_LAUNCH_CHECK();
   // partial layout per block: [dgamma d | dbeta d]
   k_reduce_partials<<<(2 * d + 127) / 128, 128, 0, st>>>(grid, 2 * d, part, part + (size_t)kMaxBlocks * 2 * d);
@@ -313,28 +342,46 @@ int groupnorm_fwd(int64_t n, int d, int groups, float eps, const float* x, int64
   }
 }
 
-int groupnorm_bwd(int64_t n, int d, int groups, float eps, const float* x, int64_t ldx, const float* gamma,
-                  const float* dy, int64_t lddy, float* dx, int64_t lddx, float* dgamma, float* dbeta, void* ws,
-                  size_t ws_bytes, cudaStream_t st) {
+static int fill_klist(KList& kl, const float* const* k, const float* c, int n);
+
+int groupnorm_bwd_rk(int64_t n, int d, int groups, float eps, const float* x, int64_t ldx, const float* gamma,
+                     const float* dy, int64_t lddy, float* dx, int64_t lddx, float* dgamma, float* dbeta, void* ws,
+                     size_t ws_bytes, cudaStream_t st, const float* a0, const float* const* kprev, const float* coef,
+                     int n_prev, float coef_self, float* a_next) {
   if (ws_bytes < gode_colreduce_workspace_bytes(2 * d) || !ws) {
     set_error("groupnorm_bwd: workspace too small");
     return GODE_EWORKSPACE;
   }
+  GODE_REQUIRE(dx || a_next, "groupnorm_bwd: nothing to write");
+  GODE_REQUIRE(!a_next || a0, "groupnorm_bwd: a_next needs a0");
   if (n == 0) {
     GODE_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * d, st));
     GODE_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * d, st));
     return GODE_OK;
   }
+  RkTail rk;
+  rk.a0 = a0;
+  rk.c_self = coef_self;
+  rk.anext = a_next;
+  int rc = fill_klist(rk.kl, kprev, coef, a_next ? n_prev : 0);
+  if (rc) return rc;
   float* part = static_cast<float*>(ws);
   const int cpg = d / groups;
   switch (cpg) {
-    case 1: return gn_bwd_t<1>(n, groups, eps, x, ldx, gamma, dy, lddy, dx, lddx, dgamma, dbeta, part, st);
-    case 2: return gn_bwd_t<2>(n, groups, eps, x, ldx, gamma, dy, lddy, dx, lddx, dgamma, dbeta, part, st);
-    case 4: return gn_bwd_t<4>(n, groups, eps, x, ldx, gamma, dy, lddy, dx, lddx, dgamma, dbeta, part, st);
-    case 8: return gn_bwd_t<8>(n, groups, eps, x, ldx, gamma, dy, lddy, dx, lddx, dgamma, dbeta, part, st);
-    case 16: return gn_bwd_t<16>(n, groups, eps, x, ldx, gamma, dy, lddy, dx, lddx, dgamma, dbeta, part, st);
+    case 1: return gn_bwd_t<1>(n, groups, eps, x, ldx, gamma, dy, lddy, dx, lddx, dgamma, dbeta, part, st, rk);
+    case 2: return gn_bwd_t<2>(n, groups, eps, x, ldx, gamma, dy, lddy, dx, lddx, dgamma, dbeta, part, st, rk);
+    case 4: return gn_bwd_t<4>(n, groups, eps, x, ldx, gamma, dy, lddy, dx, lddx, dgamma, dbeta, part, st, rk);
+    case 8: return gn_bwd_t<8>(n, groups, eps, x, ldx, gamma, dy, lddy, dx, lddx, dgamma, dbeta, part, st, rk);
+    case 16: return gn_bwd_t<16>(n, groups, eps, x, ldx, gamma, dy, lddy, dx, lddx, dgamma, dbeta, part, st, rk);
     default: set_error("groupnorm: %d channels per group unsupported (1,2,4,8,16)", cpg); return GODE_EINVAL;
   }
+}
+
+int groupnorm_bwd(int64_t n, int d, int groups, float eps, const float* x, int64_t ldx, const float* gamma,
+                  const float* dy, int64_t lddy, float* dx, int64_t lddx, float* dgamma, float* dbeta, void* ws,
+                  size_t ws_bytes, cudaStream_t st) {
+  return groupnorm_bwd_rk(n, d, groups, eps, x, ldx, gamma, dy, lddy, dx, lddx, dgamma, dbeta, ws, ws_bytes, st, nullptr,
+                          nullptr, nullptr, 0, 0.f, nullptr);
 }
 
 static int fill_klist(KList& kl, const float* const* k, const float* c, int n) {

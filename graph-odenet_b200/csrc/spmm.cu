@@ -72,6 +72,14 @@ __device__ __forceinline__ void epilogue(const gode_spmm_epilogue_t& ep, int64_t
       g.z = v.z > 0.f ? ep.mask_scale * a.z : 0.f;
       g.w = v.w > 0.f ? ep.mask_scale * a.w : 0.f;
       st_stream4(ep.gp_out + o, g);
+      if (ep.push.ptr) {   // fused halo push: the peers that reference this row get it now, over NVLink
+        const int p1 = __ldg(ep.push.ptr + row + 1);
+        for (int e = __ldg(ep.push.ptr + row); e < p1; ++e) {
+          const int64_t ent = __ldg(ep.push.ent + e);
+          float* dst = ep.push.base[ent >> 40] + (ent & 0xFFFFFFFFFFll) * ldy + c;
+          *reinterpret_cast<float4*>(dst) = g;
+        }
+      }
     }
   }
 }
@@ -761,6 +769,7 @@ int spmm_dispatch(const gode_csr_t& A, const float* X, int64_t ldx, int32_t d, f
       default: break;
     }
   }
+  GODE_REQUIRE(!ep.push.ptr, "spmm: a fused halo push needs a vectorised width (8..256, 16-byte aligned operands)");
   if (A.n_rows > 0) {
     unsigned grid = static_cast<unsigned>((A.n_rows + 7) / 8);
     k_spmm_generic<<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, X, ldx, d, Y, ldy, ep);

@@ -25,6 +25,7 @@
 //   as an MN-major operand (channels = M/N, rows = K): SBO = 128, LBO = C*32.
 #include "internal.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace gode {
 
@@ -146,7 +147,8 @@ __device__ __forceinline__ float4 normalize4(float4 x, float eps) {
 template <int D, int CPG, int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 k_rows_tc(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, const float* __restrict__ W /*[D+1, D]*/,
-          const float* __restrict__ gamma, const float* __restrict__ beta, float t, float eps, int passes) {
+          const float* __restrict__ gamma, const float* __restrict__ beta, float t, float eps, int passes,
+          const gode_push_route_t push /*MODE 0: rows peers reference are also stored into their halo tails*/) {
   using namespace tc;
   constexpr int KH = D / 2;                 // channels per staged half of K
   constexpr int NI = (16 * (KH / 16)) / 8;  // warp-instructions (8 rows x 4 chunks) per warp per half tile
@@ -302,10 +304,19 @@ k_rows_tc(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
       for (int r = warp; r < 128; r += THREADS / 32) {
         const int64_t grow = tile * 128 + r;
         if (grow >= n_rows) break;
+        int p0 = 0, p1 = 0;
+        if (MODE == 0 && push.ptr) {
+          p0 = __ldg(push.ptr + grow);
+          p1 = __ldg(push.ptr + grow + 1);
+        }
 #pragma unroll
         for (int c = lane; c < CH; c += 32) {
           const float4 o = *reinterpret_cast<const float4*>(stage + r * D + ((c ^ (r & (CH - 1))) * 4));
           __stcs(reinterpret_cast<float4*>(Out + grow * D + c * 4), o);
+          for (int e = p0; e < p1; ++e) {   // fused halo push over NVLink (posted stores)
+            const int64_t ent = __ldg(push.ent + e);
+            *reinterpret_cast<float4*>(push.base[ent >> 40] + (ent & 0xFFFFFFFFFFll) * D + c * 4) = o;
+          }
         }
       }
       __syncthreads();   // staging buffer is the A buffer of the next tile
@@ -334,7 +345,7 @@ static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 template <int D, int CPG>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restrict__ G, float* __restrict__ partial /*[grid][D][D]*/,
-           float eps, int passes) {
+           float* __restrict__ cs_partial /*[grid][D]: column sums of G over this CTA's rows*/, float eps, int passes) {
   using namespace tc;
   static_assert(D == 128, "the accumulator uses all 128 TMEM lanes");
   // Both operands are [rows, D] row-major in HBM but the reduction runs over rows, so they are transposed on the
@@ -366,7 +377,9 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
   const uint32_t tmem_d = *tmem_slot;
   constexpr uint32_t IDESC = make_idesc(D, D, false, false);
 
-  float4 ra[NI], rb[NI];
+  float4 ra[NI], rb[NI], cs_acc[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) cs_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   auto load_raw = [&](int64_t chunk) {
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
@@ -405,6 +418,7 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
       split4(xa, hi, lo);
       put(base, r, kc * 4, hi);
       put(base + MAT, r, kc * 4, lo);
+      cs_acc[i].x += rb[i].x; cs_acc[i].y += rb[i].y; cs_acc[i].z += rb[i].z; cs_acc[i].w += rb[i].w;   // padding rows are 0
       split4(rb[i], hi, lo);
       put(base + 2 * MAT, r, kc * 4, hi);
       put(base + 3 * MAT, r, kc * 4, lo);
@@ -464,9 +478,45 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
         *reinterpret_cast<float4*>(out + hc * (D / 2) + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
   }
+  // column sums of G over this CTA's rows: lanes sharing a 16-byte chunk differ in lane & 7 (the row inside an
+  // 8-row group), warps sharing it differ in warp / 2 (the row group); fixed reduction order -> deterministic
+  {
+    float* scs = reinterpret_cast<float*>(smem);   // [THREADS / 64][D]; the operand stages are free (all MMAs retired)
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      float4 v = cs_acc[i];
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+        v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+        v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+      }
+      const int g = warp * NI + i;
+      const int rg = g / (D / 16), cg = g % (D / 16);
+      const int kc = cg * 4 + (lane >> 3);
+      if ((lane & 7) == 0) *reinterpret_cast<float4*>(scs + rg * D + kc * 4) = v;
+    }
+    __syncthreads();
+    if (tid < D) {
+      float t = 0.f;
+#pragma unroll
+      for (int rg = 0; rg < RC / 8; ++rg) t += scs[rg * D + tid];
+      cs_partial[(size_t)blockIdx.x * D + tid] = t;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, D);
+}
+
+// cs[o] = sum_b cs_partial[b][o]   (column sums of dS; one block, fixed order)
+__global__ void k_wgrad_cs(int nblk, int d, const float* __restrict__ cs_partial, float* __restrict__ cs) {
+  const int o = threadIdx.x;
+  if (o >= d) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += cs_partial[(size_t)b * d + o];
+  cs[o] = s;
 }
 
 // gW1[i][o] = gamma[i] * sum_b partial[b][i][o] + beta[i] * cs[o]
@@ -482,20 +532,21 @@ __global__ void k_wgrad_finish(int nblk, int d, const float* __restrict__ partia
 
 bool wgrad_tc_supported(const gode_gcn_odefunc_t* f) { return (tc_mask() & 4) && f->d == 128 && f->groups == 32; }
 
-size_t wgrad_tc_ws_bytes(const gode_gcn_odefunc_t* f) { return sizeof(float) * (size_t)sm_count() * f->d * f->d; }
+size_t wgrad_tc_ws_bytes(const gode_gcn_odefunc_t* f) { return sizeof(float) * (size_t)sm_count() * (f->d + 1) * f->d; }
 
-// gW1 = z^T dS with z = GroupNorm(y);  cs = column sums of dS (already computed by the caller)
-int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, const float* cs, float* gW1, float* ws,
+// gW1 = z^T dS with z = GroupNorm(y);  cs (output, [d]) = column sums of dS, accumulated in the same pass over dS
+int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, float* cs, float* gW1, float* ws,
              size_t ws_bytes, cudaStream_t st) {
   constexpr int D = 128;
   GODE_REQUIRE(al16(y) && al16(gS) && al16(ws), "wgrad_tc: operands must be 16-byte aligned");
   const int64_t n_chunks = (f->A.n_rows + 31) / 32;
   int grid = static_cast<int>(n_chunks < persistent_ctas() ? n_chunks : persistent_ctas());
   if (grid < 1) grid = 1;
-  if (ws_bytes < sizeof(float) * (size_t)grid * D * D) {
+  if (ws_bytes < sizeof(float) * (size_t)grid * (D + 1) * D) {
     set_error("wgrad_tc: workspace too small");
     return GODE_EWORKSPACE;
   }
+  float* cs_partial = ws + (size_t)grid * D * D;
   constexpr size_t smem = 2 * 4 * (size_t)(D / 8) * 1184 + 64;
   static bool configured = false;
   if (!configured) {
@@ -503,7 +554,9 @@ int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, const
     configured = true;
   }
   const int passes = f->precision == GODE_PREC_TF32 ? 1 : 3;
-  k_wgrad_tc<D, 4><<<grid, tc::THREADS, smem, st>>>(f->A.n_rows, y, gS, ws, f->gn_eps, passes);
+  k_wgrad_tc<D, 4><<<grid, tc::THREADS, smem, st>>>(f->A.n_rows, y, gS, ws, cs_partial, f->gn_eps, passes);
+  GODE_LAUNCH_CHECK();
+  k_wgrad_cs<<<1, D, 0, st>>>(grid, D, cs_partial, cs);
   GODE_LAUNCH_CHECK();
   k_wgrad_finish<<<(D * D + 255) / 256, 256, 0, st>>>(grid, D, ws, f->gamma, f->beta, cs, gW1);
   GODE_LAUNCH_CHECK();
@@ -512,7 +565,7 @@ int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, const
 
 template <int D, int CPG, int MODE>
 static int launch_rows_tc(int64_t n_rows, const float* X, float* Out, const float* W, const float* gamma, const float* beta,
-                          float t, float eps, int passes, cudaStream_t st) {
+                          float t, float eps, int passes, cudaStream_t st, const gode_push_route_t* push = nullptr) {
   constexpr size_t smem = 2 * (size_t)D * D * 4 + 2 * (size_t)128 * (D / 2) * 4 + D * 4 + 64;
   static bool configured = false;
   if (!configured) {
@@ -522,7 +575,10 @@ static int launch_rows_tc(int64_t n_rows, const float* X, float* Out, const floa
   const int64_t n_tiles = (n_rows + 127) / 128;
   if (n_tiles == 0) return GODE_OK;
   const int grid = static_cast<int>(n_tiles < persistent_ctas() ? n_tiles : persistent_ctas());
-  k_rows_tc<D, CPG, MODE><<<grid, tc::THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes);
+  gode_push_route_t pr;
+  if (push) pr = *push;
+  else memset(&pr, 0, sizeof(pr));
+  k_rows_tc<D, CPG, MODE><<<grid, tc::THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr);
   GODE_LAUNCH_CHECK();
   return GODE_OK;
 }
@@ -537,8 +593,9 @@ bool input_grad_tc_supported(const gode_gcn_odefunc_t* f) { return (tc_mask() & 
 int transform_tc(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, cudaStream_t st) {
   GODE_REQUIRE(al16(y) && al16(S), "transform_tc: operands must be 16-byte aligned");
   const int passes = f->precision == GODE_PREC_TF32 ? 1 : 3;
-  if (f->d == 128) return launch_rows_tc<128, 4, 0>(f->A.n_rows, y, S, f->W, f->gamma, f->beta, t, f->gn_eps, passes, st);
-  if (f->d == 64) return launch_rows_tc<64, 2, 0>(f->A.n_rows, y, S, f->W, f->gamma, f->beta, t, f->gn_eps, passes, st);
+  const gode_push_route_t* push = f->push_S.ptr ? &f->push_S : nullptr;
+  if (f->d == 128) return launch_rows_tc<128, 4, 0>(f->A.n_rows, y, S, f->W, f->gamma, f->beta, t, f->gn_eps, passes, st, push);
+  if (f->d == 64) return launch_rows_tc<64, 2, 0>(f->A.n_rows, y, S, f->W, f->gamma, f->beta, t, f->gn_eps, passes, st, push);
   set_error("transform_tc: unsupported width %d", f->d);
   return GODE_EINVAL;
 }

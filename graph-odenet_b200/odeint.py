@@ -197,10 +197,15 @@ class GcnKernel:
                                       ops._p(y0), karr, carr, len(kprev), float(coef_self), ops._p(y_next),
                                       ops._p(ws), self.ws_bytes, ops._stream()), "gode_gcn_vjp_phase1")
 
-    def vjp_phase2(self, y, t, gP, k_a, gtheta):
+    def vjp_phase2(self, y, t, gP, k_a, gtheta, a0=None, kprev=(), coefs=(), coef_self=0.0, a_next=None):
+        """k_a = (gP^T A_hat) d[.]/dy (k_a may be None when no later stage reads it), gtheta = parameter / time terms;
+        fused a_next = a0 + sum coefs*kprev + coef_self*k_a in the tail of the GroupNorm backward."""
         ws = self._ws()
-        check(lib.gode_gcn_vjp_phase2(C.byref(self.f), ops._p(y), float(t), ops._p(gP), ops._p(k_a), ops._p(gtheta),
-                                      ops._p(ws), self.ws_bytes, ops._stream()), "gode_gcn_vjp_phase2")
+        karr = (C.c_void_p * _lib.MAX_STAGES)(*[k.data_ptr() for k in kprev])
+        carr = (C.c_float * _lib.MAX_STAGES)(*[float(c) for c in coefs])
+        check(lib.gode_gcn_vjp_phase2_rk(C.byref(self.f), ops._p(y), float(t), ops._p(gP), ops._p(k_a), ops._p(gtheta),
+                                         ops._p(a0), karr, carr, len(kprev), float(coef_self), ops._p(a_next),
+                                         ops._p(ws), self.ws_bytes, ops._stream()), "gode_gcn_vjp_phase2_rk")
 
 
 def _nz(ks, coefs):
@@ -399,13 +404,14 @@ def _gcn_aug_fixed_step(kern, tab, t0, h, y0, a0, S0, want_S):
             S_n = kern.transform(Y_n, t_n, kern.new_S())
         else:
             S_n = None
-        ka_i = kern.new()
-        kern.vjp_phase2(Y_i, t_i, gP, ka_i, gth[i])
+        # k_a of this stage and the adjoint state of the next one in the same pass (k_a is stored only if a later
+        # combination reads it)
+        ka_i = kern.new() if store else None
+        A_n = kern.new() if last else Abuf[i & 1]
+        kap, cap = _nz(ka[:i], coefs[:i])
+        kern.vjp_phase2(Y_i, t_i, gP, ka_i, gth[i], a0, kap, cap, coefs[i], A_n)
         ky.append(ky_i)
         ka.append(ka_i)
-        A_n = kern.new() if last else Abuf[i & 1]
-        kap, cap = _nz(ka, coefs)
-        ops.rk_combine(a0, kap, cap, out=A_n)
         Y_i, A_i, S_i = Y_n, A_n, S_n
         y_out, a_out, S_out = Y_n, A_n, S_n
     w = torch.tensor([float(F32(h * F32(b))) for b in tab.b], dtype=torch.float32, device=kern.dev)

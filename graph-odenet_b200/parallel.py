@@ -41,7 +41,7 @@ def init_process_group(device, backend="nccl"):
     dist.init_process_group(backend, **kw)
 
 
-MODES = ("sync", "async", "split", "p2p", "p2p-async")
+MODES = ("sync", "async", "split", "p2p", "p2p-async", "p2p-fused")
 
 
 def partition_bounds(n, world):
@@ -154,6 +154,7 @@ class HaloKernelMixin:
         self.pending = {}            # data_ptr of an operand buffer -> event / epoch of its in-flight halo exchange
         self.partial = None
         self.peer = plan.peer_for(self.d)
+        self.fused = self.peer is not None and plan.mode == "p2p-fused" and self._push_fusable()
         if plan.split is not None:
             from . import _lib
             # descriptor for the second (halo-column) pass: same parameters, halo blocks, operand offset
@@ -246,13 +247,39 @@ class HaloKernelMixin:
         finally:
             self.f = full
 
+    def _push_fusable(self):
+        return bool(lib.gode_gcn_push_fusable(C.byref(self.f)))
+
+    def _fused_begin(self, field, halo, buf):
+        """The next producer of ``buf`` also stores the peers' rows (gode_push_route_t in the descriptor)."""
+        epoch, _ = self.peer.begin(buf)
+        setattr(self.f, field, self.peer.fused_route(halo, buf))
+        return epoch
+
+    def _fused_end(self, field, buf, epoch):
+        from . import _lib
+        setattr(self.f, field, _lib.PushRoute())
+        self.pending[buf.data_ptr()] = self.peer.finish(epoch)
+
     def transform(self, y, t, out):
+        if self.fused:
+            epoch = self._fused_begin("push_S", self.plan.halo, out)
+            super().transform(y, t, out)
+            self._fused_end("push_S", out, epoch)
+            return out
         super().transform(y, t, out)
         self._exchange(self.plan.halo, out)
         return out
 
     def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0, S_next=None):
         run = lambda: super(HaloKernelMixin, self).stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next)
+        if self.fused:
+            self._wait(S)
+            if S_next is None:
+                return run()
+            epoch = self._fused_begin("push_S", self.plan.halo, S_next)   # the transform inside stage_fwd pushes S_next
+            run()
+            return self._fused_end("push_S", S_next, epoch)
         if self.plan.split is None:
             self._wait(S)
             run()
@@ -265,6 +292,11 @@ class HaloKernelMixin:
 
     def vjp_phase1(self, S, a, sign, k_y, gP, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None):
         run = lambda: super(HaloKernelMixin, self).vjp_phase1(S, a, sign, k_y, gP, y0, kprev, coefs, coef_self, y_next)
+        if self.fused:
+            self._wait(S)
+            epoch = self._fused_begin("push_gP", self.plan.halo_t, gP)     # the gather's epilogue pushes gP
+            run()
+            return self._fused_end("push_gP", gP, epoch)
         if self.plan.split is None:
             self._wait(S)
             run()
@@ -274,8 +306,8 @@ class HaloKernelMixin:
             self._with_halo_pass(part, run)
         self._exchange(self.plan.halo_t, gP)
 
-    def vjp_phase2(self, y, t, gP, k_a, gtheta):
-        run = lambda: super(HaloKernelMixin, self).vjp_phase2(y, t, gP, k_a, gtheta)
+    def vjp_phase2(self, y, t, gP, k_a, gtheta, a0=None, kprev=(), coefs=(), coef_self=0.0, a_next=None):
+        run = lambda: super(HaloKernelMixin, self).vjp_phase2(y, t, gP, k_a, gtheta, a0, kprev, coefs, coef_self, a_next)
         if self.plan.split is None:
             self._wait(gP)
             return run()
@@ -298,6 +330,10 @@ class PartitionedPlan:
                peers' flags on the device (peer.py, csrc/peer.cu).  Operand buffers come from a cudaIpc-shared arena;
       "p2p-async"  the same with the push on the high-priority side stream, so it runs underneath independent kernels
                exactly as "async" does for the NCCL exchange;
+      "p2p-fused"  no exchange kernel at all: the kernels that PRODUCE a gather operand (the tensor-core transform for S,
+               the phase-1 gather's epilogue for gP) store every row a peer references into that peer's halo tail next
+               to their own local store (posted NVLink writes riding underneath the kernel), then a one-CTA kernel
+               publishes the epoch flag.  Falls back to "p2p" for shapes the tensor-core transform does not cover;
       "split"  "async" plus a column split of each block -- ``A_own`` [n_own, n_own] and ``A_halo`` [n_own, n_halo] --
                so a gather runs in two passes: owned columns while the halo is in flight, then halo columns with the
                first pass as ``partial_in``.  Measured at 2 GPUs (N = 10 M): the second pass over all rows costs more
@@ -317,7 +353,7 @@ class PartitionedPlan:
         self.split = split                   # None, or dict(A_own, A_halo, At_own, At_halo)
         self.mode = mode
         self.comm_stream = (torch.cuda.Stream(device=self.device, priority=-1)
-                            if (mode not in ("sync", "p2p") and A.device.type == "cuda") else None)
+                            if (mode not in ("sync", "p2p", "p2p-fused") and A.device.type == "cuda") else None)
         self._peer = {}                      # feature width -> peer.PeerHalo (modes "p2p", "p2p-async")
         if self.comm_stream is not None:
             # the exchange of gP is issued right before the (persistent, one CTA per SM) transform kernel: without free
@@ -336,7 +372,10 @@ class PartitionedPlan:
         if world is None:
             world = dist.get_world_size(group) if dist.is_initialized() else 1
         import os
-        mode = mode or os.environ.get("GODE_HALO_MODE") or ("async" if world > 1 else "sync")
+        # default on GPUs: the producers push boundary rows into the peers' halo tails themselves ("p2p-fused"; it falls
+        # back to "p2p" for shapes without a tensor-core transform and to "async" when peer mappings are unavailable)
+        on_gpu = row.device.type == "cuda"
+        mode = mode or os.environ.get("GODE_HALO_MODE") or (("p2p-fused" if on_gpu else "async") if world > 1 else "sync")
         if mode not in MODES:
             raise ValueError("halo mode must be one of %s" % (MODES,))
         if world == 1:
@@ -369,12 +408,21 @@ class PartitionedPlan:
 
     def peer_for(self, d):
         """The peer-memory arena / exchange state for feature width ``d`` (collective on first use)."""
-        if not self.mode.startswith("p2p") or self.world == 1:
+        if not self.mode.startswith("p2p") or self.world == 1 or self.device.type != "cuda":
             return None
         ph = self._peer.get(d)
         if ph is None:
             from . import peer
-            ph = self._peer[d] = peer.PeerHalo(self, d, push_stream=self.comm_stream if self.mode == "p2p-async" else None)
+            try:
+                ph = self._peer[d] = peer.PeerHalo(self, d, push_stream=self.comm_stream if self.mode == "p2p-async" else None)
+            except peer.PeerSetupError as e:
+                # raised on every rank together: all of them switch to the NCCL exchange on the side stream
+                import warnings
+                warnings.warn("%s -- falling back to halo mode 'async' (NCCL)" % e)
+                self.mode = "async"
+                if self.comm_stream is None:
+                    self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
+                return None
         return ph
 
     def check_peers(self):

@@ -24,7 +24,11 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from ._lib import lib, check, PeerGroup, MAX_PEERS, PEER_HEADER_BYTES, PEER_HANDLE_BYTES
+from ._lib import lib, check, PeerGroup, PushRoute, MAX_PEERS, PEER_HEADER_BYTES, PEER_HANDLE_BYTES
+
+
+class PeerSetupError(RuntimeError):
+    """Raised on EVERY rank when the peer-memory arena could not be set up on some rank."""
 
 
 class SlotPool:
@@ -121,8 +125,9 @@ class ExchangeProtocol:
         """consumer stream waits for the recorded completion of push ``epoch``"""
 
     # protocol -----------------------------------------------------------------------------------------------------
-    def push(self, halo, buf):
-        """Issue the exchange that fills the peers' halo tails of ``buf``'s slot; returns its epoch."""
+    def begin(self, buf):
+        """Hazard handling for an exchange into ``buf``'s slot; returns (epoch, slot).  What follows is either
+        ``_emit_push`` of the data (``push``) or a producer kernel that stores the peers' rows itself, then ``finish``."""
         slot = self._slot(buf)
         n_empty, wait_epoch = self.track.before_push(slot)
         if n_empty:
@@ -131,13 +136,23 @@ class ExchangeProtocol:
             self._emit_push(self.track.issued, None, None, None)
         if wait_epoch is not None:
             self._emit_wait(wait_epoch)
+        return self.track.push(), slot
+
+    def push(self, halo, buf):
+        """Issue the exchange that fills the peers' halo tails of ``buf``'s slot; returns its epoch."""
+        epoch, slot = self.begin(buf)
         if self.side:
             self._emit_side_after_main()
-        epoch = self.track.push()
         self._emit_push(epoch, halo, buf, slot)
         if self.side:
             self._emit_done(epoch)
             self.done.add(epoch)
+        return epoch
+
+    def finish(self, epoch):
+        """Fused exchange: the producer kernel (consumer stream) has stored the peers' rows; publish the epoch."""
+        assert not self.side, "fused pushes run on the consumer stream"
+        self._emit_push(epoch, None, None, None)
         return epoch
 
     def wait(self, epoch):
@@ -191,35 +206,56 @@ class PeerHalo(ExchangeProtocol):
         self.slot_bytes = -(-self.slot_rows * d * 4 // 4096) * 4096
         self.n_slots = n_slots
         nbytes = PEER_HEADER_BYTES + n_slots * self.slot_bytes
+        # Every step that can fail locally (allocation, export, mapping a peer's arena) is followed by an agreement over
+        # all ranks, so that either every rank ends up with a working exchange or every rank raises PeerSetupError and
+        # the caller falls back to the NCCL exchange -- never a mix that would hang in a collective.
+        self.base, self.opened = None, []
         base = C.c_void_p()
-        check(lib.gode_peer_alloc(nbytes, C.byref(base)), "gode_peer_alloc")
-        self.base = base.value
         handle = (C.c_ubyte * PEER_HANDLE_BYTES)()
-        check(lib.gode_peer_export(self.base, handle), "gode_peer_export")
+        err = None
+        try:
+            check(lib.gode_peer_alloc(nbytes, C.byref(base)), "gode_peer_alloc")
+            self.base = base.value
+            check(lib.gode_peer_export(self.base, handle), "gode_peer_export")
+        except Exception as e:          # noqa: BLE001 -- reported through PeerSetupError on every rank
+            err = e
+        self._agree(err, "allocating / exporting the arena")
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(handle), group=self.group)
         g = PeerGroup()
         g.world, g.rank = self.world, self.rank
-        self.opened = []
-        for p in range(self.world):
-            if p == self.rank:
-                g.base[p] = self.base
-                continue
-            h = (C.c_ubyte * PEER_HANDLE_BYTES).from_buffer_copy(handles[p])
-            out = C.c_void_p()
-            check(lib.gode_peer_open(h, C.byref(out)), "gode_peer_open")
-            g.base[p] = out.value
-            self.opened.append(out.value)
+        try:
+            for p in range(self.world):
+                if p == self.rank:
+                    g.base[p] = self.base
+                    continue
+                h = (C.c_ubyte * PEER_HANDLE_BYTES).from_buffer_copy(handles[p])
+                out = C.c_void_p()
+                check(lib.gode_peer_open(h, C.byref(out)), "gode_peer_open")
+                g.base[p] = out.value
+                self.opened.append(out.value)
+        except Exception as e:          # noqa: BLE001
+            err = e
+        self._agree(err, "mapping the peers' arenas")
         self.g = g
         ExchangeProtocol.__init__(self, n_slots)
         self.slot_of = {}                      # data_ptr -> slot
         self.push_stream = push_stream         # None: pushes on the current stream
         self.side = push_stream is not None
         self.done_events = {}                  # epoch -> event of this rank's own push on the side stream
+        self._fused = {}                       # id(halo plan) -> (ptr, ent) device arrays of the fused push route
         # where my rows land in every peer's halo tail, for both halo plans
         self.routes = {id(plan.halo): self._route(plan.halo), id(plan.halo_t): self._route(plan.halo_t)}
         torch.cuda.synchronize(dev)
         dist.barrier(group=self.group)         # every arena is mapped and zeroed before the first flag is written
+
+    def _agree(self, err, what):
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=self.plan.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            self.close()
+            raise PeerSetupError("peer-memory halo exchange unavailable (%s failed on %s): %s" % (
+                what, "this rank" if err is not None else "another rank", err))
 
     def _route(self, halo):
         """(send_ptr[world+1], dst_row[world]) host arrays: my rows for peer p go to rows dst_row[p] + k of its buffer."""
@@ -237,6 +273,33 @@ class PeerHalo(ExchangeProtocol):
             assert recv_p[self.rank] == halo.send_counts[p], "halo plans disagree between ranks"
             dst_row.append(n_own_p + sum(recv_p[:self.rank]))
         return ((C.c_int64 * (self.world + 1))(*send_ptr), (C.c_int64 * self.world)(*dst_row))
+
+    def fused_route(self, halo, buf):
+        """_lib.PushRoute for the kernel that produces ``buf``: per owned row, the (peer, destination row) pairs."""
+        key = id(halo)
+        if key not in self._fused:
+            send_ptr, dst_row = self.routes[key]
+            dev = self.plan.device
+            n_send = int(halo.send_idx.numel())
+            sp = torch.tensor(list(send_ptr), dtype=torch.int64, device=dev)
+            counts = sp[1:] - sp[:-1]
+            peer_of = torch.repeat_interleave(torch.arange(self.world, device=dev, dtype=torch.int64), counts)
+            k = torch.arange(n_send, device=dev, dtype=torch.int64) - sp[:-1][peer_of]
+            dst = torch.tensor(list(dst_row), dtype=torch.int64, device=dev)[peer_of] + k
+            ent = (peer_of << 40) | dst
+            rows = halo.send_idx.to(torch.int64)
+            order = torch.argsort(rows, stable=True)
+            ptr = torch.zeros(halo.n_own + 1, dtype=torch.int64, device=dev)
+            ptr[1:] = torch.cumsum(torch.bincount(rows, minlength=halo.n_own), 0)
+            self._fused[key] = (ptr.to(torch.int32).contiguous(), ent[order].contiguous())
+        ptr, ent = self._fused[key]
+        r = PushRoute()
+        r.ptr, r.ent = ptr.data_ptr(), (ent.data_ptr() if ent.numel() else ptr.data_ptr())
+        off = PEER_HEADER_BYTES + self._slot(buf) * self.slot_bytes
+        for p in range(self.world):
+            if p != self.rank:
+                r.base[p] = self.g.base[p] + off
+        return r
 
     # ---- buffers ------------------------------------------------------------------------------------------------
     def new(self, rows):

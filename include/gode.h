@@ -33,6 +33,7 @@ extern "C" {
 #define GODE_EWORKSPACE (-4) /* workspace too small */
 
 #define GODE_MAX_STAGES 8
+#define GODE_MAX_PEERS 16   /* ranks of one NVLink domain the peer-memory halo exchange addresses */
 
 /* precision of the dense H*W products (GCN/layers.py:32,70 torch.mm) */
 #define GODE_PREC_FP32 0   /* fp32 result: SIMT FFMA, or 3xTF32 split on tcgen05 where the shape allows */
@@ -117,6 +118,16 @@ int gode_csr_row_values(int64_t n_rows, const int32_t* rowptr, const float* vals
 int gode_csr_heavy_rows(int64_t n_rows, const int32_t* rowptr, int32_t* heavy_rows, int32_t* heavy_chunk_ptr,
                         int32_t* counts_out, void* stream);
 
+/* Route of a fused halo push (multi-GPU, peer memory; see the "Halo exchange over NVLink peer memory" section):
+ * the kernel that PRODUCES a gather operand stores every row a peer references straight into the halo tail of that
+ * peer's operand buffer, next to its own local store, so the transfer rides underneath the producing kernel.
+ * ptr == NULL: no push.  Entries of local row r: ent[ptr[r] .. ptr[r+1]) = (peer << 40) | destination row. */
+typedef struct {
+  const int32_t* ptr;             /* device, [n_rows + 1] */
+  const int64_t* ent;             /* device */
+  float* base[GODE_MAX_PEERS];    /* peer p's operand buffer through the peer mapping (same leading dimension) */
+} gode_push_route_t;
+
 /* ------------------------------------------------------------------------------------------------
  * CSR SpMM with a fused row epilogue.
  * replaces: torch.spmm(adj, support) (+ bias, + F.relu, + residual) -- GCN/layers.py:33-35,71-73,
@@ -144,6 +155,7 @@ typedef struct {
   const float* acc_in;     /* [n_rows, ld] or NULL: partial sums added to acc before the bias (the product with
                               another column block of the same rows -- the row-partitioned path gathers the owned
                               columns while the halo is in flight, then the halo columns with acc_in) */
+  gode_push_route_t push;  /* gp_out rows are also stored into the peers' buffers (ptr NULL: off) */
 } gode_spmm_epilogue_t;
 
 /* ws: n_chunks * d floats of scratch for the heavy-row partial sums (0 bytes when n_heavy == 0) */
@@ -235,9 +247,15 @@ typedef struct {
    * still addresses the buffers from row 0. */
   int64_t gather_row_offset;
   const float* partial_in;
+  /* Fused halo pushes (ptr NULL: off): rows of every support S the transform writes / of every gP that phase 1 of the
+   * VJP writes are also stored into the peers' halo tails.  Needs the tensor-core transform (gode_gcn_push_fusable). */
+  gode_push_route_t push_S;
+  gode_push_route_t push_gP;
 } gode_gcn_odefunc_t;
 
 size_t gode_gcn_workspace_bytes(const gode_gcn_odefunc_t* f);
+/* 1 when the kernels this descriptor selects can carry push_S / push_gP, else 0 */
+int gode_gcn_push_fusable(const gode_gcn_odefunc_t* f);
 
 /* S[n_rows, d] = [t || GN(y)] W */
 int gode_gcn_transform(const gode_gcn_odefunc_t* f, const float* y, float t, float* S,
@@ -270,6 +288,13 @@ int gode_gcn_vjp_phase1(const gode_gcn_odefunc_t* f, const float* S, const float
                         float coef_self, float* y_next, void* ws, size_t ws_bytes, void* stream);
 int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, float t, const float* gP,
                         float* k_a, float* gtheta, void* ws, size_t ws_bytes, void* stream);
+/* phase2 with the Runge-Kutta combination of the adjoint state fused behind the GroupNorm backward:
+ *   a_next = a0 + sum_j coef[j] kprev[j] + coef_self k_a      (a_next may be null: plain phase2)
+ * k_a may be null when no later stage reads it (then only a_next is written). */
+int gode_gcn_vjp_phase2_rk(const gode_gcn_odefunc_t* f, const float* y, float t, const float* gP,
+                           float* k_a, float* gtheta, const float* a0, const float* const* kprev_host,
+                           const float* coef_host, int32_t n_prev, float coef_self, float* a_next,
+                           void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GAT attention aggregation (segmented softmax / scatter over the edge list).
@@ -350,7 +375,6 @@ int gode_gather_rows(int64_t n_idx, const int32_t* idx, int32_t d, const float* 
  * published `epoch`, at most timeout_ns; on time-out the status word becomes GODE_PEER_TIMEOUT (read it with
  * gode_peer_status, which synchronises the stream).
  * ---------------------------------------------------------------------------------------------- */
-#define GODE_MAX_PEERS 16
 #define GODE_PEER_HANDLE_BYTES 64
 #define GODE_PEER_HEADER_BYTES 4096
 #define GODE_PEER_COUNTER_OFFSET 128

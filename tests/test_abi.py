@@ -48,9 +48,12 @@ def test_no_cpu_fallback():
 def test_struct_layouts_match_header():
     """ctypes mirrors of the two ABI structs have the C layout (sizes computed from the header's field order)."""
     from graph_odenet_b200 import _lib
-    assert ctypes.sizeof(_lib.SpmmEpilogue) == 8 + 8 + 8 + 8 + 8 * 8 + 4 * 8 + 4 + 4 + 8 + 8 + 8 + 8 + 8
+    route = 8 + 8 + 16 * 8
+    assert ctypes.sizeof(_lib.PushRoute) == route
+    assert ctypes.sizeof(_lib.SpmmEpilogue) == 8 + 8 + 8 + 8 + 8 * 8 + 4 * 8 + 4 + 4 + 8 + 8 + 8 + 8 + 8 + route
     assert ctypes.sizeof(_lib.Csr) == 2 * 8 + 6 * 8 + 2 * 4
-    assert ctypes.sizeof(_lib.GcnOdeFunc) == 2 * ctypes.sizeof(_lib.Csr) + 4 * 4 + 4 * 8 + 8 + 8
+    assert ctypes.sizeof(_lib.GcnOdeFunc) == 2 * ctypes.sizeof(_lib.Csr) + 4 * 4 + 4 * 8 + 8 + 8 + 2 * route
+    assert ctypes.sizeof(_lib.PeerGroup) == 4 + 4 + 16 * 8
 
 
 def test_model_surface_matches_reference_keys():

@@ -40,7 +40,9 @@ def test_partitioned_plan_world1_matches_plain_plan():
                                                 ("rk4", "smooth", "split"), ("dopri5", "relu", "async"),
                                                 ("dopri5", "smooth", "split"), ("rk4", "smooth", "p2p"),
                                                 ("rk4", "relu", "p2p-async"), ("rk4", "smooth", "p2p-async"),
-                                                ("dopri5", "smooth", "p2p"), ("dopri5", "relu", "p2p-async")])
+                                                ("dopri5", "smooth", "p2p"), ("dopri5", "relu", "p2p-async"),
+                                                ("rk4", "smooth", "p2p-fused"), ("rk4", "relu", "p2p-fused"),
+                                                ("dopri5", "smooth", "p2p-fused")])
 def test_two_gpus_match_one(method, regime, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")

@@ -35,6 +35,11 @@ class RecProtocol(peer.ExchangeProtocol):
     def __init__(self, n_slots, side, prog):
         super().__init__(n_slots)
         self.side, self.prog, self.n_ev, self.n_empty = side, prog, 0, 0
+        self.fused_epochs = set()              # epochs whose remote stores were issued by a producer kernel
+
+    def finish(self, epoch):
+        self.fused_epochs.add(epoch)
+        return super().finish(epoch)
 
     def new(self, rows):
         return FakeBuf(self, self.pool.acquire())
@@ -42,12 +47,21 @@ class RecProtocol(peer.ExchangeProtocol):
     def _slot(self, buf):
         return buf.slot
 
+    def begin(self, buf):
+        epoch, slot = super().begin(buf)
+        buf.version = epoch
+        return epoch, slot
+
+    def fused_route(self, halo, buf):
+        return None
+
     def _emit_push(self, epoch, halo, buf, slot):
-        if buf is not None:
-            buf.version = epoch
-        else:
+        stream = "side" if self.side else "main"
+        if buf is not None:                    # stand-alone push kernel: remote stores, then the flag
+            self.prog.append((stream, "rwrite", epoch, slot))
+        elif epoch not in self.fused_epochs:   # an empty exchange of the hazard rule
             self.n_empty += 1
-        self.prog.append(("side" if self.side else "main", "push", epoch, slot))
+        self.prog.append((stream, "signal", epoch))
 
     def _emit_wait(self, epoch):
         self.prog.append(("main", "wait", epoch))
@@ -80,25 +94,35 @@ class RecBase:
         self.d, self.n, self.dev, self.nfe = 4, plan.n_rows, torch.device("cpu"), 0
         self.n_theta = (self.d + 1) * self.d + 3 * self.d + 1
 
+    f = types.SimpleNamespace()
+
     def new(self):
         return torch.zeros(1)
+
+    def _produce(self, buf):
+        if getattr(self, "fused", False):      # the producer kernel stores the peers' rows itself
+            self.prog.append(("main", "rwrite", buf.version, buf.slot))
 
     def _gather(self, buf):
         self.prog.append(("main", "gather_begin", buf.slot, buf.version))
         self.prog.append(("main", "gather_end", buf.slot, buf.version))
 
     def transform(self, y, t, out):
+        self._produce(out)
         return out
 
     def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0, S_next=None):
         self.nfe += 1
         self._gather(S)
+        if S_next is not None:
+            self._produce(S_next)
 
     def vjp_phase1(self, S, a, sign, k_y, gP, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None):
         self.nfe += 1
         self._gather(S)
+        self._produce(gP)
 
-    def vjp_phase2(self, y, t, gP, k_a, gtheta):
+    def vjp_phase2(self, y, t, gP, k_a, gtheta, a0=None, kprev=(), coefs=(), coef_self=0.0, a_next=None):
         gtheta.zero_()
         self._gather(gP)
 
@@ -107,11 +131,15 @@ class RecKernel(parallel.HaloKernelMixin, RecBase):
     def reduce_small(self, t):
         return t
 
+    def _push_fusable(self):
+        return True
 
-def record_program(proto_cls, side, method, step_size, n_steps, n_slots=8):
+
+def record_program(proto_cls, mode, method, step_size, n_steps, n_slots=8):
     prog = []
+    side = mode == "p2p-async"
     proto = proto_cls(n_slots, side, prog)
-    plan = types.SimpleNamespace(mode="p2p-async" if side else "p2p", world=4, split=None, n_rows=10, n_global=40,
+    plan = types.SimpleNamespace(mode=mode, world=4, split=None, n_rows=10, n_global=40,
                                  halo=types.SimpleNamespace(n_halo=3), halo_t=types.SimpleNamespace(n_halo=3),
                                  group=None, comm_stream=None, peer_for=lambda d: proto)
     for _ in range(n_steps):
@@ -154,16 +182,20 @@ def simulate(prog, world, rng, max_ops=10 ** 7):
                     continue
             elif kind == "record":
                 events[r].add(op[1])
-            elif kind == "push":
+            elif kind == "rwrite":
                 epoch, slot = op[1], op[2]
                 for p in range(world):
                     if p == r:
                         continue
-                    if slot is not None:
-                        if slot in active[p]:
-                            return "rank %d pushed epoch %d into slot %d while rank %d gathers version %d" % (
-                                r, epoch, slot, p, active[p][slot])
-                        ver[p][(slot, r)] = epoch
+                    if slot in active[p]:
+                        return "rank %d stored epoch %d into slot %d while rank %d gathers version %d" % (
+                            r, epoch, slot, p, active[p][slot])
+                    ver[p][(slot, r)] = epoch
+            elif kind == "signal":
+                epoch = op[1]
+                for p in range(world):
+                    if p == r:
+                        continue
                     if flags[p][r] > epoch:
                         return "flag of rank %d at rank %d went back from %d to %d" % (r, p, flags[p][r], epoch)
                     flags[p][r] = epoch
@@ -190,11 +222,11 @@ def _no_cuda_combine(monkeypatch):
     monkeypatch.setattr(ops, "rk_combine", lambda y0, ks, cs, out=None: out)
 
 
-@pytest.mark.parametrize("side", [False, True])
+@pytest.mark.parametrize("mode", ["p2p", "p2p-async", "p2p-fused"])
 @pytest.mark.parametrize("method,step_size", [("rk4", None), ("rk4", 0.25), ("midpoint", 0.5), ("euler", 0.5)])
-def test_protocol_is_safe_under_random_interleaving(side, method, step_size):
-    prog, proto = record_program(RecProtocol, side, method, step_size, n_steps=3)
-    assert any(op[1] == "push" for op in prog)
+def test_protocol_is_safe_under_random_interleaving(mode, method, step_size):
+    prog, proto = record_program(RecProtocol, mode, method, step_size, n_steps=3)
+    assert any(op[1] == "rwrite" for op in prog) and any(op[1] == "signal" for op in prog)
     rng = random.Random(1234)
     for world in (2, 4):
         for _ in range(40):
@@ -205,8 +237,8 @@ def test_rk4_steady_state_needs_no_empty_exchange():
     """With the solver's buffer rotation (two gP buffers, fresh S per stage, round-robin slots) the hazard rule never
     has to insert an empty exchange: 12 exchanges per rk4 fwd+bwd step on grid [0, 1] (4 + 4 supports -- the adjoint's
     first stage reuses the support of f(t1) -- and 4 masked adjoints), as PartitionedPlan.halo_bytes_per_step counts."""
-    for side in (False, True):
-        prog, proto = record_program(RecProtocol, side, "rk4", None, n_steps=4)
+    for mode in ("p2p", "p2p-async", "p2p-fused"):
+        prog, proto = record_program(RecProtocol, mode, "rk4", None, n_steps=4)
         assert proto.n_empty == 0
         assert proto.track.issued == 4 * 12
 
@@ -217,6 +249,7 @@ def _single_buffer_program(proto_cls, side, rounds=6):
     buf = proto.new(1)
     for _ in range(rounds):
         e = proto.push(object(), buf)
+        buf.version = e
         proto.wait(e)
         proto.note_read(buf)
         prog.append(("main", "gather_begin", buf.slot, buf.version))
