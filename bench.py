@@ -65,18 +65,22 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples nvidia-smi clocks / throttle reasons.  Started before the warm-up (nvidia-smi takes a few hundred ms to
+    produce its first row); ``mark_begin`` / ``mark_end`` bracket the timed region and the summary uses the rows that
+    fall inside it -- or, when the region is shorter than the sampling period, the rows of the warm-up that ran the
+    same workload right before it (said so in ``window``)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index=0, period_ms=100):
+        self.rows, self.proc, self.index, self.period_ms = [], None, index, period_ms
+        self.t_load = self.t0 = self.t1 = None
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -86,10 +90,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def __exit__(self, *exc):
+    def mark_load(self):
+        self.t_load = time.perf_counter()
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
         if self.proc:
+            time.sleep(self.period_ms / 1e3)      # let the row of the last interval arrive
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -97,21 +111,33 @@ class ClockSampler:
                 pass
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
+
+        def collect(lo, hi):
+            sm, mx, reasons = [], [], set()
+            for ts, r in self.rows:
+                if lo is not None and not (lo <= ts <= hi):
+                    continue
+                try:
+                    sm.append(float(r[0]))
+                    mx.append(float(r[1]))
+                    for nm, v in zip(names, r[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nm)
+                except Exception:
+                    continue
+            return sm, mx, reasons
+
+        window = "timed region"
+        sm, mx, reasons = collect(self.t0, (self.t1 or 0) + 2 * self.period_ms / 1e3) if self.t0 is not None else ([], [], set())
+        if len(sm) < 2 and self.t_load is not None:
+            window = "warm-up + timed region (same workload; the timed region is shorter than two sampling periods)"
+            sm, mx, reasons = collect(self.t_load, (self.t1 or time.perf_counter()) + 2 * self.period_ms / 1e3)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": "no nvidia-smi rows"}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -276,8 +302,12 @@ def run_ours(a):
             dist.barrier()
             torch.cuda.synchronize()
 
+    clk = ClockSampler(local).start()
     blk.nfe = 0
-    for _ in range(max(a.warmup, 3)):
+    step(x_dev.detach())                         # first step: allocator growth, lazy kernel attributes
+    sync()
+    clk.mark_load()
+    for _ in range(max(a.warmup, 3) - 1):
         step(x_dev.detach())
     sync()
     nfe_per_step = blk.nfe // max(a.warmup, 3)
@@ -288,13 +318,15 @@ def run_ours(a):
     lib.gode_profile_enable(1)
     launches0 = lib.gode_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        sync()
-        ev0.record()
-        for _ in range(a.steps):
-            loss = step(x_dev.detach())
-        ev1.record()
-        sync()
+    sync()
+    clk.mark_begin()
+    ev0.record()
+    for _ in range(a.steps):
+        loss = step(x_dev.detach())
+    ev1.record()
+    sync()
+    clk.mark_end()
+    clk.stop()
     ms = ev0.elapsed_time(ev1) / a.steps
     if world > 1:
         plan.check_peers()                       # a timed-out device-side wait on a peer's flag invalidates the run

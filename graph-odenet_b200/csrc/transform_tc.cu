@@ -111,6 +111,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Streams that are read once are latency-bound when only the registers of one staged tile are in flight per SM
+// (32 KB / ~1.5 us = 3 TB/s over 148 SMs -- what these kernels measured).  Asking L2 for the lines of later tiles costs
+// no registers and turns the eventual loads into L2 hits.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ float tf32_hi(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -327,6 +332,234 @@ k_rows_tc(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
   if (warp == 0) tmem_dealloc(tmem_d, D);
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_rows_ws: the same product as k_rows_tc, warp-specialised so that the three phases of a tile overlap:
+//   warps 0-3 (producers): HBM -> registers (two quarter-K stages ahead) -> normalise / split -> shared memory;
+//                          thread 0 issues the MMAs of a stage as soon as the four warps have stored it;
+//   tensor core          : 4 quarter-K stages x (K/8 steps) x 3 passes into one of TWO TMEM accumulators;
+//   warps 4-7 (epilogue) : previous tile's accumulator -> registers -> (+rowvec) -> staging -> full-sector row stores
+//                          (and, MODE 0 with a push route, the peers' halo tails over NVLink).
+// A stage is released by the tcgen05.commit of the MMAs that read it, an accumulator by the epilogue warps once
+// they have read it out, so the tensor pipe, the shared-memory stores and the HBM streams of consecutive tiles run
+// concurrently instead of back to back as in k_rows_tc.
+// Shared memory: B hi|lo (2 x D*D*4) + 2 A stages x (hi|lo) of 128 rows x 32 channels (64 KB) + 32 KB staging.
+// ------------------------------------------------------------------------------------------------
+namespace tc {
+__device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+}  // namespace tc
+
+template <int D, int CPG, int MODE>
+__global__ void __launch_bounds__(tc::THREADS, 1)
+k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, const float* __restrict__ W /*[D+1, D]*/,
+          const float* __restrict__ gamma, const float* __restrict__ beta, float t, float eps, int passes,
+          const gode_push_route_t push, const int pf_tiles /*L2 prefetch distance in tiles of this CTA (0: off)*/) {
+  using namespace tc;
+  static_assert(D == 128, "k_rows_ws is laid out for 128 channels");
+  constexpr int KQ = 32;                        // channels per A stage (a quarter of K)
+  constexpr int NQ = D / KQ;                    // stages per tile
+  constexpr int NI = 8;                         // warp-instructions (8 rows x 4 chunks) per producer warp per stage
+  constexpr uint32_t RSB = D * 32;              // 8-row-group stride of the B tile (full K)
+  constexpr uint32_t RSA = KQ * 32;             // 8-row-group stride of an A stage
+  constexpr uint32_t B_BYTES = D * D * 4;
+  constexpr uint32_t A_BYTES = 128 * KQ * 4;    // one of hi / lo of one stage
+  constexpr uint32_t STG_BYTES = 128 * (D / 2) * 4;   // staging: 128 rows x half of the columns
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sBhi = smem;
+  unsigned char* sBlo = smem + B_BYTES;
+  unsigned char* sA = smem + 2 * B_BYTES;                 // stage s: hi at sA + s*2*A_BYTES, lo right behind it
+  float* stage = reinterpret_cast<float*>(sA + 4 * A_BYTES);
+  float* sRow = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(stage) + STG_BYTES);   // [D] rowvec
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + D);   // [0,1] a_empty, [2,3] acc_full, [4,5] acc_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n_tiles = (n_rows + 127) / 128;
+  if ((int64_t)blockIdx.x >= n_tiles) return;
+  const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  // ---- one-time setup (all 8 warps): barriers, TMEM (two accumulators), B operand, row vector ----------------
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 1);
+    mbar_init(&bars[4], 128);
+    mbar_init(&bars[5], 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 2 * D);
+  const float* W1 = W + D;
+  for (int n = tid; n < D; n += THREADS) {
+    float r = 0.f;
+    if (MODE == 0) {
+      r = t * __ldg(W + n);
+      for (int k = 0; k < D; ++k) r = fmaf(__ldg(beta + k), __ldg(W1 + (int64_t)k * D + n), r);
+    }
+    sRow[n] = r;
+  }
+  for (int g = warp; g < (D / 8) * (D / 16); g += THREADS / 32) {
+    const int ng = g / (D / 16), cg = g % (D / 16);
+    const int n = ng * 8 + (lane & 7), kc = cg * 4 + (lane >> 3);
+    float4 b;
+    if (MODE == 0) {
+      const int k = kc * 4;
+      b.x = __ldg(gamma + k) * __ldg(W1 + (int64_t)k * D + n);
+      b.y = __ldg(gamma + k + 1) * __ldg(W1 + (int64_t)(k + 1) * D + n);
+      b.z = __ldg(gamma + k + 2) * __ldg(W1 + (int64_t)(k + 2) * D + n);
+      b.w = __ldg(gamma + k + 3) * __ldg(W1 + (int64_t)(k + 3) * D + n);
+    } else {
+      b = __ldg(reinterpret_cast<const float4*>(W1 + (int64_t)n * D + kc * 4));
+    }
+    float4 hi, lo;
+    split4(b, hi, lo);
+    const uint32_t off = ng * RSB + kc * 128 + (lane & 7) * 16;
+    *reinterpret_cast<float4*>(sBhi + off) = hi;
+    *reinterpret_cast<float4*>(sBlo + off) = lo;
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t IDESC = make_idesc(128, D, false, false);
+
+  if (warp < 4) {
+    // =============================== producers + MMA issue ===============================================
+    const uint32_t bHi = smem_u32(sBhi), bLo = smem_u32(sBlo);
+    const int64_t n_steps = my_tiles * NQ;
+    float4 raw[2][NI];
+    auto load_raw = [&](float4 (&r)[NI], int64_t step) {
+      const int64_t tile = blockIdx.x + (step / NQ) * (int64_t)gridDim.x;
+      const int q = static_cast<int>(step % NQ);
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int g = warp * NI + i;                 // 0..31: 16 row groups x 2 chunk groups
+        const int rg = g >> 1, cg = g & 1;
+        const int64_t row = tile * 128 + rg * 8 + (lane & 7);
+        const int kc = cg * 4 + (lane >> 3);
+        r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (step < n_steps && row < n_rows) r[i] = __ldcs(reinterpret_cast<const float4*>(X + row * D + q * KQ + kc * 4));
+        if (pf_tiles > 0 && step + pf_tiles * NQ < n_steps) {   // same bytes of the tile pf_tiles visits ahead
+          const int64_t prow = row + pf_tiles * (int64_t)gridDim.x * 128;
+          if (prow < n_rows) prefetch_l2(X + prow * D + q * KQ + kc * 4);
+        }
+      }
+    };
+    auto store_stage = [&](const float4 (&r)[NI], int s) {
+      unsigned char* aHi = sA + (size_t)s * 2 * A_BYTES;
+      unsigned char* aLo = aHi + A_BYTES;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int g = warp * NI + i;
+        const int rg = g >> 1, cg = g & 1;
+        const int kc = cg * 4 + (lane >> 3);
+        float4 hi, lo;
+        split4(normalize4<CPG>(r[i], eps), hi, lo);
+        const uint32_t off = rg * RSA + kc * 128 + (lane & 7) * 16;
+        *reinterpret_cast<float4*>(aHi + off) = hi;
+        *reinterpret_cast<float4*>(aLo + off) = lo;
+      }
+    };
+    auto do_step = [&](float4 (&r)[NI], int64_t step) {
+      const int s = static_cast<int>(step & 1);
+      const int64_t use = step >> 1;               // how many times stage s has been filled before
+      if (use >= 1) mbar_wait(&bars[s], static_cast<uint32_t>((use - 1) & 1));   // MMAs of its previous contents retired
+      store_stage(r, s);
+      load_raw(r, step + 2);                       // two stages ahead, into the registers just consumed
+      fence_async_smem();
+      tc_fence_before();
+      bar_sync_named(1, 128);
+      if (tid == 0) {
+        const int64_t it = step / NQ;
+        const int q = static_cast<int>(step % NQ);
+        const int b = static_cast<int>(it & 1);
+        if (q == 0 && it >= 2) mbar_wait(&bars[4 + b], static_cast<uint32_t>(((it >> 1) - 1) & 1));   // epilogue has read it out
+        tc_fence_after();
+        const uint32_t aHi = smem_u32(sA + (size_t)s * 2 * A_BYTES), aLo = aHi + A_BYTES;
+        const uint32_t tmem_d = tmem_base + b * D;
+#pragma unroll
+        for (int ks = 0; ks < KQ / 8; ++ks) {
+          const uint32_t kb = q * (KQ / 8) + ks;
+          const uint64_t da_hi = make_desc(aHi + ks * 256, 128, RSA), da_lo = make_desc(aLo + ks * 256, 128, RSA);
+          const uint64_t db_hi = make_desc(bHi + kb * 256, 128, RSB), db_lo = make_desc(bLo + kb * 256, 128, RSB);
+          mma_tf32(tmem_d, da_hi, db_hi, IDESC, (q | ks) != 0 ? 1u : 0u);
+          if (passes == 3) {
+            mma_tf32(tmem_d, da_lo, db_hi, IDESC, 1u);
+            mma_tf32(tmem_d, da_hi, db_lo, IDESC, 1u);
+          }
+        }
+        mma_commit(&bars[s]);                      // stage s is free once these MMAs have read it
+        if (q == NQ - 1) mma_commit(&bars[2 + b]); // accumulator b is complete
+      }
+    };
+    load_raw(raw[0], 0);
+    load_raw(raw[1], 1);
+    for (int64_t step = 0; step < n_steps; step += 2) {   // n_steps is a multiple of NQ = 4
+      do_step(raw[0], step);
+      do_step(raw[1], step + 1);
+    }
+  } else {
+    // =============================== epilogue ==============================================================
+    constexpr int HC = D / 2;                      // columns per staging pass
+    constexpr int CHH = HC / 4;                    // 16-byte chunks per staged half row (16)
+    const int q = warp & 3;
+    const int et = tid - 128;                      // 0..127
+    const int row = q * 32 + lane;                 // TMEM lane = row of the tile
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = blockIdx.x + it * (int64_t)gridDim.x;
+      const int b = static_cast<int>(it & 1);
+      mbar_wait(&bars[2 + b], static_cast<uint32_t>((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + b * D + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int cb = 0; cb < HC; cb += 32) {
+          float v[32];
+          tmem_ld32(tmem_d + h * HC + cb, v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int col = h * HC + cb + j;
+            const int chunk = ((cb + j) >> 2) ^ (row & (CHH - 1));
+            float4 o = make_float4(v[j] + sRow[col], v[j + 1] + sRow[col + 1], v[j + 2] + sRow[col + 2], v[j + 3] + sRow[col + 3]);
+            *reinterpret_cast<float4*>(stage + row * HC + chunk * 4) = o;
+          }
+        }
+        if (h == 1) {                              // the accumulator has been read out completely
+          tc_fence_before();
+          mbar_arrive(&bars[4 + b]);
+        }
+        bar_sync_named(2, 128);
+        // 128 rows x 16 chunks: a warp instruction stores two 256-byte half rows
+#pragma unroll 4
+        for (int i = 0; i < (128 * CHH) / 128; ++i) {
+          const int idx = i * 128 + et;
+          const int r = idx / CHH, c = idx % CHH;
+          const int64_t grow = tile * 128 + r;
+          if (grow < n_rows) {
+            const float4 o = *reinterpret_cast<const float4*>(stage + r * HC + ((c ^ (r & (CHH - 1))) * 4));
+            __stcs(reinterpret_cast<float4*>(Out + grow * D + h * HC + c * 4), o);
+            if (MODE == 0 && push.ptr) {           // fused halo push over NVLink (posted stores)
+              const int p1 = __ldg(push.ptr + grow + 1);
+              for (int e = __ldg(push.ptr + grow); e < p1; ++e) {
+                const int64_t ent = __ldg(push.ent + e);
+                *reinterpret_cast<float4*>(push.base[ent >> 40] + (ent & 0xFFFFFFFFFFll) * D + h * HC + c * 4) = o;
+              }
+            }
+          }
+        }
+        bar_sync_named(2, 128);                    // staging is reused by the next pass
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 2 * D);
+}
+
 // GODE_TC: bit 0 = transform, bit 1 = input gradient, bit 2 = weight gradient on tcgen05 (default all)
 static int tc_mask() {
   static const int m = [] {
@@ -345,7 +578,8 @@ static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 template <int D, int CPG>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restrict__ G, float* __restrict__ partial /*[grid][D][D]*/,
-           float* __restrict__ cs_partial /*[grid][D]: column sums of G over this CTA's rows*/, float eps, int passes) {
+           float* __restrict__ cs_partial /*[grid][D]: column sums of G over this CTA's rows*/, float eps, int passes,
+           const int pf_chunks /*L2 prefetch distance in chunks of this CTA (0: off)*/) {
   using namespace tc;
   static_assert(D == 128, "the accumulator uses all 128 TMEM lanes");
   // Both operands are [rows, D] row-major in HBM but the reduction runs over rows, so they are transposed on the
@@ -392,6 +626,11 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
       if (row < n_rows) {
         ra[i] = __ldcs(reinterpret_cast<const float4*>(Yin + row * D + kc * 4));
         rb[i] = __ldcs(reinterpret_cast<const float4*>(G + row * D + kc * 4));
+      }
+      const int64_t prow = row + pf_chunks * (int64_t)gridDim.x * RC;
+      if (pf_chunks > 0 && prow < n_rows) {
+        prefetch_l2(Yin + prow * D + kc * 4);
+        prefetch_l2(G + prow * D + kc * 4);
       }
     }
   };
@@ -554,11 +793,43 @@ int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, float
     configured = true;
   }
   const int passes = f->precision == GODE_PREC_TF32 ? 1 : 3;
-  k_wgrad_tc<D, 4><<<grid, tc::THREADS, smem, st>>>(f->A.n_rows, y, gS, ws, cs_partial, f->gn_eps, passes);
+  static const int pf = [] {
+    const char* e = getenv("GODE_TC_PREFETCH");   // in units of 128 rows per CTA, as for k_rows_ws (default 2, 0 = off)
+    return (e ? atoi(e) : 2) * 4;
+  }();
+  k_wgrad_tc<D, 4><<<grid, tc::THREADS, smem, st>>>(f->A.n_rows, y, gS, ws, cs_partial, f->gn_eps, passes, pf);
   GODE_LAUNCH_CHECK();
   k_wgrad_cs<<<1, D, 0, st>>>(grid, D, cs_partial, cs);
   GODE_LAUNCH_CHECK();
   k_wgrad_finish<<<(D * D + 255) / 256, 256, 0, st>>>(grid, D, ws, f->gamma, f->beta, cs, gW1);
+  GODE_LAUNCH_CHECK();
+  return GODE_OK;
+}
+
+// GODE_ROWS_WS: 1 (default) = warp-specialised k_rows_ws for d = 128, 0 = the single-pipeline k_rows_tc
+static bool rows_ws_enabled() {
+  static const int m = [] {
+    const char* e = getenv("GODE_ROWS_WS");
+    return e ? atoi(e) : 1;
+  }();
+  return m != 0;
+}
+
+template <int CPG, int MODE>
+static int launch_rows_ws(int64_t n_rows, const float* X, float* Out, const float* W, const float* gamma, const float* beta,
+                          float t, float eps, int passes, cudaStream_t st, const gode_push_route_t& pr, int grid) {
+  constexpr int D = 128;
+  constexpr size_t smem = 2 * (size_t)D * D * 4 + 4 * (size_t)128 * 32 * 4 + (size_t)128 * (D / 2) * 4 + D * 4 + 128;
+  static bool configured = false;
+  if (!configured) {
+    GODE_CHECK_CUDA(cudaFuncSetAttribute(k_rows_ws<D, CPG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  static const int pf = [] {
+    const char* e = getenv("GODE_TC_PREFETCH");   // L2 prefetch distance in tiles per CTA (default 2, 0 = off)
+    return e ? atoi(e) : 2;
+  }();
+  k_rows_ws<D, CPG, MODE><<<grid, tc::THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf);
   GODE_LAUNCH_CHECK();
   return GODE_OK;
 }
@@ -578,6 +849,7 @@ static int launch_rows_tc(int64_t n_rows, const float* X, float* Out, const floa
   gode_push_route_t pr;
   if (push) pr = *push;
   else memset(&pr, 0, sizeof(pr));
+  if (D == 128 && rows_ws_enabled()) return launch_rows_ws<CPG, MODE>(n_rows, X, Out, W, gamma, beta, t, eps, passes, st, pr, grid);
   k_rows_tc<D, CPG, MODE><<<grid, tc::THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr);
   GODE_LAUNCH_CHECK();
   return GODE_OK;

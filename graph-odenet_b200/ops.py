@@ -378,7 +378,46 @@ class GroupNormFn(torch.autograd.Function):
         return dx, dg, db, None, None
 
 
+class SparseInputGraphConvFn(torch.autograd.Function):
+    """``spmm(adj, mm(X, W)) + b`` for a SPARSE feature matrix X: the reference densifies its
+    bag-of-words features (GCN/utils.py:192, ~1 % non-zero) and runs a dense [N, F] x [F, h] product
+    (GCN/layers.py:32); here CSR(X) W is the same gather kernel as the adjacency product, with W as the gathered
+    operand, and the weight gradient is CSR(X)^T (A_hat^T g).  X is a constant: it gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, plan_x, plan, relu):
+        w = _rowmajor(weight, "weight")
+        support = spmm(plan_x, w)
+        out = spmm(plan, support, bias=bias, relu=relu)
+        ctx.plan_x, ctx.plan, ctx.relu, ctx.has_bias = plan_x, plan, relu, bias is not None
+        ctx.save_for_backward(out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        g = _rowmajor(g, "grad")
+        if ctx.relu:
+            g = relu_mask(g, out)
+        gb = colsum(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        gw = None
+        if ctx.needs_input_grad[0]:
+            gs = spmm(ctx.plan, g, transpose=True)                   # A^T g
+            gw = spmm(ctx.plan_x, gs, transpose=True)                # X^T (A^T g)
+        return gw, gb, None, None, None
+
+
+def _is_sparse(x):
+    return isinstance(x, torch.Tensor) and x.layout == torch.sparse_coo
+
+
 def graph_conv(x, adj, weight, bias, relu=False):
+    """``x``: dense [N, F] features as the reference passes them, or -- extension -- a sparse COO tensor / a GraphPlan
+    of the feature matrix."""
+    if _is_sparse(x) or isinstance(x, GraphPlan):
+        if _is_sparse(x) and x.requires_grad:
+            raise ValueError("sparse input features are constants: requires_grad is not supported")
+        return SparseInputGraphConvFn.apply(weight, bias, plan_for(x), plan_for(adj), relu)
     return GraphConvFn.apply(x, weight, bias, plan_for(adj), relu)
 
 

@@ -200,6 +200,36 @@ def test_graph_convolution_golden(dev):
     G.assert_close(lay.bias.grad, g["gc/grad_bias"], **TOL, what="grad_bias")
 
 
+def test_graph_convolution_sparse_features(dev):
+    """a sparse bag-of-words feature matrix (about 1 % non-zero, row-normalised as GCN/utils.py:185)
+    through CSR(X) W must give what the reference's dense torch.mm(input, W) gives (oracle: gcn_ref on the dense X)."""
+    layers = _pkg()[3]
+    adj_cpu = G.cora_adj()
+    n, f, h = 2708, 1433, 16
+    gen = torch.Generator().manual_seed(11)
+    dense = (torch.rand(n, f, generator=gen) < 0.0127).float()
+    dense[:, 0] = 1.0                                             # no empty rows
+    dense = dense / dense.sum(1, keepdim=True)
+    lay = layers.GraphConvolution(f, h)
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in lay.state_dict().items()}
+    gy = G.rnd(3, n, h)
+    want = torch.relu(gcn_ref.graph_convolution(dense, adj_cpu, p["weight"], p["bias"]))
+    want.backward(gy)
+    lay = lay.to(dev)
+    outs = []
+    for x in (dense.to(dev), dense.to_sparse().to(dev)):          # dense path, sparse path
+        lay.zero_grad()
+        y = lay(x, adj_cpu.to(dev), relu=True)
+        y.backward(gy.to(dev))
+        outs.append((y.detach(), lay.weight.grad.clone(), lay.bias.grad.clone()))
+    for y, gw, gb in outs:
+        G.assert_close(y, want, **TOL, what="out")
+        G.assert_close(gw, p["weight"].grad, **TOL, what="grad_weight")
+        G.assert_close(gb, p["bias"].grad, **TOL, what="grad_bias")
+    with pytest.raises(ValueError):
+        lay(dense.to_sparse().to(dev).requires_grad_(True), adj_cpu.to(dev))
+
+
 @pytest.mark.parametrize("d", [16, 128])
 def test_odefunc_golden(d, dev):
     """ODEfunc.forward called directly (un-fused module path) and the fused kernels, against the reference."""
