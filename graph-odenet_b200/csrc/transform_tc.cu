@@ -334,10 +334,12 @@ k_rows_tc(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
 
 // ------------------------------------------------------------------------------------------------
 // k_rows_ws: the same product as k_rows_tc, warp-specialised so that the three phases of a tile overlap:
-//   warps 0-3 (producers): HBM -> registers (two quarter-K stages ahead) -> normalise / split -> shared memory;
-//                          thread 0 issues the MMAs of a stage as soon as the four warps have stored it;
-//   tensor core          : 4 quarter-K stages x (K/8 steps) x 3 passes into one of TWO TMEM accumulators;
-//   warps 4-7 (epilogue) : previous tile's accumulator -> registers -> (+rowvec) -> staging -> full-sector row stores
+//   warps 0-7 (producers): HBM -> registers (two quarter-K stages ahead) -> normalise / split -> shared memory,
+//                          then arrive on the stage's "full" mbarrier (ncu: four producer warps were issue-bound
+//                          on the conversion and everything else waited for them);
+//   warp 12 (one thread) : waits for a full stage, issues its K/8 steps x 3 passes of tcgen05.mma into one of TWO
+//                          TMEM accumulators, commits the stage's "empty" barrier;
+//   warps 8-11 (epilogue): previous tile's accumulator -> registers -> (+rowvec) -> staging -> full-sector row stores
 //                          (and, MODE 0 with a push route, the peers' halo tails over NVLink).
 // A stage is released by the tcgen05.commit of the MMAs that read it, an accumulator by the epilogue warps once
 // they have read it out, so the tensor pipe, the shared-memory stores and the HBM streams of consecutive tiles run
@@ -351,8 +353,26 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 }  // namespace tc
 
+namespace tc {
+constexpr int WS_PRODUCERS = 256;               // warps 0-7
+constexpr int WS_THREADS = WS_PRODUCERS + 128 + 32;   // + epilogue warps 8-11 + MMA warp 12
+
+// GroupNorm of one 16-byte chunk with rsqrtf (MUFU.RSQ, <= 2 ulp): the producers are issue-bound, and
+// 1 / sqrtf costs ~15 instructions per chunk more for digits the 1e-5 bar does not see
+template <int CPG>
+__device__ __forceinline__ float4 normalize4_fast(float4 x, float eps) {
+  if (CPG == 4) {
+    const float mean = (x.x + x.y + x.z + x.w) * 0.25f;
+    const float a = x.x - mean, b = x.y - mean, c = x.z - mean, d = x.w - mean;
+    const float rstd = rsqrtf((a * a + b * b + c * c + d * d) * 0.25f + eps);
+    return make_float4(a * rstd, b * rstd, c * rstd, d * rstd);
+  }
+  return normalize4<CPG>(x, eps);
+}
+}  // namespace tc
+
 template <int D, int CPG, int MODE>
-__global__ void __launch_bounds__(tc::THREADS, 1)
+__global__ void __launch_bounds__(tc::WS_THREADS, 1)
 k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, const float* __restrict__ W /*[D+1, D]*/,
           const float* __restrict__ gamma, const float* __restrict__ beta, float t, float eps, int passes,
           const gode_push_route_t push, const int pf_tiles /*L2 prefetch distance in tiles of this CTA (0: off)*/) {
@@ -360,7 +380,7 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
   static_assert(D == 128, "k_rows_ws is laid out for 128 channels");
   constexpr int KQ = 32;                        // channels per A stage (a quarter of K)
   constexpr int NQ = D / KQ;                    // stages per tile
-  constexpr int NI = 8;                         // warp-instructions (8 rows x 4 chunks) per producer warp per stage
+  constexpr int NI = 4;                         // warp-instructions (8 rows x 4 chunks) per producer warp per stage
   constexpr uint32_t RSB = D * 32;              // 8-row-group stride of the B tile (full K)
   constexpr uint32_t RSA = KQ * 32;             // 8-row-group stride of an A stage
   constexpr uint32_t B_BYTES = D * D * 4;
@@ -372,27 +392,29 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
   unsigned char* sA = smem + 2 * B_BYTES;                 // stage s: hi at sA + s*2*A_BYTES, lo right behind it
   float* stage = reinterpret_cast<float*>(sA + 4 * A_BYTES);
   float* sRow = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(stage) + STG_BYTES);   // [D] rowvec
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + D);   // [0,1] a_empty, [2,3] acc_full, [4,5] acc_empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + D);   // [0,1] a_full, [2,3] a_empty, [4,5] acc_full, [6,7] acc_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_tiles = (n_rows + 127) / 128;
   if ((int64_t)blockIdx.x >= n_tiles) return;
   const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
-  // ---- one-time setup (all 8 warps): barriers, TMEM (two accumulators), B operand, row vector ----------------
+  // ---- one-time setup (all warps): barriers, TMEM (two accumulators), B operand, row vector ------------------
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    mbar_init(&bars[0], WS_PRODUCERS);
+    mbar_init(&bars[1], WS_PRODUCERS);
     mbar_init(&bars[2], 1);
     mbar_init(&bars[3], 1);
-    mbar_init(&bars[4], 128);
-    mbar_init(&bars[5], 128);
+    mbar_init(&bars[4], 1);
+    mbar_init(&bars[5], 1);
+    mbar_init(&bars[6], 128);
+    mbar_init(&bars[7], 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, 2 * D);
   const float* W1 = W + D;
-  for (int n = tid; n < D; n += THREADS) {
+  for (int n = tid; n < D; n += WS_THREADS) {
     float r = 0.f;
     if (MODE == 0) {
       r = t * __ldg(W + n);
@@ -400,7 +422,7 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
     }
     sRow[n] = r;
   }
-  for (int g = warp; g < (D / 8) * (D / 16); g += THREADS / 32) {
+  for (int g = warp; g < (D / 8) * (D / 16); g += WS_THREADS / 32) {
     const int ng = g / (D / 16), cg = g % (D / 16);
     const int n = ng * 8 + (lane & 7), kc = cg * 4 + (lane >> 3);
     float4 b;
@@ -425,30 +447,35 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t IDESC = make_idesc(128, D, false, false);
+  const int64_t n_steps = my_tiles * NQ;
 
-  if (warp < 4) {
-    // =============================== producers + MMA issue ===============================================
-    const uint32_t bHi = smem_u32(sBhi), bLo = smem_u32(sBlo);
-    const int64_t n_steps = my_tiles * NQ;
+  if (warp < 8) {
+    // =============================== producers ============================================================
     float4 raw[2][NI];
     auto load_raw = [&](float4 (&r)[NI], int64_t step) {
       const int64_t tile = blockIdx.x + (step / NQ) * (int64_t)gridDim.x;
       const int q = static_cast<int>(step % NQ);
+      const bool live = step < n_steps;
+      const bool pf = pf_tiles > 0 && step + pf_tiles * NQ < n_steps && (lane >> 3) == 0;   // one request per row line
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int g = warp * NI + i;                 // 0..31: 16 row groups x 2 chunk groups
         const int rg = g >> 1, cg = g & 1;
         const int64_t row = tile * 128 + rg * 8 + (lane & 7);
         const int kc = cg * 4 + (lane >> 3);
+        const float* src = X + row * D + q * KQ + kc * 4;
         r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (step < n_steps && row < n_rows) r[i] = __ldcs(reinterpret_cast<const float4*>(X + row * D + q * KQ + kc * 4));
-        if (pf_tiles > 0 && step + pf_tiles * NQ < n_steps) {   // same bytes of the tile pf_tiles visits ahead
+        if (live && row < n_rows) r[i] = __ldcs(reinterpret_cast<const float4*>(src));
+        if (pf) {                                     // same bytes of the tile pf_tiles visits ahead
           const int64_t prow = row + pf_tiles * (int64_t)gridDim.x * 128;
-          if (prow < n_rows) prefetch_l2(X + prow * D + q * KQ + kc * 4);
+          if (prow < n_rows) prefetch_l2(src + pf_tiles * (int64_t)gridDim.x * 128 * D);
         }
       }
     };
-    auto store_stage = [&](const float4 (&r)[NI], int s) {
+    auto do_step = [&](float4 (&r)[NI], int64_t step) {
+      const int s = static_cast<int>(step & 1);
+      const int64_t use = step >> 1;               // how many times stage s has been filled before
+      if (use >= 1) mbar_wait(&bars[2 + s], static_cast<uint32_t>((use - 1) & 1));   // MMAs of its previous contents retired
       unsigned char* aHi = sA + (size_t)s * 2 * A_BYTES;
       unsigned char* aLo = aHi + A_BYTES;
 #pragma unroll
@@ -457,26 +484,32 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
         const int rg = g >> 1, cg = g & 1;
         const int kc = cg * 4 + (lane >> 3);
         float4 hi, lo;
-        split4(normalize4<CPG>(r[i], eps), hi, lo);
+        split4(normalize4_fast<CPG>(r[i], eps), hi, lo);
         const uint32_t off = rg * RSA + kc * 128 + (lane & 7) * 16;
         *reinterpret_cast<float4*>(aHi + off) = hi;
         *reinterpret_cast<float4*>(aLo + off) = lo;
       }
-    };
-    auto do_step = [&](float4 (&r)[NI], int64_t step) {
-      const int s = static_cast<int>(step & 1);
-      const int64_t use = step >> 1;               // how many times stage s has been filled before
-      if (use >= 1) mbar_wait(&bars[s], static_cast<uint32_t>((use - 1) & 1));   // MMAs of its previous contents retired
-      store_stage(r, s);
       load_raw(r, step + 2);                       // two stages ahead, into the registers just consumed
       fence_async_smem();
-      tc_fence_before();
-      bar_sync_named(1, 128);
-      if (tid == 0) {
+      mbar_arrive(&bars[s]);                       // a_full[s]: 256 arrivals
+    };
+    load_raw(raw[0], 0);
+    load_raw(raw[1], 1);
+    for (int64_t step = 0; step < n_steps; step += 2) {   // n_steps is a multiple of NQ = 4
+      do_step(raw[0], step);
+      do_step(raw[1], step + 1);
+    }
+  } else if (warp == 12) {
+    // =============================== MMA issue (one thread) ===============================================
+    if (lane == 0) {
+      const uint32_t bHi = smem_u32(sBhi), bLo = smem_u32(sBlo);
+      for (int64_t step = 0; step < n_steps; ++step) {
+        const int s = static_cast<int>(step & 1);
         const int64_t it = step / NQ;
         const int q = static_cast<int>(step % NQ);
         const int b = static_cast<int>(it & 1);
-        if (q == 0 && it >= 2) mbar_wait(&bars[4 + b], static_cast<uint32_t>(((it >> 1) - 1) & 1));   // epilogue has read it out
+        if (q == 0 && it >= 2) mbar_wait(&bars[6 + b], static_cast<uint32_t>(((it >> 1) - 1) & 1));   // epilogue has read it out
+        mbar_wait(&bars[s], static_cast<uint32_t>((step >> 1) & 1));                                 // stage s is stored
         tc_fence_after();
         const uint32_t aHi = smem_u32(sA + (size_t)s * 2 * A_BYTES), aLo = aHi + A_BYTES;
         const uint32_t tmem_d = tmem_base + b * D;
@@ -491,29 +524,25 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
             mma_tf32(tmem_d, da_hi, db_lo, IDESC, 1u);
           }
         }
-        mma_commit(&bars[s]);                      // stage s is free once these MMAs have read it
-        if (q == NQ - 1) mma_commit(&bars[2 + b]); // accumulator b is complete
+        mma_commit(&bars[2 + s]);                    // stage s is free once these MMAs have read it
+        if (q == NQ - 1) mma_commit(&bars[4 + b]);   // accumulator b is complete
       }
-    };
-    load_raw(raw[0], 0);
-    load_raw(raw[1], 1);
-    for (int64_t step = 0; step < n_steps; step += 2) {   // n_steps is a multiple of NQ = 4
-      do_step(raw[0], step);
-      do_step(raw[1], step + 1);
     }
   } else {
-    // =============================== epilogue ==============================================================
+    // =============================== epilogue (warps 8-11) =================================================
     constexpr int HC = D / 2;                      // columns per staging pass
     constexpr int CHH = HC / 4;                    // 16-byte chunks per staged half row (16)
-    const int q = warp & 3;
-    const int et = tid - 128;                      // 0..127
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int et = tid - WS_PRODUCERS;             // 0..127
     const int row = q * 32 + lane;                 // TMEM lane = row of the tile
+    const bool do_push = MODE == 0 && push.ptr != nullptr;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = blockIdx.x + it * (int64_t)gridDim.x;
       const int b = static_cast<int>(it & 1);
-      mbar_wait(&bars[2 + b], static_cast<uint32_t>((it >> 1) & 1));
+      mbar_wait(&bars[4 + b], static_cast<uint32_t>((it >> 1) & 1));
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + b * D + (static_cast<uint32_t>(q * 32) << 16);
+      const bool full = tile * 128 + 128 <= n_rows;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -524,29 +553,49 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
           for (int j = 0; j < 32; j += 4) {
             const int col = h * HC + cb + j;
             const int chunk = ((cb + j) >> 2) ^ (row & (CHH - 1));
-            float4 o = make_float4(v[j] + sRow[col], v[j + 1] + sRow[col + 1], v[j + 2] + sRow[col + 2], v[j + 3] + sRow[col + 3]);
-            *reinterpret_cast<float4*>(stage + row * HC + chunk * 4) = o;
+            const float4 rv = *reinterpret_cast<const float4*>(sRow + col);
+            *reinterpret_cast<float4*>(stage + row * HC + chunk * 4) = make_float4(v[j] + rv.x, v[j + 1] + rv.y, v[j + 2] + rv.z, v[j + 3] + rv.w);
           }
         }
         if (h == 1) {                              // the accumulator has been read out completely
           tc_fence_before();
-          mbar_arrive(&bars[4 + b]);
+          mbar_arrive(&bars[6 + b]);
         }
         bar_sync_named(2, 128);
-        // 128 rows x 16 chunks: a warp instruction stores two 256-byte half rows
-#pragma unroll 4
-        for (int i = 0; i < (128 * CHH) / 128; ++i) {
-          const int idx = i * 128 + et;
-          const int r = idx / CHH, c = idx % CHH;
-          const int64_t grow = tile * 128 + r;
-          if (grow < n_rows) {
-            const float4 o = *reinterpret_cast<const float4*>(stage + r * HC + ((c ^ (r & (CHH - 1))) * 4));
-            __stcs(reinterpret_cast<float4*>(Out + grow * D + h * HC + c * 4), o);
-            if (MODE == 0 && push.ptr) {           // fused halo push over NVLink (posted stores)
-              const int p1 = __ldg(push.ptr + grow + 1);
-              for (int e = __ldg(push.ptr + grow); e < p1; ++e) {
-                const int64_t ent = __ldg(push.ent + e);
-                *reinterpret_cast<float4*>(push.base[ent >> 40] + (ent & 0xFFFFFFFFFFll) * D + h * HC + c * 4) = o;
+        // 128 rows x 16 chunks: a warp instruction stores two 256-byte half rows; 16 chunks per thread
+        float* obase = Out + (tile * 128) * D + h * HC;
+        if (full && !do_push) {
+#pragma unroll
+          for (int i0 = 0; i0 < 16; i0 += 8) {
+            float4 o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int idx = (i0 + i) * 128 + et;
+              const int r = idx / CHH, c = idx % CHH;
+              o[i] = *reinterpret_cast<const float4*>(stage + r * HC + ((c ^ (r & (CHH - 1))) * 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int idx = (i0 + i) * 128 + et;
+              const int r = idx / CHH, c = idx % CHH;
+              __stcs(reinterpret_cast<float4*>(obase + (int64_t)r * D + c * 4), o[i]);
+            }
+          }
+        } else {
+#pragma unroll 2
+          for (int i = 0; i < 16; ++i) {
+            const int idx = i * 128 + et;
+            const int r = idx / CHH, c = idx % CHH;
+            const int64_t grow = tile * 128 + r;
+            if (grow < n_rows) {
+              const float4 o = *reinterpret_cast<const float4*>(stage + r * HC + ((c ^ (r & (CHH - 1))) * 4));
+              __stcs(reinterpret_cast<float4*>(obase + (int64_t)r * D + c * 4), o);
+              if (do_push) {                       // fused halo push over NVLink (posted stores)
+                const int p1 = __ldg(push.ptr + grow + 1);
+                for (int e = __ldg(push.ptr + grow); e < p1; ++e) {
+                  const int64_t ent = __ldg(push.ent + e);
+                  *reinterpret_cast<float4*>(push.base[ent >> 40] + (ent & 0xFFFFFFFFFFll) * D + h * HC + c * 4) = o;
+                }
               }
             }
           }
@@ -576,7 +625,7 @@ static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 // P[i, o] = sum_r xhat(y)[r, i] * dS[r, o]      (weight gradient before the GroupNorm affine is re-applied)
 // ------------------------------------------------------------------------------------------------
 template <int D, int CPG>
-__global__ void __launch_bounds__(tc::THREADS, 1)
+__global__ void __launch_bounds__(tc::THREADS + 32, 1)
 k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restrict__ G, float* __restrict__ partial /*[grid][D][D]*/,
            float* __restrict__ cs_partial /*[grid][D]: column sums of G over this CTA's rows*/, float eps, int passes,
            const int pf_chunks /*L2 prefetch distance in chunks of this CTA (0: off)*/) {
@@ -593,8 +642,8 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
   constexpr int NI = ((RC / 8) * (D / 16)) / (THREADS / 32);   // warp-instructions per warp per operand
   extern __shared__ __align__(1024) unsigned char smem[];
   // stage b: [A_hi | A_lo | B_hi | B_lo] at smem + b * 4 * MAT
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * 4 * MAT);   // [0],[1]: stage free; [2]: all done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * 4 * MAT);   // [0],[1]: stage free; [2]: all done; [3],[4]: stage full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_chunks = (n_rows + RC - 1) / RC;
@@ -602,6 +651,8 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], THREADS);
+    mbar_init(&bars[4], THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, D);
@@ -610,6 +661,37 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
   constexpr uint32_t IDESC = make_idesc(D, D, false, false);
+  const int64_t my_chunks = (int64_t)blockIdx.x < n_chunks ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == THREADS / 32) {
+    // ---- MMA issue (one thread of the ninth warp): a staged chunk is multiplied as soon as the eight producer warps
+    // have arrived on its "full" barrier, so no producer ever waits for the issue (ncu: 16 % of the samples of the
+    // single-barrier version sat in __syncthreads behind the issuing warp)
+    if (lane == 0) {
+      for (int64_t it = 0; it < my_chunks; ++it) {
+        const int b = static_cast<int>(it & 1);
+        mbar_wait(&bars[3 + b], static_cast<uint32_t>((it >> 1) & 1));
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + (size_t)b * 4 * MAT);
+#pragma unroll
+        for (int s = 0; s < RC / 8; ++s) {
+          const uint32_t ko = s * 2 * LBO;   // 8 rows of K = two 16-byte chunks
+          const uint64_t a_hi = make_desc(base + ko, LBO, SBO), a_lo = make_desc(base + MAT + ko, LBO, SBO);
+          const uint64_t b_hi = make_desc(base + 2 * MAT + ko, LBO, SBO), b_lo = make_desc(base + 3 * MAT + ko, LBO, SBO);
+          mma_tf32(tmem_d, a_hi, b_hi, IDESC, (it | s) != 0 ? 1u : 0u);
+          if (passes == 3) {
+            mma_tf32(tmem_d, a_lo, b_hi, IDESC, 1u);
+            mma_tf32(tmem_d, a_hi, b_lo, IDESC, 1u);
+          }
+        }
+        mma_commit(&bars[b]);
+      }
+      mma_commit(&bars[2]);   // arrives when every MMA issued above has completed
+    }
+    tc_fence_before();
+    __syncthreads();
+    return;
+  }
 
   float4 ra[NI], rb[NI], cs_acc[NI];
 #pragma unroll
@@ -651,7 +733,7 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
       const int rg = g / (D / 16), cg = g % (D / 16);
       const int kc = cg * 4 + (lane >> 3);
       const int r = rg * 8 + (lane & 7);
-      float4 xa = normalize4<CPG>(ra[i], eps);
+      float4 xa = normalize4_fast<CPG>(ra[i], eps);
       if (chunk * RC + r >= n_rows) xa = make_float4(0.f, 0.f, 0.f, 0.f);   // xhat of a padding row is not zero by itself
       float4 hi, lo;
       split4(xa, hi, lo);
@@ -677,26 +759,8 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
     store_stage(b, chunk);
     if (chunk + gridDim.x < n_chunks) load_raw(chunk + gridDim.x);
     fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t base = smem_u32(smem + (size_t)b * 4 * MAT);
-#pragma unroll
-      for (int s = 0; s < RC / 8; ++s) {
-        const uint32_t ko = s * 2 * LBO;   // 8 rows of K = two 16-byte chunks
-        const uint64_t a_hi = make_desc(base + ko, LBO, SBO), a_lo = make_desc(base + MAT + ko, LBO, SBO);
-        const uint64_t b_hi = make_desc(base + 2 * MAT + ko, LBO, SBO), b_lo = make_desc(base + 3 * MAT + ko, LBO, SBO);
-        mma_tf32(tmem_d, a_hi, b_hi, IDESC, (it | s) != 0 ? 1u : 0u);
-        if (passes == 3) {
-          mma_tf32(tmem_d, a_lo, b_hi, IDESC, 1u);
-          mma_tf32(tmem_d, a_hi, b_lo, IDESC, 1u);
-        }
-      }
-      mma_commit(&bars[b]);
-    }
+    mbar_arrive(&bars[3 + b]);
   }
-  if (tid == 0) mma_commit(&bars[2]);   // arrives when every MMA issued above has completed
   mbar_wait(&bars[2], 0);
   tc_fence_after();
   {
@@ -736,7 +800,7 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
       const int kc = cg * 4 + (lane >> 3);
       if ((lane & 7) == 0) *reinterpret_cast<float4*>(scs + rg * D + kc * 4) = v;
     }
-    __syncthreads();
+    bar_sync_named(1, THREADS);
     if (tid < D) {
       float t = 0.f;
 #pragma unroll
@@ -797,7 +861,7 @@ int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, float
     const char* e = getenv("GODE_TC_PREFETCH");   // in units of 128 rows per CTA, as for k_rows_ws (default 2, 0 = off)
     return (e ? atoi(e) : 2) * 4;
   }();
-  k_wgrad_tc<D, 4><<<grid, tc::THREADS, smem, st>>>(f->A.n_rows, y, gS, ws, cs_partial, f->gn_eps, passes, pf);
+  k_wgrad_tc<D, 4><<<grid, tc::THREADS + 32, smem, st>>>(f->A.n_rows, y, gS, ws, cs_partial, f->gn_eps, passes, pf);
   GODE_LAUNCH_CHECK();
   k_wgrad_cs<<<1, D, 0, st>>>(grid, D, cs_partial, cs);
   GODE_LAUNCH_CHECK();
@@ -829,7 +893,7 @@ static int launch_rows_ws(int64_t n_rows, const float* X, float* Out, const floa
     const char* e = getenv("GODE_TC_PREFETCH");   // L2 prefetch distance in tiles per CTA (default 2, 0 = off)
     return e ? atoi(e) : 2;
   }();
-  k_rows_ws<D, CPG, MODE><<<grid, tc::THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf);
+  k_rows_ws<D, CPG, MODE><<<grid, tc::WS_THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf);
   GODE_LAUNCH_CHECK();
   return GODE_OK;
 }
