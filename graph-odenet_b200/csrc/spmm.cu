@@ -132,6 +132,12 @@ __device__ __forceinline__ void gather_range(float4 (&acc)[VPL], int e0, int e1,
       v = __ldcs(vals + e);
     }
     const int cnt = min(LPR, e1 - e0 - off);  // may be <= 0 for a finished range
+    // Entries past the end of the range are padded with the range's own first column and weight 0, so that the last,
+    // partial batch is gathered with U independent loads like every other one (a sequential tail -- one dependent load
+    // after the other -- was what made 4 rows in flight beat 8: 223.5 vs 235.0 ms per step at N = 10 M).  The padded
+    // loads repeat a line this warp has just requested; multiplying a real neighbour's row by 0 cannot introduce a
+    // NaN the exact sum would not have.
+    const int cpad = __shfl_sync(0xffffffffu, c, sub * LPR);
 #pragma unroll
     for (int j = 0; j < LPR; j += U) {
       int cj[U];
@@ -141,12 +147,14 @@ __device__ __forceinline__ void gather_range(float4 (&acc)[VPL], int e0, int e1,
         cj[q] = __shfl_sync(0xffffffffu, c, sub * LPR + j + q);
         vj[q] = __shfl_sync(0xffffffffu, v, sub * LPR + j + q);
       }
-      if (j + U <= cnt) {
+      if (j < cnt) {
         float4 x[U][VPL];
 #pragma unroll
-        for (int q = 0; q < U; ++q)
+        for (int q = 0; q < U; ++q) {
+          const int cq = (j + q < cnt) ? cj[q] : cpad;
 #pragma unroll
-          for (int u = 0; u < VPL; ++u) x[q][u] = ld_ro4(xl + (int64_t)cj[q] * ldx + u * 4);
+          for (int u = 0; u < VPL; ++u) x[q][u] = ld_ro4(xl + (int64_t)cq * ldx + u * 4);
+        }
 #pragma unroll
         for (int q = 0; q < U; ++q)
 #pragma unroll
@@ -154,10 +162,6 @@ __device__ __forceinline__ void gather_range(float4 (&acc)[VPL], int e0, int e1,
             acc[u].x += vj[q] * x[q][u].x; acc[u].y += vj[q] * x[q][u].y;
             acc[u].z += vj[q] * x[q][u].z; acc[u].w += vj[q] * x[q][u].w;
           }
-      } else if (j < cnt) {
-#pragma unroll
-        for (int q = 0; q < U; ++q)
-          if (j + q < cnt) fma_row<VPL>(acc, vj[q], xl + (int64_t)cj[q] * ldx);
       }
     }
   }
@@ -170,8 +174,8 @@ __device__ __forceinline__ int warp_max_over_subs(int v) {
   return v;
 }
 
-template <int LPR, int VPL>
-__global__ void __launch_bounds__(256) k_spmm_vec(int64_t n_rows, const int32_t* __restrict__ rowptr,
+template <int LPR, int VPL, int MINB = 1, int UN = UNR>
+__global__ void __launch_bounds__(256, MINB) k_spmm_vec(int64_t n_rows, const int32_t* __restrict__ rowptr,
                                                   const int32_t* __restrict__ colidx, const float* __restrict__ vals,
                                                   const float* __restrict__ X, int64_t ldx, float* __restrict__ Y,
                                                   int64_t ldy, const gode_spmm_epilogue_t ep, const int prefetch) {
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(256) k_spmm_vec(int64_t n_rows, const int32_t*
   float4 acc[VPL];
 #pragma unroll
   for (int u = 0; u < VPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-  gather_range<LPR, VPL>(acc, e0, e1, maxlen, sub, sl, colidx, vals, X + col0, ldx);
+  gather_range<LPR, VPL, UN>(acc, e0, e1, maxlen, sub, sl, colidx, vals, X + col0, ldx);
   if (valid && !heavy) epilogue<VPL>(ep, row, col0, acc, Y, ldy);
 }
 
@@ -378,8 +382,8 @@ static int launch_pw(const gode_csr_t& A, const float* X, int64_t ldx, float* Y,
 }
 
 // one sub-warp per chunk of a heavy row -> partial[chunk][d]
-template <int LPR, int VPL>
-__global__ void __launch_bounds__(256) k_spmm_heavy_partial(int n_heavy, int n_chunks, const int32_t* __restrict__ heavy_rows,
+template <int LPR, int VPL, int MINB = 1, int UN = UNR>
+__global__ void __launch_bounds__(256, MINB) k_spmm_heavy_partial(int n_heavy, int n_chunks, const int32_t* __restrict__ heavy_rows,
                                                             const int32_t* __restrict__ chunk_ptr,
                                                             const int32_t* __restrict__ rowptr,
                                                             const int32_t* __restrict__ colidx, const float* __restrict__ vals,
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(256) k_spmm_heavy_partial(int n_heavy, int n_c
   float4 acc[VPL];
 #pragma unroll
   for (int u = 0; u < VPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-  gather_range<LPR, VPL>(acc, e0, e1, maxlen, sub, sl, colidx, vals, X + col0, ldx);
+  gather_range<LPR, VPL, UN>(acc, e0, e1, maxlen, sub, sl, colidx, vals, X + col0, ldx);
   if (chunk < n_chunks) {
 #pragma unroll
     for (int u = 0; u < VPL; ++u) *reinterpret_cast<float4*>(partial + (int64_t)chunk * D + col0 + u * 4) = acc[u];
@@ -510,13 +514,44 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
       const char* e = getenv("GODE_SPMM_PREFETCH");   // 1 (default): L2-prefetch the epilogue operands before the gather
       return e ? atoi(e) : 1;
     }();
-    k_spmm_vec<LPR, VPL><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, X, ldx, Y, ldy, ep, prefetch);
+    // Resident CTAs per SM (register cap) x neighbour rows in flight per lane.  The compiler's own choice is 64
+    // registers = 4 CTAs; measured at N = 10 M (ms per bare A^T gather / per gather with epilogue):
+    //   4 CTAs x 8 rows: 12.63 / 15.44   6 x 8: 11.21 / 13.31   6 x 4: 10.47 / 12.51   8 x 4: 9.95 / 11.77  <- default
+    // (GODE_SPMM_MINB, GODE_SPMM_UNR): full occupancy with short batches wins -- the gather is a latency chain per warp
+    // (rowptr -> colidx -> batches of neighbour rows), and 64 resident warps hide it better than deeper batches do.
+    static const int minb = [] {
+      const char* e = getenv("GODE_SPMM_MINB");
+      return e ? atoi(e) : 8;
+    }();
+    static const int unr = [] {
+      const char* e = getenv("GODE_SPMM_UNR");
+      return e ? atoi(e) : 4;
+    }();
+#define GODE_VEC_LAUNCH(MB, UU)                                                                                     \
+  k_spmm_vec<LPR, VPL, MB, UU><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, X, ldx, Y, ldy, ep, prefetch)
+    if constexpr (LPR == 32 && VPL == 1) {
+      if (minb == 5 && unr == 8) GODE_VEC_LAUNCH(5, 8);
+      else if (minb == 6 && unr == 8) GODE_VEC_LAUNCH(6, 8);
+      else if (minb == 7 && unr == 8) GODE_VEC_LAUNCH(7, 8);
+      else if (minb == 8 && unr == 8) GODE_VEC_LAUNCH(8, 8);
+      else if (minb == 6 && unr == 4) GODE_VEC_LAUNCH(6, 4);
+      else if (minb == 8 && unr == 4) GODE_VEC_LAUNCH(8, 4);
+      else if (minb == 8 && unr == 2) GODE_VEC_LAUNCH(8, 2);
+      else GODE_VEC_LAUNCH(1, 8);
+    } else {
+      GODE_VEC_LAUNCH(1, UNR);
+    }
+#undef GODE_VEC_LAUNCH
     GODE_LAUNCH_CHECK();
   }
   if (A.n_heavy > 0) {
     unsigned g1 = static_cast<unsigned>((A.n_chunks + RPB - 1) / RPB);
-    k_spmm_heavy_partial<LPR, VPL><<<g1, 256, 0, st>>>(A.n_heavy, A.n_chunks, A.heavy_rows, A.heavy_chunk_ptr, A.rowptr,
-                                                      A.colidx, A.vals, X, ldx, ws);
+    if constexpr (LPR == 32 && VPL == 1)   // same occupancy / unroll point as the main kernel (launch_vec's table)
+      k_spmm_heavy_partial<LPR, VPL, 8, 4><<<g1, 256, 0, st>>>(A.n_heavy, A.n_chunks, A.heavy_rows, A.heavy_chunk_ptr,
+                                                              A.rowptr, A.colidx, A.vals, X, ldx, ws);
+    else
+      k_spmm_heavy_partial<LPR, VPL><<<g1, 256, 0, st>>>(A.n_heavy, A.n_chunks, A.heavy_rows, A.heavy_chunk_ptr, A.rowptr,
+                                                        A.colidx, A.vals, X, ldx, ws);
     GODE_LAUNCH_CHECK();
     unsigned g2 = static_cast<unsigned>((A.n_heavy + RPB - 1) / RPB);
     k_spmm_heavy_finish<LPR, VPL><<<g2, 256, 0, st>>>(A.n_heavy, A.heavy_rows, A.heavy_chunk_ptr, ws, Y, ldy, ep);

@@ -42,6 +42,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
          (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46);
 }
 
+// K-major operand in the 128-byte-swizzled canonical layout (cute::UMMA Layout_K_SW128_Atom): a row is 128 contiguous
+// bytes (32 tf32), 16-byte chunk c of row r sits at chunk position c ^ (r % 8), 8-row groups are SBO = 1024 bytes
+// apart, LBO = 16 bytes; K steps advance the start address by raw bytes inside the row.  The tile must be 1024-byte
+// aligned.  layout_type = SWIZZLE_128B (2) in bits [61,64).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
+  return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
   // InstrDescriptor: c_format=F32 (1<<4) | a_format=TF32 (2<<7) | b_format=TF32 (2<<10) | a_major<<15 | b_major<<16
   // | (N>>3)<<17 | (M>>4)<<24
@@ -382,7 +391,7 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
   constexpr int NQ = D / KQ;                    // stages per tile
   constexpr int NI = 4;                         // warp-instructions (8 rows x 4 chunks) per producer warp per stage
   constexpr uint32_t RSB = D * 32;              // 8-row-group stride of the B tile (full K)
-  constexpr uint32_t RSA = KQ * 32;             // 8-row-group stride of an A stage
+  constexpr uint32_t RSA = KQ * 32;             // 8-row-group stride of an A stage (8 rows x 128 bytes = one swizzle atom)
   constexpr uint32_t B_BYTES = D * D * 4;
   constexpr uint32_t A_BYTES = 128 * KQ * 4;    // one of hi / lo of one stage
   constexpr uint32_t STG_BYTES = 128 * (D / 2) * 4;   // staging: 128 rows x half of the columns
@@ -452,18 +461,18 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
   if (warp < 8) {
     // =============================== producers ============================================================
     float4 raw[2][NI];
+    // A warp instruction covers 4 rows x 128 bytes: the 8 lanes of a quarter warp read the 8 chunks of ONE row, so every
+    // quarter-warp request is one 128-byte line (with lane -> row, as in k_rows_tc, each quarter warp touched 8 lines
+    // and the L1 LSU pipe -- 80 % busy in ncu -- spent 32 wavefronts per LDG.128 instead of 4).
     auto load_raw = [&](float4 (&r)[NI], int64_t step) {
       const int64_t tile = blockIdx.x + (step / NQ) * (int64_t)gridDim.x;
       const int q = static_cast<int>(step % NQ);
       const bool live = step < n_steps;
-      const bool pf = pf_tiles > 0 && step + pf_tiles * NQ < n_steps && (lane >> 3) == 0;   // one request per row line
+      const bool pf = pf_tiles > 0 && step + pf_tiles * NQ < n_steps && (lane & 7) == 0;   // one request per row line
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
-        const int g = warp * NI + i;                 // 0..31: 16 row groups x 2 chunk groups
-        const int rg = g >> 1, cg = g & 1;
-        const int64_t row = tile * 128 + rg * 8 + (lane & 7);
-        const int kc = cg * 4 + (lane >> 3);
-        const float* src = X + row * D + q * KQ + kc * 4;
+        const int64_t row = tile * 128 + (warp * NI + i) * 4 + (lane >> 3);
+        const float* src = X + row * D + q * KQ + (lane & 7) * 4;
         r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live && row < n_rows) r[i] = __ldcs(reinterpret_cast<const float4*>(src));
         if (pf) {                                     // same bytes of the tile pf_tiles visits ahead
@@ -480,12 +489,11 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
       unsigned char* aLo = aHi + A_BYTES;
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
-        const int g = warp * NI + i;
-        const int rg = g >> 1, cg = g & 1;
-        const int kc = cg * 4 + (lane >> 3);
+        const int rr = (warp * NI + i) * 4 + (lane >> 3);      // row of the tile
         float4 hi, lo;
         split4(normalize4_fast<CPG>(r[i], eps), hi, lo);
-        const uint32_t off = rg * RSA + kc * 128 + (lane & 7) * 16;
+        // 128-byte-swizzled K-major stage: a quarter warp fills one 128-byte row -> conflict-free
+        const uint32_t off = (rr >> 3) * RSA + (rr & 7) * 128 + (((lane & 7) ^ (rr & 7)) << 4);
         *reinterpret_cast<float4*>(aHi + off) = hi;
         *reinterpret_cast<float4*>(aLo + off) = lo;
       }
@@ -516,7 +524,7 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
 #pragma unroll
         for (int ks = 0; ks < KQ / 8; ++ks) {
           const uint32_t kb = q * (KQ / 8) + ks;
-          const uint64_t da_hi = make_desc(aHi + ks * 256, 128, RSA), da_lo = make_desc(aLo + ks * 256, 128, RSA);
+          const uint64_t da_hi = make_desc_sw128(aHi + ks * 32), da_lo = make_desc_sw128(aLo + ks * 32);
           const uint64_t db_hi = make_desc(bHi + kb * 256, 128, RSB), db_lo = make_desc(bLo + kb * 256, 128, RSB);
           mma_tf32(tmem_d, da_hi, db_hi, IDESC, (q | ks) != 0 ? 1u : 0u);
           if (passes == 3) {
@@ -633,11 +641,14 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
   static_assert(D == 128, "the accumulator uses all 128 TMEM lanes");
   // Both operands are [rows, D] row-major in HBM but the reduction runs over rows, so they are transposed on the
   // way into shared memory and used as ordinary K-major operands: element (channel i, row r) of a staged tile at
-  //     (i/8)*SBO + (r/4)*LBO + (i%8)*16 + (r%4)*4,   LBO = 144, SBO = 1184
-  // (core matrices stay 128 B contiguous; the 16 B / 32 B skews make the 4-byte transposing stores of a warp hit 32
-  // distinct banks).
+  //     (i/8)*SBO + (r/4)*LBO + (i%8)*16 + (r%4)*4,   LBO = 144, SBO = 1168
+  // (core matrices stay 128 B contiguous).  A warp instruction loads 4 rows x 128 bytes -- the 8 lanes of a quarter
+  // warp read ONE 128-byte line (lane -> row made every quarter warp touch 8 lines: 32 LSU wavefronts per LDG.128
+  // instead of 4, with the L1 LSU pipe 79 % busy in ncu) -- and its 4-byte transposing stores then go to channel
+  // 4*(lane%8)+j, row lane/8: word bank = 16*(kc%2) + 4*(kc/2) + lane/8 + const with SBO = 16 bytes mod 128, i.e. 32
+  // distinct banks.
   constexpr int RC = 32;                       // rows (= K) per staged chunk
-  constexpr uint32_t LBO = 144, SBO = 1184;
+  constexpr uint32_t LBO = 144, SBO = 1168;
   constexpr uint32_t MAT = (D / 8) * SBO;      // bytes of one staged operand tile
   constexpr int NI = ((RC / 8) * (D / 16)) / (THREADS / 32);   // warp-instructions per warp per operand
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -699,10 +710,8 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
   auto load_raw = [&](int64_t chunk) {
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-      const int g = warp * NI + i;
-      const int rg = g / (D / 16), cg = g % (D / 16);
-      const int64_t row = chunk * RC + rg * 8 + (lane & 7);
-      const int kc = cg * 4 + (lane >> 3);
+      const int64_t row = chunk * RC + warp * 4 + (lane >> 3);   // warp -> row quad, i -> 32-channel quarter
+      const int kc = i * 8 + (lane & 7);
       ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       rb[i] = ra[i];
       if (row < n_rows) {
@@ -729,10 +738,8 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
     unsigned char* base = smem + (size_t)b * 4 * MAT;
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-      const int g = warp * NI + i;
-      const int rg = g / (D / 16), cg = g % (D / 16);
-      const int kc = cg * 4 + (lane >> 3);
-      const int r = rg * 8 + (lane & 7);
+      const int kc = i * 8 + (lane & 7);
+      const int r = warp * 4 + (lane >> 3);
       float4 xa = normalize4_fast<CPG>(ra[i], eps);
       if (chunk * RC + r >= n_rows) xa = make_float4(0.f, 0.f, 0.f, 0.f);   // xhat of a padding row is not zero by itself
       float4 hi, lo;
@@ -781,30 +788,28 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
         *reinterpret_cast<float4*>(out + hc * (D / 2) + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
   }
-  // column sums of G over this CTA's rows: lanes sharing a 16-byte chunk differ in lane & 7 (the row inside an
-  // 8-row group), warps sharing it differ in warp / 2 (the row group); fixed reduction order -> deterministic
+  // column sums of G over this CTA's rows: lanes sharing a 16-byte chunk differ in lane / 8 (the row inside a quad),
+  // warps hold different row quads; fixed reduction order -> deterministic
   {
-    float* scs = reinterpret_cast<float*>(smem);   // [THREADS / 64][D]; the operand stages are free (all MMAs retired)
+    float* scs = reinterpret_cast<float*>(smem);   // [8 warps][D]; the operand stages are free (all MMAs retired)
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
       float4 v = cs_acc[i];
 #pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
+      for (int o = 8; o < 32; o <<= 1) {
         v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
         v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
         v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
         v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
       }
-      const int g = warp * NI + i;
-      const int rg = g / (D / 16), cg = g % (D / 16);
-      const int kc = cg * 4 + (lane >> 3);
-      if ((lane & 7) == 0) *reinterpret_cast<float4*>(scs + rg * D + kc * 4) = v;
+      const int kc = i * 8 + (lane & 7);
+      if ((lane >> 3) == 0) *reinterpret_cast<float4*>(scs + warp * D + kc * 4) = v;
     }
     bar_sync_named(1, THREADS);
     if (tid < D) {
       float t = 0.f;
 #pragma unroll
-      for (int rg = 0; rg < RC / 8; ++rg) t += scs[rg * D + tid];
+      for (int w = 0; w < THREADS / 32; ++w) t += scs[w * D + tid];
       cs_partial[(size_t)blockIdx.x * D + tid] = t;
     }
   }
@@ -850,7 +855,7 @@ int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, float
     return GODE_EWORKSPACE;
   }
   float* cs_partial = ws + (size_t)grid * D * D;
-  constexpr size_t smem = 2 * 4 * (size_t)(D / 8) * 1184 + 64;
+  constexpr size_t smem = 2 * 4 * (size_t)(D / 8) * 1168 + 64;
   static bool configured = false;
   if (!configured) {
     GODE_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_tc<D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -858,7 +863,7 @@ int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, float
   }
   const int passes = f->precision == GODE_PREC_TF32 ? 1 : 3;
   static const int pf = [] {
-    const char* e = getenv("GODE_TC_PREFETCH");   // in units of 128 rows per CTA, as for k_rows_ws (default 2, 0 = off)
+    const char* e = getenv("GODE_WGRAD_PREFETCH");   // L2 prefetch distance in units of 128 rows per CTA (default 2, 0 = off)
     return (e ? atoi(e) : 2) * 4;
   }();
   k_wgrad_tc<D, 4><<<grid, tc::THREADS + 32, smem, st>>>(f->A.n_rows, y, gS, ws, cs_partial, f->gn_eps, passes, pf);
@@ -890,8 +895,8 @@ static int launch_rows_ws(int64_t n_rows, const float* X, float* Out, const floa
     configured = true;
   }
   static const int pf = [] {
-    const char* e = getenv("GODE_TC_PREFETCH");   // L2 prefetch distance in tiles per CTA (default 2, 0 = off)
-    return e ? atoi(e) : 2;
+    const char* e = getenv("GODE_TC_PREFETCH");   // L2 prefetch distance in tiles per CTA (default 0 = off: measured
+    return e ? atoi(e) : 0;                       // 2.28 ms without vs 2.39 ms with, N = 10 M; the loads are not the limit)
   }();
   k_rows_ws<D, CPG, MODE><<<grid, tc::WS_THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf);
   GODE_LAUNCH_CHECK();
