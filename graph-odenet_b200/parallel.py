@@ -155,6 +155,12 @@ class HaloKernelMixin:
         self.partial = None
         self.peer = plan.peer_for(self.d)
         self.fused = self.peer is not None and plan.mode == "p2p-fused" and self._push_fusable()
+        # The support S is pushed by the stand-alone kernel unless GODE_FUSE_S=1: remote stores need many warps in flight
+        # to reach NVLink speed, and the warp-specialised transform has four epilogue warps per SM (measured at 2 GPUs,
+        # N = 10 M: 4.2 ms per transform with the push in its epilogue vs 1.2 ms + 1.2 ms for transform + push kernel);
+        # the phase-1 gather, with 64 resident warps per SM, hides its gP push completely and keeps it fused.
+        import os
+        self.fused_S = self.fused and os.environ.get("GODE_FUSE_S", "0") == "1"
         if plan.split is not None:
             from . import _lib
             # descriptor for the second (halo-column) pass: same parameters, halo blocks, operand offset
@@ -262,7 +268,7 @@ class HaloKernelMixin:
         self.pending[buf.data_ptr()] = self.peer.finish(epoch)
 
     def transform(self, y, t, out):
-        if self.fused:
+        if self.fused_S:
             epoch = self._fused_begin("push_S", self.plan.halo, out)
             super().transform(y, t, out)
             self._fused_end("push_S", out, epoch)
@@ -273,7 +279,7 @@ class HaloKernelMixin:
 
     def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0, S_next=None):
         run = lambda: super(HaloKernelMixin, self).stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next)
-        if self.fused:
+        if self.fused_S:
             self._wait(S)
             if S_next is None:
                 return run()

@@ -99,8 +99,9 @@ class RecBase:
     def new(self):
         return torch.zeros(1)
 
-    def _produce(self, buf):
-        if getattr(self, "fused", False):      # the producer kernel stores the peers' rows itself
+    def _produce(self, buf, kind="S"):
+        fused = getattr(self, "fused_S", False) if kind == "S" else getattr(self, "fused", False)
+        if fused:                              # the producer kernel stores the peers' rows itself
             self.prog.append(("main", "rwrite", buf.version, buf.slot))
 
     def _gather(self, buf):
@@ -120,7 +121,7 @@ class RecBase:
     def vjp_phase1(self, S, a, sign, k_y, gP, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None):
         self.nfe += 1
         self._gather(S)
-        self._produce(gP)
+        self._produce(gP, "gP")
 
     def vjp_phase2(self, y, t, gP, k_a, gtheta, a0=None, kprev=(), coefs=(), coef_self=0.0, a_next=None):
         gtheta.zero_()
@@ -222,9 +223,11 @@ def _no_cuda_combine(monkeypatch):
     monkeypatch.setattr(ops, "rk_combine", lambda y0, ks, cs, out=None: out)
 
 
-@pytest.mark.parametrize("mode", ["p2p", "p2p-async", "p2p-fused"])
+@pytest.mark.parametrize("mode", ["p2p", "p2p-async", "p2p-fused", "p2p-fused+S"])
 @pytest.mark.parametrize("method,step_size", [("rk4", None), ("rk4", 0.25), ("midpoint", 0.5), ("euler", 0.5)])
-def test_protocol_is_safe_under_random_interleaving(mode, method, step_size):
+def test_protocol_is_safe_under_random_interleaving(mode, method, step_size, monkeypatch):
+    monkeypatch.setenv("GODE_FUSE_S", "1" if mode.endswith("+S") else "0")
+    mode = mode.replace("+S", "")
     prog, proto = record_program(RecProtocol, mode, method, step_size, n_steps=3)
     assert any(op[1] == "rwrite" for op in prog) and any(op[1] == "signal" for op in prog)
     rng = random.Random(1234)
