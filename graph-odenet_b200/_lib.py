@@ -40,9 +40,16 @@ class Csr(C.Structure):
                 ("heavy_rows", vp), ("heavy_chunk_ptr", vp), ("n_heavy", i32), ("n_chunks", i32)]
 
 
+GAT_CHUNK = 64
+
+
+class GatHeavy(C.Structure):
+    _fields_ = [("n_heavy", i32), ("n_chunks", i32), ("nodes", vp), ("cptr", vp), ("chunk_node", vp), ("chunk_e0", vp)]
+
+
 class GatGraph(C.Structure):
     _fields_ = [("n_nodes", i64), ("n_edges", i64), ("tptr", vp), ("t_src", vp), ("t_tgt", vp), ("sptr", vp),
-                ("s_tgt", vp), ("s_pos", vp)]
+                ("s_tgt", vp), ("s_pos", vp), ("t_heavy", GatHeavy), ("s_heavy", GatHeavy)]
 
 
 class GcnOdeFunc(C.Structure):
@@ -102,8 +109,9 @@ _PROTOS = {
     "gode_peer_status": (C.c_int, [C.POINTER(PeerGroup), C.POINTER(i32), vp]),
     "gode_edge_matvec": (C.c_int, [i64, i32, vp, vp, vp, i64, vp, vp]),
     "gode_edge_matvec_bwd": (C.c_int, [i64, i32, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp]),
-    "gode_gat_fwd": (C.c_int, [C.POINTER(GatGraph), i32, i32, vp, i64, f32, vp, i64, vp, vp, vp, vp]),
-    "gode_gat_bwd_workspace_bytes": (sz, [i64, i32]),
+    "gode_gat_fwd_workspace_bytes": (sz, [C.POINTER(GatGraph), i32, i32]),
+    "gode_gat_fwd": (C.c_int, [C.POINTER(GatGraph), i32, i32, vp, i64, f32, vp, i64, vp, vp, vp, vp, sz, vp]),
+    "gode_gat_bwd_workspace_bytes": (sz, [C.POINTER(GatGraph), i32, i32]),
     "gode_gat_bwd": (C.c_int, [C.POINTER(GatGraph), i32, i32, vp, i64, vp, i64, vp, vp, vp, i64, vp, vp, sz, vp]),
 }
 

@@ -70,17 +70,48 @@ __global__ void __launch_bounds__(256) k_gat_amax(int64_t n_edges, int H, const 
   }
 }
 
-// one thread per (node, head); CH >= oh channels held in registers
-template <int CH>
-__global__ void __launch_bounds__(128) k_gat_fwd(int64_t n_nodes, int H, int oh, const int32_t* __restrict__ tptr,
+// Segments.  One thread owns one (segment, head) pair and walks the segment in edge order.  A segment is a whole node
+// (LIGHT pass: nodes with more than GODE_GAT_CHUNK edges are skipped) or one chunk of GODE_GAT_CHUNK consecutive edges
+// of such a hub node (CHUNK pass: partial sums go to a workspace, a finishing kernel adds a node's chunks in chunk
+// order -- deterministic, no atomics).  Without the split a power-law hub (4.7e4 in-edges on the 1 M-node
+// Citeseer-shaped graph) is one thread's sequential loop: 57 ms for the source pass alone.
+struct GatHeavy {
+  int n_heavy, n_chunks;
+  const int32_t* nodes;       // [n_heavy] hub nodes
+  const int32_t* cptr;        // [n_heavy + 1] chunk range of each hub
+  const int32_t* chunk_node;  // [n_chunks]
+  const int32_t* chunk_e0;    // [n_chunks] first edge of the chunk
+};
+
+template <bool CHUNK>
+__device__ __forceinline__ bool gat_segment(int64_t seg, const int32_t* __restrict__ ptr, const GatHeavy& hv, int64_t& n, int& e0,
+                                            int& e1) {
+  if (CHUNK) {
+    n = __ldg(hv.chunk_node + seg);
+    e0 = __ldg(hv.chunk_e0 + seg);
+    e1 = min(e0 + GODE_GAT_CHUNK, __ldg(ptr + n + 1));
+    return true;
+  }
+  n = seg;
+  e0 = __ldg(ptr + n);
+  e1 = __ldg(ptr + n + 1);
+  return (e1 - e0) <= GODE_GAT_CHUNK;
+}
+
+// one thread per (segment, head); CH >= oh channels held in registers
+template <int CH, bool CHUNK>
+__global__ void __launch_bounds__(128) k_gat_fwd(int64_t n_seg, int H, int oh, const int32_t* __restrict__ tptr,
                                                  const int32_t* __restrict__ t_src, const float* __restrict__ P, int64_t ldp,
                                                  float eps, const unsigned long long* __restrict__ amax_key,
                                                  float* __restrict__ out, int64_t ldo, float* __restrict__ den_out,
-                                                 int* __restrict__ nan_flag) {
+                                                 int* __restrict__ nan_flag, GatHeavy hv, float* __restrict__ part) {
   const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (gid >= n_nodes * H) return;
-  const int64_t n = gid / H;
-  const int h = static_cast<int>(gid - n * H);
+  if (gid >= n_seg * H) return;
+  const int64_t seg = gid / H;
+  const int h = static_cast<int>(gid - seg * H);
+  int64_t n;
+  int e0, e1;
+  if (!gat_segment<CHUNK>(seg, tptr, hv, n, e0, e1)) return;
   const int C = H * oh;
   const float amax = key_max(amax_key[h]);
   const float* pn = P + n * ldp;
@@ -92,7 +123,6 @@ __global__ void __launch_bounds__(128) k_gat_fwd(int64_t n_nodes, int H, int oh,
     num[j] = 0.f;
   }
   float den = 0.f;
-  const int e0 = __ldg(tptr + n), e1 = __ldg(tptr + n + 1);
   for (int e = e0; e < e1; ++e) {
     const float* ps = P + (int64_t)__ldg(t_src + e) * ldp;
     const float w = expf(__ldg(ps + 2 * C + h) + at - amax);
@@ -100,6 +130,43 @@ __global__ void __launch_bounds__(128) k_gat_fwd(int64_t n_nodes, int H, int oh,
 #pragma unroll
     for (int j = 0; j < CH; ++j)
       if (j < oh) num[j] += fmaxf(__ldg(ps + h * oh + j) + pt[j], 0.f) * w;
+  }
+  if (CHUNK) {
+    float* p = part + gid * (CH + 1);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) p[j] = num[j];
+    p[CH] = den;
+    return;
+  }
+  den += eps;
+  den_out[n * H + h] = den;
+  bool bad = den != den;
+#pragma unroll
+  for (int j = 0; j < CH; ++j)
+    if (j < oh) {
+      const float o = num[j] / den;
+      bad = bad || (o != o);
+      out[n * ldo + h * oh + j] = o;
+    }
+  if (bad) *nan_flag = 1;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(128) k_gat_fwd_finish(int H, int oh, float eps, GatHeavy hv, const float* __restrict__ part,
+                                                        float* __restrict__ out, int64_t ldo, float* __restrict__ den_out,
+                                                        int* __restrict__ nan_flag) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)hv.n_heavy * H) return;
+  const int i = static_cast<int>(gid / H), h = static_cast<int>(gid % H);
+  const int64_t n = hv.nodes[i];
+  float num[CH], den = 0.f;
+#pragma unroll
+  for (int j = 0; j < CH; ++j) num[j] = 0.f;
+  for (int c = hv.cptr[i]; c < hv.cptr[i + 1]; ++c) {
+    const float* p = part + ((int64_t)c * H + h) * (CH + 1);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) num[j] += p[j];
+    den += p[CH];
   }
   den += eps;
   den_out[n * H + h] = den;
@@ -115,17 +182,21 @@ __global__ void __launch_bounds__(128) k_gat_fwd(int64_t n_nodes, int H, int oh,
 }
 
 // target pass of the backward: dPt, dat (registers), per-edge d a_e (by-target order) for the source pass
-template <int CH>
-__global__ void __launch_bounds__(128) k_gat_bwd_tgt(int64_t n_nodes, int H, int oh, const int32_t* __restrict__ tptr,
+template <int CH, bool CHUNK>
+__global__ void __launch_bounds__(128) k_gat_bwd_tgt(int64_t n_seg, int H, int oh, const int32_t* __restrict__ tptr,
                                                      const int32_t* __restrict__ t_src, const float* __restrict__ P,
                                                      int64_t ldp, const unsigned long long* __restrict__ amax_key,
                                                      const float* __restrict__ out, int64_t ldo,
                                                      const float* __restrict__ den, const float* __restrict__ g, int64_t ldg,
-                                                     float* __restrict__ dP, float* __restrict__ dA) {
+                                                     float* __restrict__ dP, float* __restrict__ dA, GatHeavy hv,
+                                                     float* __restrict__ part) {
   const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (gid >= n_nodes * H) return;
-  const int64_t n = gid / H;
-  const int h = static_cast<int>(gid - n * H);
+  if (gid >= n_seg * H) return;
+  const int64_t seg = gid / H;
+  const int h = static_cast<int>(gid - seg * H);
+  int64_t n;
+  int e0, e1;
+  if (!gat_segment<CHUNK>(seg, tptr, hv, n, e0, e1)) return;
   const int C = H * oh;
   const float amax = key_max(amax_key[h]);
   const float* pn = P + n * ldp;
@@ -143,7 +214,6 @@ __global__ void __launch_bounds__(128) k_gat_bwd_tgt(int64_t n_nodes, int H, int
     }
   }
   float dat = 0.f;
-  const int e0 = __ldg(tptr + n), e1 = __ldg(tptr + n + 1);
   for (int e = e0; e < e1; ++e) {
     const float* ps = P + (int64_t)__ldg(t_src + e) * ldp;
     const float w = expf(__ldg(ps + 2 * C + h) + at - amax);
@@ -161,6 +231,13 @@ __global__ void __launch_bounds__(128) k_gat_bwd_tgt(int64_t n_nodes, int H, int
     dat += da;
     dA[(int64_t)e * H + h] = da;
   }
+  if (CHUNK) {
+    float* p = part + gid * (CH + 1);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) p[j] = dpt[j];
+    p[CH] = dat;
+    return;
+  }
   float* dpn = dP + n * ldp;
 #pragma unroll
   for (int j = 0; j < CH; ++j)
@@ -169,17 +246,21 @@ __global__ void __launch_bounds__(128) k_gat_bwd_tgt(int64_t n_nodes, int H, int
 }
 
 // source pass: dPs, das over the by-source grouping (s_tgt = target of the edge, s_pos = its by-target position)
-template <int CH>
-__global__ void __launch_bounds__(128) k_gat_bwd_src(int64_t n_nodes, int H, int oh, const int32_t* __restrict__ sptr,
+template <int CH, bool CHUNK>
+__global__ void __launch_bounds__(128) k_gat_bwd_src(int64_t n_seg, int H, int oh, const int32_t* __restrict__ sptr,
                                                      const int32_t* __restrict__ s_tgt, const int32_t* __restrict__ s_pos,
                                                      const float* __restrict__ P, int64_t ldp,
                                                      const unsigned long long* __restrict__ amax_key,
                                                      const float* __restrict__ den, const float* __restrict__ g, int64_t ldg,
-                                                     const float* __restrict__ dA, float* __restrict__ dP) {
+                                                     const float* __restrict__ dA, float* __restrict__ dP, GatHeavy hv,
+                                                     float* __restrict__ part) {
   const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (gid >= n_nodes * H) return;
-  const int64_t s = gid / H;
-  const int h = static_cast<int>(gid - s * H);
+  if (gid >= n_seg * H) return;
+  const int64_t seg = gid / H;
+  const int h = static_cast<int>(gid - seg * H);
+  int64_t s;
+  int e0, e1;
+  if (!gat_segment<CHUNK>(seg, sptr, hv, s, e0, e1)) return;
   const int C = H * oh;
   const float amax = key_max(amax_key[h]);
   const float* psn = P + s * ldp;
@@ -191,7 +272,6 @@ __global__ void __launch_bounds__(128) k_gat_bwd_src(int64_t n_nodes, int H, int
     dps[j] = 0.f;
   }
   float das = 0.f;
-  const int e0 = __ldg(sptr + s), e1 = __ldg(sptr + s + 1);
   for (int e = e0; e < e1; ++e) {
     const int64_t n = __ldg(s_tgt + e);
     const float* pt = P + n * ldp;
@@ -204,11 +284,42 @@ __global__ void __launch_bounds__(128) k_gat_bwd_src(int64_t n_nodes, int H, int
       }
     das += __ldg(dA + (int64_t)__ldg(s_pos + e) * H + h);
   }
+  if (CHUNK) {
+    float* p = part + gid * (CH + 1);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) p[j] = dps[j];
+    p[CH] = das;
+    return;
+  }
   float* dpn = dP + s * ldp;
 #pragma unroll
   for (int j = 0; j < CH; ++j)
     if (j < oh) dpn[h * oh + j] = dps[j];
   dpn[2 * C + h] = das;
+}
+
+// adds a hub's chunk partials in chunk order: dP[n, col0 + h*oh + j] and dP[n, colA + h]
+template <int CH>
+__global__ void __launch_bounds__(128) k_gat_bwd_finish(int H, int oh, GatHeavy hv, const float* __restrict__ part,
+                                                        float* __restrict__ dP, int64_t ldp, int col0, int colA) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)hv.n_heavy * H) return;
+  const int i = static_cast<int>(gid / H), h = static_cast<int>(gid % H);
+  const int64_t n = hv.nodes[i];
+  float acc[CH], da = 0.f;
+#pragma unroll
+  for (int j = 0; j < CH; ++j) acc[j] = 0.f;
+  for (int c = hv.cptr[i]; c < hv.cptr[i + 1]; ++c) {
+    const float* p = part + ((int64_t)c * H + h) * (CH + 1);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) acc[j] += p[j];
+    da += p[CH];
+  }
+  float* dpn = dP + n * ldp;
+#pragma unroll
+  for (int j = 0; j < CH; ++j)
+    if (j < oh) dpn[col0 + h * oh + j] = acc[j];
+  dpn[colA + h] = da;
 }
 
 // d amax[h] = -sum_e dA[e, h]  goes to the arg-max edge: das[src*] and dat[tgt*]
@@ -226,27 +337,71 @@ __global__ void k_gat_bwd_max(int H, int C, const unsigned long long* __restrict
   dP[(int64_t)t_tgt[pos] * ldp + 2 * C + H + h] += d;
 }
 
+static GatHeavy heavy_of(const gode_gat_graph_t* G, bool by_source) {
+  GatHeavy hv;
+  const gode_gat_heavy_t& h = by_source ? G->s_heavy : G->t_heavy;
+  hv.n_heavy = h.n_heavy;
+  hv.n_chunks = h.n_chunks;
+  hv.nodes = h.nodes;
+  hv.cptr = h.cptr;
+  hv.chunk_node = h.chunk_node;
+  hv.chunk_e0 = h.chunk_e0;
+  return hv;
+}
+
+static unsigned grid_for(int64_t work) { return static_cast<unsigned>((work + 127) / 128); }
+
 template <int CH>
 static int gat_fwd_t(const gode_gat_graph_t* G, int H, int oh, const float* P, int64_t ldp, float eps, float* out, int64_t ldo,
-                     float* den, unsigned long long* amax_key, int* nan_flag, cudaStream_t st) {
-  const int64_t work = G->n_nodes * H;
-  k_gat_fwd<CH><<<static_cast<unsigned>((work + 127) / 128), 128, 0, st>>>(G->n_nodes, H, oh, G->tptr, G->t_src, P, ldp, eps,
-                                                                          amax_key, out, ldo, den, nan_flag);
+                     float* den, unsigned long long* amax_key, int* nan_flag, float* part, cudaStream_t st) {
+  const GatHeavy hv = heavy_of(G, false);
+  k_gat_fwd<CH, false><<<grid_for(G->n_nodes * H), 128, 0, st>>>(G->n_nodes, H, oh, G->tptr, G->t_src, P, ldp, eps, amax_key, out,
+                                                                 ldo, den, nan_flag, hv, nullptr);
   GODE_LAUNCH_CHECK();
+  if (hv.n_chunks > 0) {
+    k_gat_fwd<CH, true><<<grid_for((int64_t)hv.n_chunks * H), 128, 0, st>>>(hv.n_chunks, H, oh, G->tptr, G->t_src, P, ldp, eps,
+                                                                            amax_key, out, ldo, den, nan_flag, hv, part);
+    GODE_LAUNCH_CHECK();
+    k_gat_fwd_finish<CH><<<grid_for((int64_t)hv.n_heavy * H), 128, 0, st>>>(H, oh, eps, hv, part, out, ldo, den, nan_flag);
+    GODE_LAUNCH_CHECK();
+  }
   return GODE_OK;
 }
 
 template <int CH>
 static int gat_bwd_t(const gode_gat_graph_t* G, int H, int oh, const float* P, int64_t ldp, const float* out, int64_t ldo,
                      const float* den, const unsigned long long* amax_key, const float* g, int64_t ldg, float* dP, float* dA,
-                     cudaStream_t st) {
-  const int64_t work = G->n_nodes * H;
-  const unsigned grid = static_cast<unsigned>((work + 127) / 128);
-  k_gat_bwd_tgt<CH><<<grid, 128, 0, st>>>(G->n_nodes, H, oh, G->tptr, G->t_src, P, ldp, amax_key, out, ldo, den, g, ldg, dP, dA);
+                     float* part, cudaStream_t st) {
+  const int C = H * oh;
+  const GatHeavy ht = heavy_of(G, false), hs = heavy_of(G, true);
+  k_gat_bwd_tgt<CH, false><<<grid_for(G->n_nodes * H), 128, 0, st>>>(G->n_nodes, H, oh, G->tptr, G->t_src, P, ldp, amax_key, out,
+                                                                     ldo, den, g, ldg, dP, dA, ht, nullptr);
   GODE_LAUNCH_CHECK();
-  k_gat_bwd_src<CH><<<grid, 128, 0, st>>>(G->n_nodes, H, oh, G->sptr, G->s_tgt, G->s_pos, P, ldp, amax_key, den, g, ldg, dA, dP);
+  if (ht.n_chunks > 0) {
+    k_gat_bwd_tgt<CH, true><<<grid_for((int64_t)ht.n_chunks * H), 128, 0, st>>>(ht.n_chunks, H, oh, G->tptr, G->t_src, P, ldp,
+                                                                                amax_key, out, ldo, den, g, ldg, dP, dA, ht, part);
+    GODE_LAUNCH_CHECK();
+    k_gat_bwd_finish<CH><<<grid_for((int64_t)ht.n_heavy * H), 128, 0, st>>>(H, oh, ht, part, dP, ldp, C, 2 * C + H);
+    GODE_LAUNCH_CHECK();
+  }
+  k_gat_bwd_src<CH, false><<<grid_for(G->n_nodes * H), 128, 0, st>>>(G->n_nodes, H, oh, G->sptr, G->s_tgt, G->s_pos, P, ldp,
+                                                                     amax_key, den, g, ldg, dA, dP, hs, nullptr);
   GODE_LAUNCH_CHECK();
+  if (hs.n_chunks > 0) {
+    k_gat_bwd_src<CH, true><<<grid_for((int64_t)hs.n_chunks * H), 128, 0, st>>>(hs.n_chunks, H, oh, G->sptr, G->s_tgt, G->s_pos, P,
+                                                                                ldp, amax_key, den, g, ldg, dA, dP, hs, part);
+    GODE_LAUNCH_CHECK();
+    k_gat_bwd_finish<CH><<<grid_for((int64_t)hs.n_heavy * H), 128, 0, st>>>(H, oh, hs, part, dP, ldp, 0, 2 * C);
+    GODE_LAUNCH_CHECK();
+  }
   return GODE_OK;
+}
+
+static int ch_of(int oh) { return oh <= 8 ? 8 : oh <= 16 ? 16 : oh <= 32 ? 32 : 64; }
+
+static size_t part_bytes(const gode_gat_graph_t* G, int H, int oh) {
+  const int64_t nc = G->t_heavy.n_chunks > G->s_heavy.n_chunks ? G->t_heavy.n_chunks : G->s_heavy.n_chunks;
+  return align_up(sizeof(float) * static_cast<size_t>(nc > 0 ? nc : 1) * H * (ch_of(oh) + 1), 256);
 }
 
 }  // namespace gode
@@ -259,20 +414,36 @@ static int gat_check(const gode_gat_graph_t* G, int H, int oh, int64_t ldp) {
   GODE_REQUIRE(ldp >= 2LL * H * oh + 2 * H, "gat: ldp too small for [Ps | Pt | as | at]");
   GODE_REQUIRE(G->n_nodes == 0 || (G->tptr && G->sptr), "gat: null segment pointers");
   GODE_REQUIRE(G->n_edges == 0 || (G->t_src && G->t_tgt && G->s_tgt && G->s_pos), "gat: null edge arrays");
+  for (const gode_gat_heavy_t* h : {&G->t_heavy, &G->s_heavy}) {
+    GODE_REQUIRE(h->n_heavy >= 0 && h->n_chunks >= 0, "gat: bad hub table");
+    GODE_REQUIRE(h->n_chunks == 0 || (h->nodes && h->cptr && h->chunk_node && h->chunk_e0), "gat: null hub table");
+  }
   return GODE_OK;
 }
 
-extern "C" size_t gode_gat_bwd_workspace_bytes(int64_t n_edges, int32_t heads) {
+extern "C" size_t gode_gat_fwd_workspace_bytes(const gode_gat_graph_t* G, int32_t heads, int32_t oh) {
+  if (!G || heads < 1 || oh < 1) return 0;
+  return part_bytes(G, heads, oh);
+}
+
+extern "C" size_t gode_gat_bwd_workspace_bytes(const gode_gat_graph_t* G, int32_t heads, int32_t oh) {
+  if (!G || heads < 1 || oh < 1) return 0;
+  const int64_t n_edges = G->n_edges;
   return align_up(sizeof(float) * static_cast<size_t>(n_edges > 0 ? n_edges : 1) * heads, 256) + align_up(sizeof(float) * 64, 256) +
-         align_up(gode_colreduce_workspace_bytes(heads), 256);
+         align_up(gode_colreduce_workspace_bytes(heads), 256) + part_bytes(G, heads, oh);
 }
 
 extern "C" int gode_gat_fwd(const gode_gat_graph_t* G, int32_t heads, int32_t oh, const float* P, int64_t ldp, float eps,
                             float* out, int64_t ldo, float* den, unsigned long long* amax_key, int32_t* nan_flag,
-                            void* stream) {
+                            void* ws, size_t ws_bytes, void* stream) {
   int rc = gat_check(G, heads, oh, ldp);
   if (rc) return rc;
   GODE_REQUIRE(ldo >= heads * oh && amax_key && nan_flag && (G->n_nodes == 0 || (P && out && den)), "gat_fwd: bad argument");
+  if (G->t_heavy.n_chunks > 0 && (!ws || ws_bytes < part_bytes(G, heads, oh))) {
+    set_error("gat_fwd: workspace too small");
+    return GODE_EWORKSPACE;
+  }
+  float* part = static_cast<float*>(ws);
   cudaStream_t st = as_stream(stream);
   GODE_CHECK_CUDA(cudaMemsetAsync(amax_key, 0, sizeof(unsigned long long) * heads, st));
   if (G->n_nodes == 0) return GODE_OK;
@@ -284,10 +455,10 @@ extern "C" int gode_gat_fwd(const gode_gat_graph_t* G, int32_t heads, int32_t oh
                                                               nan_flag);
     GODE_LAUNCH_CHECK();
   }
-  if (oh <= 8) return gat_fwd_t<8>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, st);
-  if (oh <= 16) return gat_fwd_t<16>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, st);
-  if (oh <= 32) return gat_fwd_t<32>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, st);
-  return gat_fwd_t<64>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, st);
+  if (oh <= 8) return gat_fwd_t<8>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, part, st);
+  if (oh <= 16) return gat_fwd_t<16>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, part, st);
+  if (oh <= 32) return gat_fwd_t<32>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, part, st);
+  return gat_fwd_t<64>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, part, st);
 }
 
 extern "C" int gode_gat_bwd(const gode_gat_graph_t* G, int32_t heads, int32_t oh, const float* P, int64_t ldp, const float* out,
@@ -296,7 +467,7 @@ extern "C" int gode_gat_bwd(const gode_gat_graph_t* G, int32_t heads, int32_t oh
   int rc = gat_check(G, heads, oh, ldp);
   if (rc) return rc;
   GODE_REQUIRE(amax_key && (G->n_nodes == 0 || (P && out && den && gout && dP)), "gat_bwd: null pointer");
-  if (!ws || ws_bytes < gode_gat_bwd_workspace_bytes(G->n_edges, heads)) {
+  if (!ws || ws_bytes < gode_gat_bwd_workspace_bytes(G, heads, oh)) {
     set_error("gat_bwd: workspace too small");
     return GODE_EWORKSPACE;
   }
@@ -307,10 +478,11 @@ extern "C" int gode_gat_bwd(const gode_gat_graph_t* G, int32_t heads, int32_t oh
   float* dsum = ar.take<float>(64);
   const size_t red_bytes = gode_colreduce_workspace_bytes(heads);
   float* red = reinterpret_cast<float*>(ar.take<char>(red_bytes));
-  if (oh <= 8) rc = gat_bwd_t<8>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, st);
-  else if (oh <= 16) rc = gat_bwd_t<16>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, st);
-  else if (oh <= 32) rc = gat_bwd_t<32>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, st);
-  else rc = gat_bwd_t<64>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, st);
+  float* part = reinterpret_cast<float*>(ar.take<char>(part_bytes(G, heads, oh)));
+  if (oh <= 8) rc = gat_bwd_t<8>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, part, st);
+  else if (oh <= 16) rc = gat_bwd_t<16>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, part, st);
+  else if (oh <= 32) rc = gat_bwd_t<32>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, part, st);
+  else rc = gat_bwd_t<64>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, part, st);
   if (rc) return rc;
   if (G->n_edges > 0) {
     if ((rc = colsum(G->n_edges, heads, dA, heads, dsum, red, red_bytes, st))) return rc;

@@ -515,8 +515,29 @@ class GatGraph:
         g.n_nodes, g.n_edges = self.n_nodes, E
         g.tptr, g.t_src, g.t_tgt = self.tptr.data_ptr(), self.t_src.data_ptr(), self.t_tgt.data_ptr()
         g.sptr, g.s_tgt, g.s_pos = self.sptr.data_ptr(), self.s_tgt.data_ptr(), self.s_pos.data_ptr()
+        self._hub_tables = [self._hubs(self.tptr, g.t_heavy), self._hubs(self.sptr, g.s_heavy)]   # keep the tensors alive
         self.c = g
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+
+
+    def _hubs(self, ptr, h):
+        """Hub table of one grouping (gode_gat_heavy_t): nodes with more than GAT_CHUNK edges, cut into chunks."""
+        lim = _lib.GAT_CHUNK
+        deg = (ptr[1:] - ptr[:-1]).to(torch.int64)
+        nodes = torch.nonzero(deg > lim).squeeze(1)
+        if nodes.numel() == 0:
+            h.n_heavy = h.n_chunks = 0
+            return ()
+        nch = (deg[nodes] + lim - 1) // lim
+        cptr = torch.zeros(nodes.numel() + 1, dtype=torch.int64, device=ptr.device)
+        cptr[1:] = torch.cumsum(nch, 0)
+        chunk_node = torch.repeat_interleave(nodes, nch)
+        local = torch.arange(int(cptr[-1]), device=ptr.device, dtype=torch.int64) - torch.repeat_interleave(cptr[:-1], nch)
+        chunk_e0 = ptr[chunk_node].to(torch.int64) + local * lim
+        t = tuple(x.to(torch.int32).contiguous() for x in (nodes, cptr, chunk_node, chunk_e0))
+        h.n_heavy, h.n_chunks = int(nodes.numel()), int(chunk_node.numel())
+        h.nodes, h.cptr, h.chunk_node, h.chunk_e0 = (x.data_ptr() for x in t)
+        return t
 
 
 _gat_cache = {}
@@ -558,8 +579,10 @@ class GatConvFn(torch.autograd.Function):
         out = torch.empty(graph.n_nodes, C_, dtype=torch.float32, device=x.device)
         den = torch.empty(graph.n_nodes, H, dtype=torch.float32, device=x.device)
         amax = torch.empty(H, dtype=torch.int64, device=x.device)
+        nb = lib.gode_gat_fwd_workspace_bytes(C.byref(graph.c), H, oh)
+        ws = workspace(nb, x.device, "gat_fwd")
         check(lib.gode_gat_fwd(C.byref(graph.c), H, oh, _p(P), ldp, float(eps), _p(out), out.stride(0), _p(den), _p(amax),
-                               _p(graph.nan_flag), _stream()), "gode_gat_fwd")
+                               _p(graph.nan_flag), _p(ws), nb, _stream()), "gode_gat_fwd")
         ctx.graph, ctx.H, ctx.oh, ctx.i = graph, H, oh, i
         ctx.has_bias = (f_bias is not None, w_bias is not None)
         ctx.save_for_backward(x, wcat, P, out, den, amax)
@@ -573,7 +596,7 @@ class GatConvFn(torch.autograd.Function):
         ldp = 2 * C_ + 2 * H
         g = _rowmajor(g, "grad").contiguous()
         dP = torch.empty_like(P)
-        nb = lib.gode_gat_bwd_workspace_bytes(graph.n_edges, H)
+        nb = lib.gode_gat_bwd_workspace_bytes(C.byref(graph.c), H, oh)
         ws = workspace(nb, x.device, "gat")
         check(lib.gode_gat_bwd(C.byref(graph.c), H, oh, _p(P), ldp, _p(out), out.stride(0), _p(den), _p(amax), _p(g),
                                g.stride(0), _p(dP), _p(ws), nb, _stream()), "gode_gat_bwd")

@@ -314,6 +314,17 @@ int gode_gcn_vjp_phase2_rk(const gode_gcn_odefunc_t* f, const float* y, float t,
  * bwd writes dP[N, ldp] (columns [0, 2C+2H) are written, padding is left alone); the caller finishes with
  * dx = dP W^T and dW = x^T dP.
  * ---------------------------------------------------------------------------------------------- */
+/* Hub nodes of one grouping: a node with more than GODE_GAT_CHUNK edges is cut into chunks of GODE_GAT_CHUNK consecutive
+ * edges that separate threads reduce; its chunks are added in chunk order (deterministic).  n_chunks == 0: no hubs. */
+#define GODE_GAT_CHUNK 64
+typedef struct {
+  int32_t n_heavy, n_chunks;
+  const int32_t* nodes;       /* [n_heavy] */
+  const int32_t* cptr;        /* [n_heavy + 1] chunk range of each hub */
+  const int32_t* chunk_node;  /* [n_chunks] */
+  const int32_t* chunk_e0;    /* [n_chunks] first edge of the chunk (position in the grouping) */
+} gode_gat_heavy_t;
+
 typedef struct {
   int64_t n_nodes;
   int64_t n_edges;
@@ -323,11 +334,15 @@ typedef struct {
   const int32_t* sptr;   /* [n_nodes + 1] segments by source */
   const int32_t* s_tgt;  /* [n_edges] target node of each edge, by-source order */
   const int32_t* s_pos;  /* [n_edges] by-target position of each edge, by-source order */
+  gode_gat_heavy_t t_heavy;  /* hubs of the by-target grouping */
+  gode_gat_heavy_t s_heavy;  /* hubs of the by-source grouping */
 } gode_gat_graph_t;
 
+size_t gode_gat_fwd_workspace_bytes(const gode_gat_graph_t* g, int32_t heads, int32_t oh);
 int gode_gat_fwd(const gode_gat_graph_t* g, int32_t heads, int32_t oh, const float* P, int64_t ldp, float eps,
-                 float* out, int64_t ldo, float* den, unsigned long long* amax_key, int32_t* nan_flag, void* stream);
-size_t gode_gat_bwd_workspace_bytes(int64_t n_edges, int32_t heads);
+                 float* out, int64_t ldo, float* den, unsigned long long* amax_key, int32_t* nan_flag,
+                 void* ws, size_t ws_bytes, void* stream);
+size_t gode_gat_bwd_workspace_bytes(const gode_gat_graph_t* g, int32_t heads, int32_t oh);
 int gode_gat_bwd(const gode_gat_graph_t* g, int32_t heads, int32_t oh, const float* P, int64_t ldp,
                  const float* out, int64_t ldo, const float* den, const unsigned long long* amax_key,
                  const float* gout, int64_t ldg, float* dP, void* ws, size_t ws_bytes, void* stream);

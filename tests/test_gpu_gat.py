@@ -116,6 +116,47 @@ def test_gat_matches_oracle(i, o, heads):
         G.assert_close(p.grad, pc[k].grad, rtol=1e-5, atol_scale=2e-5, what=k, atol_abs=1e-5 if k == "w.bias" else 0.0)
 
 
+@pytest.mark.parametrize("heads,o", [(1, 16), (8, 16)])
+def test_gat_hub_nodes_are_chunked(heads, o):
+    """Power-law hubs: nodes with more than GODE_GAT_CHUNK (64) in- or out-edges are reduced by several threads whose
+    partial sums are added in chunk order; one hub has exactly 64 edges, one 65, one 1000 -- against the oracle."""
+    ops, layers, _ = _pkg()
+    n, i = 1500, 12
+    rng = np.random.default_rng(5)
+    src = [rng.integers(0, n, 3000)]
+    tgt = [rng.integers(0, n, 3000)]
+    for hub, deg in ((7, 64), (8, 65), (9, 1000)):
+        src += [rng.integers(0, n, deg), np.full(deg, hub)]          # hub as target, then hub as source
+        tgt += [np.full(deg, hub), rng.integers(0, n, deg)]
+    src = torch.from_numpy(np.concatenate(src).astype(np.int64))
+    tgt = torch.from_numpy(np.concatenate(tgt).astype(np.int64))
+    perm = torch.from_numpy(rng.permutation(src.numel()))
+    src, tgt = src[perm], tgt[perm]
+    torch.manual_seed(3)
+    lay = layers.GraphConvolution(i, o, heads=heads)
+    x = torch.randn(n, i)
+    gy = torch.randn(n, o * heads)
+    pc = {k: v.detach().clone().requires_grad_(True) for k, v in lay.state_dict().items()}
+    xo = x.clone().requires_grad_(True)
+    hs = [(pc["f.weight"][h * o:(h + 1) * o], pc["f.bias"][h * o:(h + 1) * o], pc["w.weight"][h:h + 1], pc["w.bias"][h:h + 1])
+          for h in range(heads)]
+    yo = gat_ref.gat_multihead(xo, src, tgt, hs)
+    yo.backward(gy)
+    lay = lay.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    graph = ops.gat_graph_for(src.to(DEV), tgt.to(DEV), n)
+    indeg, outdeg = torch.bincount(tgt, minlength=n), torch.bincount(src, minlength=n)
+    assert graph.c.t_heavy.n_heavy == int((indeg > 64).sum()) >= 2
+    assert graph.c.s_heavy.n_heavy == int((outdeg > 64).sum()) >= 2
+    assert graph.c.t_heavy.n_chunks == int(((indeg[indeg > 64] + 63) // 64).sum())
+    y = lay(xg, src.to(DEV), tgt.to(DEV), None)
+    y.backward(gy.to(DEV))
+    G.assert_close(y, yo, rtol=1e-5, atol_scale=1e-5, what="out")
+    G.assert_close(xg.grad, xo.grad, rtol=1e-5, atol_scale=1e-5, what="grad_x")
+    for k, p in lay.named_parameters():
+        G.assert_close(p.grad, pc[k].grad, rtol=1e-5, atol_scale=2e-5, what=k, atol_abs=1e-5 if k == "w.bias" else 0.0)
+
+
 def test_gat_empty_and_degenerate():
     ops, layers, _ = _pkg()
     lay = layers.GraphConvolution(4, 8).to(DEV)
