@@ -398,24 +398,37 @@ def run_ours(a):
     # ---- e2e: public API, host buffers ------------------------------------------------------------
     e2e = None
     if not a.no_e2e:
+        # Input pipeline of a training loop: the step's input lives in pinned host memory and is copied to the device every
+        # step; the copy of step k+1 is issued on a copy stream while step k computes (two staging buffers), exactly what a
+        # DataLoader with pin_memory + non_blocking prefetch does.  Every step still pays its own 5.12 GB host->device copy
+        # and a device->host read of its loss inside the timed region.
         x_host = torch.empty(n_loc, d, dtype=torch.float32, pin_memory=True)
         x_host.copy_(x_dev)
-        x_stage = torch.empty_like(x_dev)
+        x_stage = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+        copy_stream = torch.cuda.Stream(device=dev)
 
-        def e2e_step():
-            x_stage.copy_(x_host, non_blocking=True)
-            return float(step(x_stage.detach()).item())
+        def issue_copy(k):
+            with torch.cuda.stream(copy_stream):
+                x_stage[k & 1].copy_(x_host, non_blocking=True)
 
-        e2e_step()
+        def e2e_step(k):
+            torch.cuda.current_stream().wait_stream(copy_stream)      # input k has arrived
+            issue_copy(k + 1)                                         # its buffer was last read by step k-1, which has finished
+            return float(step(x_stage[k & 1].detach()).item())
+
+        issue_copy(0)
+        e2e_step(0)                                                   # warm-up; leaves copy 1 in flight
         sync()
         t0 = time.perf_counter()
-        for _ in range(a.steps):
-            e2e_step()
-        sync()
+        for k in range(1, a.steps + 1):                               # steady state: one copy issued and one awaited per step
+            e2e_step(k)
+        sync()                                                        # includes the last copy issued
         e_ms = max_over_ranks((time.perf_counter() - t0) / a.steps * 1e3)
         e2e = {"value": nnz * nfe_per_step / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * d * 4,
                "d2h_bytes_per_step": 4 * world, "ms_per_step": e_ms,
-               "note": "graph plan stays resident across steps as adj.cuda() does in GCN/train_res.py:57; bytes are "
+               "note": "module API (ODEBlock forward / backward + Adam) on host buffers: each step's input is copied from "
+                       "pinned host memory (the copy of step k+1 overlaps step k, two staging buffers) and its loss is read "
+                       "back; graph plan stays resident across steps as adj.cuda() does in GCN/train_res.py:57; bytes are "
                        "summed over ranks (each rank copies its own rows)"}
         del x_host, x_stage
 
