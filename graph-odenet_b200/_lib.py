@@ -90,6 +90,7 @@ _PROTOS = {
     "gode_gcn_workspace_bytes": (sz, [C.POINTER(GcnOdeFunc)]),
     "gode_gcn_push_fusable": (C.c_int, [C.POINTER(GcnOdeFunc)]),
     "gode_gcn_transform": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, sz, vp]),
+    "gode_gcn_transform_rows": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, i64, i64, vp, sz, vp]),
     "gode_gcn_stage_fwd": (C.c_int, [C.POINTER(GcnOdeFunc), vp, vp, vp, C.POINTER(vp), C.POINTER(f32), i32, f32, vp,
                                      f32, vp, vp, sz, vp]),
     "gode_gcn_stage_vjp": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, f32, vp, vp, vp, vp, sz, vp]),
@@ -105,6 +106,7 @@ _PROTOS = {
     "gode_peer_open": (C.c_int, [vp, C.POINTER(vp)]),
     "gode_peer_close": (C.c_int, [vp]),
     "gode_halo_push": (C.c_int, [C.POINTER(PeerGroup), C.c_uint32, vp, vp, vp, i64, i32, vp, i64, i64, i32, vp]),
+    "gode_halo_push_part": (C.c_int, [C.POINTER(PeerGroup), C.c_uint32, vp, vp, vp, vp, i64, i32, vp, i64, i64, i32, i32, vp]),
     "gode_peer_wait": (C.c_int, [C.POINTER(PeerGroup), C.c_uint32, C.c_uint64, vp]),
     "gode_peer_status": (C.c_int, [C.POINTER(PeerGroup), C.POINTER(i32), vp]),
     "gode_edge_matvec": (C.c_int, [i64, i32, vp, vp, vp, i64, vp, vp]),

@@ -11,7 +11,8 @@
 namespace gode {
 
 // transform_tc.cu (tcgen05 kernels)
-int transform_tc(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, cudaStream_t st);
+int transform_tc(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, cudaStream_t st, int64_t row0 = 0,
+                 int64_t n_rows = -1);
 bool transform_tc_supported(const gode_gcn_odefunc_t* f);
 int input_grad_tc(const gode_gcn_odefunc_t* f, const float* gS, float* gz, cudaStream_t st);
 bool wgrad_tc_supported(const gode_gcn_odefunc_t* f);
@@ -149,6 +150,28 @@ extern "C" int gode_gcn_transform(const gode_gcn_odefunc_t* f, const float* y, f
   rc = carve(f, ws, ws_bytes, w);
   if (rc) return rc;
   return transform_impl(f, y, t, S, w, as_stream(stream));
+}
+
+extern "C" int gode_gcn_transform_rows(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, int64_t row0,
+                                       int64_t n_rows, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check(f);
+  if (rc) return rc;
+  GODE_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= f->A.n_rows, "gcn_transform_rows: row range outside the block");
+  if (n_rows == 0) return GODE_OK;
+  GODE_REQUIRE(y && S, "gcn_transform_rows: null pointer");
+  GcnWs w;
+  rc = carve(f, ws, ws_bytes, w);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  ProfScope prof(GODE_PROF_TRANSFORM, st);
+  if (transform_tc_supported(f)) return transform_tc(f, y, t, S, st, row0, n_rows);
+  GODE_REQUIRE(!f->push_S.ptr, "gcn_transform_rows: a fused halo push needs the tensor-core transform");
+  const int d = f->d;
+  const float* yr = y + row0 * d;
+  float* Sr = S + row0 * d;
+  rc = groupnorm_fwd(n_rows, d, f->groups, f->gn_eps, yr, d, f->gamma, f->beta, w.bufC, d, st);
+  if (rc) return rc;
+  return gemm_simt(0, 0, n_rows, d, d, 1.f, w.bufC, d, f->W + d, d, 0.f, Sr, d, 1, nullptr, 0, st, f->W, t);
 }
 
 extern "C" int gode_gcn_stage_fwd(const gode_gcn_odefunc_t* f, const float* S, float* k_out, const float* y0,

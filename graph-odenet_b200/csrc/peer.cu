@@ -46,7 +46,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // rotated peer order so that at any moment the ranks write to different destinations.
 __global__ void __launch_bounds__(256) k_halo_push4(PushArgs a, const int32_t* __restrict__ send_idx, int d4,
                                                     const float4* __restrict__ src, int64_t lds4, int64_t ldd4,
-                                                    unsigned int* __restrict__ counter, uint32_t epoch) {
+                                                    unsigned int* __restrict__ counter, uint32_t epoch, int signal) {
   const int64_t n_rows = a.vstart[a.n_seg];
   const int64_t total = n_rows * d4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(256) k_halo_push4(PushArgs a, const int32_t* _
     const float4 val = __ldg(src + (int64_t)s * lds4 + c);
     reinterpret_cast<float4*>(a.dst[j])[k * ldd4 + c] = val;
   }
+  if (!signal) return;   // a part of a pipelined exchange: the last part publishes the epoch (same stream, in order)
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -136,12 +137,12 @@ extern "C" int gode_peer_close(void* p) {
   return GODE_OK;
 }
 
-extern "C" int gode_halo_push(const gode_peer_group_t* g, uint32_t epoch, const int32_t* send_idx,
-                              const int64_t* send_ptr, const int64_t* dst_row, int64_t buf_offset, int32_t d,
-                              const float* src, int64_t lds, int64_t ldd, int32_t max_ctas, void* stream) {
+static int halo_push_impl(const gode_peer_group_t* g, uint32_t epoch, const int32_t* send_idx, const int64_t* seg_begin,
+                          const int64_t* seg_end, const int64_t* dst_row, int64_t buf_offset, int32_t d, const float* src,
+                          int64_t lds, int64_t ldd, int32_t max_ctas, int32_t signal, void* stream) {
   GODE_REQUIRE(g && g->world >= 1 && g->world <= GODE_MAX_PEERS && g->rank >= 0 && g->rank < g->world,
                "halo_push: bad peer group");
-  GODE_REQUIRE(send_ptr && dst_row && d > 0 && d % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "halo_push: bad shape");
+  GODE_REQUIRE(seg_begin && seg_end && dst_row && d > 0 && d % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "halo_push: bad shape");
   GODE_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (buf_offset & 15) == 0, "halo_push: misaligned operand");
   if (g->world == 1) return GODE_OK;
   PushArgs a;
@@ -153,17 +154,18 @@ extern "C" int gode_halo_push(const gode_peer_group_t* g, uint32_t epoch, const 
     const int p = (g->rank + s) % g->world;
     GODE_REQUIRE(g->base[p] != nullptr, "halo_push: peer arena not opened");
     a.flag[a.n_flag++] = reinterpret_cast<uint32_t*>(g->base[p]) + g->rank;
-    const int64_t cnt = send_ptr[p + 1] - send_ptr[p];
-    GODE_REQUIRE(cnt >= 0, "halo_push: send_ptr not monotone");
+    const int64_t cnt = seg_end[p] - seg_begin[p];
+    GODE_REQUIRE(cnt >= 0, "halo_push: negative segment");
     if (cnt == 0) continue;
     a.vstart[a.n_seg] = v;
-    a.send_off[a.n_seg] = send_ptr[p];
+    a.send_off[a.n_seg] = seg_begin[p];
     a.dst[a.n_seg] = reinterpret_cast<float*>(static_cast<char*>(g->base[p]) + buf_offset) + dst_row[p] * ldd;
     ++a.n_seg;
     v += cnt;
   }
   a.vstart[a.n_seg] = v;
   GODE_REQUIRE(v == 0 || (send_idx && src), "halo_push: null pointer");
+  if (v == 0 && !signal) return GODE_OK;
   const int d4 = d / 4;
   int64_t blocks = (v * d4 + 255) / 256;
   int64_t cap = max_ctas > 0 ? max_ctas : 8LL * sm_count();
@@ -171,9 +173,23 @@ extern "C" int gode_halo_push(const gode_peer_group_t* g, uint32_t epoch, const 
   if (blocks < 1) blocks = 1;
   unsigned int* counter = reinterpret_cast<unsigned int*>(static_cast<char*>(g->base[g->rank]) + GODE_PEER_COUNTER_OFFSET);
   k_halo_push4<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
-      a, send_idx, d4, reinterpret_cast<const float4*>(src), lds / 4, ldd / 4, counter, epoch);
+      a, send_idx, d4, reinterpret_cast<const float4*>(src), lds / 4, ldd / 4, counter, epoch, signal);
   GODE_LAUNCH_CHECK();
   return GODE_OK;
+}
+
+extern "C" int gode_halo_push(const gode_peer_group_t* g, uint32_t epoch, const int32_t* send_idx,
+                              const int64_t* send_ptr, const int64_t* dst_row, int64_t buf_offset, int32_t d,
+                              const float* src, int64_t lds, int64_t ldd, int32_t max_ctas, void* stream) {
+  GODE_REQUIRE(send_ptr != nullptr, "halo_push: null send_ptr");
+  return halo_push_impl(g, epoch, send_idx, send_ptr, send_ptr + 1, dst_row, buf_offset, d, src, lds, ldd, max_ctas, 1, stream);
+}
+
+extern "C" int gode_halo_push_part(const gode_peer_group_t* g, uint32_t epoch, const int32_t* send_idx,
+                                   const int64_t* seg_begin, const int64_t* seg_end, const int64_t* dst_row,
+                                   int64_t buf_offset, int32_t d, const float* src, int64_t lds, int64_t ldd,
+                                   int32_t max_ctas, int32_t signal, void* stream) {
+  return halo_push_impl(g, epoch, send_idx, seg_begin, seg_end, dst_row, buf_offset, d, src, lds, ldd, max_ctas, signal, stream);
 }
 
 extern "C" int gode_peer_wait(const gode_peer_group_t* g, uint32_t epoch, uint64_t timeout_ns, void* stream) {

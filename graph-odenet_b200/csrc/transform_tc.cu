@@ -931,12 +931,20 @@ static bool rows_tc_shape(const gode_gcn_odefunc_t* f) {
 bool transform_tc_supported(const gode_gcn_odefunc_t* f) { return (tc_mask() & 1) && rows_tc_shape(f); }
 bool input_grad_tc_supported(const gode_gcn_odefunc_t* f) { return (tc_mask() & 2) && rows_tc_shape(f); }
 
-int transform_tc(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, cudaStream_t st) {
+int transform_tc(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, cudaStream_t st, int64_t row0, int64_t n_rows) {
   GODE_REQUIRE(al16(y) && al16(S), "transform_tc: operands must be 16-byte aligned");
   const int passes = f->precision == GODE_PREC_TF32 ? 1 : 3;
   const gode_push_route_t* push = f->push_S.ptr ? &f->push_S : nullptr;
-  if (f->d == 128) return launch_rows_tc<128, 4, 0>(f->A.n_rows, y, S, f->W, f->gamma, f->beta, t, f->gn_eps, passes, st, push);
-  if (f->d == 64) return launch_rows_tc<64, 2, 0>(f->A.n_rows, y, S, f->W, f->gamma, f->beta, t, f->gn_eps, passes, st, push);
+  if (n_rows < 0) {        // whole block
+    row0 = 0;
+    n_rows = f->A.n_rows;
+  }
+  GODE_REQUIRE(row0 >= 0 && row0 + n_rows <= f->A.n_rows, "transform_tc: row range outside the block");
+  GODE_REQUIRE(!push || row0 == 0, "transform_tc: a fused push addresses rows from 0");
+  y += row0 * f->d;
+  S += row0 * f->d;
+  if (f->d == 128) return launch_rows_tc<128, 4, 0>(n_rows, y, S, f->W, f->gamma, f->beta, t, f->gn_eps, passes, st, push);
+  if (f->d == 64) return launch_rows_tc<64, 2, 0>(n_rows, y, S, f->W, f->gamma, f->beta, t, f->gn_eps, passes, st, push);
   set_error("transform_tc: unsupported width %d", f->d);
   return GODE_EINVAL;
 }

@@ -161,6 +161,12 @@ class HaloKernelMixin:
         # the phase-1 gather, with 64 resident warps per SM, hides its gP push completely and keeps it fused.
         import os
         self.fused_S = self.fused and os.environ.get("GODE_FUSE_S", "0") == "1"
+        # GODE_PIPE_S = number of row chunks (default 0 = off): the transform and the push of S pipelined over row chunks --
+        # chunk c is pushed on the side stream while chunk c+1 is transformed, and in the adjoint the whole exchange rides
+        # underneath phase 2; all flag writes then go to the side stream.  Measured at 2 GPUs (N = 10 M): 119.1 ms per step
+        # with 4 chunks vs 119.9 ms without -- what the overlap hides (outside 16.8 -> 8.3 ms) the concurrent push takes back
+        # from the kernels it runs next to (transform 9.3 -> 14.5, A^T gather 18.8 -> 20.5 ms) -- so it stays opt-in.
+        self.pipe_S = int(os.environ.get("GODE_PIPE_S", "0")) if (self.fused and not self.fused_S and self.peer.side) else 0
         if plan.split is not None:
             from . import _lib
             # descriptor for the second (halo-column) pass: same parameters, halo blocks, operand offset
@@ -267,7 +273,22 @@ class HaloKernelMixin:
         setattr(self.f, field, _lib.PushRoute())
         self.pending[buf.data_ptr()] = self.peer.finish(epoch)
 
+    def _transform_pipelined(self, y, t, out):
+        """S = transform(y, t) in row chunks on the current stream, each chunk's boundary rows pushed on the side stream."""
+        bounds = self.peer.part_bounds(self.pipe_S)
+        ws = self._ws()
+
+        def produce(c):
+            check(lib.gode_gcn_transform_rows(C.byref(self.f), ops._p(y), float(t), ops._p(out), bounds[c],
+                                              bounds[c + 1] - bounds[c], ops._p(ws), self.ws_bytes, ops._stream()),
+                  "gode_gcn_transform_rows")
+
+        self.pending[out.data_ptr()] = self.peer.push_pipelined(self.plan.halo, out, self.pipe_S, produce)
+        return out
+
     def transform(self, y, t, out):
+        if self.pipe_S:
+            return self._transform_pipelined(y, t, out)
         if self.fused_S:
             epoch = self._fused_begin("push_S", self.plan.halo, out)
             super().transform(y, t, out)
@@ -279,6 +300,12 @@ class HaloKernelMixin:
 
     def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0, S_next=None):
         run = lambda: super(HaloKernelMixin, self).stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next)
+        if self.pipe_S:
+            self._wait(S)
+            super(HaloKernelMixin, self).stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, None)
+            if S_next is not None:
+                self._transform_pipelined(y_next, t_next, S_next)
+            return
         if self.fused_S:
             self._wait(S)
             if S_next is None:
@@ -359,7 +386,7 @@ class PartitionedPlan:
         self.split = split                   # None, or dict(A_own, A_halo, At_own, At_halo)
         self.mode = mode
         self.comm_stream = (torch.cuda.Stream(device=self.device, priority=-1)
-                            if (mode not in ("sync", "p2p", "p2p-fused") and A.device.type == "cuda") else None)
+                            if (mode not in ("sync", "p2p") and A.device.type == "cuda") else None)
         self._peer = {}                      # feature width -> peer.PeerHalo (modes "p2p", "p2p-async")
         if self.comm_stream is not None:
             # the exchange of gP is issued right before the (persistent, one CTA per SM) transform kernel: without free
@@ -420,7 +447,9 @@ class PartitionedPlan:
         if ph is None:
             from . import peer
             try:
-                ph = self._peer[d] = peer.PeerHalo(self, d, push_stream=self.comm_stream if self.mode == "p2p-async" else None)
+                import os
+                side = self.mode == "p2p-async" or (self.mode == "p2p-fused" and os.environ.get("GODE_PIPE_S", "0") != "0")
+                ph = self._peer[d] = peer.PeerHalo(self, d, push_stream=self.comm_stream if side else None)
             except peer.PeerSetupError as e:
                 # raised on every rank together: all of them switch to the NCCL exchange on the side stream
                 import warnings

@@ -115,6 +115,9 @@ class ExchangeProtocol:
     def _emit_wait(self, epoch):
         raise NotImplementedError
 
+    def _emit_push_part(self, epoch, halo, buf, slot, part, n_parts):
+        raise NotImplementedError
+
     def _emit_side_after_main(self):
         """side stream waits for everything enqueued on the consumer stream so far"""
 
@@ -150,9 +153,28 @@ class ExchangeProtocol:
         return epoch
 
     def finish(self, epoch):
-        """Fused exchange: the producer kernel (consumer stream) has stored the peers' rows; publish the epoch."""
-        assert not self.side, "fused pushes run on the consumer stream"
+        """Fused exchange: the producer kernel (consumer stream) has stored the peers' rows; publish the epoch -- on the
+        push stream, like every other flag write, ordered after the producer."""
+        if self.side:
+            self._emit_side_after_main()
         self._emit_push(epoch, None, None, None)
+        if self.side:
+            self._emit_done(epoch)
+            self.done.add(epoch)
+        return epoch
+
+    def push_pipelined(self, halo, buf, n_parts, produce):
+        """One exchange in ``n_parts`` row chunks: ``produce(c)`` enqueues the producer of chunk c on the consumer stream,
+        the rows of that chunk are pushed on the side stream while the next chunk is produced; the last part publishes
+        the epoch.  Needs the side stream (flag writes stay on one stream)."""
+        assert self.side, "the pipelined exchange needs the side stream"
+        epoch, slot = self.begin(buf)
+        for c in range(n_parts):
+            produce(c)
+            self._emit_side_after_main()
+            self._emit_push_part(epoch, halo, buf, slot, c, n_parts)
+        self._emit_done(epoch)
+        self.done.add(epoch)
         return epoch
 
     def wait(self, epoch):
@@ -244,6 +266,7 @@ class PeerHalo(ExchangeProtocol):
         self.side = push_stream is not None
         self.done_events = {}                  # epoch -> event of this rank's own push on the side stream
         self._fused = {}                       # id(halo plan) -> (ptr, ent) device arrays of the fused push route
+        self._part_cache = {}                  # (id(halo plan), n_parts) -> per-chunk segment ranges
         # where my rows land in every peer's halo tail, for both halo plans
         self.routes = {id(plan.halo): self._route(plan.halo), id(plan.halo_t): self._route(plan.halo_t)}
         torch.cuda.synchronize(dev)
@@ -336,6 +359,41 @@ class PeerHalo(ExchangeProtocol):
         off = PEER_HEADER_BYTES + slot * self.slot_bytes
         check(lib.gode_halo_push(C.byref(self.g), epoch, ops._p(halo.send_idx), send_ptr, dst_row, off, self.d,
                                  ops._p(buf), buf.stride(0), self.d, self.max_ctas, stream), "gode_halo_push")
+
+    def part_bounds(self, n_parts):
+        """Row bounds of the chunks of a pipelined exchange (multiples of 128 rows: the transform's tile)."""
+        n = self.plan.n_rows
+        tiles = -(-n // 128)
+        return [min(n, 128 * ((tiles * c) // n_parts)) for c in range(n_parts)] + [n]
+
+    def _parts(self, halo, n_parts):
+        """Per chunk: (seg_begin[world], seg_end[world], dst_row[world]) host arrays -- the entries of every peer's send
+        segment (sorted by row) whose row falls into the chunk."""
+        key = (id(halo), n_parts)
+        if key not in self._part_cache:
+            send_ptr, dst_row = self.routes[id(halo)]
+            sp = list(send_ptr)
+            rows = halo.send_idx.to(torch.int64)
+            bounds = torch.tensor(self.part_bounds(n_parts), dtype=torch.int64, device=rows.device)
+            cut = []                                    # cut[p][c]: first entry of peer p's segment with row >= bounds[c]
+            for p_ in range(self.world):
+                seg = rows[sp[p_]:sp[p_ + 1]]
+                cut.append((torch.searchsorted(seg, bounds) + sp[p_]).tolist() if seg.numel() else [sp[p_]] * (n_parts + 1))
+            out = []
+            for c in range(n_parts):
+                b = (C.c_int64 * self.world)(*[cut[p_][c] for p_ in range(self.world)])
+                e = (C.c_int64 * self.world)(*[cut[p_][c + 1] for p_ in range(self.world)])
+                dr = (C.c_int64 * self.world)(*[dst_row[p_] + cut[p_][c] - sp[p_] for p_ in range(self.world)])
+                out.append((b, e, dr))
+            self._part_cache[key] = out
+        return self._part_cache[key]
+
+    def _emit_push_part(self, epoch, halo, buf, slot, part, n_parts):
+        b, e, dr = self._parts(halo, n_parts)[part]
+        off = PEER_HEADER_BYTES + slot * self.slot_bytes
+        check(lib.gode_halo_push_part(C.byref(self.g), epoch, ops._p(halo.send_idx), b, e, dr, off, self.d, ops._p(buf),
+                                      buf.stride(0), self.d, self.max_ctas, 1 if part == n_parts - 1 else 0,
+                                      self._push_stream_handle()), "gode_halo_push_part")
 
     def _emit_wait(self, epoch):
         check(lib.gode_peer_wait(C.byref(self.g), epoch, self.timeout_ns, ops._stream()), "gode_peer_wait")

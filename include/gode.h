@@ -260,6 +260,10 @@ int gode_gcn_push_fusable(const gode_gcn_odefunc_t* f);
 /* S[n_rows, d] = [t || GN(y)] W */
 int gode_gcn_transform(const gode_gcn_odefunc_t* f, const float* y, float t, float* S,
                        void* ws, size_t ws_bytes, void* stream);
+/* The same transform on rows [row0, row0 + n_rows) of the block (y and S are the block's base pointers): lets the caller
+ * pipeline the transform of one row chunk with the halo push of the previous one. */
+int gode_gcn_transform_rows(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, int64_t row0, int64_t n_rows,
+                            void* ws, size_t ws_bytes, void* stream);
 
 /* k_out = relu(A_hat S + b); optional y_next (RK combination, see gode_spmm_epilogue_t);
  * optional S_next = transform(y_next, t_next) (needs y_next). */
@@ -409,6 +413,12 @@ int gode_peer_close(void* p);
 int gode_halo_push(const gode_peer_group_t* g, uint32_t epoch, const int32_t* send_idx, const int64_t* send_ptr,
                    const int64_t* dst_row, int64_t buf_offset, int32_t d, const float* src, int64_t lds,
                    int64_t ldd, int32_t max_ctas, void* stream);
+/* One part of a pipelined exchange: the entries send_idx[seg_begin[p] .. seg_end[p]) of peer p go to rows dst_row[p] + k;
+ * only the call with signal != 0 (the last part, issued on the same stream) publishes the epoch. */
+int gode_halo_push_part(const gode_peer_group_t* g, uint32_t epoch, const int32_t* send_idx,
+                        const int64_t* seg_begin, const int64_t* seg_end, const int64_t* dst_row,
+                        int64_t buf_offset, int32_t d, const float* src, int64_t lds, int64_t ldd,
+                        int32_t max_ctas, int32_t signal, void* stream);
 int gode_peer_wait(const gode_peer_group_t* g, uint32_t epoch, uint64_t timeout_ns, void* stream);
 int gode_peer_status(const gode_peer_group_t* g, int32_t* status_host, void* stream);
 

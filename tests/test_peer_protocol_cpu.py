@@ -66,6 +66,14 @@ class RecProtocol(peer.ExchangeProtocol):
     def _emit_wait(self, epoch):
         self.prog.append(("main", "wait", epoch))
 
+    def part_bounds(self, n_parts):
+        return list(range(n_parts + 1))
+
+    def _emit_push_part(self, epoch, halo, buf, slot, part, n_parts):
+        self.prog.append(("side", "rwrite", epoch, slot))
+        if part == n_parts - 1:
+            self.prog.append(("side", "signal", epoch))
+
     def _emit_side_after_main(self):
         self.n_ev += 1
         self.prog.append(("main", "record", "m%d" % self.n_ev))
@@ -135,10 +143,15 @@ class RecKernel(parallel.HaloKernelMixin, RecBase):
     def _push_fusable(self):
         return True
 
+    def _transform_pipelined(self, y, t, out):      # the CUDA chunk launches replaced by nothing: only the protocol is replayed
+        self.pending[out.data_ptr()] = self.peer.push_pipelined(self.plan.halo, out, self.pipe_S, lambda c: None)
+        return out
+
 
 def record_program(proto_cls, mode, method, step_size, n_steps, n_slots=8):
+    import os
     prog = []
-    side = mode == "p2p-async"
+    side = mode == "p2p-async" or (mode == "p2p-fused" and os.environ.get("GODE_PIPE_S", "0") != "0")
     proto = proto_cls(n_slots, side, prog)
     plan = types.SimpleNamespace(mode=mode, world=4, split=None, n_rows=10, n_global=40,
                                  halo=types.SimpleNamespace(n_halo=3), halo_t=types.SimpleNamespace(n_halo=3),
@@ -223,11 +236,12 @@ def _no_cuda_combine(monkeypatch):
     monkeypatch.setattr(ops, "rk_combine", lambda y0, ks, cs, out=None: out)
 
 
-@pytest.mark.parametrize("mode", ["p2p", "p2p-async", "p2p-fused", "p2p-fused+S"])
+@pytest.mark.parametrize("mode", ["p2p", "p2p-async", "p2p-fused", "p2p-fused+S", "p2p-fused+pipe"])
 @pytest.mark.parametrize("method,step_size", [("rk4", None), ("rk4", 0.25), ("midpoint", 0.5), ("euler", 0.5)])
 def test_protocol_is_safe_under_random_interleaving(mode, method, step_size, monkeypatch):
     monkeypatch.setenv("GODE_FUSE_S", "1" if mode.endswith("+S") else "0")
-    mode = mode.replace("+S", "")
+    monkeypatch.setenv("GODE_PIPE_S", "3" if mode.endswith("+pipe") else "0")
+    mode = mode.replace("+S", "").replace("+pipe", "")
     prog, proto = record_program(RecProtocol, mode, method, step_size, n_steps=3)
     assert any(op[1] == "rwrite" for op in prog) and any(op[1] == "signal" for op in prog)
     rng = random.Random(1234)
@@ -236,11 +250,12 @@ def test_protocol_is_safe_under_random_interleaving(mode, method, step_size, mon
             assert simulate(prog, world, rng) is None
 
 
-def test_rk4_steady_state_needs_no_empty_exchange():
+def test_rk4_steady_state_needs_no_empty_exchange(monkeypatch):
     """With the solver's buffer rotation (two gP buffers, fresh S per stage, round-robin slots) the hazard rule never
     has to insert an empty exchange: 12 exchanges per rk4 fwd+bwd step on grid [0, 1] (4 + 4 supports -- the adjoint's
     first stage reuses the support of f(t1) -- and 4 masked adjoints), as PartitionedPlan.halo_bytes_per_step counts."""
-    for mode in ("p2p", "p2p-async", "p2p-fused"):
+    for mode, pipe in (("p2p", "0"), ("p2p-async", "0"), ("p2p-fused", "0"), ("p2p-fused", "4")):
+        monkeypatch.setenv("GODE_PIPE_S", pipe)
         prog, proto = record_program(RecProtocol, mode, "rk4", None, n_steps=4)
         assert proto.n_empty == 0
         assert proto.track.issued == 4 * 12
