@@ -17,6 +17,7 @@ from .. import ops
 from ..GCN.models import GroupNorm
 from .layers import EdgeEncoderMLP, EdgeGraphConvolution, MyLinear, TransitionMLP
 from .mpnn import MPNN_enn_edge
+from .set2set import Set2Set
 
 
 def get_output_function(type, target_features):
@@ -87,6 +88,85 @@ class MPNN_ENN_K_Sum(nn.Module):
         x = self.mpnn(x, Esrc, Etgt, edge_data)
         x = ops.LinearFn.apply(x, self.output.weight.t(), self.output.bias, False)
         x = ops.scatter_add_rows(x, batch, batch_size)
+        return self.output_function(x)
+
+
+class MPNN_ENN_K_Set2Set(nn.Module):
+    """QC/layer_models.py:55-82.  The reference builds ``MPNN_enn`` here and calls ``set_T`` on it, which that class does
+    not have (AttributeError at construction); the evident intent -- the message-passing core of ``MPNN_ENN_K_Sum`` with
+    the Set2Set readout -- is what this class builds.  The readout keeps the first ``hidden`` columns of q* (:79)."""
+
+    def __init__(self, node_features=None, edge_features=None, target_features=1, hidden_features=73, num_layers=3,
+                 s2s_processing_steps=12, type="regression", dropout=0.5, **kwargs):
+        super().__init__()
+        self.input = nn.Linear(in_features=node_features, out_features=hidden_features)
+        self.ee = EdgeEncoderMLP(edge_features, hidden_features)
+        self.mpnn = MPNN_enn_edge(edge_features, hidden_features)
+        self.mpnn.set_T(num_layers)
+        self.s2s = Set2Set(hidden_features, s2s_processing_steps, num_layers=1)
+        self.output = nn.Linear(in_features=hidden_features, out_features=target_features)
+        self.type = type
+        self.output_function = get_output_function(type, target_features)
+
+    def forward(self, node_features, edge_features, Esrc, Etgt, batch, batch_size=None):
+        edge_data = self.ee(edge_features)
+        x = ops.LinearFn.apply(node_features, self.input.weight.t(), self.input.bias, False)
+        x = self.mpnn(x, Esrc, Etgt, edge_data)
+        x = self.s2s(x, batch)[:, :x.size(1)]
+        x = ops.LinearFn.apply(x, self.output.weight.t(), self.output.bias, False)
+        return self.output_function(x)
+
+
+class EdgeGCN_K_Set2Set(nn.Module):
+    """mlpin -> K x (EdgeGC [+ relu + dropout]) -> Set2Set (first ``hidden`` columns of q*) -> mlpout
+    (QC/layer_models.py:125-163)."""
+
+    def __init__(self, node_features=None, edge_features=None, target_features=1, hidden_features=73, num_layers=3,
+                 s2s_processing_steps=12, type="regression", dropout=0.5, **kwargs):
+        super().__init__()
+        self.mlpin = TransitionMLP(node_features, hidden_features)
+        self.gcmid = nn.ModuleList([EdgeGraphConvolution(hidden_features, hidden_features) for _ in range(num_layers)])
+        self.mlpout = TransitionMLP(hidden_features, target_features)
+        self.dropout = dropout
+        self.ee = EdgeEncoderMLP(edge_features, hidden_features)
+        self.s2s = Set2Set(hidden_features, s2s_processing_steps, num_layers=1)
+        self.type = type
+        self.output_function = get_output_function(type, target_features)
+
+    def forward(self, node_features, edge_features, Esrc, Etgt, batch, batch_size=None):
+        ef = self.ee(edge_features)
+        x = self.mlpin(node_features)
+        for gc in self.gcmid[:-1]:
+            x = F.relu(gc(x, Esrc, Etgt, ef))
+            x = F.dropout(x, self.dropout, training=self.training)
+        x = self.gcmid[-1](x, Esrc, Etgt, ef)
+        x = self.s2s(x, batch)[:, :x.size(1)]
+        x = self.mlpout(x)
+        return self.output_function(x)
+
+
+class EdgeRES1_K_Set2Set(nn.Module):
+    """mlpin -> RESKnorm(hidden, hidden, hidden, nlayers = K, residue_layers = 1) -> Set2Set -> mlpout
+    (QC/layer_models.py:166-197).  As in the reference it cannot be built at the default hidden = 73
+    (GroupNorm(32, 73) raises ValueError)."""
+
+    def __init__(self, node_features=None, edge_features=None, target_features=1, hidden_features=73, num_layers=3,
+                 s2s_processing_steps=12, type="regression", dropout=0.5, **kwargs):
+        super().__init__()
+        self.mlpin = TransitionMLP(node_features, hidden_features)
+        self.gcmid = RESKnorm(hidden_features, hidden_features, hidden_features, nlayers=num_layers, residue_layers=1)
+        self.mlpout = TransitionMLP(hidden_features, target_features)
+        self.ee = EdgeEncoderMLP(edge_features, hidden_features)
+        self.s2s = Set2Set(hidden_features, s2s_processing_steps, num_layers=1)
+        self.type = type
+        self.output_function = get_output_function(type, target_features)
+
+    def forward(self, node_features, edge_features, Esrc, Etgt, batch, batch_size=None):
+        ef = self.ee(edge_features)
+        x = self.mlpin(node_features)
+        x = self.gcmid(x, Esrc, Etgt, ef)
+        x = self.s2s(x, batch)[:, :x.size(1)]
+        x = self.mlpout(x)
         return self.output_function(x)
 
 

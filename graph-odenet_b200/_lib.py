@@ -99,6 +99,8 @@ _PROTOS = {
     "gode_gcn_vjp_phase2": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, vp, vp, sz, vp]),
     "gode_gcn_vjp_phase2_rk": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(f32), i32,
                                          f32, vp, vp, sz, vp]),
+    "gode_segment_attend_fwd": (C.c_int, [i32, i32, vp, vp, i64, vp, i64, vp, vp, i64, vp]),
+    "gode_segment_attend_bwd": (C.c_int, [i32, i32, vp, vp, i64, vp, i64, vp, vp, i64, vp, i64, vp, i64, vp]),
     "gode_gather_rows": (C.c_int, [i64, vp, i32, vp, i64, vp, i64, vp]),
     "gode_peer_alloc": (C.c_int, [sz, C.POINTER(vp)]),
     "gode_peer_free": (C.c_int, [vp]),

@@ -663,6 +663,37 @@ def scatter_add_rows(x, index, n_rows):
     return PlanMatmulFn.apply(x, index_plan(index, n_rows), None)
 
 
+class SegmentAttendFn(torch.autograd.Function):
+    """r[g] = sum_i softmax_g(<x_i, q_g>) x_i over the nodes of graph g (QC/set2set.py:60-75) -- gode_segment_attend_*."""
+
+    @staticmethod
+    def forward(ctx, x, q, gptr):
+        x, q = _rowmajor(x, "x"), _rowmajor(q, "q")
+        B, h = q.shape
+        a = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        r = torch.empty(B, h, dtype=torch.float32, device=x.device)
+        check(lib.gode_segment_attend_fwd(B, h, _p(gptr), _p(x), x.stride(0), _p(q), q.stride(0), _p(a), _p(r), r.stride(0),
+                                          _stream()), "gode_segment_attend_fwd")
+        ctx.save_for_backward(x, q, a, gptr)
+        return r
+
+    @staticmethod
+    def backward(ctx, dr):
+        x, q, a, gptr = ctx.saved_tensors
+        dr = _rowmajor(dr, "grad").contiguous()
+        B, h = q.shape
+        dx = torch.empty_like(x) if x.is_contiguous() else torch.empty(x.shape, dtype=torch.float32, device=x.device)
+        dq = torch.empty(B, h, dtype=torch.float32, device=x.device)
+        check(lib.gode_segment_attend_bwd(B, h, _p(gptr), _p(x), x.stride(0), _p(q), q.stride(0), _p(a), _p(dr), dr.stride(0),
+                                          _p(dx), dx.stride(0), _p(dq), dq.stride(0), _stream()), "gode_segment_attend_bwd")
+        return dx, dq, None
+
+
+def segment_attend(x, q, gptr):
+    """``gptr`` int32 [B + 1]: nodes of graph g are rows gptr[g] .. gptr[g+1] of ``x``."""
+    return SegmentAttendFn.apply(x, q, gptr)
+
+
 def incidence_plan(Etgt, n_nodes=None):
     """Plan of the reference's ``Etgt`` (dense one-hot [N, E], QC/datasets/utils.py:214; also accepted: sparse COO,
     or the target index vector [E] with ``n_nodes``)."""

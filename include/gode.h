@@ -368,6 +368,19 @@ int gode_edge_matvec_bwd(int64_t n_edges, int32_t f, const float* edge_data, con
                          float* ds_msg, float* d_edge_data, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Attention readout over the nodes of each graph of a batch: the inner step of Set2Set.
+ * replaces: QC/set2set.py:60-75 (e = <x_i, q[batch_i]>, per-graph softmax in a Python loop over the batch with boolean
+ *           masks, scatter_add of a * x).  Nodes of graph g are rows gptr[g] .. gptr[g+1] of x (block-diagonal batches).
+ *   fwd: a[i] = softmax_g(<x_i, q_g>)  (a [N] is saved for the backward),  r[g, :] = sum_i a[i] x[i, :]
+ *   bwd: dx [N, h] and dq [B, h] from dr [B, h].   h <= 256.  A graph without nodes gives r = 0.
+ * ---------------------------------------------------------------------------------------------- */
+int gode_segment_attend_fwd(int32_t n_graphs, int32_t h, const int32_t* gptr, const float* x, int64_t ldx,
+                            const float* q, int64_t ldq, float* a, float* r, int64_t ldr, void* stream);
+int gode_segment_attend_bwd(int32_t n_graphs, int32_t h, const int32_t* gptr, const float* x, int64_t ldx,
+                            const float* q, int64_t ldq, const float* a, const float* dr, int64_t lddr,
+                            float* dx, int64_t lddx, float* dq, int64_t lddq, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Halo pack for the row-partitioned (multi-GPU) path: dst[i, :] = src[idx[i], :].
  * The reference is single-device; this packs the rows of the SpMM operand of
  * torch.spmm(adj, support) (GCN/layers.py:71) that peer ranks reference, ordered by destination rank,

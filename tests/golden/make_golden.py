@@ -18,6 +18,7 @@ Outputs (all small, committed):
   gcn_golden.npz       GraphConvolution / ODEfunc / ODEfunc2 / ODEBlock / whole-model outputs + grads
   gat_golden.npz       GAT GraphConvolution + ODEfunc outputs + grads
   qc_golden.npz        QC EdgeGraphConvolution / EdgeEncoderMLP / EdgeGCN_K_Sum outputs + grads
+  set2set_golden.npz   QC Set2Set readout and EdgeGCN_K_Set2Set outputs + grads (``--only-set2set`` regenerates it alone)
 """
 from __future__ import annotations
 
@@ -309,10 +310,62 @@ def main():
     e = rnd(99, 20, 5)
     Q.update({"ee/out": ee(e).detach().numpy(), **sd_np(ee, "ee/p/")})
     np.savez_compressed(os.path.join(HERE, "qc_golden.npz"), **Q)
+    make_set2set()
     for fn in sorted(os.listdir(HERE)):
         if fn.endswith(".npz"):
             print(fn, os.path.getsize(os.path.join(HERE, fn)) // 1024, "KiB")
 
 
+def make_set2set():
+    """set2set_golden.npz: the reference's Set2Set readout (QC/set2set.py:9-77) and EdgeGCN_K_Set2Set
+    (QC/layer_models.py:125-163) on seeded inputs -- outputs and gradients."""
+    _install_shims()
+    qc = load_ref("QC", names=("set2set", "layer_models"))
+    S = {}
+    torch.manual_seed(11)
+    C_, steps = 24, 3
+    s2s = qc.set2set.Set2Set(C_, steps, num_layers=1)
+    sizes = [7, 1, 12, 3, 18, 9]                       # graphs of very different sizes, one singleton
+    batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    x = rnd(401, int(batch.numel()), C_).requires_grad_(True)
+    g = rnd(402, len(sizes), 2 * C_)
+    out = s2s(x, batch)
+    out.backward(g)
+    S.update({"s2s/x": x.detach().numpy(), "s2s/batch": batch.numpy().astype(np.int32), "s2s/g": g.numpy(),
+              "s2s/out": out.detach().numpy(), "s2s/grad_x": x.grad.numpy(), **sd_np(s2s, "s2s/p/"),
+              **{"s2s/grad/" + k: v.grad.numpy() for k, v in s2s.named_parameters()}})
+    # whole model, hidden 24, K = 3, regression head with 12 targets
+    torch.manual_seed(12)
+    model = qc.layer_models.EdgeGCN_K_Set2Set(node_features=13, edge_features=5, target_features=12, hidden_features=24,
+                                              num_layers=3, s2s_processing_steps=3, type="regression", dropout=0.0)
+    model.eval()
+    nN = int(batch.numel())
+    rs = np.random.RandomState(13)
+    # edges inside each molecule (block diagonal), a few per node
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    es, et = [], []
+    for b, n_b in enumerate(sizes):
+        m = 3 * n_b
+        es.append(offs[b] + rs.randint(0, n_b, m))
+        et.append(offs[b] + rs.randint(0, n_b, m))
+    esrc = torch.from_numpy(np.concatenate(es).astype(np.int64))
+    etgt = torch.from_numpy(np.concatenate(et).astype(np.int64))
+    nE = int(esrc.numel())
+    Etgt = torch.zeros(nN, nE)
+    Etgt[etgt, torch.arange(nE)] = 1.0
+    nf = rnd(403, nN, 13)
+    ef = rnd(404, nE, 5)
+    gy = rnd(405, len(sizes), 12)
+    y = model(nf, ef, esrc, Etgt, batch)
+    y.backward(gy)
+    S.update({"m/nf": nf.numpy(), "m/ef": ef.numpy(), "m/esrc": esrc.numpy().astype(np.int32),
+              "m/etgt": etgt.numpy().astype(np.int32), "m/gy": gy.numpy(), "m/out": y.detach().numpy(),
+              **sd_np(model, "m/p/"), **{"m/grad/" + k: v.grad.numpy() for k, v in model.named_parameters() if v.grad is not None}})
+    np.savez_compressed(os.path.join(HERE, "set2set_golden.npz"), **S)
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-set2set" in sys.argv:
+        make_set2set()
+    else:
+        main()

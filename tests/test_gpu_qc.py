@@ -193,3 +193,55 @@ def test_qc_model_surface():
         lm.RESKnorm(73, 73, 73, nlayers=3)          # GroupNorm(32, 73): the reference cannot build this either
     m = lm.MPNN_ENN_K_Sum(node_features=13, edge_features=5, target_features=12, hidden_features=16)
     assert "mpnn.update_net.weight_ih" in m.state_dict() and "ee.mlp.mlp.layers.0.linear.weight" in m.state_dict()
+
+
+def test_set2set_golden():
+    """Set2Set readout on gode_segment_attend_* against the reference fixture: q*, input gradient, LSTM gradients."""
+    _pkg()
+    from graph_odenet_b200.QC import set2set
+    g = G.load("set2set_golden")
+    s2s = set2set.Set2Set(24, 3)
+    s2s.load_state_dict(G.params(g, "s2s/p/"))
+    s2s = s2s.to(DEV)
+    x = torch.from_numpy(g["s2s/x"].copy()).to(DEV).requires_grad_(True)
+    batch = torch.from_numpy(g["s2s/batch"].astype(np.int64)).to(DEV)
+    out = s2s(x, batch)
+    out.backward(torch.from_numpy(g["s2s/g"]).to(DEV))
+    G.assert_close(out, g["s2s/out"], rtol=1e-5, atol_scale=1e-5, what="q*")
+    G.assert_close(x.grad, g["s2s/grad_x"], rtol=1e-5, atol_scale=1e-5, what="grad_x")
+    for k, v in s2s.named_parameters():
+        G.assert_close(v.grad, g["s2s/grad/" + k], rtol=1e-5, atol_scale=2e-5, what=k)
+    # unsorted batch vector: same result as the sorted one (nodes are regrouped internally)
+    perm = torch.randperm(x.shape[0], generator=torch.Generator().manual_seed(1)).to(DEV)
+    out2 = s2s(x.detach()[perm], batch[perm])
+    G.assert_close(out2, g["s2s/out"], rtol=1e-5, atol_scale=1e-5, what="q* (unsorted batch)")
+
+
+def test_edge_gcn_k_set2set_golden():
+    layer_models = _pkg()[3]
+    g = G.load("set2set_golden")
+    model = layer_models.EdgeGCN_K_Set2Set(node_features=13, edge_features=5, target_features=12, hidden_features=24,
+                                           num_layers=3, s2s_processing_steps=3, type="regression", dropout=0.0)
+    model.load_state_dict(G.params(g, "m/p/"))
+    model = model.to(DEV).eval()
+    batch = torch.from_numpy(g["s2s/batch"].astype(np.int64)).to(DEV)
+    y = model(torch.from_numpy(g["m/nf"]).to(DEV), torch.from_numpy(g["m/ef"]).to(DEV),
+              torch.from_numpy(g["m/esrc"].astype(np.int64)).to(DEV), torch.from_numpy(g["m/etgt"].astype(np.int64)).to(DEV), batch)
+    y.backward(torch.from_numpy(g["m/gy"]).to(DEV))
+    G.assert_close(y, g["m/out"], rtol=1e-5, atol_scale=1e-5, what="model out")
+    for k, v in model.named_parameters():
+        if "m/grad/" + k in g:
+            G.assert_close(v.grad, g["m/grad/" + k], rtol=1e-5, atol_scale=5e-5, what=k)
+
+
+def test_set2set_model_surface():
+    _, synth, _, layer_models, _ = _pkg()
+    kw = dict(node_features=13, edge_features=5, target_features=12, num_layers=3, s2s_processing_steps=2)
+    m = layer_models.MPNN_ENN_K_Set2Set(hidden_features=16, **kw)
+    assert {"input.weight", "s2s.lstm.weight_ih_l0", "mpnn.update_net.weight_ih", "output.bias"} <= set(m.state_dict())
+    with pytest.raises(ValueError):                       # GroupNorm(32, 73), as in the reference
+        layer_models.EdgeRES1_K_Set2Set(hidden_features=73, **kw)
+    r = layer_models.EdgeRES1_K_Set2Set(hidden_features=64, **kw).to(DEV).eval()
+    b = synth.qm9_like_batch(5, 64, seed=3, device=DEV)
+    out = r(b["node_features"], b["edge_features"], b["esrc"], b["etgt"], b["batch"])
+    assert out.shape == (5, 12) and bool(torch.isfinite(out).all())

@@ -197,3 +197,27 @@ def test_qc_edge_encoder_matches_reference():
     g = G.load("qc_golden")
     out = qc_ref.edge_encoder(G.rnd(99, 20, 5), G.params(g, "ee/p/"), "", 8)
     G.assert_close(out, g["ee/out"], rtol=1e-6, atol_scale=1e-6, what="ee")
+
+
+def test_set2set_matches_reference():
+    """The restated Set2Set readout and EdgeGCN_K_Set2Set against the unmodified reference (set2set_golden.npz)."""
+    from oracle import qc_ref
+    g = G.load("set2set_golden")
+    p = {k: v.requires_grad_(True) for k, v in G.params(g, "s2s/p/").items()}
+    x = torch.from_numpy(g["s2s/x"].copy()).requires_grad_(True)
+    batch = torch.from_numpy(g["s2s/batch"].astype(np.int64))
+    out = qc_ref.set2set(x, batch, p, steps=3)
+    out.backward(torch.from_numpy(g["s2s/g"]))
+    G.assert_close(out, g["s2s/out"], rtol=1e-5, atol_scale=1e-5, what="q*")
+    G.assert_close(x.grad, g["s2s/grad_x"], rtol=1e-5, atol_scale=1e-5, what="grad_x")
+    for k, v in p.items():
+        G.assert_close(v.grad, g["s2s/grad/" + k], rtol=1e-5, atol_scale=2e-5, what=k)
+    # whole model
+    pm = {k: v.requires_grad_(True) for k, v in G.params(g, "m/p/").items()}
+    y = qc_ref.edge_gcn_k_set2set(torch.from_numpy(g["m/nf"]), torch.from_numpy(g["m/ef"]),
+                                  torch.from_numpy(g["m/esrc"].astype(np.int64)), torch.from_numpy(g["m/etgt"].astype(np.int64)),
+                                  batch, pm, num_layers=3, hidden=24, steps=3)
+    y.backward(torch.from_numpy(g["m/gy"]))
+    G.assert_close(y, g["m/out"], rtol=1e-5, atol_scale=1e-5, what="model out")
+    for k in ("gcmid.0.weight", "mlpin.mlp.layers.0.linear.weight", "s2s.lstm.weight_ih_l0", "ee.mlp.mlp.layers.1.weight"):
+        G.assert_close(pm[k].grad, g["m/grad/" + k], rtol=1e-5, atol_scale=2e-5, what=k)
