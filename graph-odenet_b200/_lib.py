@@ -80,6 +80,7 @@ _PROTOS = {
     "gode_spmm_csr_f32": (C.c_int, [C.POINTER(Csr), vp, i64, i32, vp, i64, C.POINTER(SpmmEpilogue), vp, sz, vp]),
     "gode_gemm_f32": (C.c_int, [i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, f32, vp, i64, i32, i32, vp, sz, vp]),
     "gode_linear_f32": (C.c_int, [i32, i64, i64, i64, vp, i64, vp, i64, vp, i32, vp, i64, vp]),
+    "gode_gemm_tc_f32": (C.c_int, [i64, i64, i64, vp, i64, vp, i64, vp, i32, vp, i64, i32, vp]),
     "gode_groupnorm_fwd": (C.c_int, [i64, i32, i32, f32, vp, i64, vp, vp, vp, i64, vp]),
     "gode_groupnorm_bwd": (C.c_int, [i64, i32, i32, f32, vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, sz, vp]),
     "gode_colreduce_workspace_bytes": (sz, [i32]),

@@ -959,4 +959,257 @@ int input_grad_tc(const gode_gcn_odefunc_t* f, const float* gS, float* gz, cudaS
   return GODE_EINVAL;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// k_gemm_tc: general  C[M, N] = act(A[M, K] * Bt[N, K]^T + bias)  on tcgen05, 3xTF32 -- the dense products that are
+// not the d x d ones above: the QC edge encoder (QC/layers.py:76-86: [E, 2667] x [2667, 5329], 28.4 MFLOP per edge --
+// SURVEY 8a "dominates QC"), the GAT node projections, the input layer of the GCN models.
+//
+// STATUS: written at the end of round 1 without GPU time left to run it -- it compiles for sm_100a and shares every
+// building block with k_rows_ws (which is parity-green), but it has NOT been executed yet.  It is therefore reachable
+// only through gode_gemm_tc_f32 (nothing in the package calls it) and its GPU test is skipped unless
+// GODE_TEST_EXPERIMENTAL=1.  Round 2: run that test, then route ops.linear / LinearFn through it.
+//
+// Both operands are K-major (K contiguous): a weight stored [K, N] is transposed once by the caller.  One persistent CTA
+// per SM walks 128 x 128 output tiles (tile index = tm + tiles_m * tn, so concurrently running CTAs share one B tile);
+// K is consumed in stages of 32 (one 128-byte swizzle atom): eight producer warps load the A and the B part of a stage
+// (a quarter warp reads one 128-byte line), split hi / lo, store both into 128-byte-swizzled K-major stages of a 3-deep
+// ring and arrive on the stage's "full" barrier; one thread issues 4 K-steps x 3 passes of tcgen05.mma per stage into one
+// of two TMEM accumulators and commits the stage's "empty" barrier; four epilogue warps drain the previous tile
+// (bias, ReLU, swizzled staging, row stores).  Rows / columns / K beyond the matrix are zero-filled on load and masked on
+// store, so M, N, K are arbitrary; 128-bit accesses need lda, ldb (ldc) % 4 == 0 and 16-byte aligned bases, otherwise the
+// kernel falls back to 32-bit accesses.
+// ------------------------------------------------------------------------------------------------
+namespace tc {
+constexpr int GT_STAGES = 3;
+}
+
+__global__ void __launch_bounds__(tc::WS_THREADS, 1)
+k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ Bt, int64_t ldb,
+          float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int relu, int passes, int vec_in, int vec_out) {
+  using namespace tc;
+  constexpr int BK = 32;                          // K per stage: one 128-byte swizzle atom of tf32
+  constexpr int NI = 4;                           // warp-instructions per producer warp per operand per stage
+  constexpr uint32_t T_BYTES = 128 * BK * 4;      // one of hi / lo of one operand of one stage (16 KB)
+  constexpr uint32_t STAGE_BYTES = 4 * T_BYTES;   // A_hi | A_lo | B_hi | B_lo
+  constexpr uint32_t STG_BYTES = 128 * 64 * 4;    // epilogue staging: 128 rows x 64 columns
+  extern __shared__ __align__(1024) unsigned char smem[];
+  float* stage = reinterpret_cast<float*>(smem + GT_STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(stage) + STG_BYTES);
+  // bars: [0, S) full, [S, 2S) empty, [2S, 2S+2) acc_full, [2S+2, 2S+4) acc_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GT_STAGES + 4);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tiles_m = (M + 127) / 128, tiles_n = (N + 127) / 128;
+  const int64_t n_tiles = tiles_m * tiles_n;
+  if ((int64_t)blockIdx.x >= n_tiles) return;
+  const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int64_t KS = (K + BK - 1) / BK;           // stages per tile
+  const int64_t n_steps = my_tiles * KS;
+
+  if (tid == 0) {
+    for (int s = 0; s < GT_STAGES; ++s) {
+      mbar_init(&bars[s], WS_PRODUCERS);
+      mbar_init(&bars[GT_STAGES + s], 1);
+    }
+    mbar_init(&bars[2 * GT_STAGES + 0], 1);
+    mbar_init(&bars[2 * GT_STAGES + 1], 1);
+    mbar_init(&bars[2 * GT_STAGES + 2], 128);
+    mbar_init(&bars[2 * GT_STAGES + 3], 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t IDESC = make_idesc(128, 128, false, false);
+
+  if (warp < 8) {
+    // =============================== producers ============================================================
+    // registers of one step: 4 chunks of A and 4 of B (row = (warp * 4 + i) * 4 + lane / 8, 16-byte chunk = lane % 8)
+    float4 raw[2][2 * NI];
+    auto load_op = [&](const float* __restrict__ P, int64_t ld, int64_t rows, int64_t row, int64_t k) -> float4 {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < rows && k < K) {
+        const float* src = P + row * ld + k;
+        if (vec_in) {
+          v = __ldg(reinterpret_cast<const float4*>(src));     // in bounds of the padded row (ld % 4 == 0, ld >= K)
+          if (k + 3 >= K) {
+            if (k + 1 >= K) v.y = 0.f;
+            if (k + 2 >= K) v.z = 0.f;
+            v.w = 0.f;
+          }
+        } else {
+          v.x = __ldg(src);
+          if (k + 1 < K) v.y = __ldg(src + 1);
+          if (k + 2 < K) v.z = __ldg(src + 2);
+          if (k + 3 < K) v.w = __ldg(src + 3);
+        }
+      }
+      return v;
+    };
+    auto load_raw = [&](float4 (&r)[2 * NI], int64_t step) {
+      if (step >= n_steps) return;
+      const int64_t t = blockIdx.x + (step / KS) * (int64_t)gridDim.x;
+      const int64_t tm = t % tiles_m, tn = t / tiles_m;
+      const int64_t k = (step % KS) * BK + (lane & 7) * 4;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int rr = (warp * NI + i) * 4 + (lane >> 3);
+        r[i] = load_op(A, lda, M, tm * 128 + rr, k);
+        r[NI + i] = load_op(Bt, ldb, N, tn * 128 + rr, k);
+      }
+    };
+    auto do_step = [&](float4 (&r)[2 * NI], int64_t step) {
+      if (step >= n_steps) return;
+      const int s = static_cast<int>(step % GT_STAGES);
+      const int64_t use = step / GT_STAGES;
+      if (use >= 1) mbar_wait(&bars[GT_STAGES + s], static_cast<uint32_t>((use - 1) & 1));
+      unsigned char* base = smem + (size_t)s * STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int rr = (warp * NI + i) * 4 + (lane >> 3);
+        const uint32_t off = (rr >> 3) * 1024 + (rr & 7) * 128 + (((lane & 7) ^ (rr & 7)) << 4);
+        float4 hi, lo;
+        split4(r[i], hi, lo);
+        *reinterpret_cast<float4*>(base + off) = hi;
+        *reinterpret_cast<float4*>(base + T_BYTES + off) = lo;
+        split4(r[NI + i], hi, lo);
+        *reinterpret_cast<float4*>(base + 2 * T_BYTES + off) = hi;
+        *reinterpret_cast<float4*>(base + 3 * T_BYTES + off) = lo;
+      }
+      load_raw(r, step + 2);
+      fence_async_smem();
+      mbar_arrive(&bars[s]);
+    };
+    load_raw(raw[0], 0);
+    load_raw(raw[1], 1);
+    for (int64_t step = 0; step < n_steps; step += 2) {
+      do_step(raw[0], step);
+      do_step(raw[1], step + 1);
+    }
+  } else if (warp == 12) {
+    // =============================== MMA issue (one thread) ===============================================
+    if (lane == 0) {
+      for (int64_t step = 0; step < n_steps; ++step) {
+        const int s = static_cast<int>(step % GT_STAGES);
+        const int64_t it = step / KS, ks = step % KS;
+        const int b = static_cast<int>(it & 1);
+        if (ks == 0 && it >= 2) mbar_wait(&bars[2 * GT_STAGES + 2 + b], static_cast<uint32_t>(((it >> 1) - 1) & 1));
+        mbar_wait(&bars[s], static_cast<uint32_t>((step / GT_STAGES) & 1));
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t tmem_d = tmem_base + b * 128;
+#pragma unroll
+        for (int q = 0; q < BK / 8; ++q) {
+          const uint64_t a_hi = make_desc_sw128(base + q * 32), a_lo = make_desc_sw128(base + T_BYTES + q * 32);
+          const uint64_t b_hi = make_desc_sw128(base + 2 * T_BYTES + q * 32), b_lo = make_desc_sw128(base + 3 * T_BYTES + q * 32);
+          mma_tf32(tmem_d, a_hi, b_hi, IDESC, (ks | q) != 0 ? 1u : 0u);
+          if (passes == 3) {
+            mma_tf32(tmem_d, a_lo, b_hi, IDESC, 1u);
+            mma_tf32(tmem_d, a_hi, b_lo, IDESC, 1u);
+          }
+        }
+        mma_commit(&bars[GT_STAGES + s]);
+        if (ks == KS - 1) mma_commit(&bars[2 * GT_STAGES + b]);
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 8-11) =================================================
+    constexpr int HC = 64, CHH = 16;
+    const int q = warp & 3;
+    const int et = tid - WS_PRODUCERS;
+    const int row = q * 32 + lane;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t t = blockIdx.x + it * (int64_t)gridDim.x;
+      const int64_t tm = t % tiles_m, tn = t / tiles_m;
+      const int b = static_cast<int>(it & 1);
+      mbar_wait(&bars[2 * GT_STAGES + b], static_cast<uint32_t>((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + b * 128 + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int cb = 0; cb < HC; cb += 32) {
+          float v[32];
+          tmem_ld32(tmem_d + h * HC + cb, v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int64_t col = tn * 128 + h * HC + cb + j;
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (bias) {
+              if (col < N) o.x += __ldg(bias + col);
+              if (col + 1 < N) o.y += __ldg(bias + col + 1);
+              if (col + 2 < N) o.z += __ldg(bias + col + 2);
+              if (col + 3 < N) o.w += __ldg(bias + col + 3);
+            }
+            if (relu) {
+              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            const int chunk = ((cb + j) >> 2) ^ (row & (CHH - 1));
+            *reinterpret_cast<float4*>(stage + row * HC + chunk * 4) = o;
+          }
+        }
+        if (h == 1) {
+          tc_fence_before();
+          mbar_arrive(&bars[2 * GT_STAGES + 2 + b]);
+        }
+        bar_sync_named(2, 128);
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const int idx = i * 128 + et;
+          const int r = idx / CHH, c = idx % CHH;
+          const int64_t grow = tm * 128 + r;
+          const int64_t col = tn * 128 + h * HC + c * 4;
+          if (grow < M && col < N) {
+            const float4 o = *reinterpret_cast<const float4*>(stage + r * HC + ((c ^ (r & (CHH - 1))) * 4));
+            float* dst = C + grow * ldc + col;
+            if (vec_out && col + 3 < N) {
+              *reinterpret_cast<float4*>(dst) = o;
+            } else {
+              dst[0] = o.x;
+              if (col + 1 < N) dst[1] = o.y;
+              if (col + 2 < N) dst[2] = o.z;
+              if (col + 3 < N) dst[3] = o.w;
+            }
+          }
+        }
+        bar_sync_named(2, 128);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+int gemm_tc(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc,
+            const float* bias, int relu, int precision, cudaStream_t st) {
+  GODE_REQUIRE(M >= 0 && N >= 0 && K >= 1 && lda >= K && ldb >= K && ldc >= N, "gemm_tc: bad shape");
+  if (M == 0 || N == 0) return GODE_OK;
+  GODE_REQUIRE(A && Bt && C, "gemm_tc: null pointer");
+  constexpr size_t smem = tc::GT_STAGES * 4 * (size_t)128 * 32 * 4 + (size_t)128 * 64 * 4 + 256;
+  static bool configured = false;
+  if (!configured) {
+    GODE_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int64_t n_tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  const int grid = static_cast<int>(n_tiles < persistent_ctas() ? n_tiles : persistent_ctas());
+  const int vec_in = (lda % 4 == 0) && (ldb % 4 == 0) && al16(A) && al16(Bt);
+  const int vec_out = (ldc % 4 == 0) && al16(C);
+  k_gemm_tc<<<grid, tc::WS_THREADS, smem, st>>>(M, N, K, A, lda, Bt, ldb, C, ldc, bias, relu,
+                                                precision == GODE_PREC_TF32 ? 1 : 3, vec_in, vec_out);
+  GODE_LAUNCH_CHECK();
+  return GODE_OK;
+}
+
 }  // namespace gode
+
+// C[M, N] = act(A[M, K] * Bt[N, K]^T + bias) on tcgen05 (3xTF32, or single-pass TF32 with GODE_PREC_TF32).  EXPERIMENTAL in
+// round 1: see the status note at k_gemm_tc.
+extern "C" int gode_gemm_tc_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bt, int64_t ldb,
+                                const float* bias, int32_t relu, float* C, int64_t ldc, int32_t precision, void* stream) {
+  return gode::gemm_tc(M, N, K, A, lda, Bt, ldb, C, ldc, bias, relu, precision, gode::as_stream(stream));
+}

@@ -182,6 +182,14 @@ int gode_linear_f32(int32_t transB, int64_t M, int64_t N, int64_t K, const float
                     const float* B, int64_t ldb, const float* bias, int32_t relu, float* C, int64_t ldc,
                     void* stream);
 
+/* The same Linear on the tensor cores (tcgen05, fp32 result by 3xTF32; precision = GODE_PREC_TF32 for one pass):
+ *   C[M, N] = act(A[M, K] * Bt[N, K]^T + bias)      -- both operands K-major: a weight stored [K, N] is transposed first.
+ * Arbitrary M, N, K (edges are zero-filled / masked); 128-bit accesses when lda, ldb, ldc are multiples of 4 and the bases
+ * 16-byte aligned.  For the QC edge encoder (QC/layers.py:76-86: [E, 2667] x [2667, 5329]).
+ * EXPERIMENTAL in round 1: compiled, not yet run on hardware; nothing in the package calls it (see csrc/transform_tc.cu). */
+int gode_gemm_tc_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bt, int64_t ldb,
+                     const float* bias, int32_t relu, float* C, int64_t ldc, int32_t precision, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Row-wise GroupNorm on [n, d] (groups of d/groups contiguous channels per row).
  * replaces: nn.GroupNorm(min(32,d), d) -- GCN/models.py:165,175 (ATen formula

@@ -1,0 +1,52 @@
+"""GPU tests of code that was written without GPU time left to run it (round 1): skipped unless GODE_TEST_EXPERIMENTAL=1.
+
+``gode_gemm_tc_f32`` -- the general tcgen05 3xTF32 GEMM (csrc/transform_tc.cu, k_gemm_tc) that is to carry the QC edge
+encoder and the GAT projections; nothing in the package calls it yet.  Round 2: run
+
+    GODE_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -x -q
+
+and only then route ``ops.linear`` through it.
+"""
+import ctypes as C
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("GODE_TEST_EXPERIMENTAL") != "1", reason="experimental kernels: opt-in")]
+
+
+@pytest.mark.parametrize("M,N,K,pad", [(128, 128, 32, True), (128, 128, 128, True), (300, 200, 70, True), (1000, 533, 267, True),
+                                       (257, 129, 33, False), (4096, 256, 1024, True), (5, 3, 1, False)])
+@pytest.mark.parametrize("relu,use_bias", [(0, False), (1, True)])
+def test_gemm_tc_matches_fp64(M, N, K, pad, relu, use_bias):
+    import graph_odenet_b200  # noqa: F401
+    from graph_odenet_b200 import ops
+    from graph_odenet_b200._lib import lib, check
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(M * 7 + N * 3 + K)
+    ld = lambda n: (n + 3) // 4 * 4 if pad else n
+    A = torch.zeros(M, ld(K), device=dev)
+    Bt = torch.zeros(N, ld(K), device=dev)
+    A[:, :K] = torch.randn(M, K, device=dev, generator=g)
+    Bt[:, :K] = torch.randn(N, K, device=dev, generator=g)
+    if pad:                                    # padding must not leak into the product
+        A[:, K:] = 1e6
+        Bt[:, K:] = -1e6
+    bias = torch.randn(N, device=dev, generator=g) if use_bias else None
+    Cm = torch.full((M, ld(N)), float("nan"), device=dev)
+    check(lib.gode_gemm_tc_f32(M, N, K, ops._p(A), A.stride(0), ops._p(Bt), Bt.stride(0), ops._p(bias), relu, ops._p(Cm),
+                               Cm.stride(0), 0, ops._stream()), "gode_gemm_tc_f32")
+    torch.cuda.synchronize()
+    want = A[:, :K].double() @ Bt[:, :K].double().t()
+    if use_bias:
+        want = want + bias.double()
+    if relu:
+        want = want.clamp_min(0)
+    got = Cm[:, :N].double()
+    scale = float(want.abs().max())
+    assert torch.isfinite(got).all()
+    assert float((got - want).abs().max()) <= 2e-6 * scale * max(1.0, K ** 0.5 / 8), (float((got - want).abs().max()), scale)
+    if ld(N) > N:
+        assert torch.isnan(Cm[:, N:]).all()                      # columns beyond N are never written
