@@ -430,6 +430,39 @@ def group_norm(x, groups, gamma, beta, eps=1e-5):
 # --------------------------------------------------------------------------------------------------
 
 
+def _tc_gemm_enabled(M, N, K):
+    """The general tcgen05 GEMM (gode_gemm_tc_f32) is EXPERIMENTAL in round 1 (compiled, not yet run on hardware): it is
+    used only with GODE_GEMM_TC=1, and only for products large enough to fill 128 x 128 tiles."""
+    import os
+    return os.environ.get("GODE_GEMM_TC", "0") == "1" and M >= 512 and N >= 64 and K >= 32
+
+
+def _pad4(t):
+    """Row-major copy of a 2-D tensor whose leading dimension is a multiple of 4 floats (128-bit accesses); a view of the
+    padded buffer with the original shape."""
+    ld = (t.shape[1] + 3) // 4 * 4
+    if t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0:
+        return t
+    buf = torch.zeros(t.shape[0], ld, dtype=torch.float32, device=t.device)
+    buf[:, :t.shape[1]].copy_(t)
+    return buf[:, :t.shape[1]]
+
+
+def gemm_tc(a, bt, bias=None, relu=False, out=None):
+    """``act(a @ bt.T + bias)`` with both operands K-major -- gode_gemm_tc_f32 (experimental, see ``_tc_gemm_enabled``)."""
+    a, bt = _pad4(_rowmajor(a, "a")), _pad4(_rowmajor(bt, "bt"))
+    M, K = a.shape
+    N = bt.shape[0]
+    if bt.shape[1] != K:
+        raise ValueError("gemm_tc: inner dimensions differ")
+    if out is None:
+        out = torch.empty(M, (N + 3) // 4 * 4, dtype=torch.float32, device=a.device)[:, :N]
+    b = _req(bias, "bias").contiguous() if bias is not None else None
+    check(lib.gode_gemm_tc_f32(M, N, K, _p(a), a.stride(0), _p(bt), bt.stride(0), _p(b), int(relu), _p(out), out.stride(0),
+                               _lib.PREC_FP32, _stream()), "gode_gemm_tc_f32")
+    return out
+
+
 def linear(x, weight, bias=None, relu=False, weight_is_out_in=False, out=None):
     """``act(x @ W + b)`` via gode_linear_f32.  ``weight`` is [in, out] (QC MyLinear) or, with
     ``weight_is_out_in``, [out, in] (nn.Linear)."""
@@ -439,6 +472,8 @@ def linear(x, weight, bias=None, relu=False, weight_is_out_in=False, out=None):
     N = w.shape[0] if weight_is_out_in else w.shape[1]
     if (w.shape[1] if weight_is_out_in else w.shape[0]) != K:
         raise ValueError("linear: inner dimensions differ")
+    if out is None and _tc_gemm_enabled(x.shape[0], N, K):
+        return gemm_tc(x, w if weight_is_out_in else w.t(), bias, relu)      # [in, out] weights are transposed once
     if out is None:
         out = torch.empty(x.shape[0], N, dtype=torch.float32, device=x.device)
     b = _req(bias, "bias").contiguous() if bias is not None else None
@@ -465,8 +500,15 @@ class LinearFn(torch.autograd.Function):
         g = _rowmajor(g, "grad")
         if ctx.relu:
             g = relu_mask(g, out)
-        gx = gemm(g, w, trans_b=True) if ctx.needs_input_grad[0] else None
-        gw = gemm(x, g, trans_a=True, splits=_splits_for(x.shape[0], x.shape[1], g.shape[1])) if ctx.needs_input_grad[1] else None
+        M, K, N = x.shape[0], x.shape[1], g.shape[1]
+        if _tc_gemm_enabled(M, min(K, N), min(K, N)):
+            # dX = g W^T: g is K-major over N, W [K, N] is the "Bt" of that product as stored; dW = x^T g reduces over the
+            # rows, so both operands are transposed first (two library copies, ~1 % of the product's time)
+            gx = gemm_tc(g, w) if ctx.needs_input_grad[0] else None
+            gw = gemm_tc(x.t(), g.t()) if ctx.needs_input_grad[1] else None
+        else:
+            gx = gemm(g, w, trans_b=True) if ctx.needs_input_grad[0] else None
+            gw = gemm(x, g, trans_a=True, splits=_splits_for(M, K, N)) if ctx.needs_input_grad[1] else None
         gb = colsum(g) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return gx, gw, gb, None
 
