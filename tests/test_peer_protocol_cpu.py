@@ -298,3 +298,44 @@ def test_slot_pool_round_robin_and_exhaustion():
     pool.release(1)
     pool.release(0)
     assert pool.acquire() == 0 and pool.acquire() == 1     # cursor wrapped past slot 2
+
+
+def test_fused_route_and_chunk_ranges_are_exact_index_maps():
+    """The index work of the peer-memory exchange is bit-exact: the per-row (peer, destination row) lists of the fused push
+    and the per-chunk segment ranges of the pipelined push must reproduce, entry for entry, what the stand-alone push does
+    with (send_idx, send_ptr, dst_row) -- checked on CPU tensors through the unbound PeerHalo methods."""
+    import ctypes as C
+    world, rank, n_own = 4, 1, 1000
+    rng = torch.Generator().manual_seed(3)
+    segs = [torch.sort(torch.randperm(n_own, generator=rng)[:k])[0] for k in (300, 0, 170, 999)]   # peer 1 = this rank: empty
+    send_idx = torch.cat(segs).to(torch.int32)
+    send_ptr = [0]
+    for s_ in segs:
+        send_ptr.append(send_ptr[-1] + int(s_.numel()))
+    dst_row = [5000, 0, 7000, 9000]
+    halo = types.SimpleNamespace(send_idx=send_idx, n_own=n_own)
+    base = [10 ** 9 * (p + 1) for p in range(world)]
+    fake = types.SimpleNamespace(world=world, rank=rank, plan=types.SimpleNamespace(device=torch.device("cpu"), n_rows=n_own),
+                                 routes={id(halo): ((C.c_int64 * (world + 1))(*send_ptr), (C.c_int64 * world)(*dst_row))},
+                                 _fused={}, _part_cache={}, slot_bytes=4096, g=types.SimpleNamespace(base=base),
+                                 _slot=lambda buf: 2)
+    fake.part_bounds = lambda n: peer.PeerHalo.part_bounds(fake, n)
+    # fused route: expected multiset of (row, peer, dst) triples
+    want = sorted((int(r), p, dst_row[p] + k) for p in range(world) for k, r in enumerate(segs[p].tolist()))
+    peer.PeerHalo.fused_route(fake, halo, object())
+    ptr, ent = fake._fused[id(halo)]
+    got = sorted((r, int(e) >> 40, int(e) & 0xFFFFFFFFFF) for r in range(n_own) for e in ent[int(ptr[r]):int(ptr[r + 1])].tolist())
+    assert got == want and int(ptr[-1]) == send_idx.numel()
+    # chunk ranges: every chunk's entries have rows inside the chunk, destinations continue where the previous chunk stopped
+    for n_parts in (1, 3, 4):
+        bounds = peer.PeerHalo.part_bounds(fake, n_parts)
+        assert bounds[0] == 0 and bounds[-1] == n_own and all(b % 128 == 0 for b in bounds[:-1])
+        parts = peer.PeerHalo._parts(fake, halo, n_parts)
+        for p in range(world):
+            pos = send_ptr[p]
+            for c, (b, e, dr) in enumerate(parts):
+                assert b[p] == pos and dr[p] == dst_row[p] + (pos - send_ptr[p])
+                rows = send_idx[b[p]:e[p]]
+                assert bool(((rows >= bounds[c]) & (rows < bounds[c + 1])).all())
+                pos = e[p]
+            assert pos == send_ptr[p + 1]
