@@ -203,6 +203,240 @@ __global__ void __launch_bounds__(256, MINB) k_spmm_vec(int64_t n_rows, const in
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// k_spmm_sb: the gather for one WARP per row (d = 128 / 256) with the column indices broadcast through SHARED MEMORY.
+//
+// Round 2 microbenchmark (tools/l2_gather_bench.cu, profiles/r02_l2_gather.jsonl): with no CSR at all this B200 delivers
+// random 512 B rows from L2 to the SMs at 16.9 - 17.9 TB/s (= 62 B/clk/SM, the L2 -> L1 fill port), while k_spmm_vec
+// reaches 11.2 TB/s with its L1 LSU data pipe 85 % busy.  The difference is the index broadcast: k_spmm_vec holds a
+// row's (col, val) pairs one per lane and broadcasts them with two SHFLs per neighbour row, and a SHFL occupies the same
+// LSU pipe as the 4 wavefronts of the 512 B row load it feeds.  Here the 32 pairs of a batch are stored to the warp's
+// 256-byte slot of shared memory once (1 + 1 wavefronts) and read back four at a time with broadcast LDS.128 (one
+// wavefront per 4 neighbours): 10 LSU wavefronts of index traffic per 32 neighbours instead of 64.
+//   ROWVAL: the matrix is row-constant (gode_csr_t.row_vals; the reference's D^-1 (A + I) is) -> the values stream is not
+//   read at all and the row sum is scaled once.
+// ------------------------------------------------------------------------------------------------
+template <int VPL, int UN, bool ROWVAL>
+__device__ __forceinline__ void gather_range_sb(float4 (&acc)[VPL], int e0, int e1, int lane, int* __restrict__ sidx,
+                                                float* __restrict__ sval, const int32_t* __restrict__ colidx,
+                                                const float* __restrict__ vals, const float* __restrict__ xl, int64_t ldx) {
+  for (int off = e0; off < e1; off += 32) {
+    const int e = off + lane;
+    int c = 0;
+    float v = 0.f;
+    if (e < e1) {
+      c = __ldcs(colidx + e);
+      if (!ROWVAL) v = __ldcs(vals + e);
+    }
+    __syncwarp();                       // every lane has finished reading the previous batch
+    sidx[lane] = c;
+    if (!ROWVAL) sval[lane] = v;
+    __syncwarp();
+    const int cnt = min(32, e1 - off);
+#pragma unroll 2
+    for (int j = 0; j < cnt; j += UN) {
+      int cj[UN];
+      float vj[UN];
+#pragma unroll
+      for (int q = 0; q < UN; q += 4) {
+        const int4 t = *reinterpret_cast<const int4*>(sidx + j + q);
+        cj[q] = t.x; cj[q + 1] = t.y; cj[q + 2] = t.z; cj[q + 3] = t.w;
+        if (!ROWVAL) {
+          const float4 w = *reinterpret_cast<const float4*>(sval + j + q);
+          vj[q] = w.x; vj[q + 1] = w.y; vj[q + 2] = w.z; vj[q + 3] = w.w;
+        }
+      }
+      float4 x[UN][VPL];
+#pragma unroll
+      for (int q = 0; q < UN; ++q) {
+        const bool on = j + q < cnt;    // predicated-off loads are not issued; the batch still goes out back to back
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) {
+          x[q][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (on) x[q][u] = ld_ro4(xl + (int64_t)cj[q] * ldx + u * 128);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < UN; ++q)
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) {
+          if (ROWVAL) {
+            acc[u].x += x[q][u].x; acc[u].y += x[q][u].y; acc[u].z += x[q][u].z; acc[u].w += x[q][u].w;
+          } else {   // entries past the range carry weight 0 (and x = 0)
+            acc[u].x += vj[q] * x[q][u].x; acc[u].y += vj[q] * x[q][u].y;
+            acc[u].z += vj[q] * x[q][u].z; acc[u].w += vj[q] * x[q][u].w;
+          }
+        }
+    }
+  }
+}
+
+// lane l owns channels [4l, 4l+4) of every 128-channel block (VPL blocks): a neighbour row is VPL coalesced 512 B requests
+template <int VPL>
+__device__ __forceinline__ void epilogue_sb(const gode_spmm_epilogue_t& ep, int64_t row, int lane, float4 (&acc)[VPL],
+                                            float* __restrict__ Y, int64_t ldy) {
+#pragma unroll
+  for (int u = 0; u < VPL; ++u) {
+    float4 one[1] = {acc[u]};
+    epilogue<1>(ep, row, lane * 4 + u * 128, one, Y, ldy);
+  }
+}
+
+template <int VPL, int MINB, int UN, bool ROWVAL>
+__global__ void __launch_bounds__(256, MINB) k_spmm_sb(int64_t n_rows, const int32_t* __restrict__ rowptr,
+                                                       const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                                       const float* __restrict__ row_vals, const float* __restrict__ X,
+                                                       int64_t ldx, float* __restrict__ Y, int64_t ldy,
+                                                       const gode_spmm_epilogue_t ep, const int prefetch) {
+  __shared__ __align__(16) int s_idx[8][32];
+  __shared__ __align__(16) float s_val[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = blockIdx.x * (int64_t)8 + w;
+  if (row >= n_rows) return;            // whole warp
+  const int e0 = __ldg(rowptr + row);
+  int e1 = __ldg(rowptr + row + 1);
+  const bool heavy = (e1 - e0) > GODE_HEAVY_ROW;
+  if (heavy) return;
+  if (prefetch) {
+#pragma unroll
+    for (int u = 0; u < VPL; ++u) epilogue_prefetch<1>(ep, row, lane * 4 + u * 128, ldy);
+  }
+  float4 acc[VPL];
+#pragma unroll
+  for (int u = 0; u < VPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  gather_range_sb<VPL, UN, ROWVAL>(acc, e0, e1, lane, s_idx[w], s_val[w], colidx, vals, X + lane * 4, ldx);
+  if (ROWVAL) {
+    const float rv = __ldg(row_vals + row);
+#pragma unroll
+    for (int u = 0; u < VPL; ++u) { acc[u].x *= rv; acc[u].y *= rv; acc[u].z *= rv; acc[u].w *= rv; }
+  }
+  epilogue_sb<VPL>(ep, row, lane, acc, Y, ldy);
+}
+
+// chunks of the heavy rows with the same gather -> partial[chunk][d] (values always applied: partial sums of a row-constant
+// matrix would need the row value in the finishing kernel)
+template <int VPL, int UN>
+__global__ void __launch_bounds__(256) k_spmm_sb_heavy(int n_heavy, int n_chunks, const int32_t* __restrict__ heavy_rows,
+                                                       const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ rowptr,
+                                                       const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                                       const float* __restrict__ X, int64_t ldx, float* __restrict__ partial) {
+  __shared__ __align__(16) int s_idx[8][32];
+  __shared__ __align__(16) float s_val[8][32];
+  constexpr int D = VPL * 128;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int chunk = blockIdx.x * 8 + w;
+  if (chunk >= n_chunks) return;
+  int lo = 0, hi = n_heavy - 1;  // last heavy row whose first chunk is <= chunk
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(chunk_ptr + mid) <= chunk) lo = mid; else hi = mid - 1;
+  }
+  const int row = __ldg(heavy_rows + lo);
+  const int r0 = __ldg(rowptr + row), r1 = __ldg(rowptr + row + 1);
+  const int e0 = r0 + (chunk - __ldg(chunk_ptr + lo)) * GODE_HEAVY_CHUNK;
+  const int e1 = min(r1, e0 + GODE_HEAVY_CHUNK);
+  float4 acc[VPL];
+#pragma unroll
+  for (int u = 0; u < VPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  gather_range_sb<VPL, UN, false>(acc, e0, e1, lane, s_idx[w], s_val[w], colidx, vals, X + lane * 4, ldx);
+#pragma unroll
+  for (int u = 0; u < VPL; ++u) *reinterpret_cast<float4*>(partial + (int64_t)chunk * D + lane * 4 + u * 128) = acc[u];
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// k_spmm_ts: row-TILE staged gather (d = 128).  Round 2 finding: with its index broadcast made cheaper (k_spmm_sb above) the
+// gather got SLOWER, so the L1 LSU pipe is not what separates k_spmm_vec (11 TB/s of neighbour rows) from the no-CSR
+// microbenchmark (17 TB/s): it is the dependent chain rowptr -> (col, val) -> neighbour rows that every warp pays for every
+// row -- two DRAM latencies before the first useful byte, for a median row of far fewer than 20 entries on a power-law
+// graph.  Here a CTA owns TS_ROWS consecutive rows: all 256 threads first copy the tile's rowptr slice and its (col, val)
+// entries into shared memory with coalesced loads (ONE exposed latency per tile, hidden by the other resident CTAs), then
+// the 8 warps pull rows from a shared counter (long and short rows balance out) and gather with indices read from shared
+// memory by broadcast LDS.  CTAs are still dispatched in row order, so the L2 window of a locality-ordered graph is kept
+// (the persistent-warp variant lost it).  Rows that do not fit the staging capacity read their indices from global memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int TS_ROWS = 64;
+constexpr int TS_CAP = 2048;   // staged entries per tile (avg tile: 64 rows x 19.6 = 1254)
+
+template <int MINB, int UN, bool ROWVAL>
+__global__ void __launch_bounds__(256, MINB) k_spmm_ts(int64_t n_rows, const int32_t* __restrict__ rowptr,
+                                                       const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                                       const float* __restrict__ row_vals, const float* __restrict__ X,
+                                                       int64_t ldx, float* __restrict__ Y, int64_t ldy,
+                                                       const gode_spmm_epilogue_t ep, const int prefetch) {
+  __shared__ int s_ptr[TS_ROWS + 1];
+  __shared__ int s_idx[TS_CAP];
+  __shared__ float s_val[ROWVAL ? 1 : TS_CAP];
+  __shared__ int s_next;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t row0 = blockIdx.x * (int64_t)TS_ROWS;
+  const int nr = static_cast<int>(min((int64_t)TS_ROWS, n_rows - row0));
+  if (tid <= nr) s_ptr[tid] = __ldg(rowptr + row0 + tid);
+  if (tid == 0) s_next = 0;
+  __syncthreads();
+  const int t0 = s_ptr[0];
+  const int nst = min(s_ptr[nr] - t0, TS_CAP);
+  for (int i = tid; i < nst; i += 256) {
+    s_idx[i] = __ldcs(colidx + t0 + i);
+    if (!ROWVAL) s_val[i] = __ldcs(vals + t0 + i);
+  }
+  __syncthreads();
+  const float* __restrict__ xl = X + lane * 4;
+  for (;;) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(&s_next, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= nr) break;
+    const int e0 = s_ptr[r], e1 = s_ptr[r + 1];
+    if (e1 - e0 > GODE_HEAVY_ROW) continue;          // hub rows: k_spmm_heavy_partial / finish
+    const int64_t row = row0 + r;
+    if (prefetch) epilogue_prefetch<1>(ep, row, lane * 4, ldy);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool staged = e1 - t0 <= nst;              // this row's entries are all in shared memory
+#pragma unroll 2
+    for (int j = e0; j < e1; j += UN) {
+      int cj[UN];
+      float vj[UN];
+#pragma unroll
+      for (int q = 0; q < UN; ++q) {
+        const bool on = j + q < e1;
+        cj[q] = 0;
+        vj[q] = 0.f;
+        if (on) {
+          if (staged) {
+            cj[q] = s_idx[j + q - t0];
+            if (!ROWVAL) vj[q] = s_val[j + q - t0];
+          } else {
+            cj[q] = __ldg(colidx + j + q);
+            if (!ROWVAL) vj[q] = __ldg(vals + j + q);
+          }
+        }
+      }
+      float4 x[UN];
+#pragma unroll
+      for (int q = 0; q < UN; ++q) {
+        x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j + q < e1) x[q] = ld_ro4(xl + (int64_t)cj[q] * ldx);
+      }
+#pragma unroll
+      for (int q = 0; q < UN; ++q) {
+        if (ROWVAL) {
+          acc.x += x[q].x; acc.y += x[q].y; acc.z += x[q].z; acc.w += x[q].w;
+        } else {
+          acc.x += vj[q] * x[q].x; acc.y += vj[q] * x[q].y; acc.z += vj[q] * x[q].z; acc.w += vj[q] * x[q].w;
+        }
+      }
+    }
+    if (ROWVAL) {
+      const float rv = __ldg(row_vals + row);
+      acc.x *= rv; acc.y *= rv; acc.z *= rv; acc.w *= rv;
+    }
+    float4 one[1] = {acc};
+    epilogue<1>(ep, row, lane * 4, one, Y, ldy);
+  }
+}
+
+
 // L1-locality variant: ONE 1024-thread CTA per SM walks a contiguous tile of TILE_ROWS rows, so the neighbour
 // rows its 32 warps gather (in a locality-ordered graph: a band around the tile) stay resident in that SM's L1
 // and are served at L1 bandwidth (128 B/clk/SM) instead of L2 bandwidth (~42 B/clk/SM).
@@ -500,6 +734,86 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
     // 3: one 1024-thread CTA per SM on a row tile.
     return e ? atoi(e) : 0;
   }();
+  static const int minb_sb = [] {
+    const char* e = getenv("GODE_SPMM_MINB");
+    return e ? atoi(e) : 8;
+  }();
+  static const int unr_sb = [] {
+    const char* e = getenv("GODE_SPMM_UNR");
+    return e ? atoi(e) : 4;
+  }();
+  static const int use_rowval = [] {
+    const char* e = getenv("GODE_SPMM_ROWVAL");   // 1 (default): skip the values stream of a row-constant matrix
+    return e ? atoi(e) : 1;
+  }();
+  if (LPR == 32 && variant == 6) {
+    if constexpr (LPR == 32) {
+      // k_spmm_sb: indices broadcast through shared memory (see the kernel's header)
+      static const int prefetch_sb = [] {
+        const char* e = getenv("GODE_SPMM_PREFETCH");
+        return e ? atoi(e) : 1;
+      }();
+      const bool rv = use_rowval && A.row_vals != nullptr;
+      if (A.n_rows > 0) {
+        unsigned grid = static_cast<unsigned>((A.n_rows + 7) / 8);
+#define GODE_SB_LAUNCH(MB, UU)                                                                                          \
+  do {                                                                                                                  \
+    if (rv) k_spmm_sb<VPL, MB, UU, true><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, A.row_vals, X, ldx, Y, ldy, ep, prefetch_sb); \
+    else k_spmm_sb<VPL, MB, UU, false><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, nullptr, X, ldx, Y, ldy, ep, prefetch_sb);    \
+  } while (0)
+        if (VPL > 1 || (minb_sb == 4 && unr_sb == 8)) GODE_SB_LAUNCH(4, 8);   // d = 256: two float4 per lane need the registers
+        else if (minb_sb == 6 && unr_sb == 8) GODE_SB_LAUNCH(6, 8);
+        else if (minb_sb == 6 && unr_sb == 4) GODE_SB_LAUNCH(6, 4);
+        else GODE_SB_LAUNCH(8, 4);
+#undef GODE_SB_LAUNCH
+        GODE_LAUNCH_CHECK();
+      }
+      if (A.n_heavy > 0) {
+        unsigned g1 = static_cast<unsigned>((A.n_chunks + 7) / 8);
+        k_spmm_sb_heavy<VPL, 8><<<g1, 256, 0, st>>>(A.n_heavy, A.n_chunks, A.heavy_rows, A.heavy_chunk_ptr, A.rowptr, A.colidx,
+                                                    A.vals, X, ldx, ws);
+        GODE_LAUNCH_CHECK();
+        unsigned g2 = static_cast<unsigned>((A.n_heavy + RPB - 1) / RPB);
+        k_spmm_heavy_finish<LPR, VPL><<<g2, 256, 0, st>>>(A.n_heavy, A.heavy_rows, A.heavy_chunk_ptr, ws, Y, ldy, ep);
+        GODE_LAUNCH_CHECK();
+      }
+      return GODE_OK;
+    }
+  }
+  if (variant == 7 && LPR == 32 && VPL == 1) {
+    if constexpr (LPR == 32 && VPL == 1) {
+      static const int prefetch_ts = [] {
+        const char* e = getenv("GODE_SPMM_PREFETCH");
+        return e ? atoi(e) : 1;
+      }();
+      const bool rv = use_rowval && A.row_vals != nullptr;
+      if (A.n_rows > 0) {
+        unsigned grid = static_cast<unsigned>((A.n_rows + TS_ROWS - 1) / TS_ROWS);
+#define GODE_TS_LAUNCH(MB, UU)                                                                                          \
+  do {                                                                                                                  \
+    if (rv) k_spmm_ts<MB, UU, true><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, A.row_vals, X, ldx, Y, ldy, ep, prefetch_ts); \
+    else k_spmm_ts<MB, UU, false><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, nullptr, X, ldx, Y, ldy, ep, prefetch_ts);    \
+  } while (0)
+        if (minb_sb == 6 && unr_sb == 8) GODE_TS_LAUNCH(6, 8);
+        else if (minb_sb == 6 && unr_sb == 4) GODE_TS_LAUNCH(6, 4);
+        else if (minb_sb == 4 && unr_sb == 8) GODE_TS_LAUNCH(4, 8);
+        else if (minb_sb == 8 && unr_sb == 8) GODE_TS_LAUNCH(8, 8);
+        else GODE_TS_LAUNCH(8, 4);
+#undef GODE_TS_LAUNCH
+        GODE_LAUNCH_CHECK();
+      }
+      if (A.n_heavy > 0) {
+        unsigned g1 = static_cast<unsigned>((A.n_chunks + RPB - 1) / RPB);
+        k_spmm_heavy_partial<LPR, VPL><<<g1, 256, 0, st>>>(A.n_heavy, A.n_chunks, A.heavy_rows, A.heavy_chunk_ptr, A.rowptr,
+                                                          A.colidx, A.vals, X, ldx, ws);
+        GODE_LAUNCH_CHECK();
+        unsigned g2 = static_cast<unsigned>((A.n_heavy + RPB - 1) / RPB);
+        k_spmm_heavy_finish<LPR, VPL><<<g2, 256, 0, st>>>(A.n_heavy, A.heavy_rows, A.heavy_chunk_ptr, ws, Y, ldy, ep);
+        GODE_LAUNCH_CHECK();
+      }
+      return GODE_OK;
+    }
+  }
   if (A.n_rows > 0 && (variant == 5 || variant == 4)) {
     int rc = variant == 5 ? launch_pw<LPR, VPL, 8, 3>(A, X, ldx, Y, ldy, ep, st) : launch_pw<LPR, VPL, 4, 4>(A, X, ldx, Y, ldy, ep, st);
     if (rc) return rc;

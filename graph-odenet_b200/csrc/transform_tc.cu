@@ -4,8 +4,11 @@
 // [t || GroupNorm(x)] (GCN/models.py:175-178), and the two products its autograd issues (dS W^T and z^T dS).
 //
 // fp32 result on the 5th-generation tensor cores: every fp32 operand is split x = hi + lo with hi = tf32(x)
-// (cvt.rna) and lo = x - hi, and three kind::tf32 MMAs accumulate hi*hi + lo*hi + hi*lo in TMEM (the dropped
-// lo*lo term is 2^-22 relative).  GODE_PREC_TF32 issues the hi*hi pass only.
+// (cvt.rna) and lo = tf32(x - hi) (rounded too: the MMA truncates its operands), and three kind::tf32 MMAs compute
+// hi*hi + lo*hi + hi*lo (the dropped lo*lo term is 2^-22 relative).  The correction terms go to their own TMEM
+// accumulator and the hi*hi products of the two halves of K to two more; the epilogue adds the three with
+// round-to-nearest fp32 adds (the MMA's own accumulate loses low bits at every K step).  Measured against fp64 the result
+// is as accurate as cuBLAS SGEMM (profiles/r02_transform_accuracy.jsonl).  GODE_PREC_TF32 issues the hi*hi pass only.
 //
 // k_rows_tc  (M = 128 rows per tile, N = K = D):     Out[r,:] = A[r,:] * B + rowvec
 //     MODE 0  transform : A = xhat(y) (GroupNorm statistics computed on load, affine folded into B),
@@ -131,9 +134,13 @@ __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float(r);
 }
 
-__device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
+// x = hi + lo with hi = tf32(x) (round to nearest).  lo = x - hi is exact in fp32 but carries up to 13 significant bits;
+// the MMA reads only its top 11 (it TRUNCATES the operand to tf32), a biased error of up to 2^-23 |x|.  With `rnd` the
+// residual is itself rounded to nearest tf32 (as CUTLASS's 3xTF32 does), halving that error and removing the bias.
+__device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo, bool rnd = true) {
   hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
   lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
+  if (rnd) { lo.x = tf32_hi(lo.x); lo.y = tf32_hi(lo.y); lo.z = tf32_hi(lo.z); lo.w = tf32_hi(lo.w); }
 }
 
 // GroupNorm statistics of one 16-byte chunk (4 channels): CPG = 4 -> one group, CPG = 2 -> two groups; no affine
@@ -188,7 +195,7 @@ k_rows_tc(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(tmem_slot, D);
+  if (warp == 0) tmem_alloc(tmem_slot, 2 * D);   // columns [0, D): hi*hi; [D, 2D): the correction terms (added in the epilogue)
   const float* W1 = W + D;   // rows 1..D of the [D+1, D] weight
   for (int n = tid; n < D; n += THREADS) {
     float r = 0.f;
@@ -281,8 +288,8 @@ k_rows_tc(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
           const uint64_t db_hi = make_desc(bHi + ks * 256, 128, RSB), db_lo = make_desc(bLo + ks * 256, 128, RSB);
           mma_tf32(tmem_d, da_hi, db_hi, IDESC, (half | s) != 0 ? 1u : 0u);
           if (passes == 3) {
-            mma_tf32(tmem_d, da_lo, db_hi, IDESC, 1u);
-            mma_tf32(tmem_d, da_hi, db_lo, IDESC, 1u);
+            mma_tf32(tmem_d + D, da_lo, db_hi, IDESC, (half | s) != 0 ? 1u : 0u);
+            mma_tf32(tmem_d + D, da_hi, db_lo, IDESC, 1u);
           }
         }
         mma_commit(bar);
@@ -304,6 +311,12 @@ k_rows_tc(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
       for (int cb = 0; cb < HC; cb += 32) {
         float v[32];
         tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + hc * HC + cb, v);
+        if (passes == 3) {
+          float w[32];
+          tmem_ld32(tmem_d + D + (static_cast<uint32_t>(q * 32) << 16) + hc * HC + cb, w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += w[j];
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const int col = hc * HC + cb + j;
@@ -338,7 +351,7 @@ k_rows_tc(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, D);
+  if (warp == 0) tmem_dealloc(tmem_d, 2 * D);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -362,6 +375,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 }  // namespace tc
 
+#ifndef GODE_TC_ACC_DEFAULT
+// 19 = rounded residuals | separate correction accumulator | 2 hi*hi accumulators over K.  Measured against fp64 on a B200
+// (profiles/r02_transform_accuracy.jsonl, N = 262 144, d = 128): rms error / max|S| 3.87e-8 and max error 4.7e-7 -- the
+// same as cuBLAS fp32 SGEMM (3.92e-8, 5.0e-7) and the SIMT FFMA path (3.92e-8, 5.0e-7) -- with 0 of 33.5 M ReLU masks
+// differing from the fp64 result, for +13 % kernel time over round 1's single accumulator with truncated residuals
+// (1.72e-7, 1.29e-6, whose mask flips cost 2e-4..6e-4 in the gradients).
+#define GODE_TC_ACC_DEFAULT 19
+#endif
+
 namespace tc {
 constexpr int WS_PRODUCERS = 256;               // warps 0-7
 constexpr int WS_THREADS = WS_PRODUCERS + 128 + 32;   // + epilogue warps 8-11 + MMA warp 12
@@ -384,9 +406,18 @@ template <int D, int CPG, int MODE>
 __global__ void __launch_bounds__(tc::WS_THREADS, 1)
 k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, const float* __restrict__ W /*[D+1, D]*/,
           const float* __restrict__ gamma, const float* __restrict__ beta, float t, float eps, int passes,
-          const gode_push_route_t push, const int pf_tiles /*L2 prefetch distance in tiles of this CTA (0: off)*/) {
+          const gode_push_route_t push, const int pf_tiles /*L2 prefetch distance in tiles of this CTA (0: off)*/,
+          const int cfg /*accuracy configuration of the 3xTF32 product, see rows_acc_cfg()*/) {
   using namespace tc;
   static_assert(D == 128, "k_rows_ws is laid out for 128 channels");
+  // cfg: bit 0 round the lo residuals to tf32 | bit 1 correction terms (lo*hi, hi*lo[, lo*lo]) in their own TMEM
+  // accumulator, added to the hi*hi one by the epilogue with round-to-nearest fp32 adds | bit 2 also issue lo*lo |
+  // bit 3 1/sqrtf instead of rsqrtf in the GroupNorm | bits 4-5: (number of hi*hi accumulators over K) - 1; more than
+  // one leaves no TMEM for double buffering (512 columns = 4 accumulators of 128)
+  const bool rnd_lo = cfg & 1, sep = (cfg & 2) != 0, lolo = (cfg & 4) != 0, precise_gn = (cfg & 8) != 0;
+  const int nmain = 1 + ((cfg >> 4) & 3);
+  const int nacc = nmain + (sep ? 1 : 0);
+  const int nbuf = nacc <= 2 ? 2 : 1;
   constexpr int KQ = 32;                        // channels per A stage (a quarter of K)
   constexpr int NQ = D / KQ;                    // stages per tile
   constexpr int NI = 4;                         // warp-instructions (8 rows x 4 chunks) per producer warp per stage
@@ -421,7 +452,7 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
     mbar_init(&bars[7], 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 2 * D);
+  if (warp == 0) tmem_alloc(tmem_slot, 4 * D);
   const float* W1 = W + D;
   for (int n = tid; n < D; n += WS_THREADS) {
     float r = 0.f;
@@ -445,7 +476,7 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
       b = __ldg(reinterpret_cast<const float4*>(W1 + (int64_t)n * D + kc * 4));
     }
     float4 hi, lo;
-    split4(b, hi, lo);
+    split4(b, hi, lo, rnd_lo);
     const uint32_t off = ng * RSB + kc * 128 + (lane & 7) * 16;
     *reinterpret_cast<float4*>(sBhi + off) = hi;
     *reinterpret_cast<float4*>(sBlo + off) = lo;
@@ -491,7 +522,7 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
       for (int i = 0; i < NI; ++i) {
         const int rr = (warp * NI + i) * 4 + (lane >> 3);      // row of the tile
         float4 hi, lo;
-        split4(normalize4_fast<CPG>(r[i], eps), hi, lo);
+        split4(precise_gn ? normalize4<CPG>(r[i], eps) : normalize4_fast<CPG>(r[i], eps), hi, lo, rnd_lo);
         // 128-byte-swizzled K-major stage: a quarter warp fills one 128-byte row -> conflict-free
         const uint32_t off = (rr >> 3) * RSA + (rr & 7) * 128 + (((lane & 7) ^ (rr & 7)) << 4);
         *reinterpret_cast<float4*>(aHi + off) = hi;
@@ -511,29 +542,39 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
     // =============================== MMA issue (one thread) ===============================================
     if (lane == 0) {
       const uint32_t bHi = smem_u32(sBhi), bLo = smem_u32(sBlo);
+      uint32_t started = 0;                          // accumulators of the current tile that hold a value already
       for (int64_t step = 0; step < n_steps; ++step) {
         const int s = static_cast<int>(step & 1);
         const int64_t it = step / NQ;
         const int q = static_cast<int>(step % NQ);
-        const int b = static_cast<int>(it & 1);
-        if (q == 0 && it >= 2) mbar_wait(&bars[6 + b], static_cast<uint32_t>(((it >> 1) - 1) & 1));   // epilogue has read it out
+        const int b = static_cast<int>(it % nbuf);
+        const int64_t use = it / nbuf;               // how many tiles have used accumulator set b before
+        if (q == 0) {
+          started = 0;
+          if (use >= 1) mbar_wait(&bars[6 + b], static_cast<uint32_t>((use - 1) & 1));   // epilogue has read it out
+        }
         mbar_wait(&bars[s], static_cast<uint32_t>((step >> 1) & 1));                                 // stage s is stored
         tc_fence_after();
         const uint32_t aHi = smem_u32(sA + (size_t)s * 2 * A_BYTES), aLo = aHi + A_BYTES;
-        const uint32_t tmem_d = tmem_base + b * D;
+        const uint32_t tmem_set = tmem_base + b * nacc * D;
 #pragma unroll
         for (int ks = 0; ks < KQ / 8; ++ks) {
-          const uint32_t kb = q * (KQ / 8) + ks;
+          const uint32_t kb = q * (KQ / 8) + ks;     // K step of the tile, 0..15
           const uint64_t da_hi = make_desc_sw128(aHi + ks * 32), da_lo = make_desc_sw128(aLo + ks * 32);
           const uint64_t db_hi = make_desc(bHi + kb * 256, 128, RSB), db_lo = make_desc(bLo + kb * 256, 128, RSB);
-          mma_tf32(tmem_d, da_hi, db_hi, IDESC, (q | ks) != 0 ? 1u : 0u);
+          const uint32_t am = (kb * nmain) >> 4;     // hi*hi accumulator of this K step
+          mma_tf32(tmem_set + am * D, da_hi, db_hi, IDESC, (started >> am) & 1u);
+          started |= 1u << am;
           if (passes == 3) {
-            mma_tf32(tmem_d, da_lo, db_hi, IDESC, 1u);
-            mma_tf32(tmem_d, da_hi, db_lo, IDESC, 1u);
+            const uint32_t ac = sep ? static_cast<uint32_t>(nmain) : am;
+            mma_tf32(tmem_set + ac * D, da_lo, db_hi, IDESC, (started >> ac) & 1u);
+            started |= 1u << ac;
+            mma_tf32(tmem_set + ac * D, da_hi, db_lo, IDESC, 1u);
+            if (lolo) mma_tf32(tmem_set + ac * D, da_lo, db_lo, IDESC, 1u);
           }
         }
         mma_commit(&bars[2 + s]);                    // stage s is free once these MMAs have read it
-        if (q == NQ - 1) mma_commit(&bars[4 + b]);   // accumulator b is complete
+        if (q == NQ - 1) mma_commit(&bars[4 + b]);   // accumulator set b is complete
       }
     }
   } else {
@@ -546,10 +587,11 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
     const bool do_push = MODE == 0 && push.ptr != nullptr;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = blockIdx.x + it * (int64_t)gridDim.x;
-      const int b = static_cast<int>(it & 1);
-      mbar_wait(&bars[4 + b], static_cast<uint32_t>((it >> 1) & 1));
+      const int b = static_cast<int>(it % nbuf);
+      mbar_wait(&bars[4 + b], static_cast<uint32_t>((it / nbuf) & 1));
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + b * D + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t tmem_d = tmem_base + b * nacc * D + (static_cast<uint32_t>(q * 32) << 16);
+      const int nread = passes == 3 ? nacc : nmain;   // a single-pass product never touches the correction accumulator
       const bool full = tile * 128 + 128 <= n_rows;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
@@ -557,6 +599,12 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
         for (int cb = 0; cb < HC; cb += 32) {
           float v[32];
           tmem_ld32(tmem_d + h * HC + cb, v);
+          for (int a = 1; a < nread; ++a) {          // partial products over K and the correction terms: fp32 RN adds
+            float w[32];
+            tmem_ld32(tmem_d + a * D + h * HC + cb, w);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += w[j];
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const int col = h * HC + cb + j;
@@ -614,16 +662,13 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 2 * D);
+  if (warp == 0) tmem_dealloc(tmem_base, 4 * D);
 }
 
 // GODE_TC: bit 0 = transform, bit 1 = input gradient, bit 2 = weight gradient on tcgen05 (default all)
-static int tc_mask() {
-  static const int m = [] {
-    const char* e = getenv("GODE_TC");
-    return e ? atoi(e) : 7;
-  }();
-  return m;
+static int tc_mask() {   // read at every call (a getenv is ~100 ns): tools compare the paths inside one process
+  const char* e = getenv("GODE_TC");
+  return e ? atoi(e) : 7;
 }
 static bool tc_enabled() { return tc_mask() != 0; }
 
@@ -632,8 +677,18 @@ static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 // ------------------------------------------------------------------------------------------------
 // P[i, o] = sum_r xhat(y)[r, i] * dS[r, o]      (weight gradient before the GroupNorm affine is re-applied)
 // ------------------------------------------------------------------------------------------------
+// The reduction runs over ALL rows of a CTA (68 000 at N = 10 M: 8 400 K steps x 3 passes).  Left in one TMEM accumulator
+// the MMA's own accumulate -- which drops low bits at every step -- cost 9e-5 relative L2 against fp64 at 2 M rows (round 2
+// measurement).  So the accumulation is hierarchical: WG_DRAIN staged chunks (512 rows) go into one of two TMEM accumulator
+// sets (hi*hi and the correction terms apart), and four drain warps add a finished set into fp32 running sums in shared
+// memory with round-to-nearest adds while the MMAs continue into the other set.
+namespace tc {
+constexpr int WG_DRAIN = 16;                    // staged chunks (of 32 rows) per TMEM accumulation group
+constexpr int WG_THREADS = THREADS + 32 + 128;  // producers (warps 0-7) + MMA issue (warp 8) + drain (warps 9-12)
+}
+
 template <int D, int CPG>
-__global__ void __launch_bounds__(tc::THREADS + 32, 1)
+__global__ void __launch_bounds__(tc::WG_THREADS, 1)
 k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restrict__ G, float* __restrict__ partial /*[grid][D][D]*/,
            float* __restrict__ cs_partial /*[grid][D]: column sums of G over this CTA's rows*/, float eps, int passes,
            const int pf_chunks /*L2 prefetch distance in chunks of this CTA (0: off)*/) {
@@ -653,8 +708,10 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
   constexpr int NI = ((RC / 8) * (D / 16)) / (THREADS / 32);   // warp-instructions per warp per operand
   extern __shared__ __align__(1024) unsigned char smem[];
   // stage b: [A_hi | A_lo | B_hi | B_lo] at smem + b * 4 * MAT
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * 4 * MAT);   // [0],[1]: stage free; [2]: all done; [3],[4]: stage full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  // bars: [0],[1] stage free; [2] all MMAs done; [3],[4] stage full; [5],[6] accumulator set full; [7],[8] set drained
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * 4 * MAT);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  float4* sums = reinterpret_cast<float4*>(smem + 2 * 4 * MAT + 128);   // running sums: [D / 4 column chunks][D channel rows]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_chunks = (n_rows + RC - 1) / RC;
@@ -664,9 +721,13 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
     mbar_init(&bars[2], 1);
     mbar_init(&bars[3], THREADS);
     mbar_init(&bars[4], THREADS);
+    mbar_init(&bars[5], 1);
+    mbar_init(&bars[6], 1);
+    mbar_init(&bars[7], 128);
+    mbar_init(&bars[8], 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(tmem_slot, D);
+  if (warp == 0) tmem_alloc(tmem_slot, 4 * D);   // two sets of (hi*hi | correction) accumulators
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -681,24 +742,70 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
     if (lane == 0) {
       for (int64_t it = 0; it < my_chunks; ++it) {
         const int b = static_cast<int>(it & 1);
+        const int64_t g = it / WG_DRAIN;                 // accumulation group
+        const int ab = static_cast<int>(g & 1);          // its accumulator set
+        const bool first = it % WG_DRAIN == 0;
+        if (first && g >= 2) mbar_wait(&bars[7 + ab], static_cast<uint32_t>(((g >> 1) - 1) & 1));   // group g-2 has been drained
         mbar_wait(&bars[3 + b], static_cast<uint32_t>((it >> 1) & 1));
         tc_fence_after();
         const uint32_t base = smem_u32(smem + (size_t)b * 4 * MAT);
+        const uint32_t t_main = tmem_d + ab * 2 * D, t_corr = t_main + D;
 #pragma unroll
         for (int s = 0; s < RC / 8; ++s) {
           const uint32_t ko = s * 2 * LBO;   // 8 rows of K = two 16-byte chunks
           const uint64_t a_hi = make_desc(base + ko, LBO, SBO), a_lo = make_desc(base + MAT + ko, LBO, SBO);
           const uint64_t b_hi = make_desc(base + 2 * MAT + ko, LBO, SBO), b_lo = make_desc(base + 3 * MAT + ko, LBO, SBO);
-          mma_tf32(tmem_d, a_hi, b_hi, IDESC, (it | s) != 0 ? 1u : 0u);
+          const uint32_t acc = (first && s == 0) ? 0u : 1u;
+          mma_tf32(t_main, a_hi, b_hi, IDESC, acc);
           if (passes == 3) {
-            mma_tf32(tmem_d, a_lo, b_hi, IDESC, 1u);
-            mma_tf32(tmem_d, a_hi, b_lo, IDESC, 1u);
+            mma_tf32(t_corr, a_lo, b_hi, IDESC, acc);
+            mma_tf32(t_corr, a_hi, b_lo, IDESC, 1u);
           }
         }
         mma_commit(&bars[b]);
+        if (it % WG_DRAIN == WG_DRAIN - 1 || it == my_chunks - 1) mma_commit(&bars[5 + ab]);   // this group's sums are complete
       }
       mma_commit(&bars[2]);   // arrives when every MMA issued above has completed
     }
+    tc_fence_before();
+    __syncthreads();
+    return;
+  }
+  if (warp > THREADS / 32) {
+    // ---- drain (warps 9-12): finished accumulator sets -> fp32 running sums in shared memory (RN adds), then -> partial
+    const int q = warp & 3;                       // the TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;                // channel i = TMEM lane; a thread only ever touches its own row of sums
+#pragma unroll 4
+    for (int c4 = 0; c4 < D / 4; ++c4) sums[c4 * D + row] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t n_groups = (my_chunks + WG_DRAIN - 1) / WG_DRAIN;
+    for (int64_t g = 0; g < n_groups; ++g) {
+      const int ab = static_cast<int>(g & 1);
+      mbar_wait(&bars[5 + ab], static_cast<uint32_t>((g >> 1) & 1));
+      tc_fence_after();
+      const uint32_t t_main = tmem_d + ab * 2 * D + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int cb = 0; cb < D; cb += 32) {
+        float v[32];
+        tmem_ld32(t_main + cb, v);
+        if (passes == 3) {
+          float w[32];
+          tmem_ld32(t_main + D + cb, w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += w[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 t = sums[((cb + j) >> 2) * D + row];
+          t.x += v[j]; t.y += v[j + 1]; t.z += v[j + 2]; t.w += v[j + 3];
+          sums[((cb + j) >> 2) * D + row] = t;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bars[7 + ab]);
+    }
+    float* out = partial + (size_t)blockIdx.x * D * D + (size_t)row * D;
+#pragma unroll 4
+    for (int c4 = 0; c4 < D / 4; ++c4) *reinterpret_cast<float4*>(out + c4 * 4) = sums[c4 * D + row];
     tc_fence_before();
     __syncthreads();
     return;
@@ -768,26 +875,8 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
     fence_async_smem();
     mbar_arrive(&bars[3 + b]);
   }
-  mbar_wait(&bars[2], 0);
+  mbar_wait(&bars[2], 0);   // every MMA has retired: the operand stages are free for the column-sum reduction below
   tc_fence_after();
-  {
-    const int q = warp & 3, hc = warp >> 2;
-    const int row = q * 32 + lane;   // channel i
-    float* out = partial + (size_t)blockIdx.x * D * D + (size_t)row * D;
-#pragma unroll
-    for (int cb = 0; cb < D / 2; cb += 32) {
-      float v[32];
-      if (it > 0) {
-        tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + hc * (D / 2) + cb, v);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(out + hc * (D / 2) + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    }
-  }
   // column sums of G over this CTA's rows: lanes sharing a 16-byte chunk differ in lane / 8 (the row inside a quad),
   // warps hold different row quads; fixed reduction order -> deterministic
   {
@@ -815,7 +904,7 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, D);
+  if (warp == 0) tmem_dealloc(tmem_d, 4 * D);
 }
 
 // cs[o] = sum_b cs_partial[b][o]   (column sums of dS; one block, fixed order)
@@ -855,7 +944,7 @@ int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, float
     return GODE_EWORKSPACE;
   }
   float* cs_partial = ws + (size_t)grid * D * D;
-  constexpr size_t smem = 2 * 4 * (size_t)(D / 8) * 1168 + 64;
+  constexpr size_t smem = 2 * 4 * (size_t)(D / 8) * 1168 + 128 + (size_t)D * D * 4;
   static bool configured = false;
   if (!configured) {
     GODE_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_tc<D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -866,13 +955,20 @@ int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, float
     const char* e = getenv("GODE_WGRAD_PREFETCH");   // L2 prefetch distance in units of 128 rows per CTA (default 2, 0 = off)
     return (e ? atoi(e) : 2) * 4;
   }();
-  k_wgrad_tc<D, 4><<<grid, tc::THREADS + 32, smem, st>>>(f->A.n_rows, y, gS, ws, cs_partial, f->gn_eps, passes, pf);
+  k_wgrad_tc<D, 4><<<grid, tc::WG_THREADS, smem, st>>>(f->A.n_rows, y, gS, ws, cs_partial, f->gn_eps, passes, pf);
   GODE_LAUNCH_CHECK();
   k_wgrad_cs<<<1, D, 0, st>>>(grid, D, cs_partial, cs);
   GODE_LAUNCH_CHECK();
   k_wgrad_finish<<<(D * D + 255) / 256, 256, 0, st>>>(grid, D, ws, f->gamma, f->beta, cs, gW1);
   GODE_LAUNCH_CHECK();
   return GODE_OK;
+}
+
+// GODE_TC_ACC: accuracy configuration of the 3xTF32 products of k_rows_ws (bit field, see the kernel).  Read at every
+// launch so that one process can compare configurations (tools/transform_accuracy.py).
+static int rows_acc_cfg() {
+  const char* e = getenv("GODE_TC_ACC");
+  return e ? atoi(e) : GODE_TC_ACC_DEFAULT;
 }
 
 // GODE_ROWS_WS: 1 (default) = warp-specialised k_rows_ws for d = 128, 0 = the single-pipeline k_rows_tc
@@ -898,7 +994,8 @@ static int launch_rows_ws(int64_t n_rows, const float* X, float* Out, const floa
     const char* e = getenv("GODE_TC_PREFETCH");   // L2 prefetch distance in tiles per CTA (default 0 = off: measured
     return e ? atoi(e) : 0;                       // 2.28 ms without vs 2.39 ms with, N = 10 M; the loads are not the limit)
   }();
-  k_rows_ws<D, CPG, MODE><<<grid, tc::WS_THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf);
+  k_rows_ws<D, CPG, MODE><<<grid, tc::WS_THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf,
+                                                            rows_acc_cfg());
   GODE_LAUNCH_CHECK();
   return GODE_OK;
 }
@@ -965,25 +1062,28 @@ int input_grad_tc(const gode_gcn_odefunc_t* f, const float* gS, float* gz, cudaS
 // not the d x d ones above: the QC edge encoder (QC/layers.py:76-86: [E, 2667] x [2667, 5329], 28.4 MFLOP per edge --
 // SURVEY 8a "dominates QC"), the GAT node projections, the input layer of the GCN models.
 //
-// STATUS: written at the end of round 1 without GPU time left to run it -- it compiles for sm_100a and shares every
-// building block with k_rows_ws (which is parity-green), but it has NOT been executed yet.  It is therefore reachable
-// only through gode_gemm_tc_f32 (nothing in the package calls it) and its GPU test is skipped unless
-// GODE_TEST_EXPERIMENTAL=1.  Round 2: run that test, then route ops.linear / LinearFn through it.
+// Round 2: first run on a B200 green (tests/test_gpu_gemm_tc.py, 14 shapes against fp64); ops.linear routes large products here.
 //
 // Both operands are K-major (K contiguous): a weight stored [K, N] is transposed once by the caller.  One persistent CTA
 // per SM walks 128 x 128 output tiles (tile index = tm + tiles_m * tn, so concurrently running CTAs share one B tile);
 // K is consumed in stages of 32 (one 128-byte swizzle atom): eight producer warps load the A and the B part of a stage
-// (a quarter warp reads one 128-byte line), split hi / lo, store both into 128-byte-swizzled K-major stages of a 3-deep
+// (a quarter warp reads one 128-byte line), split hi / lo, store both into 128-byte-swizzled K-major stages of a 2-deep
 // ring and arrive on the stage's "full" barrier; one thread issues 4 K-steps x 3 passes of tcgen05.mma per stage into one
-// of two TMEM accumulators and commits the stage's "empty" barrier; four epilogue warps drain the previous tile
-// (bias, ReLU, swizzled staging, row stores).  Rows / columns / K beyond the matrix are zero-filled on load and masked on
+// of two TMEM accumulator sets and commits the stage's "empty" barrier; four epilogue warps drain finished sets into
+// shared-memory running sums and finish a tile (bias, ReLU, row stores).  Rows / columns / K beyond the matrix are zero-filled on load and masked on
 // store, so M, N, K are arbitrary; 128-bit accesses need lda, ldb (ldc) % 4 == 0 and 16-byte aligned bases, otherwise the
 // kernel falls back to 32-bit accesses.
 // ------------------------------------------------------------------------------------------------
 namespace tc {
-constexpr int GT_STAGES = 3;
+constexpr int GT_STAGES = 2;   // operand stages (64 KB each: A_hi | A_lo | B_hi | B_lo of 128 x 32)
+constexpr int GT_KG = 8;       // stages (K = 256 = 32 MMA K steps) accumulated inside the tensor core before a drain
 }
 
+// Accumulation is hierarchical, as in k_wgrad_tc: the MMA's own fp32 accumulate drops low bits at EVERY K step (measured:
+// ~0.5 ulp per step, one-sided), which over the 334 K steps of the QC edge encoder (K = 2667) would be 2e-5 -- above the
+// 1e-5 bar.  So GT_KG stages go into one of two TMEM accumulator sets (hi*hi and the correction terms apart), and the four
+// epilogue warps add every finished set into fp32 running sums in shared memory (round-to-nearest adds) while the MMAs
+// continue into the other set; after a tile's last group the sums get bias / ReLU and are stored as full rows.
 __global__ void __launch_bounds__(tc::WS_THREADS, 1)
 k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ Bt, int64_t ldb,
           float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int relu, int passes, int vec_in, int vec_out) {
@@ -992,11 +1092,11 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
   constexpr int NI = 4;                           // warp-instructions per producer warp per operand per stage
   constexpr uint32_t T_BYTES = 128 * BK * 4;      // one of hi / lo of one operand of one stage (16 KB)
   constexpr uint32_t STAGE_BYTES = 4 * T_BYTES;   // A_hi | A_lo | B_hi | B_lo
-  constexpr uint32_t STG_BYTES = 128 * 64 * 4;    // epilogue staging: 128 rows x 64 columns
+  constexpr uint32_t SUM_BYTES = 128 * 128 * 4;   // running sums of one output tile
   extern __shared__ __align__(1024) unsigned char smem[];
-  float* stage = reinterpret_cast<float*>(smem + GT_STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(stage) + STG_BYTES);
-  // bars: [0, S) full, [S, 2S) empty, [2S, 2S+2) acc_full, [2S+2, 2S+4) acc_empty
+  float* sums = reinterpret_cast<float*>(smem + GT_STAGES * STAGE_BYTES);   // [128 rows][32 chunks of 4, XOR-swizzled by row]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(sums) + SUM_BYTES);
+  // bars: [0, S) full, [S, 2S) empty, [2S, 2S+2) set_full, [2S+2, 2S+4) set_drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GT_STAGES + 4);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1018,7 +1118,7 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
     mbar_init(&bars[2 * GT_STAGES + 3], 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp == 0) tmem_alloc(tmem_slot, 512);   // two accumulator sets x (hi*hi | correction terms)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1092,96 +1192,110 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
   } else if (warp == 12) {
     // =============================== MMA issue (one thread) ===============================================
     if (lane == 0) {
+      int64_t g = 0;                                 // accumulation groups issued so far (over all tiles of this CTA)
       for (int64_t step = 0; step < n_steps; ++step) {
         const int s = static_cast<int>(step % GT_STAGES);
-        const int64_t it = step / KS, ks = step % KS;
-        const int b = static_cast<int>(it & 1);
-        if (ks == 0 && it >= 2) mbar_wait(&bars[2 * GT_STAGES + 2 + b], static_cast<uint32_t>(((it >> 1) - 1) & 1));
+        const int64_t ks = step % KS;
+        const int set = static_cast<int>(g & 1);
+        const bool first = ks % GT_KG == 0;          // first stage of its group
+        if (first && g >= 2) mbar_wait(&bars[2 * GT_STAGES + 2 + set], static_cast<uint32_t>(((g >> 1) - 1) & 1));
         mbar_wait(&bars[s], static_cast<uint32_t>((step / GT_STAGES) & 1));
         tc_fence_after();
         const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint32_t tmem_d = tmem_base + b * 128;
+        const uint32_t tmem_d = tmem_base + set * 256;
 #pragma unroll
         for (int q = 0; q < BK / 8; ++q) {
           const uint64_t a_hi = make_desc_sw128(base + q * 32), a_lo = make_desc_sw128(base + T_BYTES + q * 32);
           const uint64_t b_hi = make_desc_sw128(base + 2 * T_BYTES + q * 32), b_lo = make_desc_sw128(base + 3 * T_BYTES + q * 32);
-          mma_tf32(tmem_d, a_hi, b_hi, IDESC, (ks | q) != 0 ? 1u : 0u);
+          const uint32_t acc = (first && q == 0) ? 0u : 1u;
+          mma_tf32(tmem_d, a_hi, b_hi, IDESC, acc);
           if (passes == 3) {
-            mma_tf32(tmem_d, a_lo, b_hi, IDESC, 1u);
-            mma_tf32(tmem_d, a_hi, b_lo, IDESC, 1u);
+            mma_tf32(tmem_d + 128, a_lo, b_hi, IDESC, acc);
+            mma_tf32(tmem_d + 128, a_hi, b_lo, IDESC, 1u);
           }
         }
         mma_commit(&bars[GT_STAGES + s]);
-        if (ks == KS - 1) mma_commit(&bars[2 * GT_STAGES + b]);
+        if (ks % GT_KG == GT_KG - 1 || ks == KS - 1) {
+          mma_commit(&bars[2 * GT_STAGES + set]);    // this group's partial product is complete
+          ++g;
+        }
       }
     }
   } else {
-    // =============================== epilogue (warps 8-11) =================================================
-    constexpr int HC = 64, CHH = 16;
+    // =============================== drain + epilogue (warps 8-11) ========================================
+    constexpr int CH = 32;                           // 16-byte chunks per row of the sums tile
     const int q = warp & 3;
     const int et = tid - WS_PRODUCERS;
-    const int row = q * 32 + lane;
+    const int row = q * 32 + lane;                   // TMEM lane = tile row; a thread adds into its own row only
+    const int64_t n_groups = (KS + GT_KG - 1) / GT_KG;
+    int64_t g = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t t = blockIdx.x + it * (int64_t)gridDim.x;
       const int64_t tm = t % tiles_m, tn = t / tiles_m;
-      const int b = static_cast<int>(it & 1);
-      mbar_wait(&bars[2 * GT_STAGES + b], static_cast<uint32_t>((it >> 1) & 1));
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + b * 128 + (static_cast<uint32_t>(q * 32) << 16);
+      for (int64_t gi = 0; gi < n_groups; ++gi, ++g) {
+        const int set = static_cast<int>(g & 1);
+        mbar_wait(&bars[2 * GT_STAGES + set], static_cast<uint32_t>((g >> 1) & 1));
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + set * 256 + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-#pragma unroll
-        for (int cb = 0; cb < HC; cb += 32) {
+        for (int cb = 0; cb < 128; cb += 32) {
           float v[32];
-          tmem_ld32(tmem_d + h * HC + cb, v);
+          tmem_ld32(tmem_d + cb, v);
+          if (passes == 3) {
+            float w[32];
+            tmem_ld32(tmem_d + 128 + cb, w);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += w[j];
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const int64_t col = tn * 128 + h * HC + cb + j;
+            float4* p = reinterpret_cast<float4*>(sums + row * 128 + ((((cb + j) >> 2) ^ (row & (CH - 1))) << 2));
             float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (bias) {
-              if (col < N) o.x += __ldg(bias + col);
-              if (col + 1 < N) o.y += __ldg(bias + col + 1);
-              if (col + 2 < N) o.z += __ldg(bias + col + 2);
-              if (col + 3 < N) o.w += __ldg(bias + col + 3);
+            if (gi > 0) {
+              const float4 old = *p;
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
             }
-            if (relu) {
-              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-            }
-            const int chunk = ((cb + j) >> 2) ^ (row & (CHH - 1));
-            *reinterpret_cast<float4*>(stage + row * HC + chunk * 4) = o;
+            *p = o;
           }
         }
-        if (h == 1) {
-          tc_fence_before();
-          mbar_arrive(&bars[2 * GT_STAGES + 2 + b]);
-        }
-        bar_sync_named(2, 128);
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int idx = i * 128 + et;
-          const int r = idx / CHH, c = idx % CHH;
-          const int64_t grow = tm * 128 + r;
-          const int64_t col = tn * 128 + h * HC + c * 4;
-          if (grow < M && col < N) {
-            const float4 o = *reinterpret_cast<const float4*>(stage + r * HC + ((c ^ (r & (CHH - 1))) * 4));
-            float* dst = C + grow * ldc + col;
-            if (vec_out && col + 3 < N) {
-              *reinterpret_cast<float4*>(dst) = o;
-            } else {
-              dst[0] = o.x;
-              if (col + 1 < N) dst[1] = o.y;
-              if (col + 2 < N) dst[2] = o.z;
-              if (col + 3 < N) dst[3] = o.w;
-            }
-          }
-        }
-        bar_sync_named(2, 128);
+        tc_fence_before();
+        mbar_arrive(&bars[2 * GT_STAGES + 2 + set]);
       }
+      bar_sync_named(2, 128);                        // every row of the tile's sums is final
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const int idx = i * 128 + et;
+        const int r = idx / CH, c = idx % CH;
+        const int64_t grow = tm * 128 + r;
+        const int64_t col = tn * 128 + c * 4;
+        if (grow < M && col < N) {
+          float4 o = *reinterpret_cast<const float4*>(sums + r * 128 + ((c ^ (r & (CH - 1))) << 2));
+          if (bias) {
+            o.x += __ldg(bias + col);
+            if (col + 1 < N) o.y += __ldg(bias + col + 1);
+            if (col + 2 < N) o.z += __ldg(bias + col + 2);
+            if (col + 3 < N) o.w += __ldg(bias + col + 3);
+          }
+          if (relu) {
+            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+          }
+          float* dst = C + grow * ldc + col;
+          if (vec_out && col + 3 < N) {
+            *reinterpret_cast<float4*>(dst) = o;
+          } else {
+            dst[0] = o.x;
+            if (col + 1 < N) dst[1] = o.y;
+            if (col + 2 < N) dst[2] = o.z;
+            if (col + 3 < N) dst[3] = o.w;
+          }
+        }
+      }
+      bar_sync_named(2, 128);                        // the next tile's first group overwrites the sums
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 int gemm_tc(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc,
@@ -1189,7 +1303,7 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const 
   GODE_REQUIRE(M >= 0 && N >= 0 && K >= 1 && lda >= K && ldb >= K && ldc >= N, "gemm_tc: bad shape");
   if (M == 0 || N == 0) return GODE_OK;
   GODE_REQUIRE(A && Bt && C, "gemm_tc: null pointer");
-  constexpr size_t smem = tc::GT_STAGES * 4 * (size_t)128 * 32 * 4 + (size_t)128 * 64 * 4 + 256;
+  constexpr size_t smem = tc::GT_STAGES * 4 * (size_t)128 * 32 * 4 + (size_t)128 * 128 * 4 + 256;
   static bool configured = false;
   if (!configured) {
     GODE_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1207,8 +1321,7 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const 
 
 }  // namespace gode
 
-// C[M, N] = act(A[M, K] * Bt[N, K]^T + bias) on tcgen05 (3xTF32, or single-pass TF32 with GODE_PREC_TF32).  EXPERIMENTAL in
-// round 1: see the status note at k_gemm_tc.
+// C[M, N] = act(A[M, K] * Bt[N, K]^T + bias) on tcgen05 (3xTF32, or single-pass TF32 with GODE_PREC_TF32).
 extern "C" int gode_gemm_tc_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bt, int64_t ldb,
                                 const float* bias, int32_t relu, float* C, int64_t ldc, int32_t precision, void* stream) {
   return gode::gemm_tc(M, N, K, A, lda, Bt, ldb, C, ldc, bias, relu, precision, gode::as_stream(stream));

@@ -28,6 +28,11 @@ from ._lib import lib, check
 
 F32 = np.float32
 
+# Test instrumentation (tests/test_gpu_gcn.py::test_mask_conditioned_parity): when set to a list, the fused GCN engine
+# appends the ReLU mask (k > 0) of every function evaluation to it, in evaluation order, so that the CPU oracle can be run
+# on exactly the masks the CUDA path used (the parity protocol SURVEY 8c(5) applies to dropout masks).
+MASK_LOG = None
+
 # ---------------------------------------------------------------------------------------------
 # Butcher tableaux: c (nodes), a (strictly lower rows), b (weights)
 # ---------------------------------------------------------------------------------------------
@@ -181,21 +186,29 @@ class GcnKernel:
         """k_out = f(.) from its support S; fused y_next = y0 + sum coefs*kprev + coef_self*k; S_next = transform."""
         self.nfe += 1
         ws = self._ws()
+        if MASK_LOG is not None and k_out is None:
+            k_out = self.new()
         karr = (C.c_void_p * _lib.MAX_STAGES)(*[k.data_ptr() for k in kprev])
         carr = (C.c_float * _lib.MAX_STAGES)(*[float(c) for c in coefs])
         check(lib.gode_gcn_stage_fwd(C.byref(self.f), ops._p(S), ops._p(k_out), ops._p(y0), karr, carr, len(kprev),
                                      float(coef_self), ops._p(y_next), float(t_next), ops._p(S_next), ops._p(ws),
                                      self.ws_bytes, ops._stream()), "gode_gcn_stage_fwd")
+        if MASK_LOG is not None:
+            MASK_LOG.append(k_out > 0)
 
     def vjp_phase1(self, S, a, sign, k_y, gP, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None):
         """k_y = f(.), gP = sign*a*(k_y>0), fused y_next = y0 + sum coefs*kprev + coef_self*k_y -- one SpMM launch."""
         self.nfe += 1
         ws = self._ws()
+        if MASK_LOG is not None and k_y is None:
+            k_y = self.new()
         karr = (C.c_void_p * _lib.MAX_STAGES)(*[k.data_ptr() for k in kprev])
         carr = (C.c_float * _lib.MAX_STAGES)(*[float(c) for c in coefs])
         check(lib.gode_gcn_vjp_phase1(C.byref(self.f), ops._p(S), ops._p(a), float(sign), ops._p(k_y), ops._p(gP),
                                       ops._p(y0), karr, carr, len(kprev), float(coef_self), ops._p(y_next),
                                       ops._p(ws), self.ws_bytes, ops._stream()), "gode_gcn_vjp_phase1")
+        if MASK_LOG is not None:
+            MASK_LOG.append(k_y > 0)
 
     def vjp_phase2(self, y, t, gP, k_a, gtheta, a0=None, kprev=(), coefs=(), coef_self=0.0, a_next=None):
         """k_a = (gP^T A_hat) d[.]/dy (k_a may be None when no later stage reads it), gtheta = parameter / time terms;

@@ -431,10 +431,11 @@ def group_norm(x, groups, gamma, beta, eps=1e-5):
 
 
 def _tc_gemm_enabled(M, N, K):
-    """The general tcgen05 GEMM (gode_gemm_tc_f32) is EXPERIMENTAL in round 1 (compiled, not yet run on hardware): it is
-    used only with GODE_GEMM_TC=1, and only for products large enough to fill 128 x 128 tiles."""
+    """Products large enough to fill 128 x 128 tiles go to the general tcgen05 GEMM (gode_gemm_tc_f32: 3xTF32 with
+    hierarchical accumulation, as accurate as an fp32 SGEMM -- tests/test_gpu_gemm_tc.py); GODE_GEMM_TC=0 keeps everything
+    on the SIMT kernel."""
     import os
-    return os.environ.get("GODE_GEMM_TC", "0") == "1" and M >= 512 and N >= 64 and K >= 32
+    return os.environ.get("GODE_GEMM_TC", "1") != "0" and M >= 512 and N >= 64 and K >= 32
 
 
 def _pad4(t):
@@ -449,7 +450,7 @@ def _pad4(t):
 
 
 def gemm_tc(a, bt, bias=None, relu=False, out=None):
-    """``act(a @ bt.T + bias)`` with both operands K-major -- gode_gemm_tc_f32 (experimental, see ``_tc_gemm_enabled``)."""
+    """``act(a @ bt.T + bias)`` with both operands K-major -- gode_gemm_tc_f32."""
     a, bt = _pad4(_rowmajor(a, "a")), _pad4(_rowmajor(bt, "bt"))
     M, K = a.shape
     N = bt.shape[0]

@@ -44,6 +44,28 @@ def odefunc2(t, x, p, adj, prefix=""):
     return group_norm(h, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"])
 
 
+class MaskedOdefunc:
+    """``odefunc`` with the ReLU replaced by recorded masks, one per function evaluation in evaluation order:
+    ``f = pre * mask`` instead of ``relu(pre) = pre * (pre > 0)``.  Feeding the masks the CUDA path used makes the oracle
+    differentiate the SAME piecewise-linear branch, so gradients can be compared at fp32 rounding (1e-5) even when a
+    pre-activation within rounding distance of zero would otherwise fall on different sides in the two implementations
+    (the parity protocol of SURVEY 8c(5), applied to ReLU masks instead of dropout masks).  ``flips`` counts the elements
+    whose recorded mask differs from the oracle's own sign test."""
+
+    def __init__(self, masks):
+        self.masks, self.i, self.flips, self.total = list(masks), 0, 0, 0
+
+    def __call__(self, t, x, p, adj, prefix=""):
+        xn = group_norm(x, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"])
+        tt = torch.ones_like(xn[:, :1]) * t
+        pre = graph_convolution(torch.cat([tt, xn], 1), adj, p[prefix + "gc1.weight"], p.get(prefix + "gc1.bias"))
+        m = self.masks[self.i]
+        self.i += 1
+        self.flips += int(((pre.detach() > 0) != m).sum())
+        self.total += m.numel()
+        return pre * m.to(pre.dtype)
+
+
 class _Func(torch.nn.Module):
     """Adapter giving a functional ODE function a ``parameters()`` list and an ``nfe`` counter."""
 

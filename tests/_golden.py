@@ -21,6 +21,48 @@ def rnd(seed, *shape, scale=1.0):
     return torch.from_numpy((np.random.RandomState(seed).standard_normal(shape) * scale).astype(np.float32))
 
 
+def fill_params(model, seed=7):
+    """Deterministic parameters chosen by NAME (numpy legacy RandomState seeded with crc32(name) ^ seed), so that the fixture
+    generator (reference modules) and the tests (B200 modules) hold identical parameters without storing them -- and a
+    parameter name that exists on one side only is an immediate KeyError/shape error.  2-D weights are Xavier-normal,
+    vectors named ``*norm*.weight`` are 1 + 0.25 N(0,1), every other vector is 0.1 N(0,1)."""
+    import zlib
+    with torch.no_grad():
+        for name, p in sorted(model.named_parameters()):
+            rs = np.random.RandomState((zlib.crc32(name.encode()) ^ seed) & 0x7FFFFFFF)
+            v = rs.standard_normal(tuple(p.shape)).astype(np.float32)
+            if p.dim() >= 2:
+                v *= np.float32((2.0 / (p.shape[0] + p.shape[1])) ** 0.5)
+            elif "norm" in name and name.endswith("weight"):
+                v = np.float32(1.0) + np.float32(0.25) * v
+            else:
+                v *= np.float32(0.1)
+            p.copy_(torch.from_numpy(v))
+    return model
+
+
+GRAD_SAMPLE = 4096
+
+
+def grad_sample(t):
+    """Large gradient tensors are stored as a fixed strided sample (at most GRAD_SAMPLE elements) plus their norm."""
+    flat = torch.as_tensor(t).detach().reshape(-1)
+    stride = max(1, (flat.numel() + GRAD_SAMPLE - 1) // GRAD_SAMPLE)
+    return flat[::stride]
+
+
+def pubmed_features(n, nfeat=500, per_row=50, seed=0):
+    """``ind.pubmed.allx`` is missing from the reference checkout, so Pubmed runs on the real graph
+    with synthetic TF-IDF-like features: ~50 non-zeros per row, row-normalised as GCN/utils.py:185 does."""
+    rs = np.random.RandomState(seed)
+    x = np.zeros((n, nfeat), np.float32)
+    cols = rs.randint(0, nfeat, size=(n, per_row))
+    vals = rs.rand(n, per_row).astype(np.float32) + np.float32(0.1)
+    np.put_along_axis(x, cols, vals, axis=1)
+    x /= x.sum(1, keepdims=True)
+    return torch.from_numpy(x)
+
+
 def params(fix, prefix):
     """state_dict-style mapping of torch tensors stored under ``prefix``."""
     return {k[len(prefix):]: torch.from_numpy(v.copy()) for k, v in fix.items() if k.startswith(prefix)}
@@ -48,8 +90,12 @@ def dense_features(ds):
     return torch.from_numpy(np.asarray(m.todense(), dtype=np.float32))
 
 
-def assert_close(a, b, rtol=1e-5, atol_scale=1e-5, what="", atol_abs=0.0):
-    """|a-b| <= rtol*|b| + atol_scale*max|b| + atol_abs elementwise (fp32 parity bar, stated at the call site)."""
+def assert_close(a, b, rtol=1e-5, atol_scale=1e-5, what="", atol_abs=0.0, outliers=None):
+    """|a-b| <= rtol*|b| + atol_scale*max|b| + atol_abs elementwise (fp32 parity bar, stated at the call site).
+
+    ``outliers=(frac, tol)``: at most ``frac`` of the elements may miss the bar, and those must still be within
+    ``tol * max|b|`` -- for quantities where a few elements are legitimately ill-conditioned (stated at the call site)
+    while the bulk must hold the fp32 bar."""
     a = torch.as_tensor(a).detach().cpu().double()
     b = torch.as_tensor(b).detach().cpu().double()
     assert a.shape == b.shape, (what, a.shape, b.shape)
@@ -57,6 +103,10 @@ def assert_close(a, b, rtol=1e-5, atol_scale=1e-5, what="", atol_abs=0.0):
     err = (a - b).abs()
     tol = rtol * b.abs() + atol_scale * scale + atol_abs
     bad = err > tol
+    if outliers is not None and bool(bad.any()):
+        frac, otol = outliers
+        if int(bad.sum()) <= frac * bad.numel() and float(err.max()) <= otol * scale:
+            return
     if bool(bad.any()):
         i = int(torch.argmax(err - tol))
         raise AssertionError("%s: max err %.3e (scale %.3e) at flat %d: got %.8e want %.8e; %d/%d bad" % (

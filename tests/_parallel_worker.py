@@ -32,7 +32,7 @@ def main():
         blk.odefunc.norm1.bias.uniform_(-0.5, 0.5)
         if smooth:
             # every pre-activation far above zero: ReLU never switches, the function is smooth, and differently ordered
-            # fp32 sums must agree to rounding (1e-5); the default regime has mask flips (tools/sensitivity.py)
+            # fp32 sums must agree to rounding (1e-5)
             blk.odefunc.gc1.bias.fill_(6.0)
     g = torch.Generator(device=dev).manual_seed(9)
     x_all = 0.5 * torch.randn(n, d, device=dev, generator=g)
@@ -73,14 +73,13 @@ def main():
         for (name, _), a, b in zip(blk.named_parameters(), gp_p, gp_1):
             errs["g_" + name] = rel(a, b)
         print("world=%d mode=%s method=%s nfe %d/%d errs %s stats %s / %s" % (world, pplan.mode, method, nfe_p, nfe_1, errs, st_p, st_1), flush=True)
-        # y: 1e-6 relative L2.  Gradients: 1e-5 in the smooth regime; with active ReLUs a 1e-7 difference in a
-        # pre-activation flips mask elements and moves the summed gradients by 1e-4..1e-3 (measured: tools/sensitivity.py)
-        gtol = 1e-5 if smooth else 5e-3
+        # y: 1e-6 relative L2; gradients: 1e-5 relative L2 in both regimes (the partitioned gather only reorders fp32 sums)
+        gtol = 1e-5
         if method == "dopri5":
             # the adaptive controller turns rounding-level differences of the error norm into slightly different step
-            # sizes, i.e. O(rtol) = 1e-5 differences of the solution and 1e-4 of the adjoint gradients, with identical
+            # sizes, i.e. O(rtol) = 1e-5 differences of the solution and of the adjoint gradients, with identical
             # accepted / rejected step counts (asserted below)
-            gtol = max(gtol, 2e-3)
+            gtol = 1e-4
         ok = nfe_p == nfe_1 and errs["y"] < 1e-6 and all(v < gtol for v in errs.values())
         if method == "dopri5":
             ok = ok and st_p == st_1

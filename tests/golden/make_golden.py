@@ -364,8 +364,118 @@ def make_set2set():
     np.savez_compressed(os.path.join(HERE, "set2set_golden.npz"), **S)
 
 
+# ---------------------------------------------------------------------------------------------------
+# every model class of GCN/models.py, one GAT model family, Citeseer and Pubmed (VERDICT r01 missing #1, #2)
+# ---------------------------------------------------------------------------------------------------
+
+# (fixture key, class, constructor kwargs, solver method or None); nhid = 128 keeps GroupNorm well conditioned (4 channels
+# per group); the reference's default nhid = 16 is the degenerate case of SURVEY F8 and is covered by gcn_golden.npz
+GCN_MODEL_CASES = [
+    ("GCN", "GCN", {}, None), ("RGCN2", "RGCN2", {}, None), ("GCN3norm", "GCN3norm", {}, None),
+    ("RGCN3fullnorm", "RGCN3fullnorm", {}, None), ("ODEGCN3fullnorm_rk4", "ODEGCN3fullnorm", {}, "rk4"),
+    ("GCNK4", "GCNK", {"nlayers": 4}, None), ("GCNKnorm4", "GCNKnorm", {"nlayers": 4}, None),
+    ("RESK1_4", "RESK1", {"nlayers": 4}, None), ("RESK2_6", "RESK2", {"nlayers": 6}, None),
+    ("RESK_5_r2", "RESK", {"nlayers": 5, "residue_layers": 2}, None),
+    ("RESK_6_r3", "RESK", {"nlayers": 6, "residue_layers": 3}, None),
+    ("RESK1norm4", "RESK1norm", {"nlayers": 4}, None), ("RESK2norm6", "RESK2norm", {"nlayers": 6}, None),
+    ("RESKnorm_5_r2", "RESKnorm", {"nlayers": 5, "residue_layers": 2}, None),
+    ("ODEK1_4_rk4", "ODEK1", {"nlayers": 4}, "rk4"), ("ODEK1_3_dopri5", "ODEK1", {"nlayers": 3}, "dopri5"),
+    ("ODEK2_5_rk4", "ODEK2", {"nlayers": 5}, "rk4"),
+    # the reference passes `dropout` as the ODE block's tolerance (GCN/models.py:587): dopri5 at rtol = atol = 0.5
+    ("ODEK2_4_dopri5", "ODEK2", {"nlayers": 4}, "dopri5"),
+]
+DATASET_CASES = [  # (dataset, fixture key, class, kwargs, method, nhid)
+    ("citeseer", "ODEGCN3_rk4", "ODEGCN3", {}, "rk4", 128), ("citeseer", "ODEGCN3_dopri5", "ODEGCN3", {}, "dopri5", 128),
+    ("citeseer", "RGCN3", "RGCN3", {}, None, 128), ("citeseer", "ODEGCN3_rk4_h16", "ODEGCN3", {}, "rk4", 16),
+    ("pubmed", "ODEGCN3_rk4", "ODEGCN3", {}, "rk4", 128), ("pubmed", "RGCN3", "RGCN3", {}, None, 128),
+    ("pubmed", "RESK1_4", "RESK1", {"nlayers": 4}, None, 128), ("pubmed", "ODEK1_3_dopri5", "ODEK1", {"nlayers": 3}, "dopri5", 64),
+]
+GAT_MODEL_CASES = [("RGCN3", "RGCN3", {}, None), ("ODEGCN3_rk4", "ODEGCN3", {}, "rk4"), ("RESK1_4", "RESK1", {"nlayers": 4}, None)]
+
+
+def _run_model_case(models_mod, cls_name, kw, method, nfeat, nhid, nclass, inputs, labels, idx_train, G_, key):
+    from tests import _golden as TG
+    stats = {}
+    if method:
+        set_method(models_mod, method, None, stats)
+    model = getattr(models_mod, cls_name)(nfeat=nfeat, nhid=nhid, nclass=nclass, dropout=0.5, **kw)
+    TG.fill_params(model)
+    model.eval()
+    has_ode = method is not None
+    if has_ode:
+        model.nfe = 0
+    out = model(*inputs)
+    nfe_f = int(model.nfe) if has_ode else 0
+    if has_ode:
+        model.nfe = 0
+    loss = torch.nn.functional.nll_loss(out[idx_train], labels[idx_train])
+    loss.backward()
+    nfe_b = int(model.nfe) if has_ode else 0
+    G_.update({key + "out": out.detach().numpy(), key + "loss": np.float32(loss.item()),
+               key + "nfe_f": np.int64(nfe_f), key + "nfe_b": np.int64(nfe_b),
+               key + "acc_f": np.int64(stats.get("forward", {}).get("accepted", 0)),
+               key + "rej_f": np.int64(stats.get("forward", {}).get("rejected", 0)),
+               key + "acc_b": np.int64(stats.get("backward", {}).get("accepted", 0)),
+               key + "rej_b": np.int64(stats.get("backward", {}).get("rejected", 0))})
+    for pn, p_ in model.named_parameters():
+        if p_.grad is None:
+            continue
+        G_[key + "grad/" + pn] = TG.grad_sample(p_.grad).numpy().copy()
+        G_[key + "gradnorm/" + pn] = np.float64(p_.grad.double().norm().item())
+    print(key, "loss %.6f nfe %d/%d" % (loss.item(), nfe_f, nfe_b), stats)
+
+
+def make_models():
+    """models_golden.npz: logits, loss, NFE / step counts and (sampled) parameter gradients of every model class of the
+    reference on Cora, plus Citeseer (real features) and Pubmed (real graph, synthetic features) cases and a GAT family.
+    Parameters are not stored: both sides fill them by name with tests/_golden.py:fill_params."""
+    _install_shims()
+    from tests import _golden as TG
+    gcn = load_ref("GCN")
+    gat = load_ref("GAT")
+    M = {}
+    data = {}
+    for ds in ("cora", "citeseer", "pubmed"):
+        c = np.load(os.path.join(HERE, "planetoid_%s.npz" % ds))
+        n = int(c["n"])
+        adj = TG.coo_adj(c["coo_row"], c["coo_col"], c["coo_val"], n)
+        if ds != "pubmed":
+            import scipy.sparse as sp
+            m = sp.csr_matrix((c["feat_data"], c["feat_indices"], c["feat_indptr"]), shape=(n, int(c["nfeat"])))
+            feats = torch.from_numpy(np.asarray(m.todense(), dtype=np.float32))
+            labels = torch.from_numpy(c["labels"].astype(np.int64))
+            idx = torch.from_numpy(c["idx_train"].astype(np.int64))
+        else:
+            feats = TG.pubmed_features(n)
+            labels = torch.from_numpy(np.random.RandomState(1).randint(0, 3, n).astype(np.int64))
+            idx = torch.arange(60)
+        data[ds] = (c, n, adj, feats, labels, idx)
+
+    c, n, adj, feats, labels, idx = data["cora"]
+    for key, cls_name, kw, method in GCN_MODEL_CASES:
+        _run_model_case(gcn.models, cls_name, kw, method, feats.shape[1], 128, 7, (feats, adj), labels, idx, M, "cora/%s/" % key)
+    for ds, key, cls_name, kw, method, nhid in DATASET_CASES:
+        c, n, adj, feats, labels, idx = data[ds]
+        _run_model_case(gcn.models, cls_name, kw, method, feats.shape[1], nhid, int(labels.max()) + 1, (feats, adj), labels, idx, M,
+                        "%s/%s/" % (ds, key))
+    # GAT family on the Cora edge list (GAT/utils.py:187-196: each undirected edge once)
+    c, n, adj, feats, labels, idx = data["cora"]
+    src = torch.from_numpy(c["gat_src"].astype(np.int64))
+    tgt = torch.from_numpy(c["gat_tgt"].astype(np.int64))
+    E = len(src)
+    Mtgt = torch.sparse_coo_tensor(torch.stack([tgt, torch.arange(E)]), torch.ones(E), (n, E))
+    for key, cls_name, kw, method in GAT_MODEL_CASES:
+        _run_model_case(gat.models, cls_name, kw, method, feats.shape[1], 128, 7, (feats, src, tgt, Mtgt), labels, idx, M,
+                        "gat_cora/%s/" % key)
+    np.savez_compressed(os.path.join(HERE, "models_golden.npz"), **M)
+    print("models_golden.npz", os.path.getsize(os.path.join(HERE, "models_golden.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     if "--only-set2set" in sys.argv:
         make_set2set()
+    elif "--only-models" in sys.argv:
+        make_models()
     else:
         main()
+        make_models()

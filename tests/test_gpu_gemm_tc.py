@@ -1,24 +1,16 @@
-"""GPU tests of code that was written without GPU time left to run it (round 1): skipped unless GODE_TEST_EXPERIMENTAL=1.
-
-``gode_gemm_tc_f32`` -- the general tcgen05 3xTF32 GEMM (csrc/transform_tc.cu, k_gemm_tc) that is to carry the QC edge
-encoder and the GAT projections; nothing in the package calls it yet.  Round 2: run
-
-    GODE_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -x -q
-
-and only then route ``ops.linear`` through it.
-"""
+"""``gode_gemm_tc_f32`` -- the general tcgen05 3xTF32 GEMM (csrc/transform_tc.cu, k_gemm_tc) that carries the QC edge
+encoder, the GAT projections and the input layers -- against fp64 on shapes that exercise every edge: partial tiles in M, N
+and K, unaligned leading dimensions, K long enough for several accumulation groups, padding that must not leak."""
 import ctypes as C
-import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("GODE_TEST_EXPERIMENTAL") != "1", reason="experimental kernels: opt-in")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("M,N,K,pad", [(128, 128, 32, True), (128, 128, 128, True), (300, 200, 70, True), (1000, 533, 267, True),
-                                       (257, 129, 33, False), (4096, 256, 1024, True), (5, 3, 1, False)])
+                                       (257, 129, 33, False), (4096, 256, 1024, True), (5, 3, 1, False), (700, 384, 2667, True)])
 @pytest.mark.parametrize("relu,use_bias", [(0, False), (1, True)])
 def test_gemm_tc_matches_fp64(M, N, K, pad, relu, use_bias):
     import graph_odenet_b200  # noqa: F401
@@ -47,6 +39,10 @@ def test_gemm_tc_matches_fp64(M, N, K, pad, relu, use_bias):
     got = Cm[:, :N].double()
     scale = float(want.abs().max())
     assert torch.isfinite(got).all()
-    assert float((got - want).abs().max()) <= 2e-6 * scale * max(1.0, K ** 0.5 / 8), (float((got - want).abs().max()), scale)
+    # an fp32 SGEMM's own error grows like sqrt(K) * 6e-8; the bar is 2e-6 of the result's scale for every K tested
+    err = float((got - want).abs().max())
+    lib_err = float(((A[:, :K] @ Bt[:, :K].t() + (bias if use_bias else 0)).clamp_min(0 if relu else -float("inf")).double() - want).abs().max())
+    print("gemm_tc M=%d N=%d K=%d: max err / scale %.2e (torch fp32 matmul: %.2e)" % (M, N, K, err / scale, lib_err / scale))
+    assert err <= 2e-6 * scale, (err, scale)
     if ld(N) > N:
         assert torch.isnan(Cm[:, N:]).all()                      # columns beyond N are never written

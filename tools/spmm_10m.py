@@ -18,7 +18,7 @@ reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 d = 128
 dev = torch.device("cuda:0")
 row, col, val = synth.powerlaw_graph(n, avg_degree=20, locality=loc, window=win or None, seed=0, device=dev)
-plan = ops.GraphPlan.from_coo(row, col, val, n, n, build_transpose=False)
+plan = ops.GraphPlan.from_coo(row, col, val, n, n, build_transpose=True)
 del row, col, val
 torch.cuda.empty_cache()
 x = torch.randn(n, d, device=dev)
@@ -42,8 +42,23 @@ def timed(fn):
 
 ms = timed(lambda: ops.spmm(plan, x, out=out))
 print("variant=%s bulk=%s N=%d loc=%.2f win=%d nnz=%d heavy=%d bare: %.3f ms compulsory %.0f GB/s gather-model %.0f GB/s" % (
-    os.environ.get("GODE_SPMM_VARIANT", "5"), os.environ.get("GODE_SPMM_BULK", "0"), n, loc, win, nnz, plan.n_heavy, ms,
+    os.environ.get("GODE_SPMM_VARIANT", "0"), os.environ.get("GODE_SPMM_BULK", "0"), n, loc, win, nnz, plan.n_heavy, ms,
     comp / ms / 1e6, (nnz * d * 4 + comp) / ms / 1e6), flush=True)
+
+ms_t = timed(lambda: ops.spmm(plan, x, out=out, transpose=True))
+print("   A^T gather (values per entry, no row-constant shortcut): %.3f ms" % ms_t, flush=True)
+chk = ops.spmm(plan, x)
+ref = torch.zeros_like(chk)
+# spot check against a segment-sum of 2000 rows (variant-independent reference in fp64)
+rows = torch.randint(0, n, (2000,), device=dev)
+rp = plan.rowptr.to(torch.int64)
+errs = []
+for r in rows.tolist()[:200]:
+    cols = plan.colidx[rp[r]:rp[r + 1]].to(torch.int64)
+    want = (plan.vals[rp[r]:rp[r + 1]].double()[:, None] * x[cols].double()).sum(0)
+    errs.append(float((chk[r].double() - want).abs().max() / (want.abs().max() + 1e-30)))
+print("   max relative row error vs fp64 on 200 rows: %.2e" % max(errs), flush=True)
+del chk, ref
 
 # with the stage-4 epilogue of rk4: bias + relu + y_next = y0 + c1 k1 + c2 k2 + c3 k3 + c_self k
 y0 = torch.randn(n, d, device=dev)
