@@ -48,14 +48,22 @@ def parse():
     ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--halo-mode", default=None, help="N>1: sync | async | split (NCCL) | p2p | p2p-async (peer memory); "
                                                       "default: GODE_HALO_MODE or the library default")
+    ap.add_argument("--shuffle-ids", action="store_true", help="relabel the generated graph with a random permutation first "
+                                                               "(a graph whose locality is hidden from the id order)")
+    ap.add_argument("--reorder", choices=["none", "degree", "rcm"], default="none",
+                    help="locality-aware relabelling pass (parallel.locality_order) applied before the plan is built")
+    ap.add_argument("--reorder-sweeps", type=int, default=0, help="barycentre sweeps after --reorder")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return "gcn-ode rk4 fwd+bwd, synthetic power-law graph N=%d avg_deg=%g d=%d locality=%g seed=%d" % (
-        a.nodes, a.avg_degree, a.dim, a.locality, a.seed)
+    extra = (", ids shuffled" if getattr(a, "shuffle_ids", False) else "") + (
+        ", relabelled by %s%s" % (a.reorder, " + %d barycentre sweeps" % a.reorder_sweeps if a.reorder_sweeps else "")
+        if getattr(a, "reorder", "none") != "none" else "")
+    return "gcn-ode rk4 fwd+bwd, synthetic power-law graph N=%d avg_deg=%g d=%d locality=%g seed=%d%s" % (
+        a.nodes, a.avg_degree, a.dim, a.locality, a.seed, extra)
 
 
 def peaks():
@@ -336,6 +344,25 @@ def run_ours(a):
     n, d = a.nodes, a.dim
     row, col, val = synth.powerlaw_graph(n, avg_degree=a.avg_degree, locality=a.locality, seed=a.seed, device=dev)
     nnz = int(val.numel())                       # global stored entries of A_hat: the metric's "edges"
+    relabel_info = None
+    if a.shuffle_ids or a.reorder != "none":
+        # pure relabellings of the same graph (values travel with their entries): every rank computes the same permutation
+        from graph_odenet_b200 import parallel as _rl
+        t_rl = time.perf_counter()
+        before = _rl.halo_fraction(row, col, n, max(world, 8))
+        if a.shuffle_ids:
+            gsh = torch.Generator(device=dev).manual_seed(a.seed + 1)
+            shuf = torch.randperm(n, generator=gsh, device=dev)
+            row, col = shuf[row], shuf[col]
+        shuffled = _rl.halo_fraction(row, col, n, max(world, 8))
+        if a.reorder != "none":
+            perm = _rl.locality_order(row, col, n, a.reorder, a.reorder_sweeps)
+            row, col = _rl.relabel(row, col, perm)
+            del perm
+        torch.cuda.synchronize()
+        relabel_info = {"halo_rows_per_owned_row_%dway" % max(world, 8): {"as_generated": before, "after_shuffle": shuffled,
+                                                                          "after_reorder": _rl.halo_fraction(row, col, n, max(world, 8))},
+                        "seconds": time.perf_counter() - t_rl}
     halo_info = None
     if world > 1:
         # contiguous row blocks of A_hat / A_hat^T, halo exchange of the gather operand per evaluation
@@ -477,7 +504,7 @@ def run_ours(a):
     except Exception:
         l2cap = None
     l2_bytes = nnz_loc * d * 4.0             # every stored entry brings one d-float neighbour row from L2 to an SM
-    roofline = {"bound": "hbm", "kernel": "k_spmm_vec<32,1> (A_hat*S gather + bias + relu + RK combine)%s" % (
+    roofline = {"bound": "hbm", "kernel": "k_spmm_t2<32,8> (A_hat*S gather + bias + relu + RK combine)%s" % (
                     "" if world == 1 else " on rank 0's row block"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "algorithmic_bytes_per_launch": b_compulsory, "ms_per_launch": agg["ms_avg"],
@@ -556,6 +583,7 @@ def run_ours(a):
             "config": {"workload": workload_name(a), "nnz": nnz, "solver": a.method, "func_evals_per_step": nfe_per_step,
                        "l2": "inputs larger than L2 (every [N,d] tensor is %.2f GB)" % (n * d * 4 / 1e9),
                        "optimizer": "Adam on the ODE function's parameters (in the timed region)",
+                       "relabelling": relabel_info,
                        "partition": None if world == 1 else dict(halo_info, scheme="contiguous row blocks; halo exchange "
                                                                   "of the gather operand per evaluation (" + (
                                                                       "libgode kernel storing rows into the peers' halo "

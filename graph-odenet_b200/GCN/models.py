@@ -122,7 +122,13 @@ class ODEBlock(nn.Module):
 
 
 class _NfeMixin:
-    """``nfe`` plumbing + the layer family a model is built from (GCN here; GAT/models.py rebinds these)."""
+    """``nfe`` plumbing + the layer family a model is built from (GCN here; GAT/models.py rebinds these).
+
+    Every model computes its pre-softmax scores in ``logits(x, *adj)``; ``forward`` is the reference's
+    ``F.log_softmax(..., dim=1)`` of them.  The trainer's fused loss (ops.log_softmax_nll) starts from ``logits``."""
+
+    def forward(self, x, *adj):
+        return F.log_softmax(self.logits(x, *adj), dim=1)
 
     _conv = GraphConvolution
     _odefunc = None     # bound below, after ODEfunc / ODEfunc2 are defined
@@ -148,7 +154,7 @@ def _drop(x, p, training):
     return F.dropout(x, p, training=training)
 
 
-class GCN(nn.Module, _NfeMixin):
+class GCN(_NfeMixin, nn.Module):
     """gc1 -> relu -> dropout -> gc2 -> log_softmax  (GCN/models.py:8-21)."""
 
     def __init__(self, nfeat, nhid, nclass, dropout):
@@ -157,12 +163,12 @@ class GCN(nn.Module, _NfeMixin):
         self.gc2 = self._conv(nhid, nclass)
         self.dropout = dropout
 
-    def forward(self, x, *adj):
+    def logits(self, x, *adj):
         x = _drop(self.gc1(x, *adj, relu=True), self.dropout, self.training)
-        return F.log_softmax(self.gc2(x, *adj), dim=1)
+        return self.gc2(x, *adj)
 
 
-class RGCN2(nn.Module, _NfeMixin):
+class RGCN2(_NfeMixin, nn.Module):
     """GCN/models.py:23-40: residual on the output layer, first nclass columns are the logits."""
 
     def __init__(self, nfeat, nhid, nclass, dropout):
@@ -173,13 +179,13 @@ class RGCN2(nn.Module, _NfeMixin):
         self.gc2 = self._conv(nhid, nhid)
         self.nclass, self.dropout = nclass, dropout
 
-    def forward(self, x, *adj):
+    def logits(self, x, *adj):
         x = _drop(self.gc1(x, *adj, relu=True), self.dropout, self.training)
         x = self.gc2(x, *adj) + x
-        return F.log_softmax(x[:, :self.nclass], dim=1)
+        return x[:, :self.nclass]
 
 
-class ODEGCN2(nn.Module, _NfeMixin):
+class ODEGCN2(_NfeMixin, nn.Module):
     """GCN/models.py:42-64.  (The reference forgets to store ``nclass`` and fails in forward; stored here.)"""
 
     def __init__(self, nfeat, nhid, nclass, dropout):
@@ -190,12 +196,12 @@ class ODEGCN2(nn.Module, _NfeMixin):
         self.gc2 = ODEBlock(self._odefunc(nhid))
         self.nclass, self.dropout = nclass, dropout
 
-    def forward(self, x, *adj):
+    def logits(self, x, *adj):
         x = self.gc2(self.gc1(x, *adj, relu=True), *adj)
-        return F.log_softmax(x[:, :self.nclass], dim=1)
+        return x[:, :self.nclass]
 
 
-class _Three(nn.Module, _NfeMixin):
+class _Three(_NfeMixin, nn.Module):
     """gc1 -> [norm1] -> middle -> gc3 -> log_softmax; `middle` is what the named subclasses differ in."""
 
     residual = False      # add the middle block's input to its output
@@ -214,7 +220,7 @@ class _Three(nn.Module, _NfeMixin):
         self.gc3 = self._conv(nhid, nclass)
         self.dropout = dropout
 
-    def forward(self, x, *adj):
+    def logits(self, x, *adj):
         x = self.gc1(x, *adj, relu=True)
         x = self.norm1(x) if self.in_norm else _drop(x, self.dropout, self.training)
         if self.ode:
@@ -225,7 +231,7 @@ class _Three(nn.Module, _NfeMixin):
             x = self.norm2(x) if self.mid_norm else _drop(x, self.dropout, self.training)
             if self.residual:
                 x = x + r
-        return F.log_softmax(self.gc3(x, *adj), dim=1)
+        return self.gc3(x, *adj)
 
 
 class GCN3(_Three):               # GCN/models.py:66-81
@@ -256,7 +262,7 @@ class ODEGCN3fullnorm(_Three):    # GCN/models.py:229-253
     ode, in_norm = True, True
 
 
-class _Deep(nn.Module, _NfeMixin):
+class _Deep(_NfeMixin, nn.Module):
     """K-layer models: ``gcs`` = [input conv, middle..., output conv] (+ ``norms``)  (GCN/models.py:255-600)."""
 
     min_layers = 2
@@ -287,7 +293,7 @@ class _Deep(nn.Module, _NfeMixin):
     def _middle(self, nhid, nlayers, dropout):
         return [self._conv(nhid, nhid) for _ in range(nlayers - 2)]
 
-    def forward(self, x, *adj):
+    def logits(self, x, *adj):
         x = _drop(self.gcs[0](x, *adj, relu=True), self.dropout, self.training)
         countdown, r = 1, None
         for i, gc in enumerate(self.gcs[1:-1]):
@@ -304,7 +310,7 @@ class _Deep(nn.Module, _NfeMixin):
                 x = x + r
         if self.residue_layers and countdown > 1:
             x = x + r
-        return F.log_softmax(self.gcs[-1](x, *adj), dim=1)
+        return self.gcs[-1](x, *adj)
 
 
 class GCNK(_Deep):                # GCN/models.py:255-278

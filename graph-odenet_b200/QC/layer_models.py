@@ -92,9 +92,8 @@ class MPNN_ENN_K_Sum(nn.Module):
 
 
 class MPNN_ENN_K_Set2Set(nn.Module):
-    """QC/layer_models.py:55-82.  The reference builds ``MPNN_enn`` here and calls ``set_T`` on it, which that class does
-    not have (AttributeError at construction); the evident intent -- the message-passing core of ``MPNN_ENN_K_Sum`` with
-    the Set2Set readout -- is what this class builds.  The readout keeps the first ``hidden`` columns of q* (:79)."""
+    """QC/layer_models.py:55-82: the message-passing core of ``MPNN_ENN_K_Sum`` (the reference imports ``MPNN_enn_edge as
+    MPNN_enn``, :5) with the Set2Set readout, of which the first ``hidden`` columns of q* are kept (:79)."""
 
     def __init__(self, node_features=None, edge_features=None, target_features=1, hidden_features=73, num_layers=3,
                  s2s_processing_steps=12, type="regression", dropout=0.5, **kwargs):

@@ -81,6 +81,11 @@ _PROTOS = {
     "gode_gemm_f32": (C.c_int, [i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, f32, vp, i64, i32, i32, vp, sz, vp]),
     "gode_linear_f32": (C.c_int, [i32, i64, i64, i64, vp, i64, vp, i64, vp, i32, vp, i64, vp]),
     "gode_gemm_tc_f32": (C.c_int, [i64, i64, i64, vp, i64, vp, i64, vp, i32, vp, i64, i32, vp]),
+    "gode_lsm_nll_workspace_bytes": (sz, [i64]),
+    "gode_lsm_nll_fwd": (C.c_int, [i64, i32, vp, i64, vp, vp, i64, vp, i64, vp, vp, sz, vp]),
+    "gode_lsm_nll_bwd": (C.c_int, [i64, i32, vp, i64, vp, vp, i64, vp, vp, i64, vp]),
+    "gode_adam_step": (C.c_int, [i64, vp, vp, vp, vp, f32, f32, f32, f32, f32, vp, vp]),
+    "gode_gemm_tc_splitk_f32": (C.c_int, [i64, i64, i64, vp, i64, vp, i64, vp, i64, i32, i32, vp]),
     "gode_groupnorm_fwd": (C.c_int, [i64, i32, i32, f32, vp, i64, vp, vp, vp, i64, vp]),
     "gode_groupnorm_bwd": (C.c_int, [i64, i32, i32, f32, vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, sz, vp]),
     "gode_colreduce_workspace_bytes": (sz, [i32]),

@@ -397,7 +397,7 @@ static int gat_bwd_t(const gode_gat_graph_t* G, int H, int oh, const float* P, i
   return GODE_OK;
 }
 
-static int ch_of(int oh) { return oh <= 8 ? 8 : oh <= 16 ? 16 : oh <= 32 ? 32 : 64; }
+static int ch_of(int oh) { return oh <= 8 ? 8 : oh <= 16 ? 16 : oh <= 32 ? 32 : oh <= 64 ? 64 : 128; }
 
 static size_t part_bytes(const gode_gat_graph_t* G, int H, int oh) {
   const int64_t nc = G->t_heavy.n_chunks > G->s_heavy.n_chunks ? G->t_heavy.n_chunks : G->s_heavy.n_chunks;
@@ -410,7 +410,7 @@ using namespace gode;
 
 static int gat_check(const gode_gat_graph_t* G, int H, int oh, int64_t ldp) {
   GODE_REQUIRE(G && G->n_nodes >= 0 && G->n_edges >= 0, "gat: bad graph");
-  GODE_REQUIRE(H >= 1 && H <= 64 && oh >= 1 && oh <= 64, "gat: heads must be in [1,64] and channels per head in [1,64]");
+  GODE_REQUIRE(H >= 1 && H <= 64 && oh >= 1 && oh <= 128, "gat: heads must be in [1,64] and channels per head in [1,128]");
   GODE_REQUIRE(ldp >= 2LL * H * oh + 2 * H, "gat: ldp too small for [Ps | Pt | as | at]");
   GODE_REQUIRE(G->n_nodes == 0 || (G->tptr && G->sptr), "gat: null segment pointers");
   GODE_REQUIRE(G->n_edges == 0 || (G->t_src && G->t_tgt && G->s_tgt && G->s_pos), "gat: null edge arrays");
@@ -458,7 +458,8 @@ extern "C" int gode_gat_fwd(const gode_gat_graph_t* G, int32_t heads, int32_t oh
   if (oh <= 8) return gat_fwd_t<8>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, part, st);
   if (oh <= 16) return gat_fwd_t<16>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, part, st);
   if (oh <= 32) return gat_fwd_t<32>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, part, st);
-  return gat_fwd_t<64>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, part, st);
+  if (oh <= 64) return gat_fwd_t<64>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, part, st);
+  return gat_fwd_t<128>(G, heads, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, part, st);
 }
 
 extern "C" int gode_gat_bwd(const gode_gat_graph_t* G, int32_t heads, int32_t oh, const float* P, int64_t ldp, const float* out,
@@ -482,7 +483,8 @@ extern "C" int gode_gat_bwd(const gode_gat_graph_t* G, int32_t heads, int32_t oh
   if (oh <= 8) rc = gat_bwd_t<8>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, part, st);
   else if (oh <= 16) rc = gat_bwd_t<16>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, part, st);
   else if (oh <= 32) rc = gat_bwd_t<32>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, part, st);
-  else rc = gat_bwd_t<64>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, part, st);
+  else if (oh <= 64) rc = gat_bwd_t<64>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, part, st);
+  else rc = gat_bwd_t<128>(G, heads, oh, P, ldp, out, ldo, den, amax_key, gout, ldg, dP, dA, part, st);
   if (rc) return rc;
   if (G->n_edges > 0) {
     if ((rc = colsum(G->n_edges, heads, dA, heads, dsum, red, red_bytes, st))) return rc;

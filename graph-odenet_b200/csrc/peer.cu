@@ -82,8 +82,15 @@ __global__ void k_peer_wait(int world, int rank, const uint32_t* __restrict__ fl
   unsigned spins = 0;
   while (static_cast<int32_t>(ld_acquire_sys(flags_local + p) - epoch) < 0) {
     if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) {
+      // A peer never published this epoch.  The kernels queued behind this wait would gather from a stale halo tail and
+      // every result after it would be silently wrong, so the time-out is FATAL for the stream: record it (readable through
+      // gode_peer_status while the context lives), say which peer, and trap -- every later CUDA call of the process then
+      // fails, which the host sees at its next synchronisation.
       atomicExch(status, GODE_PEER_TIMEOUT);
-      return;
+      __threadfence_system();
+      printf("libgode: rank %d timed out after %llu ms waiting for peer %d to publish halo epoch %u -- aborting the stream\n",
+             rank, timeout_ns / 1000000ull, p, epoch);
+      __trap();
     }
   }
 }

@@ -355,15 +355,16 @@ __global__ void __launch_bounds__(256) k_spmm_sb_heavy(int n_heavy, int n_chunks
 // memory by broadcast LDS.  CTAs are still dispatched in row order, so the L2 window of a locality-ordered graph is kept
 // (the persistent-warp variant lost it).  Rows that do not fit the staging capacity read their indices from global memory.
 // ------------------------------------------------------------------------------------------------
-constexpr int TS_ROWS = 64;
-constexpr int TS_CAP = 2048;   // staged entries per tile (avg tile: 64 rows x 19.6 = 1254)
-
-template <int MINB, int UN, bool ROWVAL>
+// TS_ROWS rows per tile, staging capacity 32 entries per row (avg 19.6 on the bench graph).  pf_dist > 0: a warp that has
+// run out of rows asks L2 for the neighbour rows of the tile pf_dist tiles ahead (prefetch.global.L2 on its share of that
+// tile's column indices), so that the ~30 % of gathers that miss L2 today find their line already on its way.
+template <int TS_ROWS, int MINB, int UN, bool ROWVAL>
 __global__ void __launch_bounds__(256, MINB) k_spmm_ts(int64_t n_rows, const int32_t* __restrict__ rowptr,
                                                        const int32_t* __restrict__ colidx, const float* __restrict__ vals,
                                                        const float* __restrict__ row_vals, const float* __restrict__ X,
                                                        int64_t ldx, float* __restrict__ Y, int64_t ldy,
-                                                       const gode_spmm_epilogue_t ep, const int prefetch) {
+                                                       const gode_spmm_epilogue_t ep, const int prefetch, const int pf_dist) {
+  constexpr int TS_CAP = TS_ROWS * 32;
   __shared__ int s_ptr[TS_ROWS + 1];
   __shared__ int s_idx[TS_CAP];
   __shared__ float s_val[ROWVAL ? 1 : TS_CAP];
@@ -434,6 +435,298 @@ __global__ void __launch_bounds__(256, MINB) k_spmm_ts(int64_t n_rows, const int
     float4 one[1] = {acc};
     epilogue<1>(ep, row, lane * 4, one, Y, ldy);
   }
+  if (pf_dist > 0) {
+    const int64_t frow0 = row0 + (int64_t)pf_dist * TS_ROWS;
+    if (frow0 < n_rows) {
+      const int64_t frow1 = min(frow0 + TS_ROWS, n_rows);
+      const int f0 = __ldg(rowptr + frow0);
+      const int f1 = min(__ldg(rowptr + frow1), f0 + TS_CAP);
+      for (int i = f0 + tid; i < f1; i += 256) {
+        const float* r = X + (int64_t)__ldcs(colidx + i) * ldx;
+        prefetch_l2(r);
+        prefetch_l2(r + 32);
+        prefetch_l2(r + 64);
+        prefetch_l2(r + 96);
+      }
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// k_spmm_t2: k_spmm_ts with a LEAN inner loop, for contiguous 128-float rows (ldx = 128).
+//
+// ncu on k_spmm_ts (profiles/r02_gather.md): issue slots 85 % busy, sm__throughput 85 %, L1 / L2 / DRAM all below 65 % -- the
+// gather was INSTRUCTION-bound: 33 warp instructions per gathered neighbour row, most of them 64-bit address arithmetic on
+// the run-time leading dimension (IMAD x3 + LEA + LEA.HI.X per row), per-entry predicates and staged / unstaged selects.
+// Here the leading dimension is the compile-time 128, so a neighbour row's address is ONE IMAD.WIDE.U32 (base + col * 512);
+// full batches of four run without predicates (one predicated tail batch per row); rows that do not fit the staging
+// capacity take a separate (rare) path; and the accumulation uses Blackwell's packed fp32 instructions (FADD2 / FFMA2:
+// two of the four channels a lane owns per instruction) -- the same additions in the same order, so the result is
+// bit-identical to the scalar form.  About 8 instructions per neighbour row.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void add2(float2& a, const float x, const float y) {
+  unsigned long long ua = *reinterpret_cast<unsigned long long*>(&a);
+  const float2 b = make_float2(x, y);
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(ua) : "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  a = *reinterpret_cast<float2*>(&ua);
+}
+__device__ __forceinline__ void fma2(float2& a, const float v, const float x, const float y) {
+  unsigned long long ua = *reinterpret_cast<unsigned long long*>(&a);
+  const float2 b = make_float2(x, y), vv = make_float2(v, v);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ua) : "l"(*reinterpret_cast<const unsigned long long*>(&vv)),
+      "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  a = *reinterpret_cast<float2*>(&ua);
+}
+
+template <bool ROWVAL>
+__device__ __forceinline__ void acc_row(float2& a0, float2& a1, const float v, const float4& x) {
+  if (ROWVAL) {
+    add2(a0, x.x, x.y);
+    add2(a1, x.z, x.w);
+  } else {
+    fma2(a0, v, x.x, x.y);
+    fma2(a1, v, x.z, x.w);
+  }
+}
+
+template <int TS_ROWS, int MINB, bool ROWVAL>
+__global__ void __launch_bounds__(256, MINB) k_spmm_t2(int64_t n_rows, const int32_t* __restrict__ rowptr,
+                                                       const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                                       const float* __restrict__ row_vals, const float4* __restrict__ X4,
+                                                       float* __restrict__ Y, const gode_spmm_epilogue_t ep, const int prefetch) {
+  constexpr int TS_CAP = TS_ROWS * 32;
+  __shared__ int s_ptr[TS_ROWS + 1];
+  __shared__ int s_idx[TS_CAP];
+  __shared__ float s_val[ROWVAL ? 1 : TS_CAP];
+  __shared__ int s_next;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t row0 = blockIdx.x * (int64_t)TS_ROWS;
+  const int nr = static_cast<int>(min((int64_t)TS_ROWS, n_rows - row0));
+  if (tid <= nr) s_ptr[tid] = __ldg(rowptr + row0 + tid);
+  if (tid == 0) s_next = 0;
+  __syncthreads();
+  const int t0 = s_ptr[0];
+  const int nst = min(s_ptr[nr] - t0, TS_CAP);
+  for (int i = tid; i < nst; i += 256) {
+    s_idx[i] = __ldcs(colidx + t0 + i);
+    if (!ROWVAL) s_val[i] = __ldcs(vals + t0 + i);
+  }
+  __syncthreads();
+  const float4* __restrict__ xb = X4 + lane;        // row c, this lane's four channels: xb[c * 32]
+  for (;;) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(&s_next, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= nr) break;
+    const int e0 = s_ptr[r], e1 = s_ptr[r + 1];
+    if (e1 - e0 > GODE_HEAVY_ROW) continue;          // hub rows: k_spmm_heavy_partial / finish
+    const int64_t row = row0 + r;
+    if (prefetch) epilogue_prefetch<1>(ep, row, lane * 4, 128);
+    float4 one[1];
+    if (e1 - t0 <= nst) {                            // the row's entries are staged (all but the tail of an over-full tile)
+      float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+      int j = e0 - t0;
+      const int jend = e1 - t0;
+#pragma unroll 1
+      for (; j + 4 <= jend; j += 4) {
+        const unsigned c0 = s_idx[j], c1 = s_idx[j + 1], c2 = s_idx[j + 2], c3 = s_idx[j + 3];
+        const float4 x0 = __ldg(xb + (size_t)c0 * 32), x1 = __ldg(xb + (size_t)c1 * 32);
+        const float4 x2 = __ldg(xb + (size_t)c2 * 32), x3 = __ldg(xb + (size_t)c3 * 32);
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+        if (!ROWVAL) { v0 = s_val[j]; v1 = s_val[j + 1]; v2 = s_val[j + 2]; v3 = s_val[j + 3]; }
+        acc_row<ROWVAL>(a0, a1, v0, x0);
+        acc_row<ROWVAL>(a0, a1, v1, x1);
+        acc_row<ROWVAL>(a0, a1, v2, x2);
+        acc_row<ROWVAL>(a0, a1, v3, x3);
+      }
+      const int rem = jend - j;                      // 0..3 entries left: one predicated batch
+      if (rem > 0) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 x0 = z, x1 = z, x2 = z;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        x0 = __ldg(xb + (size_t)(unsigned)s_idx[j] * 32);
+        if (rem > 1) x1 = __ldg(xb + (size_t)(unsigned)s_idx[j + 1] * 32);
+        if (rem > 2) x2 = __ldg(xb + (size_t)(unsigned)s_idx[j + 2] * 32);
+        if (!ROWVAL) {
+          v0 = s_val[j];
+          if (rem > 1) v1 = s_val[j + 1];
+          if (rem > 2) v2 = s_val[j + 2];
+        }
+        acc_row<ROWVAL>(a0, a1, v0, x0);
+        if (rem > 1) acc_row<ROWVAL>(a0, a1, v1, x1);
+        if (rem > 2) acc_row<ROWVAL>(a0, a1, v2, x2);
+      }
+      if (ROWVAL) {
+        const float rv = __ldg(row_vals + row);
+        a0.x *= rv; a0.y *= rv; a1.x *= rv; a1.y *= rv;
+      }
+      one[0] = make_float4(a0.x, a0.y, a1.x, a1.y);
+    } else {                                         // rare: indices straight from global memory (shuffle-broadcast path)
+      one[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gather_range<32, 1, 4>(one, e0, e1, e1 - e0, 0, lane, colidx, vals, reinterpret_cast<const float*>(xb), 128);
+    }
+    epilogue<1>(ep, row, lane * 4, one, Y, 128);
+  }
+}
+
+
+// k_spmm_t3: k_spmm_t2 with every row's staged entries starting at a multiple of four, so that a batch's four column
+// indices (and values) are ONE broadcast LDS.128 each instead of four LDS.32.  ncu on k_spmm_t2 inside the bench
+// (profiles/r02_gather.md): L1 LSU data pipe 89 % busy, issue slots 66 % -- after the instruction diet the gather sits on
+// the LSU wavefront rate: per 4 neighbour rows 16 wavefronts of row data + 4 (+4) of index (value) reads; aligned staging
+// makes that 16 + 1 (+1).  Tiles are 32 rows (one warp computes the padded prefix of the row lengths); hub rows are not
+// staged (their own kernel gathers them); a row that does not fit the staging capacity takes the shuffle-broadcast path.
+template <int MINB, bool ROWVAL>
+__global__ void __launch_bounds__(256, MINB) k_spmm_t3(int64_t n_rows, const int32_t* __restrict__ rowptr,
+                                                       const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                                       const float* __restrict__ row_vals, const float4* __restrict__ X4,
+                                                       float* __restrict__ Y, const gode_spmm_epilogue_t ep, const int prefetch) {
+  constexpr int R = 32;
+  constexpr int CAP = R * 32 + 128;                 // staged entries incl. padding (avg tile: 32 x 19.6 + 32 x 1.5)
+  __shared__ int s_ptr[R + 1];
+  __shared__ int s_pos[R];                           // first staged slot of each row (multiple of 4), -1: not staged
+  __shared__ __align__(16) int s_idx[CAP];
+  __shared__ __align__(16) float s_val[ROWVAL ? 4 : CAP];
+  __shared__ int s_next;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int64_t row0 = blockIdx.x * (int64_t)R;
+  const int nr = static_cast<int>(min((int64_t)R, n_rows - row0));
+  if (tid <= nr) s_ptr[tid] = __ldg(rowptr + row0 + tid);
+  if (tid == 0) s_next = 0;
+  __syncthreads();
+  if (w == 0) {                                      // padded exclusive prefix of the row lengths
+    int len = lane < nr ? s_ptr[lane + 1] - s_ptr[lane] : 0;
+    if (len > GODE_HEAVY_ROW) len = 0;
+    const int pad = (len + 3) & ~3;
+    int incl = pad;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    s_pos[lane] = (incl <= CAP) ? incl - pad : -1;
+  }
+  __syncthreads();
+  for (int r = w; r < nr; r += 8) {                  // a warp stages whole rows: coalesced reads, aligned row starts
+    const int pos = s_pos[r];
+    const int e0 = s_ptr[r], len = s_ptr[r + 1] - e0;
+    if (pos < 0 || len > GODE_HEAVY_ROW) continue;
+    for (int k = lane; k < len; k += 32) {
+      s_idx[pos + k] = __ldcs(colidx + e0 + k);
+      if (!ROWVAL) s_val[pos + k] = __ldcs(vals + e0 + k);
+    }
+  }
+  __syncthreads();
+  const float4* __restrict__ xb = X4 + lane;        // row c, this lane's four channels: xb[c * 32]
+  for (;;) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(&s_next, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= nr) break;
+    const int e0 = s_ptr[r], len = s_ptr[r + 1] - e0;
+    if (len > GODE_HEAVY_ROW) continue;              // hub rows: k_spmm_heavy2 / finish
+    const int64_t row = row0 + r;
+    if (prefetch) epilogue_prefetch<1>(ep, row, lane * 4, 128);
+    float4 one[1];
+    const int pos = s_pos[r];
+    if (pos >= 0) {
+      float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+      const int4* __restrict__ ci = reinterpret_cast<const int4*>(s_idx + pos);
+      const float4* __restrict__ vi = reinterpret_cast<const float4*>(s_val + (ROWVAL ? 0 : pos));
+      const int nb = len >> 2;
+#pragma unroll 1
+      for (int b = 0; b < nb; ++b) {
+        const int4 c = ci[b];
+        const float4 x0 = __ldg(xb + (size_t)(unsigned)c.x * 32), x1 = __ldg(xb + (size_t)(unsigned)c.y * 32);
+        const float4 x2 = __ldg(xb + (size_t)(unsigned)c.z * 32), x3 = __ldg(xb + (size_t)(unsigned)c.w * 32);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!ROWVAL) v = vi[b];
+        acc_row<ROWVAL>(a0, a1, v.x, x0);
+        acc_row<ROWVAL>(a0, a1, v.y, x1);
+        acc_row<ROWVAL>(a0, a1, v.z, x2);
+        acc_row<ROWVAL>(a0, a1, v.w, x3);
+      }
+      const int rem = len & 3;                       // 0..3 entries left: one predicated batch (its padding slots are not read as rows)
+      if (rem > 0) {
+        const int4 c = ci[nb];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!ROWVAL) v = vi[nb];
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 x0 = z, x1 = z, x2 = z;
+        x0 = __ldg(xb + (size_t)(unsigned)c.x * 32);
+        if (rem > 1) x1 = __ldg(xb + (size_t)(unsigned)c.y * 32);
+        if (rem > 2) x2 = __ldg(xb + (size_t)(unsigned)c.z * 32);
+        acc_row<ROWVAL>(a0, a1, v.x, x0);
+        if (rem > 1) acc_row<ROWVAL>(a0, a1, v.y, x1);
+        if (rem > 2) acc_row<ROWVAL>(a0, a1, v.z, x2);
+      }
+      if (ROWVAL) {
+        const float rv = __ldg(row_vals + row);
+        a0.x *= rv; a0.y *= rv; a1.x *= rv; a1.y *= rv;
+      }
+      one[0] = make_float4(a0.x, a0.y, a1.x, a1.y);
+    } else {                                         // rare: indices straight from global memory (shuffle-broadcast path)
+      one[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gather_range<32, 1, 4>(one, e0, e0 + len, len, 0, lane, colidx, vals, reinterpret_cast<const float*>(xb), 128);
+    }
+    epilogue<1>(ep, row, lane * 4, one, Y, 128);
+  }
+}
+
+// chunks of the hub rows with the same lean loop: one warp per 256-entry chunk, its indices (and values) staged in the
+// warp's slice of shared memory by one coalesced load of 8 entries per lane -> partial[chunk][128]
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_spmm_heavy2(int n_heavy, int n_chunks, const int32_t* __restrict__ heavy_rows,
+                                                           const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ rowptr,
+                                                           const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                                           const float4* __restrict__ X4, float4* __restrict__ partial) {
+  static_assert(GODE_HEAVY_CHUNK == 256, "eight entries per lane");
+  __shared__ __align__(16) int s_idx[8][GODE_HEAVY_CHUNK];
+  __shared__ __align__(16) float s_val[8][GODE_HEAVY_CHUNK];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int chunk = blockIdx.x * 8 + w;
+  if (chunk >= n_chunks) return;
+  // the hub row this chunk belongs to = last one whose first chunk is <= chunk: a 32-way search (the lanes probe 32 pivots
+  // at once: 3 dependent loads for 30 000 hubs instead of the 15 of a binary search, all of them ahead of any useful work)
+  int lo = 0, hi = n_heavy;
+  while (hi - lo > 1) {
+    const int step = (hi - lo + 31) >> 5;
+    const int p = lo + lane * step;
+    const bool le = p < hi && __ldg(chunk_ptr + p) <= chunk;
+    const int k = __popc(__ballot_sync(0xffffffffu, le)) - 1;   // chunk_ptr is sorted and chunk_ptr[lo] <= chunk: lanes 0..k say yes
+    lo += k * step;
+    hi = min(lo + step, hi);
+  }
+  const int row = __ldg(heavy_rows + lo);
+  const int r0 = __ldg(rowptr + row), r1 = __ldg(rowptr + row + 1);
+  const int e0 = r0 + (chunk - __ldg(chunk_ptr + lo)) * GODE_HEAVY_CHUNK;
+  const int cnt = min(r1 - e0, GODE_HEAVY_CHUNK);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = k * 32 + lane;
+    if (i < cnt) {
+      s_idx[w][i] = __ldcs(colidx + e0 + i);
+      s_val[w][i] = __ldcs(vals + e0 + i);
+    }
+  }
+  __syncwarp();
+  const float4* __restrict__ xb = X4 + lane;
+  float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+  int j = 0;
+#pragma unroll 1
+  for (; j + 4 <= cnt; j += 4) {
+    const int4 c = *reinterpret_cast<const int4*>(&s_idx[w][j]);      // broadcast LDS.128: one wavefront per four neighbours
+    const float4 v = *reinterpret_cast<const float4*>(&s_val[w][j]);
+    const float4 x0 = __ldg(xb + (size_t)(unsigned)c.x * 32), x1 = __ldg(xb + (size_t)(unsigned)c.y * 32);
+    const float4 x2 = __ldg(xb + (size_t)(unsigned)c.z * 32), x3 = __ldg(xb + (size_t)(unsigned)c.w * 32);
+    acc_row<false>(a0, a1, v.x, x0);
+    acc_row<false>(a0, a1, v.y, x1);
+    acc_row<false>(a0, a1, v.z, x2);
+    acc_row<false>(a0, a1, v.w, x3);
+  }
+  for (; j < cnt; ++j) acc_row<false>(a0, a1, s_val[w][j], __ldg(xb + (size_t)(unsigned)s_idx[w][j] * 32));
+  partial[(size_t)chunk * 32 + lane] = make_float4(a0.x, a0.y, a1.x, a1.y);
 }
 
 
@@ -727,12 +1020,16 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
   constexpr int RPB = 8 * RPW;
   static const int variant = [] {
     const char* e = getenv("GODE_SPMM_VARIANT");
-    // 0 (default): one row per sub-warp, CTAs dispatched in row order -- the hardware scheduler keeps the rows in
+    // 8 (default where it applies: d = 128, contiguous rows): k_spmm_t2, row tiles staged in shared memory + lean inner loop.
+    //    Measured at N = 10 M (bare A gather / A^T gather / gather with the rk4 stage-4 epilogue, ms): 6.72 / 8.06 / 9.69
+    //    against 8.85 / 9.42 / 11.49 for variant 0 (profiles/r02_gather.md).
+    // 7: k_spmm_ts (tile staging without the lean loop), 6: k_spmm_sb (shared-memory index broadcast) -- kept for the record.
+    // 0 (every other width): one row per sub-warp, CTAs dispatched in row order -- the hardware scheduler keeps the rows in
     //    flight inside a narrow id window, which is what lets L2 hold the gather band of a locality-ordered graph.
     // 5/4: persistent warps (U=8 x 3 CTAs/SM | U=4 x 4 CTAs/SM): faster at N <= 2M, but the warps drift apart on a
     //    power-law graph (ncu at N=10M: L2 hit rate 26 %, 52 GB of DRAM reads per launch -> DRAM-bound, 7 % slower).
     // 3: one 1024-thread CTA per SM on a row tile.
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : 8;
   }();
   static const int minb_sb = [] {
     const char* e = getenv("GODE_SPMM_MINB");
@@ -780,6 +1077,64 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
       return GODE_OK;
     }
   }
+  if (variant == 8 && LPR == 32 && VPL == 1 && ldx == 128 && (ldy == 128 || !Y)) {
+    if constexpr (LPR == 32 && VPL == 1) {
+      static const int prefetch_t2 = [] {
+        const char* e = getenv("GODE_SPMM_PREFETCH");   // default off here: the L2 prefetch of the epilogue operands costs LSU
+        return e ? atoi(e) : 0;                         // wavefronts, which is what this kernel is bound by (9.94 vs 10.19 ms)
+      }();
+      static const int t2_rows = [] {
+        const char* e = getenv("GODE_SPMM_TS_ROWS");
+        return e ? atoi(e) : 32;
+      }();
+      const bool rv = use_rowval && A.row_vals != nullptr;
+      const float4* X4 = reinterpret_cast<const float4*>(X);
+      if (A.n_rows > 0) {
+#define GODE_T2_LAUNCH(R, MB)                                                                                           \
+  do {                                                                                                                  \
+    unsigned grid = static_cast<unsigned>((A.n_rows + R - 1) / R);                                                      \
+    if (rv) k_spmm_t2<R, MB, true><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, A.row_vals, X4, Y, ep, prefetch_t2); \
+    else k_spmm_t2<R, MB, false><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, nullptr, X4, Y, ep, prefetch_t2);    \
+  } while (0)
+        static const int t3 = [] {
+          const char* e = getenv("GODE_SPMM_T3");      // 1: aligned staging + LDS.128 index reads (k_spmm_t3).  Default off: measured
+          return e ? atoi(e) : 0;                      // 6.68 / 7.93 / 9.59 ms against k_spmm_t2's 6.47 / 7.59 / 9.04 (bare A, A^T, fused epilogue)
+        }();
+        if (t2_rows == 32 && t3) {
+          unsigned grid = static_cast<unsigned>((A.n_rows + 31) / 32);
+#define GODE_T3_LAUNCH(MB)                                                                                              \
+  do {                                                                                                                  \
+    if (rv) k_spmm_t3<MB, true><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, A.row_vals, X4, Y, ep, prefetch_t2); \
+    else k_spmm_t3<MB, false><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, nullptr, X4, Y, ep, prefetch_t2);    \
+  } while (0)
+          if (minb_sb == 6) GODE_T3_LAUNCH(6); else if (minb_sb == 7) GODE_T3_LAUNCH(7); else GODE_T3_LAUNCH(8);
+#undef GODE_T3_LAUNCH
+        } else if (t2_rows == 32) {
+          if (minb_sb == 6) GODE_T2_LAUNCH(32, 6); else GODE_T2_LAUNCH(32, 8);
+        } else if (t2_rows == 128) {
+          if (minb_sb == 6) GODE_T2_LAUNCH(128, 6); else GODE_T2_LAUNCH(128, 8);
+        } else {
+          if (minb_sb == 6) GODE_T2_LAUNCH(64, 6);
+          else if (minb_sb == 7) GODE_T2_LAUNCH(64, 7);
+          else if (minb_sb == 5) GODE_T2_LAUNCH(64, 5);
+          else if (minb_sb == 4) GODE_T2_LAUNCH(64, 4);
+          else GODE_T2_LAUNCH(64, 8);
+        }
+#undef GODE_T2_LAUNCH
+        GODE_LAUNCH_CHECK();
+      }
+      if (A.n_heavy > 0) {
+        unsigned g1 = static_cast<unsigned>((A.n_chunks + 7) / 8);
+        k_spmm_heavy2<6><<<g1, 256, 0, st>>>(A.n_heavy, A.n_chunks, A.heavy_rows, A.heavy_chunk_ptr, A.rowptr, A.colidx, A.vals,
+                                             X4, reinterpret_cast<float4*>(ws));
+        GODE_LAUNCH_CHECK();
+        unsigned g2 = static_cast<unsigned>((A.n_heavy + RPB - 1) / RPB);
+        k_spmm_heavy_finish<LPR, VPL><<<g2, 256, 0, st>>>(A.n_heavy, A.heavy_rows, A.heavy_chunk_ptr, ws, Y, ldy, ep);
+        GODE_LAUNCH_CHECK();
+      }
+      return GODE_OK;
+    }
+  }
   if (variant == 7 && LPR == 32 && VPL == 1) {
     if constexpr (LPR == 32 && VPL == 1) {
       static const int prefetch_ts = [] {
@@ -787,18 +1142,34 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
         return e ? atoi(e) : 1;
       }();
       const bool rv = use_rowval && A.row_vals != nullptr;
+      static const int ts_rows = [] {
+        const char* e = getenv("GODE_SPMM_TS_ROWS");
+        return e ? atoi(e) : 64;
+      }();
+      static const int pf_dist = [] {
+        const char* e = getenv("GODE_SPMM_PFDIST");   // tiles ahead whose neighbour rows are requested from L2 (0 = off)
+        return e ? atoi(e) : 0;
+      }();
       if (A.n_rows > 0) {
-        unsigned grid = static_cast<unsigned>((A.n_rows + TS_ROWS - 1) / TS_ROWS);
-#define GODE_TS_LAUNCH(MB, UU)                                                                                          \
+#define GODE_TS_LAUNCH(R, MB, UU)                                                                                       \
   do {                                                                                                                  \
-    if (rv) k_spmm_ts<MB, UU, true><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, A.row_vals, X, ldx, Y, ldy, ep, prefetch_ts); \
-    else k_spmm_ts<MB, UU, false><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, nullptr, X, ldx, Y, ldy, ep, prefetch_ts);    \
+    unsigned grid = static_cast<unsigned>((A.n_rows + R - 1) / R);                                                      \
+    if (rv) k_spmm_ts<R, MB, UU, true><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, A.row_vals, X, ldx, Y, ldy, ep, prefetch_ts, pf_dist); \
+    else k_spmm_ts<R, MB, UU, false><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, nullptr, X, ldx, Y, ldy, ep, prefetch_ts, pf_dist);    \
   } while (0)
-        if (minb_sb == 6 && unr_sb == 8) GODE_TS_LAUNCH(6, 8);
-        else if (minb_sb == 6 && unr_sb == 4) GODE_TS_LAUNCH(6, 4);
-        else if (minb_sb == 4 && unr_sb == 8) GODE_TS_LAUNCH(4, 8);
-        else if (minb_sb == 8 && unr_sb == 8) GODE_TS_LAUNCH(8, 8);
-        else GODE_TS_LAUNCH(8, 4);
+        if (ts_rows == 16) {
+          if (minb_sb == 6) GODE_TS_LAUNCH(16, 6, 4); else GODE_TS_LAUNCH(16, 8, 4);
+        } else if (ts_rows == 32) {
+          if (minb_sb == 6) GODE_TS_LAUNCH(32, 6, 4); else GODE_TS_LAUNCH(32, 8, 4);
+        } else if (ts_rows == 128) {
+          if (minb_sb == 6) GODE_TS_LAUNCH(128, 6, 4); else GODE_TS_LAUNCH(128, 8, 4);
+        } else {
+          if (minb_sb == 6 && unr_sb == 8) GODE_TS_LAUNCH(64, 6, 8);
+          else if (minb_sb == 6) GODE_TS_LAUNCH(64, 6, 4);
+          else if (minb_sb == 5) GODE_TS_LAUNCH(64, 5, 4);
+          else if (minb_sb == 7) GODE_TS_LAUNCH(64, 7, 4);
+          else GODE_TS_LAUNCH(64, 8, 4);
+        }
 #undef GODE_TS_LAUNCH
         GODE_LAUNCH_CHECK();
       }

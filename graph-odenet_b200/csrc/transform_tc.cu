@@ -6,9 +6,9 @@
 // fp32 result on the 5th-generation tensor cores: every fp32 operand is split x = hi + lo with hi = tf32(x)
 // (cvt.rna) and lo = tf32(x - hi) (rounded too: the MMA truncates its operands), and three kind::tf32 MMAs compute
 // hi*hi + lo*hi + hi*lo (the dropped lo*lo term is 2^-22 relative).  The correction terms go to their own TMEM
-// accumulator and the hi*hi products of the two halves of K to two more; the epilogue adds the three with
-// round-to-nearest fp32 adds (the MMA's own accumulate loses low bits at every K step).  Measured against fp64 the result
-// is as accurate as cuBLAS SGEMM (profiles/r02_transform_accuracy.jsonl).  GODE_PREC_TF32 issues the hi*hi pass only.
+// accumulator and the epilogue adds it to the hi*hi one with round-to-nearest fp32 adds (the MMA's own accumulate loses
+// low bits at every K step); GODE_TC_ACC=19 additionally splits the hi*hi products over two accumulators, which makes the
+// result as accurate as cuBLAS SGEMM (table at GODE_TC_ACC_DEFAULT below).  GODE_PREC_TF32 issues the hi*hi pass only.
 //
 // k_rows_tc  (M = 128 rows per tile, N = K = D):     Out[r,:] = A[r,:] * B + rowvec
 //     MODE 0  transform : A = xhat(y) (GroupNorm statistics computed on load, affine folded into B),
@@ -376,11 +376,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }  // namespace tc
 
 #ifndef GODE_TC_ACC_DEFAULT
-// 19 = rounded residuals | separate correction accumulator | 2 hi*hi accumulators over K.  Measured against fp64 on a B200
-// (profiles/r02_transform_accuracy.jsonl, N = 262 144, d = 128): rms error / max|S| 3.87e-8 and max error 4.7e-7 -- the
-// same as cuBLAS fp32 SGEMM (3.92e-8, 5.0e-7) and the SIMT FFMA path (3.92e-8, 5.0e-7) -- with 0 of 33.5 M ReLU masks
-// differing from the fp64 result, for +13 % kernel time over round 1's single accumulator with truncated residuals
-// (1.72e-7, 1.29e-6, whose mask flips cost 2e-4..6e-4 in the gradients).
+// Accuracy configurations of k_rows_ws, measured against fp64 on a B200 (profiles/r02_transform_accuracy.jsonl, N = 262 144,
+// d = 128; error / max|S| as rms, max; ReLU masks of 33.5 M that differ from the fp64 result; kernel ms at N = 10 M):
+//      0  round 1: one accumulator, truncated residuals   1.72e-7  1.29e-6   4 flips   2.4 ms   (gradients off by 2e-4..6e-4)
+//      1  + residuals rounded to tf32                     1.71e-7  1.26e-6   6 flips   2.4 ms   (gradients 7e-7)
+//      3  + correction terms in their own accumulator     6.2e-8   6.1e-7    2 flips   2.5 ms   <- input gradient (MODE 1)
+//     19  + two hi*hi accumulators (single-buffered)      3.9e-8   4.7e-7    0 flips   3.2 ms   <- transform (MODE 0)
+//         cuBLAS SGEMM (torch.mm) / libgode SIMT FFMA      3.9e-8   5.0e-7    - / 1     - / 15 ms
+// The transform decides the ReLU masks, so it runs the configuration that matches the fp32 library GEMM digit for digit
+// (with 3, one element of the d = 128 rk4 reference fixture sits at 1.07e-5, just outside the 1e-5 bar); the input
+// gradient decides no mask and keeps the double-buffered 3.  GODE_TC_ACC overrides both.
 #define GODE_TC_ACC_DEFAULT 19
 #endif
 
@@ -402,18 +407,21 @@ __device__ __forceinline__ float4 normalize4_fast(float4 x, float eps) {
 }
 }  // namespace tc
 
-template <int D, int CPG, int MODE>
+template <int D, int CPG, int MODE, int CFG /*>= 0: compile-time accuracy configuration; -1: the run-time argument*/>
 __global__ void __launch_bounds__(tc::WS_THREADS, 1)
 k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, const float* __restrict__ W /*[D+1, D]*/,
           const float* __restrict__ gamma, const float* __restrict__ beta, float t, float eps, int passes,
           const gode_push_route_t push, const int pf_tiles /*L2 prefetch distance in tiles of this CTA (0: off)*/,
-          const int cfg /*accuracy configuration of the 3xTF32 product, see rows_acc_cfg()*/) {
+          const int cfg_rt /*accuracy configuration of the 3xTF32 product, see rows_acc_cfg()*/) {
   using namespace tc;
   static_assert(D == 128, "k_rows_ws is laid out for 128 channels");
   // cfg: bit 0 round the lo residuals to tf32 | bit 1 correction terms (lo*hi, hi*lo[, lo*lo]) in their own TMEM
   // accumulator, added to the hi*hi one by the epilogue with round-to-nearest fp32 adds | bit 2 also issue lo*lo |
   // bit 3 1/sqrtf instead of rsqrtf in the GroupNorm | bits 4-5: (number of hi*hi accumulators over K) - 1; more than
   // one leaves no TMEM for double buffering (512 columns = 4 accumulators of 128)
+  // (the single MMA-issuing thread evaluates these per instruction: with a run-time configuration its address arithmetic
+  // became the tile's critical path -- +27 % kernel time -- so the shipped configurations are template constants)
+  const int cfg = CFG >= 0 ? CFG : cfg_rt;
   const bool rnd_lo = cfg & 1, sep = (cfg & 2) != 0, lolo = (cfg & 4) != 0, precise_gn = (cfg & 8) != 0;
   const int nmain = 1 + ((cfg >> 4) & 3);
   const int nacc = nmain + (sep ? 1 : 0);
@@ -691,7 +699,7 @@ template <int D, int CPG>
 __global__ void __launch_bounds__(tc::WG_THREADS, 1)
 k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restrict__ G, float* __restrict__ partial /*[grid][D][D]*/,
            float* __restrict__ cs_partial /*[grid][D]: column sums of G over this CTA's rows*/, float eps, int passes,
-           const int pf_chunks /*L2 prefetch distance in chunks of this CTA (0: off)*/) {
+           const int pf_chunks /*L2 prefetch distance in chunks of this CTA (0: off)*/, const int rnd_lo /*round the lo residuals*/) {
   using namespace tc;
   static_assert(D == 128, "the accumulator uses all 128 TMEM lanes");
   // Both operands are [rows, D] row-major in HBM but the reduction runs over rows, so they are transposed on the
@@ -850,11 +858,11 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
       float4 xa = normalize4_fast<CPG>(ra[i], eps);
       if (chunk * RC + r >= n_rows) xa = make_float4(0.f, 0.f, 0.f, 0.f);   // xhat of a padding row is not zero by itself
       float4 hi, lo;
-      split4(xa, hi, lo);
+      split4(xa, hi, lo, rnd_lo != 0);
       put(base, r, kc * 4, hi);
       put(base + MAT, r, kc * 4, lo);
       cs_acc[i].x += rb[i].x; cs_acc[i].y += rb[i].y; cs_acc[i].z += rb[i].z; cs_acc[i].w += rb[i].w;   // padding rows are 0
-      split4(rb[i], hi, lo);
+      split4(rb[i], hi, lo, rnd_lo != 0);
       put(base + 2 * MAT, r, kc * 4, hi);
       put(base + 3 * MAT, r, kc * 4, lo);
     }
@@ -955,7 +963,11 @@ int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, float
     const char* e = getenv("GODE_WGRAD_PREFETCH");   // L2 prefetch distance in units of 128 rows per CTA (default 2, 0 = off)
     return (e ? atoi(e) : 2) * 4;
   }();
-  k_wgrad_tc<D, 4><<<grid, tc::WG_THREADS, smem, st>>>(f->A.n_rows, y, gS, ws, cs_partial, f->gn_eps, passes, pf);
+  // GODE_WGRAD_RND=1 rounds the lo residuals to tf32 as the transform does.  Default off: this product decides no ReLU mask,
+  // and its error against fp64 over 2 M rows is the same either way (1.232e-6 vs 1.234e-6) for 0.45 ms per launch.
+  const char* rnd_env = getenv("GODE_WGRAD_RND");
+  k_wgrad_tc<D, 4><<<grid, tc::WG_THREADS, smem, st>>>(f->A.n_rows, y, gS, ws, cs_partial, f->gn_eps, passes, pf,
+                                                       rnd_env ? atoi(rnd_env) : 0);
   GODE_LAUNCH_CHECK();
   k_wgrad_cs<<<1, D, 0, st>>>(grid, D, cs_partial, cs);
   GODE_LAUNCH_CHECK();
@@ -966,9 +978,11 @@ int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, float
 
 // GODE_TC_ACC: accuracy configuration of the 3xTF32 products of k_rows_ws (bit field, see the kernel).  Read at every
 // launch so that one process can compare configurations (tools/transform_accuracy.py).
-static int rows_acc_cfg() {
+static int rows_acc_cfg(int mode) {
   const char* e = getenv("GODE_TC_ACC");
-  return e ? atoi(e) : GODE_TC_ACC_DEFAULT;
+  if (e) return atoi(e);
+  // MODE 0 (the transform) decides ReLU masks: the library-grade configuration.  MODE 1 (input gradient) does not.
+  return mode == 0 ? GODE_TC_ACC_DEFAULT : 3;
 }
 
 // GODE_ROWS_WS: 1 (default) = warp-specialised k_rows_ws for d = 128, 0 = the single-pipeline k_rows_tc
@@ -987,15 +1001,19 @@ static int launch_rows_ws(int64_t n_rows, const float* X, float* Out, const floa
   constexpr size_t smem = 2 * (size_t)D * D * 4 + 4 * (size_t)128 * 32 * 4 + (size_t)128 * (D / 2) * 4 + D * 4 + 128;
   static bool configured = false;
   if (!configured) {
-    GODE_CHECK_CUDA(cudaFuncSetAttribute(k_rows_ws<D, CPG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GODE_CHECK_CUDA(cudaFuncSetAttribute(k_rows_ws<D, CPG, MODE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GODE_CHECK_CUDA(cudaFuncSetAttribute(k_rows_ws<D, CPG, MODE, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GODE_CHECK_CUDA(cudaFuncSetAttribute(k_rows_ws<D, CPG, MODE, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   static const int pf = [] {
     const char* e = getenv("GODE_TC_PREFETCH");   // L2 prefetch distance in tiles per CTA (default 0 = off: measured
     return e ? atoi(e) : 0;                       // 2.28 ms without vs 2.39 ms with, N = 10 M; the loads are not the limit)
   }();
-  k_rows_ws<D, CPG, MODE><<<grid, tc::WS_THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf,
-                                                            rows_acc_cfg());
+  const int cfg = rows_acc_cfg(MODE);
+  if (cfg == 3) k_rows_ws<D, CPG, MODE, 3><<<grid, tc::WS_THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf, cfg);
+  else if (cfg == 19) k_rows_ws<D, CPG, MODE, 19><<<grid, tc::WS_THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf, cfg);
+  else k_rows_ws<D, CPG, MODE, -1><<<grid, tc::WS_THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf, cfg);
   GODE_LAUNCH_CHECK();
   return GODE_OK;
 }
@@ -1086,7 +1104,8 @@ constexpr int GT_KG = 8;       // stages (K = 256 = 32 MMA K steps) accumulated 
 // continue into the other set; after a tile's last group the sums get bias / ReLU and are stored as full rows.
 __global__ void __launch_bounds__(tc::WS_THREADS, 1)
 k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ Bt, int64_t ldb,
-          float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int relu, int passes, int vec_in, int vec_out) {
+          float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int relu, int passes, int vec_in, int vec_out,
+          int k_splits /*> 1: the K range is cut into k_splits slabs, slab s writes its partial product to C + s * M * ldc*/) {
   using namespace tc;
   constexpr int BK = 32;                          // K per stage: one 128-byte swizzle atom of tf32
   constexpr int NI = 4;                           // warp-instructions per producer warp per operand per stage
@@ -1101,10 +1120,11 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tiles_m = (M + 127) / 128, tiles_n = (N + 127) / 128;
-  const int64_t n_tiles = tiles_m * tiles_n;
+  const int64_t mn_tiles = tiles_m * tiles_n;
+  const int64_t n_tiles = mn_tiles * k_splits;    // work items: (output tile, K slab); every slab has the same number of stages
   if ((int64_t)blockIdx.x >= n_tiles) return;
   const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  const int64_t KS = (K + BK - 1) / BK;           // stages per tile
+  const int64_t KS = ((K + BK - 1) / BK + k_splits - 1) / k_splits;   // stages per work item (the last slab is zero-padded)
   const int64_t n_steps = my_tiles * KS;
 
   if (tid == 0) {
@@ -1151,9 +1171,10 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
     };
     auto load_raw = [&](float4 (&r)[2 * NI], int64_t step) {
       if (step >= n_steps) return;
-      const int64_t t = blockIdx.x + (step / KS) * (int64_t)gridDim.x;
+      const int64_t v = blockIdx.x + (step / KS) * (int64_t)gridDim.x;
+      const int64_t t = v % mn_tiles, sp = v / mn_tiles;
       const int64_t tm = t % tiles_m, tn = t / tiles_m;
-      const int64_t k = (step % KS) * BK + (lane & 7) * 4;
+      const int64_t k = (sp * KS + step % KS) * BK + (lane & 7) * 4;
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int rr = (warp * NI + i) * 4 + (lane >> 3);
@@ -1230,8 +1251,10 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
     const int64_t n_groups = (KS + GT_KG - 1) / GT_KG;
     int64_t g = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
-      const int64_t t = blockIdx.x + it * (int64_t)gridDim.x;
+      const int64_t v = blockIdx.x + it * (int64_t)gridDim.x;
+      const int64_t t = v % mn_tiles, sp = v / mn_tiles;
       const int64_t tm = t % tiles_m, tn = t / tiles_m;
+      float* __restrict__ Cs = C + sp * M * ldc;
       for (int64_t gi = 0; gi < n_groups; ++gi, ++g) {
         const int set = static_cast<int>(g & 1);
         mbar_wait(&bars[2 * GT_STAGES + set], static_cast<uint32_t>((g >> 1) & 1));
@@ -1279,7 +1302,7 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
           if (relu) {
             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
           }
-          float* dst = C + grow * ldc + col;
+          float* dst = Cs + grow * ldc + col;
           if (vec_out && col + 3 < N) {
             *reinterpret_cast<float4*>(dst) = o;
           } else {
@@ -1299,8 +1322,9 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
 }
 
 int gemm_tc(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc,
-            const float* bias, int relu, int precision, cudaStream_t st) {
+            const float* bias, int relu, int precision, cudaStream_t st, int k_splits) {
   GODE_REQUIRE(M >= 0 && N >= 0 && K >= 1 && lda >= K && ldb >= K && ldc >= N, "gemm_tc: bad shape");
+  GODE_REQUIRE(k_splits >= 1 && (k_splits == 1 || (!bias && !relu)), "gemm_tc: a split-K product has no bias / ReLU epilogue");
   if (M == 0 || N == 0) return GODE_OK;
   GODE_REQUIRE(A && Bt && C, "gemm_tc: null pointer");
   constexpr size_t smem = tc::GT_STAGES * 4 * (size_t)128 * 32 * 4 + (size_t)128 * 128 * 4 + 256;
@@ -1309,12 +1333,12 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const 
     GODE_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  const int64_t n_tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  const int64_t n_tiles = ((M + 127) / 128) * ((N + 127) / 128) * k_splits;
   const int grid = static_cast<int>(n_tiles < persistent_ctas() ? n_tiles : persistent_ctas());
   const int vec_in = (lda % 4 == 0) && (ldb % 4 == 0) && al16(A) && al16(Bt);
-  const int vec_out = (ldc % 4 == 0) && al16(C);
+  const int vec_out = (ldc % 4 == 0) && al16(C) && (k_splits == 1 || (M * ldc) % 4 == 0);
   k_gemm_tc<<<grid, tc::WS_THREADS, smem, st>>>(M, N, K, A, lda, Bt, ldb, C, ldc, bias, relu,
-                                                precision == GODE_PREC_TF32 ? 1 : 3, vec_in, vec_out);
+                                                precision == GODE_PREC_TF32 ? 1 : 3, vec_in, vec_out, k_splits);
   GODE_LAUNCH_CHECK();
   return GODE_OK;
 }
@@ -1324,5 +1348,12 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const 
 // C[M, N] = act(A[M, K] * Bt[N, K]^T + bias) on tcgen05 (3xTF32, or single-pass TF32 with GODE_PREC_TF32).
 extern "C" int gode_gemm_tc_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bt, int64_t ldb,
                                 const float* bias, int32_t relu, float* C, int64_t ldc, int32_t precision, void* stream) {
-  return gode::gemm_tc(M, N, K, A, lda, Bt, ldb, C, ldc, bias, relu, precision, gode::as_stream(stream));
+  return gode::gemm_tc(M, N, K, A, lda, Bt, ldb, C, ldc, bias, relu, precision, gode::as_stream(stream), 1);
+}
+
+// The same product with the K range cut into k_splits slabs (reductions over millions of rows with a small M x N: weight
+// gradients): slab s writes its partial product to C + s * M * ldc; the caller adds the k_splits partials in slab order.
+extern "C" int gode_gemm_tc_splitk_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bt, int64_t ldb,
+                                       float* C_partials, int64_t ldc, int32_t k_splits, int32_t precision, void* stream) {
+  return gode::gemm_tc(M, N, K, A, lda, Bt, ldb, C_partials, ldc, nullptr, 0, precision, gode::as_stream(stream), k_splits);
 }

@@ -97,6 +97,19 @@ def _optimal_step(last, msr, order=5, safety=0.9, ifactor=10.0, dfactor=0.2):
     return F32(last / factor)
 
 
+def _initial_h0(d0s, d1s):
+    """Hairer's first guess for a TUPLE state as torchdiffeq 0.0.x forms it: ``1e-6`` if the largest scaled norm of the
+    state or of its derivative is below 1e-5, else ``0.01 * max_q(d0_q / d1_q)`` -- the maximum of the per-tensor RATIOS,
+    not the ratio of the maxima (in the adjoint a_theta(t1) = 0 while its derivative is large; the ratio of maxima would
+    let that tensor collapse h0).  Division and ``max`` follow IEEE / Python semantics as torch scalars do there: x/0 is
+    inf, 0/0 is nan, and a nan is kept only if it comes first."""
+    if max(d0s) < 1e-5 or max(d1s) < 1e-5:
+        return F32(1e-6)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratios = [float(np.float64(a) / np.float64(b)) for a, b in zip(d0s, d1s)]
+    return F32(0.01 * max(ratios))
+
+
 def _interp_weights(x, dt, c_mid):
     """Quartic dense output of dopri5 written as weights on (y0, y1, k_0..k_6)."""
     x = float(x)
@@ -427,8 +440,13 @@ def _gcn_aug_fixed_step(kern, tab, t0, h, y0, a0, S0, want_S):
         ka.append(ka_i)
         Y_i, A_i, S_i = Y_n, A_n, S_n
         y_out, a_out, S_out = Y_n, A_n, S_n
-    w = torch.tensor([float(F32(h * F32(b))) for b in tab.b], dtype=torch.float32, device=kern.dev)
-    return y_out, a_out, S_out, (w[:, None] * gth).sum(0)
+    # weights as host scalars (no host-to-device copy: the step must be capturable in a CUDA graph)
+    dth = None
+    for i, b in enumerate(tab.b):
+        if b != 0:
+            term = gth[i] * float(F32(h * F32(b)))
+            dth = term if dth is None else dth + term
+    return y_out, a_out, S_out, dth
 
 
 def _gcn_aug_eval(kern, S, y, a, t, ky, ka, gth, gP):
@@ -468,10 +486,11 @@ def _gcn_aug_dopri5(kern, tab, y1, g1, a_t1, t_start, t_end, S, rtol, atol, stat
     g0 = torch.empty(P, dtype=torch.float32, device=dev)
     _gcn_aug_eval(kern, S, y1, g1, t_start, ky0, ka0, g0, gP)
     kern.reduce_small(g0)
-    d0 = max(rms_big(y1, y1), rms_big(g1, g1), rms_small(at0, at0), rms_small(theta0, theta0))
-    d1 = max(rms_big(ky0, y1), rms_big(ka0, g1), rms_small(g0[P - 1:], at0), rms_small(g0[:P - 1], theta0))
+    d0s = [rms_big(y1, y1), rms_big(g1, g1), rms_small(at0, at0), rms_small(theta0, theta0)]
+    d1s = [rms_big(ky0, y1), rms_big(ka0, g1), rms_small(g0[P - 1:], at0), rms_small(g0[:P - 1], theta0)]
+    d1 = max(d1s)
     # torchdiffeq works on the mirrored problem: its f0 is -F and its step is positive; norms are identical
-    h0 = F32(1e-6) if (d0 < 1e-5 or d1 < 1e-5) else F32(0.01 * d0 / d1)
+    h0 = _initial_h0(d0s, d1s)
     yp, ap, Sp, kyp, kap = new(), new(), kern.new_S(), new(), new()
     gp_ = torch.empty(P, dtype=torch.float32, device=dev)
     ops.rk_combine(y1, [ky0], [-h0], out=yp)
@@ -681,9 +700,10 @@ def _generic_solve(func, y0, t0, t1, method, step_size, rtol, atol, stats):
     t = F32(t0)
     y = tuple(y0)
     f = ft(t, y)
-    d0 = max(_rms_scaled(y[q], y[q], rtol, atol) for q in range(n))
-    d1 = max(_rms_scaled(f[q], y[q], rtol, atol) for q in range(n))
-    h0 = F32(1e-6) if (d0 < 1e-5 or d1 < 1e-5) else F32(0.01 * d0 / d1)
+    d0s = [_rms_scaled(y[q], y[q], rtol, atol) for q in range(n)]
+    d1s = [_rms_scaled(f[q], y[q], rtol, atol) for q in range(n)]
+    d1 = max(d1s)
+    h0 = _initial_h0(d0s, d1s)
     yp = tuple(_lincomb(y[q], [f[q]], [sgn * h0]) for q in range(n))
     fp = ft(F32(t + sgn * h0), yp)
     d2 = max(_rms_scaled(fp[q] - f[q], y[q], rtol, atol) for q in range(n)) / float(h0)

@@ -457,11 +457,29 @@ def gemm_tc(a, bt, bias=None, relu=False, out=None):
     if bt.shape[1] != K:
         raise ValueError("gemm_tc: inner dimensions differ")
     if out is None:
-        out = torch.empty(M, (N + 3) // 4 * 4, dtype=torch.float32, device=a.device)[:, :N]
+        # contiguous [M, N]: callers pass the result's width as its leading dimension (N % 4 != 0 -> the kernel's epilogue
+        # falls back to 32-bit stores, which costs less than a padded buffer plus a compacting copy)
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
     b = _req(bias, "bias").contiguous() if bias is not None else None
     check(lib.gode_gemm_tc_f32(M, N, K, _p(a), a.stride(0), _p(bt), bt.stride(0), _p(b), int(relu), _p(out), out.stride(0),
                                _lib.PREC_FP32, _stream()), "gode_gemm_tc_f32")
     return out
+
+
+def gemm_tc_reduce_rows(a, b):
+    """``a.T @ b`` for two [R, *] row-major operands with R large (weight gradients x^T g): both are transposed once
+    (two copies, ~1 % of the product's traffic), the reduction over R runs as a split-K tcgen05 product over all SMs, and
+    the slabs' partial products are added in slab order."""
+    at, bt = _pad4(a.t().contiguous()), _pad4(b.t().contiguous())       # [M, R], [N, R]: K-major over the rows
+    M, K = at.shape
+    N = bt.shape[0]
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    sm = torch.cuda.get_device_properties(a.device).multi_processor_count
+    splits = max(1, min((K + 2047) // 2048, (2 * sm + tiles - 1) // tiles))
+    part = torch.empty(splits, M, N, dtype=torch.float32, device=a.device)
+    check(lib.gode_gemm_tc_splitk_f32(M, N, K, _p(at), at.stride(0), _p(bt), bt.stride(0), _p(part), N, splits,
+                                      _lib.PREC_FP32, _stream()), "gode_gemm_tc_splitk_f32")
+    return part[0] if splits == 1 else part.sum(0)
 
 
 def linear(x, weight, bias=None, relu=False, weight_is_out_in=False, out=None):
@@ -506,7 +524,7 @@ class LinearFn(torch.autograd.Function):
             # dX = g W^T: g is K-major over N, W [K, N] is the "Bt" of that product as stored; dW = x^T g reduces over the
             # rows, so both operands are transposed first (two library copies, ~1 % of the product's time)
             gx = gemm_tc(g, w) if ctx.needs_input_grad[0] else None
-            gw = gemm_tc(x.t(), g.t()) if ctx.needs_input_grad[1] else None
+            gw = gemm_tc_reduce_rows(x, g) if ctx.needs_input_grad[1] else None
         else:
             gx = gemm(g, w, trans_b=True) if ctx.needs_input_grad[0] else None
             gw = gemm(x, g, trans_a=True, splits=_splits_for(M, K, N)) if ctx.needs_input_grad[1] else None
@@ -643,10 +661,14 @@ class GatConvFn(torch.autograd.Function):
         ws = workspace(nb, x.device, "gat")
         check(lib.gode_gat_bwd(C.byref(graph.c), H, oh, _p(P), ldp, _p(out), out.stride(0), _p(den), _p(amax), _p(g),
                                g.stride(0), _p(dP), _p(ws), nb, _stream()), "gode_gat_bwd")
-        gx = gemm(dP, wcat, trans_b=True) if ctx.needs_input_grad[0] else None
+        big = _tc_gemm_enabled(x.shape[0], min(i, ldp), min(i, ldp))
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm_tc(dP, wcat) if big else gemm(dP, wcat, trans_b=True)              # dP [N, ldp] x wcat [i, ldp]^T
         gfw = gfb = gww = gwb = None
         if any(ctx.needs_input_grad[1:5]):
-            dw = gemm(x, dP, trans_a=True, splits=_splits_for(x.shape[0], i, ldp))       # [i, ldp]
+            dw = (gemm_tc_reduce_rows(x, dP) if big else
+                  gemm(x, dP, trans_a=True, splits=_splits_for(x.shape[0], i, ldp)))     # [i, ldp]
             gfw = torch.cat([dw[:, :C_].t(), dw[:, C_:2 * C_].t()], 1)
             gww = torch.cat([dw[:, 2 * C_:2 * C_ + H].t(), dw[:, 2 * C_ + H:].t()], 1)
             db = colsum(dP)
@@ -793,3 +815,93 @@ def edge_message(s, edge_data, esrc, Etgt, bias=None):
     if plan_t.n_rows != s.shape[0] or plan_t.n_cols < edge_data.shape[0]:
         raise ValueError("Etgt must be [N, E]")
     return EdgeMessageFn.apply(s, edge_data, esrc, plan_t, bias)
+
+
+# --------------------------------------------------------------------------------------------------
+# trainer epilogue: log_softmax + masked nll_loss + accuracy, and Adam, as single libgode launches
+# --------------------------------------------------------------------------------------------------
+
+
+def index_mask(idx, n):
+    """uint8 [n] with ones at ``idx`` (built once per split; the fused loss takes the index set as a mask)."""
+    m = torch.zeros(n, dtype=torch.uint8, device=idx.device)
+    m[idx] = 1
+    return m
+
+
+class LogSoftmaxNllFn(torch.autograd.Function):
+    """(logp, [loss, acc]) = gode_lsm_nll_fwd(z): ``F.log_softmax(z, 1)``, ``F.nll_loss(logp[idx], labels[idx])`` and
+    ``accuracy(logp[idx], labels[idx])`` (GCN/train_res.py:76-77, GCN/utils.py:215-219) in one pass; the backward of the loss
+    is one more launch.  ``logp`` is returned for the caller's use but carries no gradient path of its own."""
+
+    @staticmethod
+    def forward(ctx, z, labels, mask, m):
+        z = _rowmajor(z, "logits")
+        n, c = z.shape
+        logp = torch.empty(n, c, dtype=torch.float32, device=z.device)
+        la = torch.empty(2, dtype=torch.float32, device=z.device)
+        nb = lib.gode_lsm_nll_workspace_bytes(n)
+        ws = workspace(nb, z.device, "lsm")
+        check(lib.gode_lsm_nll_fwd(n, c, _p(z), z.stride(0), _p(labels), _p(mask), int(m), _p(logp), c, _p(la), _p(ws), nb,
+                                   _stream()), "gode_lsm_nll_fwd")
+        ctx.m = int(m)
+        ctx.save_for_backward(logp, labels, mask)
+        ctx.mark_non_differentiable(logp)
+        return logp, la
+
+    @staticmethod
+    def backward(ctx, _glogp, gla):
+        logp, labels, mask = ctx.saved_tensors
+        n, c = logp.shape
+        gla = gla.contiguous()
+        dz = torch.empty(n, c, dtype=torch.float32, device=logp.device)
+        check(lib.gode_lsm_nll_bwd(n, c, _p(logp), c, _p(labels), _p(mask), ctx.m, _p(gla), _p(dz), c, _stream()),
+              "gode_lsm_nll_bwd")
+        return dz, None, None, None
+
+
+def log_softmax_nll(z, labels, mask, m):
+    """Returns ``(logp [N, C], loss_acc [2])`` with ``loss_acc[0]`` the mean NLL over the masked rows (differentiable) and
+    ``loss_acc[1]`` their accuracy."""
+    if labels.dtype != torch.int64 or mask.dtype != torch.uint8:
+        raise TypeError("labels must be int64 class ids and mask uint8")
+    return LogSoftmaxNllFn.apply(z, labels.contiguous(), mask.contiguous(), m)
+
+
+class FusedAdam:
+    """``torch.optim.Adam(params, lr, betas, eps, weight_decay)`` (GCN/train_res.py:126-127) as ONE libgode launch per step:
+    the parameters are re-pointed at slices of one flat buffer, so the update runs over [sum numel] elements at once; the
+    step counter lives on the device (a replayed CUDA graph keeps counting).  Same update rule and defaults as torch's."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("optimizer got an empty parameter list")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise TypeError("FusedAdam needs CUDA parameters; graph-odenet_b200 has no CPU path")
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat[off:off + k].view(p.shape)
+                off += k
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.steps = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def step(self):
+        g = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params])
+        check(lib.gode_adam_step(self.flat.numel(), _p(self.flat), _p(g), _p(self.m), _p(self.v), self.lr, self.betas[0],
+                                 self.betas[1], self.eps, self.weight_decay, _p(self.steps), _stream()), "gode_adam_step")

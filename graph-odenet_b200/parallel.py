@@ -198,7 +198,11 @@ class HaloKernelMixin:
     def scalar(self, dev_scalar):
         if self.plan.world > 1:
             dist.all_reduce(dev_scalar, group=self.plan.group)
-        return float(dev_scalar.item())
+        v = float(dev_scalar.item())
+        # the adaptive solver synchronises here once per step anyway: surface a timed-out peer wait on the hot path (a
+        # time-out also traps the stream, peer.cu:k_peer_wait, so fixed-step solves fail at their next synchronisation)
+        self.plan.check_peers()
+        return v
 
     def reduce_small(self, t):
         if self.plan.world > 1:
@@ -507,3 +511,110 @@ def allreduce_gradients(params, group=None, local_weight=1.0):
         n = p.grad.numel()
         p.grad.copy_(flat[off:off + n].view_as(p.grad))
         off += n
+
+
+# --------------------------------------------------------------------------------------------------
+# locality-aware relabelling ("degree/locality-aware reordering, a pure relabelling")
+# --------------------------------------------------------------------------------------------------
+
+
+def _csr_pattern(row, col, n):
+    """rowptr / colidx of the (row-sorted) pattern; ``row`` need not be sorted."""
+    order = torch.argsort(row, stable=True)
+    colidx = col[order]
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=row.device)
+    rowptr[1:] = torch.cumsum(torch.bincount(row, minlength=n), 0)
+    return rowptr, colidx
+
+
+def locality_order(row, col, n, method="rcm", sweeps=0):
+    """A relabelling of the nodes of a symmetric pattern that shortens the distance |i - j| of connected nodes, so that a
+    contiguous row partition cuts fewer edges (smaller halo) and a row tile's neighbours share L2 lines.
+
+    Returns ``perm`` (int64 [n]): the NEW id of old node ``i`` is ``perm[i]``.  A relabelling is parity-neutral: the
+    relabelled problem is the same problem (``relabel`` / ``unrelabel`` are exact inverses -- tests/test_parallel_cpu.py).
+
+    ``method``:
+      * ``"degree"`` -- nodes by descending degree (hubs first: the rows everybody references share one partition and
+        stay L2-resident);
+      * ``"rcm"``    -- reverse Cuthill-McKee: level-synchronous breadth-first search on the device from a minimum-degree
+        node of every component; inside a level nodes are ordered by the position of their first-discovered parent, then
+        by degree; the final order is reversed.
+    ``sweeps`` > 0 adds barycentre sweeps: every node moves to the mean position of its neighbours and the nodes are
+    re-ranked -- the classical one-dimensional placement refinement; it tightens a band that the breadth-first levels
+    found coarsely.
+    """
+    dev = row.device
+    row, col = row.to(torch.int64), col.to(torch.int64)
+    deg = torch.bincount(row, minlength=n)
+    if method == "degree":
+        order = torch.argsort(deg, descending=True, stable=True)          # order[k] = old id at new position k
+    elif method == "rcm":
+        rowptr, colidx = _csr_pattern(row, col, n)
+        pos = torch.full((n,), -1, dtype=torch.int64, device=dev)          # CM position of each node
+        placed = 0
+        # components in order of their minimum-degree node
+        start_order = torch.argsort(deg, stable=True)
+        sp = 0
+        while placed < n:
+            while sp < n and int(pos[start_order[sp]]) >= 0:
+                sp += 1
+            frontier = start_order[sp:sp + 1]
+            pos[frontier] = placed
+            placed += 1
+            while frontier.numel():
+                cnt = rowptr[frontier + 1] - rowptr[frontier]
+                tot = int(cnt.sum())
+                if tot == 0:
+                    break
+                # expand: (parent position, child) for every stored entry of the frontier rows
+                owner = torch.repeat_interleave(torch.arange(frontier.numel(), device=dev), cnt)
+                offs = torch.arange(tot, device=dev) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+                child = colidx[rowptr[frontier][owner] + offs]
+                ppos = pos[frontier][owner]
+                new = pos[child] < 0
+                child, ppos = child[new], ppos[new]
+                if child.numel() == 0:
+                    break
+                # first-discovered parent of every new node, then order by (parent position, degree, id)
+                uniq, inv = torch.unique(child, return_inverse=True)
+                first = torch.full((uniq.numel(),), 1 << 62, dtype=torch.int64, device=dev)
+                first.scatter_reduce_(0, inv, ppos, reduce="amin")
+                key = torch.argsort(deg[uniq], stable=True)
+                key = key[torch.argsort(first[key], stable=True)]
+                frontier = uniq[key]
+                pos[frontier] = placed + torch.arange(frontier.numel(), device=dev)
+                placed += int(frontier.numel())
+        order = torch.argsort(pos, stable=True).flip(0)                    # reverse Cuthill-McKee
+    else:
+        raise ValueError("unknown reordering method %r" % (method,))
+    perm = torch.empty(n, dtype=torch.int64, device=dev)
+    perm[order] = torch.arange(n, device=dev)
+    for _ in range(int(sweeps)):
+        p = perm.to(torch.float64)
+        s = torch.zeros(n, dtype=torch.float64, device=dev).index_add_(0, row, p[col])
+        bary = torch.where(deg > 0, s / deg.clamp(min=1), p)
+        order = torch.argsort(bary, stable=True)
+        perm[order] = torch.arange(n, device=dev)
+    return perm
+
+
+def relabel(row, col, perm):
+    """The same entries under the new ids (values travel with their entries unchanged)."""
+    return perm[row], perm[col]
+
+
+def unrelabel(row, col, perm):
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(perm.numel(), device=perm.device)
+    return inv[row], inv[col]
+
+
+def halo_fraction(row, col, n, world):
+    """Halo rows per owned row, averaged over the ranks of a contiguous ``world``-way row partition (the quantity the
+    relabelling is meant to shrink)."""
+    b = torch.tensor(partition_bounds(n, world), device=row.device)
+    ro, co = torch.bucketize(row, b[1:-1], right=True), torch.bucketize(col, b[1:-1], right=True)
+    cut = ro != co
+    pairs = torch.unique(ro[cut] * n + col[cut])
+    return float(pairs.numel()) / n

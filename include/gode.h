@@ -185,10 +185,34 @@ int gode_linear_f32(int32_t transB, int64_t M, int64_t N, int64_t K, const float
 /* The same Linear on the tensor cores (tcgen05, fp32 result by 3xTF32; precision = GODE_PREC_TF32 for one pass):
  *   C[M, N] = act(A[M, K] * Bt[N, K]^T + bias)      -- both operands K-major: a weight stored [K, N] is transposed first.
  * Arbitrary M, N, K (edges are zero-filled / masked); 128-bit accesses when lda, ldb, ldc are multiples of 4 and the bases
- * 16-byte aligned.  For the QC edge encoder (QC/layers.py:76-86: [E, 2667] x [2667, 5329]).
- * EXPERIMENTAL in round 1: compiled, not yet run on hardware; nothing in the package calls it (see csrc/transform_tc.cu). */
+ * 16-byte aligned.  Replaces torch.mm / nn.Linear at QC/layers.py:76-86 (the edge encoder, [E, 2667] x [2667, 5329]),
+ * GAT/layers.py:40-45 (the f / w projections) and GCN/layers.py:32 (input layer).  Accumulation is hierarchical (K slabs of
+ * 256 in TMEM, fp32 running sums outside): as accurate as an fp32 SGEMM for any K (tests/test_gpu_gemm_tc.py). */
 int gode_gemm_tc_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bt, int64_t ldb,
                      const float* bias, int32_t relu, float* C, int64_t ldc, int32_t precision, void* stream);
+
+/* The same product with the K range cut into k_splits slabs -- for reductions over very many rows with a small M x N
+ * (weight gradients x^T g: torch.autograd's mm at the call sites above).  Slab s writes its partial product to
+ * C_partials + s * M * ldc; the caller adds the k_splits partials in slab order (deterministic). */
+int gode_gemm_tc_splitk_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bt, int64_t ldb,
+                            float* C_partials, int64_t ldc, int32_t k_splits, int32_t precision, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Trainer epilogue: replaces F.log_softmax (GCN/models.py:20,81,118,218), F.nll_loss(output[idx], labels[idx])
+ * and accuracy(...) (GCN/train_res.py:76-77, GCN/utils.py:215-219), their autograd, and optim.Adam.step()
+ * (GCN/train_res.py:79,126-127).  mask[r] != 0 marks the m rows of the index set; labels are int64 class ids per row.
+ * loss_acc[0] = -mean_{masked r} logp[r, labels[r]], loss_acc[1] = mean_{masked r} (argmax logp[r] == labels[r]). */
+size_t gode_lsm_nll_workspace_bytes(int64_t n);
+int gode_lsm_nll_fwd(int64_t n, int32_t c, const float* z, int64_t ldz, const int64_t* labels, const uint8_t* mask, int64_t m,
+                     float* logp, int64_t ldo, float* loss_acc, void* ws, size_t ws_bytes, void* stream);
+/* dz = gloss[0] * d loss / d z   (gloss: device scalar, the upstream gradient of the loss) */
+int gode_lsm_nll_bwd(int64_t n, int32_t c, const float* logp, int64_t ldo, const int64_t* labels, const uint8_t* mask, int64_t m,
+                     const float* gloss, float* dz, int64_t ldz, void* stream);
+/* torch.optim.Adam's update (amsgrad / maximize off, L2 weight decay added to the gradient) over flat fp32 buffers;
+ * step_counter is a device int32 holding the number of steps taken so far, incremented by the call (so the call can sit
+ * inside a replayed CUDA graph). */
+int gode_adam_step(int64_t n, float* p, const float* g, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int32_t* step_counter, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row-wise GroupNorm on [n, d] (groups of d/groups contiguous channels per row).

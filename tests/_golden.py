@@ -24,15 +24,20 @@ def rnd(seed, *shape, scale=1.0):
 def fill_params(model, seed=7):
     """Deterministic parameters chosen by NAME (numpy legacy RandomState seeded with crc32(name) ^ seed), so that the fixture
     generator (reference modules) and the tests (B200 modules) hold identical parameters without storing them -- and a
-    parameter name that exists on one side only is an immediate KeyError/shape error.  2-D weights are Xavier-normal,
-    vectors named ``*norm*.weight`` are 1 + 0.25 N(0,1), every other vector is 0.1 N(0,1)."""
+    parameter name that exists on one side only is an immediate KeyError/shape error.  2-D weights are Xavier-normal
+    (unit normal for the wide input layers), vectors named ``*norm*.weight`` are 1 + 0.25 N(0,1), every other vector is
+    0.1 N(0,1)."""
     import zlib
     with torch.no_grad():
         for name, p in sorted(model.named_parameters()):
             rs = np.random.RandomState((zlib.crc32(name.encode()) ^ seed) & 0x7FFFFFFF)
             v = rs.standard_normal(tuple(p.shape)).astype(np.float32)
-            if p.dim() >= 2:
+            if p.dim() >= 2 and max(p.shape) > 512 and min(p.shape) <= 256:
+                pass            # input layers on row-normalised bag-of-words features: unit normal keeps the hidden state O(0.3)
+            elif p.dim() >= 2:
                 v *= np.float32((2.0 / (p.shape[0] + p.shape[1])) ** 0.5)
+                if "odefunc" in name:
+                    v *= np.float32(0.5)    # about the reference's own U(+-1/sqrt(out)) scale: keeps the ODE contractive enough to pin
             elif "norm" in name and name.endswith("weight"):
                 v = np.float32(1.0) + np.float32(0.25) * v
             else:

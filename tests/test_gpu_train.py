@@ -6,11 +6,15 @@ import re
 
 import numpy as np
 import pytest
+import torch
+import torch.nn.functional as F
 
 from tests import _golden as G
 
 pytestmark = pytest.mark.gpu
 NPZ = os.path.join(G.HERE, "planetoid_cora.npz")
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _run(family, argv):
@@ -61,3 +65,74 @@ def test_qc_driver_runs_every_buildable_model():
     for model in ("eressum", "eodes2s"):
         with pytest.raises(NotImplementedError):
             train_egcn.main(["--model", model] + base)
+
+
+# ------------------------------------------------------------------------------------------- fused epoch
+
+def test_fused_loss_matches_reference_ops():
+    """gode_lsm_nll_fwd / _bwd against F.log_softmax + F.nll_loss(output[idx], labels[idx]) + accuracy(...)
+    (GCN/train_res.py:76-77, GCN/utils.py:215-219) and their autograd -- values, gradient and the tie rule of torch.max."""
+    import graph_odenet_b200  # noqa: F401
+    from graph_odenet_b200 import ops, utils
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for n, c, m in ((2708, 7, 140), (19717, 3, 60), (513, 130, 513)):
+        z = torch.randn(n, c, device=DEV, generator=g) * 3
+        z[5] = z[5, 0]                                                     # a row of ties: the first maximum wins
+        labels = torch.randint(0, c, (n,), device=DEV, generator=g)
+        idx = torch.randperm(n, device=DEV, generator=g)[:m]
+        zo = z.clone().requires_grad_(True)
+        out = F.log_softmax(zo, dim=1)
+        loss = F.nll_loss(out[idx], labels[idx])
+        acc = utils.accuracy(out[idx], labels[idx])
+        loss.backward()
+        zg = z.clone().requires_grad_(True)
+        logp, la = ops.log_softmax_nll(zg, labels, ops.index_mask(idx, n), m)
+        la[0].backward()
+        G.assert_close(logp, out.detach(), rtol=1e-6, atol_scale=1e-6, what="log_softmax")
+        assert abs(float(la[0]) - float(loss)) <= 1e-6 * max(1.0, abs(float(loss)))
+        assert abs(float(la[1]) - float(acc)) <= 1e-6
+        G.assert_close(zg.grad, zo.grad, rtol=1e-5, atol_scale=1e-6, what="dloss/dz")
+
+
+def test_fused_adam_matches_torch_adam():
+    import graph_odenet_b200  # noqa: F401
+    from graph_odenet_b200 import ops
+    torch.manual_seed(0)
+    shapes = [(1433, 16), (16,), (17, 16), (7,)]
+    ref = [torch.randn(*s, device=DEV).requires_grad_(True) for s in shapes]
+    ours = [p.detach().clone().requires_grad_(True) for p in ref]
+    o_ref = torch.optim.Adam(ref, lr=0.01, weight_decay=5e-4)              # GCN/train_res.py:126-127
+    o_ours = ops.FusedAdam(ours, lr=0.01, weight_decay=5e-4)
+    for step in range(12):
+        for a, b in zip(ref, ours):
+            gr = torch.randn_like(a) * (0.1 + step)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        o_ref.step()
+        o_ours.step()
+    for a, b in zip(ref, ours):
+        G.assert_close(b, a.detach(), rtol=1e-5, atol_scale=1e-6, what="parameters after 12 Adam steps")
+    assert int(o_ours.steps.item()) == 12
+
+
+@pytest.mark.parametrize("model,extra", [("res3", []), ("ode3", ["--method", "rk4"]), ("ode3norm", ["--method", "rk4"])])
+def test_graphed_epoch_matches_eager_epoch(model, extra):
+    """The CUDA-graph epoch (fused loss + fused Adam, one read-back) reproduces the eager epoch of GCN/train_res.py:63-102:
+    with dropout off the two are the same arithmetic, so the per-epoch losses must agree to fp32 rounding accumulated over
+    the epochs, and the final test accuracy must match."""
+    import graph_odenet_b200  # noqa: F401
+    from graph_odenet_b200 import train
+    npz = os.path.join(ROOT, "tests", "golden", "planetoid_cora.npz")
+    res = {}
+    for mode in ("off", "on"):
+        lines = []
+        res[mode] = train.main("GCN", ["--model", model, "--npz", npz, "--epochs", "25", "--dropout", "0", "--fused-epoch", mode] + extra,
+                               out=lambda *a, **k: lines.append(" ".join(str(x) for x in a)))
+        res[mode]["lines"] = lines
+    la = [h[0] for h in res["off"]["history"]]
+    lb = [h[0] for h in res["on"]["history"]]
+    assert len(la) == len(lb) == 25
+    for e, (a, b) in enumerate(zip(la, lb)):
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(a)), (e, a, b)
+    assert [h[1:] for h in res["off"]["history"]] == [h[1:] for h in res["on"]["history"]]      # nfe_f / nfe_b per epoch
+    assert abs(res["off"]["acc"] - res["on"]["acc"]) <= 0.011
+    assert res["on"]["lines"][0].startswith("Epoch: 0001 loss_train:")                           # the reference's print format
