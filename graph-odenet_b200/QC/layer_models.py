@@ -37,7 +37,7 @@ class UnimplementedModel(nn.Module):
 
 
 def _n_graphs(batch):
-    return int(batch.max().item()) + 1
+    return int(batch.max().item()) + 1 if batch.numel() else 0      # an empty shard (batch smaller than the world) has no graphs
 
 
 class EdgeGCN_K_Sum(nn.Module):

@@ -97,14 +97,16 @@ def main(argv=None):
                 group["lr"] = args.lr
         loss, t_batch = train(train_loader, model, criterion, optimizer, epoch, evaluation, None, metric_name=metric_name,
                               log_interval=args.log_interval, world=world, global_batch=args.batch_size)
-        er1 = validate(valid_loader, model, criterion, evaluation, None, metric_name=metric_name, log_interval=args.log_interval)
+        er1 = validate(valid_loader, model, criterion, evaluation, None, metric_name=metric_name, log_interval=args.log_interval,
+                       world=world)
         is_best = metric_compare(er1, best_er1)       # the reference starts best_er1 at 0 for both metric directions
         best_er1 = metric_best(er1, best_er1)
         history.append((loss, er1, t_batch))
         if resume_dir and rank == 0:
             save_checkpoint({"epoch": epoch + 1, "state_dict": model.state_dict(), "best_er1": best_er1,
                              "optimizer": optimizer.state_dict()}, is_best=is_best, directory=resume_dir)
-    test_metric = validate(test_loader, model, criterion, evaluation, metric_name=metric_name, log_interval=args.log_interval)
+    test_metric = validate(test_loader, model, criterion, evaluation, metric_name=metric_name, log_interval=args.log_interval,
+                           world=world)
     if world > 1:
         torch.distributed.destroy_process_group()
     return {"history": history, "test": test_metric, "params": count_params(model)}

@@ -161,7 +161,7 @@ def train(train_loader, model, criterion, optimizer, epoch, evaluation, logger=N
 
 
 def validate(val_loader, model, criterion, evaluation, logger=None, target_range=(0, None), tgt_name="", metric_name="metric",
-             cuda=True, log_interval=20):
+             cuda=True, log_interval=20, world=1):
     batch_time, losses, metric = AverageMeter(), AverageMeter(), AverageMeter()
     model.eval()
     with torch.no_grad():
@@ -180,6 +180,12 @@ def validate(val_loader, model, criterion, evaluation, logger=None, target_range
                       "{metric_name} {metric.val:.4f} ({metric.avg:.4f})"
                       .format(i, len(val_loader), batch_time=batch_time, loss=losses, metric_name=metric_name, metric=metric),
                       flush=True)
+    if world > 1:
+        # every rank validated its own shard: the metric (and the checkpoint decision taken on it) is the global mean
+        from .. import parallel
+        dev = next(model.parameters()).device
+        metric.avg = parallel.allreduce_mean(metric.avg * metric.count, metric.count, dev)
+        losses.avg = parallel.allreduce_mean(losses.avg * losses.count, losses.count, dev)
     print(" * {tgt_name} Average {metric_name} {metric.avg:.3f}; Average Loss {loss.avg:.3f}"
           .format(metric_name=metric_name, metric=metric, loss=losses, tgt_name=tgt_name), flush=True)
     if logger is not None:

@@ -667,8 +667,9 @@ class GatConvFn(torch.autograd.Function):
             gx = gemm_tc(dP, wcat) if big else gemm(dP, wcat, trans_b=True)              # dP [N, ldp] x wcat [i, ldp]^T
         gfw = gfb = gww = gwb = None
         if any(ctx.needs_input_grad[1:5]):
-            dw = (gemm_tc_reduce_rows(x, dP) if big else
-                  gemm(x, dP, trans_a=True, splits=_splits_for(x.shape[0], i, ldp)))     # [i, ldp]
+            # x^T dP reduces over the N rows of two tall, narrow operands: the SIMT split-K kernel reads them as they lie
+            # (5.7 ms at N = 1 M); transposing both for the K-major tensor-core kernel costs more than it saves here
+            dw = gemm(x, dP, trans_a=True, splits=_splits_for(x.shape[0], i, ldp))       # [i, ldp]
             gfw = torch.cat([dw[:, :C_].t(), dw[:, C_:2 * C_].t()], 1)
             gww = torch.cat([dw[:, 2 * C_:2 * C_ + H].t(), dw[:, 2 * C_ + H:].t()], 1)
             db = colsum(dP)

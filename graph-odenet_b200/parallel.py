@@ -497,20 +497,36 @@ def shard_molecules(n_mol, rank, world):
 def allreduce_gradients(params, group=None, local_weight=1.0):
     """Sum ``local_weight * grad`` over ranks, in place, through one flat buffer (one NCCL all-reduce per step; the QC
     model has 14.3 M parameters = 57 MB).  With a batch-mean loss pass ``local_weight = local_batch / global_batch``
-    so the result is the gradient of the global-batch mean (QC/util.py:184 uses MSELoss's mean)."""
-    params = [p for p in params if p.grad is not None]
+    so the result is the gradient of the global-batch mean (QC/util.py:184 uses MSELoss's mean).
+
+    The buffer covers EVERY parameter that requires a gradient, with zeros for those whose ``grad`` is None on this rank
+    (an unused branch, an empty shard): all ranks therefore always issue the same-sized collective, whatever their local
+    graph looked like (a rank that skipped the call, or sent a shorter buffer, would hang or corrupt the all-reduce)."""
+    params = [p for p in params if p.requires_grad]
     if not params:
         return
-    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
     if local_weight != 1.0:
         flat.mul_(local_weight)
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, group=group)
     off = 0
     for p in params:
-        n = p.grad.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        n = p.numel()
+        if p.grad is None:
+            p.grad = flat[off:off + n].view_as(p).clone()
+        else:
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
         off += n
+
+
+def allreduce_mean(total, count, device, group=None):
+    """Global mean of a per-rank (sum, count) pair -- validation metrics of data-parallel runs (every rank then takes the
+    same checkpoint / early-stopping decision)."""
+    t = torch.tensor([float(total), float(count)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, group=group)
+    return float(t[0] / t[1].clamp(min=1.0))
 
 
 # --------------------------------------------------------------------------------------------------

@@ -183,10 +183,65 @@ def config5():
              molecules_per_sec=n_mol / (ms / 1e3))
 
 
+def config5dp(n_mol_per_rank=8192):
+    """BASELINE config 5 as it shards: molecules split data-parallel over the ranks of a torchrun launch, full
+    model replica per rank, one gradient all-reduce (57 MB) per step.  Weak scaling: every rank gets n_mol_per_rank molecules.
+
+        python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_configs.py 5dp"""
+    import torch.distributed as dist
+    from graph_odenet_b200 import parallel
+    from graph_odenet_b200.QC import layer_models
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        parallel.init_process_group(dev)
+    b = synth.qm9_like_batch(n_mol_per_rank, 73, seed=rank, device=dev)
+    torch.manual_seed(0)                                                   # identical replicas
+    model = layer_models.EdgeGCN_K_Sum(node_features=13, edge_features=5, target_features=12, hidden_features=73, num_layers=3).to(dev)
+    target = torch.randn(n_mol_per_rank, 12, device=dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    t_ar = [0.0]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = model(b["node_features"], b["edge_features"], b["esrc"], b["etgt"], b["batch"], batch_size=n_mol_per_rank)
+        torch.nn.functional.mse_loss(out, target).backward()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        parallel.allreduce_gradients(model.parameters(), local_weight=1.0 / world)
+        e1.record()
+        opt.step()
+        return e0, e1
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    k, ars = 5, []
+    for _ in range(k):
+        ars.append(step())
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev0.elapsed_time(ev1) / k, sum(a.elapsed_time(b_) for a, b_ in ars) / k], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        emit(config=5, case="EdgeGCN_K_Sum (K = 3, hidden 73) data-parallel training step, gradient all-reduce over NCCL", device="B200",
+             n_gpus=world, molecules_per_rank=n_mol_per_rank, molecules=n_mol_per_rank * world, ms_per_step=float(ms[0]),
+             allreduce_ms=float(ms[1]), grad_bytes=4 * sum(p.numel() for p in model.parameters()),
+             molecules_per_sec=n_mol_per_rank * world / (float(ms[0]) / 1e3))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["1", "2", "3", "5"]
     for w in which:
         try:
-            {"1": config1, "2": config2, "3": config3, "5": config5}[w]()
+            {"1": config1, "2": config2, "3": config3, "5": config5, "5dp": config5dp}[w]()
         except Exception as e:  # noqa: BLE001 -- a failing case must not hide the others
-            emit(config=int(w), error="%s: %s" % (type(e).__name__, e))
+            emit(config=str(w), error="%s: %s" % (type(e).__name__, e))
