@@ -490,16 +490,37 @@ __device__ __forceinline__ void acc_row(float2& a0, float2& a1, const float v, c
   }
 }
 
+// Hub rows (> GODE_HEAVY_ROW entries) INSIDE the tile's CTA.  Round 2 ncu on the separate hub kernel (profiles/r02_gather.md):
+// L2 hit rate 18 %, 11.7 GB of DRAM reads for 15.6 GB gathered -- swept on their own, the hubs' chunks find nothing of their
+// band in L2 (the reuse distance between two hubs that share neighbours is about the size of L2), while the tile sweep of
+// the light rows has exactly that band resident when it passes a hub's id.  So (opt-in, GODE_SPMM_HUBS_INLINE=1: it measured
+// SLOWER, 8.55 vs 7.08 ms per bare gather -- a CTA that meets a hub parks its 8 warps behind two block barriers and holds its
+// SM slot for the hub's whole length, which costs more than the L2 misses it avoids) the tile that contains a hub also gathers
+// it: after the light rows (block barrier) the tile's hub chunks (256 entries each) are pulled from a second shared
+// counter by all 8 warps, their partial sums go to the caller's workspace, and after another barrier one warp per hub adds
+// the chunks IN CHUNK ORDER (deterministic) and applies the epilogue.  A 100 000-entry hub keeps its CTA for ~1 ms, well
+// inside the kernel's 6 ms; the other CTAs of the wave are unaffected (dynamic CTA scheduling).
+struct HubArgs {
+  const int32_t* rows;        // sorted hub row ids (gode_csr_t.heavy_rows), nullptr: hubs are left to the separate kernels
+  const int32_t* chunk_ptr;   // first chunk of each hub in the workspace (gode_csr_t.heavy_chunk_ptr)
+  int n_heavy;
+  float4* partial;            // [n_chunks][32] float4 workspace
+};
+
 template <int TS_ROWS, int MINB, bool ROWVAL>
 __global__ void __launch_bounds__(256, MINB) k_spmm_t2(int64_t n_rows, const int32_t* __restrict__ rowptr,
                                                        const int32_t* __restrict__ colidx, const float* __restrict__ vals,
                                                        const float* __restrict__ row_vals, const float4* __restrict__ X4,
-                                                       float* __restrict__ Y, const gode_spmm_epilogue_t ep, const int prefetch) {
+                                                       float* __restrict__ Y, const gode_spmm_epilogue_t ep, const int prefetch,
+                                                       const HubArgs hub) {
   constexpr int TS_CAP = TS_ROWS * 32;
+  static_assert(TS_CAP >= 8 * 128, "the hub phase stages 128 entries per warp in the tile's index buffer");
   __shared__ int s_ptr[TS_ROWS + 1];
   __shared__ int s_idx[TS_CAP];
   __shared__ float s_val[ROWVAL ? 1 : TS_CAP];
   __shared__ int s_next;
+  __shared__ int s_nhub, s_next2, s_hub[TS_ROWS], s_hub_first[TS_ROWS + 1], s_hub_gbase[TS_ROWS];
+  if (threadIdx.x == 0) { s_nhub = 0; s_next2 = 0; }
   const int tid = threadIdx.x, lane = tid & 31;
   const int64_t row0 = blockIdx.x * (int64_t)TS_ROWS;
   const int nr = static_cast<int>(min((int64_t)TS_ROWS, n_rows - row0));
@@ -520,7 +541,10 @@ __global__ void __launch_bounds__(256, MINB) k_spmm_t2(int64_t n_rows, const int
     r = __shfl_sync(0xffffffffu, r, 0);
     if (r >= nr) break;
     const int e0 = s_ptr[r], e1 = s_ptr[r + 1];
-    if (e1 - e0 > GODE_HEAVY_ROW) continue;          // hub rows: k_spmm_heavy_partial / finish
+    if (e1 - e0 > GODE_HEAVY_ROW) {                  // hub row: gathered below (or by k_spmm_heavy2 / finish when hub.rows is null)
+      if (hub.rows && lane == 0) s_hub[atomicAdd(&s_nhub, 1)] = r;
+      continue;
+    }
     const int64_t row = row0 + r;
     if (prefetch) epilogue_prefetch<1>(ep, row, lane * 4, 128);
     float4 one[1];
@@ -566,6 +590,99 @@ __global__ void __launch_bounds__(256, MINB) k_spmm_t2(int64_t n_rows, const int
       one[0] = make_float4(0.f, 0.f, 0.f, 0.f);
       gather_range<32, 1, 4>(one, e0, e1, e1 - e0, 0, lane, colidx, vals, reinterpret_cast<const float*>(xb), 128);
     }
+    epilogue<1>(ep, row, lane * 4, one, Y, 128);
+  }
+  if (!hub.rows) return;
+  // ---- the tile's hub rows --------------------------------------------------------------------------------------
+  __syncthreads();                                   // every light row is done: the index buffer is free, s_nhub is final
+  const int nhub = s_nhub;
+  if (nhub == 0) return;                             // (uniform over the CTA)
+  const int w = tid >> 5;
+  if (w == 0) {                                      // per hub: its first chunk in the workspace, and the tile's chunk prefix
+    int nch = 0;
+    if (lane < nhub) {
+      const int r = s_hub[lane];
+      nch = (s_ptr[r + 1] - s_ptr[r] + GODE_HEAVY_CHUNK - 1) / GODE_HEAVY_CHUNK;
+      const int grow = static_cast<int>(row0) + r;
+      int lo = 0, hi = hub.n_heavy - 1;              // position of this row in the sorted hub list
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(hub.rows + mid) < grow) lo = mid + 1; else hi = mid;
+      }
+      s_hub_gbase[lane] = __ldg(hub.chunk_ptr + lo);
+    }
+    int incl = nch;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane < nhub) s_hub_first[lane] = incl - nch;
+    if (lane == 31) s_hub_first[nhub] = incl;        // lanes >= nhub carry nch = 0: the total
+  }
+  __syncthreads();
+  const int total = s_hub_first[nhub];
+  int* __restrict__ my_idx = s_idx + w * 128;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(&s_next2, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total) break;
+    int k = 0;
+    while (k + 1 < nhub && s_hub_first[k + 1] <= item) ++k;
+    const int j = item - s_hub_first[k];
+    const int r = s_hub[k];
+    const int ce0 = s_ptr[r] + j * GODE_HEAVY_CHUNK;
+    const int cnt = min(s_ptr[r + 1] - ce0, GODE_HEAVY_CHUNK);
+    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+    for (int half = 0; half < cnt; half += 128) {    // 128 entries at a time through this warp's slice of the index buffer
+      const int hc = min(128, cnt - half);
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = q * 32 + lane;
+        if (i < hc) my_idx[i] = __ldcs(colidx + ce0 + half + i);
+      }
+      __syncwarp();
+      int i = 0;
+#pragma unroll 1
+      for (; i + 4 <= hc; i += 4) {
+        const unsigned c0 = my_idx[i], c1 = my_idx[i + 1], c2 = my_idx[i + 2], c3 = my_idx[i + 3];
+        const float4 x0 = __ldg(xb + (size_t)c0 * 32), x1 = __ldg(xb + (size_t)c1 * 32);
+        const float4 x2 = __ldg(xb + (size_t)c2 * 32), x3 = __ldg(xb + (size_t)c3 * 32);
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+        if (!ROWVAL) {                               // values straight from global memory (broadcast loads, L1-resident line)
+          const float* vp = vals + ce0 + half + i;
+          v0 = __ldg(vp); v1 = __ldg(vp + 1); v2 = __ldg(vp + 2); v3 = __ldg(vp + 3);
+        }
+        acc_row<ROWVAL>(a0, a1, v0, x0);
+        acc_row<ROWVAL>(a0, a1, v1, x1);
+        acc_row<ROWVAL>(a0, a1, v2, x2);
+        acc_row<ROWVAL>(a0, a1, v3, x3);
+      }
+      for (; i < hc; ++i) {
+        const float v = ROWVAL ? 0.f : __ldg(vals + ce0 + half + i);
+        acc_row<ROWVAL>(a0, a1, v, __ldg(xb + (size_t)(unsigned)my_idx[i] * 32));
+      }
+    }
+    hub.partial[(size_t)(s_hub_gbase[k] + j) * 32 + lane] = make_float4(a0.x, a0.y, a1.x, a1.y);
+  }
+  __syncthreads();                                   // the tile's partial sums are written (and visible to this CTA)
+  for (int k = w; k < nhub; k += 8) {                // one warp per hub: chunks in order, then the row epilogue
+    const int r = s_hub[k];
+    const int nch = s_hub_first[k + 1] - s_hub_first[k];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* __restrict__ pp = hub.partial + (size_t)s_hub_gbase[k] * 32 + lane;
+    for (int j = 0; j < nch; ++j) {
+      const float4 p = pp[(size_t)j * 32];
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    const int64_t row = row0 + r;
+    if (ROWVAL) {
+      const float rv = __ldg(row_vals + row);
+      acc.x *= rv; acc.y *= rv; acc.z *= rv; acc.w *= rv;
+    }
+    float4 one[1] = {acc};
     epilogue<1>(ep, row, lane * 4, one, Y, 128);
   }
 }
@@ -1089,17 +1206,26 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
       }();
       const bool rv = use_rowval && A.row_vals != nullptr;
       const float4* X4 = reinterpret_cast<const float4*>(X);
+      static const int hubs_inline = [] {
+        const char* e = getenv("GODE_SPMM_HUBS_INLINE");   // 1: a tile's CTA also gathers its hub rows; 0 (default): separate kernels.
+        return e ? atoi(e) : 0;                            // Measured: 8.55 / 8.50 / 11.53 ms inline vs 7.08 / 7.98 / 9.97 separate (bare, A^T, fused)
+      }();
+      static const int t3 = [] {
+        const char* e = getenv("GODE_SPMM_T3");      // 1: aligned staging + LDS.128 index reads (k_spmm_t3).  Default off: measured
+        return e ? atoi(e) : 0;                      // 6.68 / 7.93 / 9.59 ms against k_spmm_t2's 6.47 / 7.59 / 9.04 (bare A, A^T, fused epilogue)
+      }();
+      HubArgs hub;
+      hub.rows = (hubs_inline && A.n_heavy > 0 && !(t2_rows == 32 && t3)) ? A.heavy_rows : nullptr;
+      hub.chunk_ptr = A.heavy_chunk_ptr;
+      hub.n_heavy = A.n_heavy;
+      hub.partial = reinterpret_cast<float4*>(ws);
       if (A.n_rows > 0) {
 #define GODE_T2_LAUNCH(R, MB)                                                                                           \
   do {                                                                                                                  \
     unsigned grid = static_cast<unsigned>((A.n_rows + R - 1) / R);                                                      \
-    if (rv) k_spmm_t2<R, MB, true><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, A.row_vals, X4, Y, ep, prefetch_t2); \
-    else k_spmm_t2<R, MB, false><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, nullptr, X4, Y, ep, prefetch_t2);    \
+    if (rv) k_spmm_t2<R, MB, true><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, A.row_vals, X4, Y, ep, prefetch_t2, hub); \
+    else k_spmm_t2<R, MB, false><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, nullptr, X4, Y, ep, prefetch_t2, hub);    \
   } while (0)
-        static const int t3 = [] {
-          const char* e = getenv("GODE_SPMM_T3");      // 1: aligned staging + LDS.128 index reads (k_spmm_t3).  Default off: measured
-          return e ? atoi(e) : 0;                      // 6.68 / 7.93 / 9.59 ms against k_spmm_t2's 6.47 / 7.59 / 9.04 (bare A, A^T, fused epilogue)
-        }();
         if (t2_rows == 32 && t3) {
           unsigned grid = static_cast<unsigned>((A.n_rows + 31) / 32);
 #define GODE_T3_LAUNCH(MB)                                                                                              \
@@ -1123,7 +1249,7 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
 #undef GODE_T2_LAUNCH
         GODE_LAUNCH_CHECK();
       }
-      if (A.n_heavy > 0) {
+      if (A.n_heavy > 0 && !hub.rows) {
         unsigned g1 = static_cast<unsigned>((A.n_chunks + 7) / 8);
         k_spmm_heavy2<6><<<g1, 256, 0, st>>>(A.n_heavy, A.n_chunks, A.heavy_rows, A.heavy_chunk_ptr, A.rowptr, A.colidx, A.vals,
                                              X4, reinterpret_cast<float4*>(ws));
