@@ -99,6 +99,8 @@ _PROTOS = {
     "gode_gcn_transform_rows": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, i64, i64, vp, sz, vp]),
     "gode_gcn_stage_fwd": (C.c_int, [C.POINTER(GcnOdeFunc), vp, vp, vp, C.POINTER(vp), C.POINTER(f32), i32, f32, vp,
                                      f32, vp, vp, sz, vp]),
+    "gode_gcn_stage_fwd_rows": (C.c_int, [C.POINTER(GcnOdeFunc), vp, vp, vp, C.POINTER(vp), C.POINTER(f32), i32, f32, vp,
+                                          i64, i64, vp, sz, vp]),
     "gode_gcn_stage_vjp": (C.c_int, [C.POINTER(GcnOdeFunc), vp, f32, vp, vp, f32, vp, vp, vp, vp, sz, vp]),
     "gode_gcn_vjp_phase1": (C.c_int, [C.POINTER(GcnOdeFunc), vp, vp, f32, vp, vp, vp, C.POINTER(vp), C.POINTER(f32), i32,
                                       f32, vp, vp, sz, vp]),

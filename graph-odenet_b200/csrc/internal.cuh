@@ -5,7 +5,8 @@
 namespace gode {
 size_t spmm_ws_bytes(const gode_csr_t& A, int d);
 int spmm_dispatch(const gode_csr_t& A, const float* X, int64_t ldx, int32_t d, float* Y, int64_t ldy,
-                  const gode_spmm_epilogue_t& ep, void* ws, size_t ws_bytes, cudaStream_t st);
+                  const gode_spmm_epilogue_t& ep, void* ws, size_t ws_bytes, cudaStream_t st, int64_t row_begin = 0,
+                  int64_t row_end = -1 /*rows [row_begin, row_end) only: d = 128 path; -1 = all rows*/);
 int gemm_simt(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B,
               int64_t ldb, float beta, float* C, int64_t ldc, int splits, void* ws, size_t ws_bytes, cudaStream_t st,
               const float* rowvec, float rowvec_scale, int relu = 0);

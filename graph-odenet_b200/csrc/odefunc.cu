@@ -210,6 +210,42 @@ extern "C" int gode_gcn_stage_fwd(const gode_gcn_odefunc_t* f, const float* S, f
   return rc;
 }
 
+// The same stage for the rows [row0, row0 + n_rows) of the block only (k_out / y_next rows outside the range are not
+// touched): the row-partitioned solver gathers a stage in row chunks so that chunk c's rows of y_next can be transformed and
+// pushed to the peers while chunk c+1 is still being gathered (parallel.py, GODE_PIPE_G).
+extern "C" int gode_gcn_stage_fwd_rows(const gode_gcn_odefunc_t* f, const float* S, float* k_out, const float* y0,
+                                       const float* const* kprev_host, const float* coef_host, int32_t n_prev, float coef_self,
+                                       float* y_next, int64_t row0, int64_t n_rows, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check(f);
+  if (rc) return rc;
+  GODE_REQUIRE(n_prev >= 0 && n_prev <= GODE_MAX_STAGES, "gcn_stage_fwd_rows: n_prev out of range");
+  GODE_REQUIRE(!y_next || y0, "gcn_stage_fwd_rows: y_next needs y0");
+  GODE_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= f->A.n_rows, "gcn_stage_fwd_rows: row range outside the block");
+  if (n_rows == 0) return GODE_OK;
+  cudaStream_t st = as_stream(stream);
+  GcnWs w;
+  rc = carve(f, ws, ws_bytes, w);
+  if (rc) return rc;
+  gode_spmm_epilogue_t ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.bias = f->b;
+  ep.relu = 1;
+  if (y_next) {
+    ep.y0 = y0;
+    ep.n_prev = n_prev;
+    for (int j = 0; j < n_prev; ++j) {
+      ep.kprev[j] = kprev_host[j];
+      ep.coef[j] = coef_host[j];
+    }
+    ep.coef_self = coef_self;
+    ep.ynext = y_next;
+  }
+  ep.acc_in = f->partial_in;
+  ProfScope prof(GODE_PROF_AGG_FWD, st);
+  return spmm_dispatch(f->A, S + f->gather_row_offset * f->d, f->d, f->d, k_out, f->d, ep, w.heavy, w.heavy_bytes, st, row0,
+                       row0 + n_rows);
+}
+
 extern "C" int gode_gcn_vjp_phase1(const gode_gcn_odefunc_t* f, const float* S, const float* a, float sign, float* k_y,
                                    float* gP, const float* y0, const float* const* kprev_host, const float* coef_host,
                                    int32_t n_prev, float coef_self, float* y_next, void* ws, size_t ws_bytes,

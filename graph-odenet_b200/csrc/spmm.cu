@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(256, MINB) k_spmm_t2(int64_t n_rows, const int
                                                        const int32_t* __restrict__ colidx, const float* __restrict__ vals,
                                                        const float* __restrict__ row_vals, const float4* __restrict__ X4,
                                                        float* __restrict__ Y, const gode_spmm_epilogue_t ep, const int prefetch,
-                                                       const HubArgs hub) {
+                                                       const HubArgs hub, const int64_t row_begin /*rows [row_begin, n_rows)*/) {
   constexpr int TS_CAP = TS_ROWS * 32;
   static_assert(TS_CAP >= 8 * 128, "the hub phase stages 128 entries per warp in the tile's index buffer");
   __shared__ int s_ptr[TS_ROWS + 1];
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(256, MINB) k_spmm_t2(int64_t n_rows, const int
   __shared__ int s_nhub, s_next2, s_hub[TS_ROWS], s_hub_first[TS_ROWS + 1], s_hub_gbase[TS_ROWS];
   if (threadIdx.x == 0) { s_nhub = 0; s_next2 = 0; }
   const int tid = threadIdx.x, lane = tid & 31;
-  const int64_t row0 = blockIdx.x * (int64_t)TS_ROWS;
+  const int64_t row0 = row_begin + blockIdx.x * (int64_t)TS_ROWS;
   const int nr = static_cast<int>(min((int64_t)TS_ROWS, n_rows - row0));
   if (tid <= nr) s_ptr[tid] = __ldg(rowptr + row0 + tid);
   if (tid == 0) s_next = 0;
@@ -797,7 +797,8 @@ template <int MINB>
 __global__ void __launch_bounds__(256, MINB) k_spmm_heavy2(int n_heavy, int n_chunks, const int32_t* __restrict__ heavy_rows,
                                                            const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ rowptr,
                                                            const int32_t* __restrict__ colidx, const float* __restrict__ vals,
-                                                           const float4* __restrict__ X4, float4* __restrict__ partial) {
+                                                           const float4* __restrict__ X4, float4* __restrict__ partial,
+                                                           const int64_t row_begin, const int64_t row_end /*only hubs in this row range*/) {
   static_assert(GODE_HEAVY_CHUNK == 256, "eight entries per lane");
   __shared__ __align__(16) int s_idx[8][GODE_HEAVY_CHUNK];
   __shared__ __align__(16) float s_val[8][GODE_HEAVY_CHUNK];
@@ -816,6 +817,7 @@ __global__ void __launch_bounds__(256, MINB) k_spmm_heavy2(int n_heavy, int n_ch
     hi = min(lo + step, hi);
   }
   const int row = __ldg(heavy_rows + lo);
+  if (row < row_begin || row >= row_end) return;    // (whole warp) a row-range call: the other ranges' hubs belong to other calls
   const int r0 = __ldg(rowptr + row), r1 = __ldg(rowptr + row + 1);
   const int e0 = r0 + (chunk - __ldg(chunk_ptr + lo)) * GODE_HEAVY_CHUNK;
   const int cnt = min(r1 - e0, GODE_HEAVY_CHUNK);
@@ -1067,13 +1069,15 @@ template <int LPR, int VPL>
 __global__ void __launch_bounds__(256) k_spmm_heavy_finish(int n_heavy, const int32_t* __restrict__ heavy_rows,
                                                            const int32_t* __restrict__ chunk_ptr,
                                                            const float* __restrict__ partial, float* __restrict__ Y,
-                                                           int64_t ldy, const gode_spmm_epilogue_t ep) {
+                                                           int64_t ldy, const gode_spmm_epilogue_t ep,
+                                                           const int64_t row_begin = 0, const int64_t row_end = INT64_MAX) {
   constexpr int RPW = 32 / LPR;
   constexpr int D = LPR * VPL * 4;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, sl = lane % LPR;
   const int h = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
   if (h >= n_heavy) return;
+  if (heavy_rows[h] < row_begin || heavy_rows[h] >= row_end) return;
   const int c0 = chunk_ptr[h], c1 = chunk_ptr[h + 1];
   const int col0 = sl * VPL * 4;
   float4 acc[VPL];
@@ -1132,7 +1136,9 @@ __global__ void __launch_bounds__(256) k_spmm_generic(int64_t n_rows, const int3
 
 template <int LPR, int VPL>
 static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y, int64_t ldy,
-                      const gode_spmm_epilogue_t& ep, float* ws, cudaStream_t st) {
+                      const gode_spmm_epilogue_t& ep, float* ws, cudaStream_t st, int64_t row_begin = 0, int64_t row_end = -1) {
+  if (row_end < 0) row_end = A.n_rows;
+  const bool sub = row_begin != 0 || row_end != A.n_rows;
   constexpr int RPW = 32 / LPR;
   constexpr int RPB = 8 * RPW;
   static const int variant = [] {
@@ -1194,7 +1200,7 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
       return GODE_OK;
     }
   }
-  if (variant == 8 && LPR == 32 && VPL == 1 && ldx == 128 && (ldy == 128 || !Y)) {
+  if ((variant == 8 || sub) && LPR == 32 && VPL == 1 && ldx == 128 && (ldy == 128 || !Y)) {
     if constexpr (LPR == 32 && VPL == 1) {
       static const int prefetch_t2 = [] {
         const char* e = getenv("GODE_SPMM_PREFETCH");   // default off here: the L2 prefetch of the epilogue operands costs LSU
@@ -1219,14 +1225,14 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
       hub.chunk_ptr = A.heavy_chunk_ptr;
       hub.n_heavy = A.n_heavy;
       hub.partial = reinterpret_cast<float4*>(ws);
-      if (A.n_rows > 0) {
+      if (row_end > row_begin) {
 #define GODE_T2_LAUNCH(R, MB)                                                                                           \
   do {                                                                                                                  \
-    unsigned grid = static_cast<unsigned>((A.n_rows + R - 1) / R);                                                      \
-    if (rv) k_spmm_t2<R, MB, true><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, A.row_vals, X4, Y, ep, prefetch_t2, hub); \
-    else k_spmm_t2<R, MB, false><<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, nullptr, X4, Y, ep, prefetch_t2, hub);    \
+    unsigned grid = static_cast<unsigned>((row_end - row_begin + R - 1) / R);                                           \
+    if (rv) k_spmm_t2<R, MB, true><<<grid, 256, 0, st>>>(row_end, A.rowptr, A.colidx, A.vals, A.row_vals, X4, Y, ep, prefetch_t2, hub, row_begin); \
+    else k_spmm_t2<R, MB, false><<<grid, 256, 0, st>>>(row_end, A.rowptr, A.colidx, A.vals, nullptr, X4, Y, ep, prefetch_t2, hub, row_begin);    \
   } while (0)
-        if (t2_rows == 32 && t3) {
+        if (t2_rows == 32 && t3 && !sub) {
           unsigned grid = static_cast<unsigned>((A.n_rows + 31) / 32);
 #define GODE_T3_LAUNCH(MB)                                                                                              \
   do {                                                                                                                  \
@@ -1252,14 +1258,18 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
       if (A.n_heavy > 0 && !hub.rows) {
         unsigned g1 = static_cast<unsigned>((A.n_chunks + 7) / 8);
         k_spmm_heavy2<6><<<g1, 256, 0, st>>>(A.n_heavy, A.n_chunks, A.heavy_rows, A.heavy_chunk_ptr, A.rowptr, A.colidx, A.vals,
-                                             X4, reinterpret_cast<float4*>(ws));
+                                             X4, reinterpret_cast<float4*>(ws), row_begin, row_end);
         GODE_LAUNCH_CHECK();
         unsigned g2 = static_cast<unsigned>((A.n_heavy + RPB - 1) / RPB);
-        k_spmm_heavy_finish<LPR, VPL><<<g2, 256, 0, st>>>(A.n_heavy, A.heavy_rows, A.heavy_chunk_ptr, ws, Y, ldy, ep);
+        k_spmm_heavy_finish<LPR, VPL><<<g2, 256, 0, st>>>(A.n_heavy, A.heavy_rows, A.heavy_chunk_ptr, ws, Y, ldy, ep, row_begin, row_end);
         GODE_LAUNCH_CHECK();
       }
       return GODE_OK;
     }
+  }
+  if (sub) {
+    set_error("spmm: a row-range call needs d = 128 with contiguous rows (the k_spmm_t2 path)");
+    return GODE_EINVAL;
   }
   if (variant == 7 && LPR == 32 && VPL == 1) {
     if constexpr (LPR == 32 && VPL == 1) {
@@ -1614,7 +1624,7 @@ size_t spmm_ws_bytes(const gode_csr_t& A, int d) {
 }
 
 int spmm_dispatch(const gode_csr_t& A, const float* X, int64_t ldx, int32_t d, float* Y, int64_t ldy,
-                  const gode_spmm_epilogue_t& ep, void* ws, size_t ws_bytes, cudaStream_t st) {
+                  const gode_spmm_epilogue_t& ep, void* ws, size_t ws_bytes, cudaStream_t st, int64_t row_begin, int64_t row_end) {
   bool vec_ok = vec_width(d) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y) && aligned16(ep.bias) &&
                 aligned16(ep.residual) && aligned16(ep.y0) && aligned16(ep.ynext) && aligned16(ep.mask_src) &&
                 aligned16(ep.gp_out) && aligned16(ep.acc_in) && aligned16(ws);
@@ -1623,25 +1633,31 @@ int spmm_dispatch(const gode_csr_t& A, const float* X, int64_t ldx, int32_t d, f
     set_error("spmm: heavy-row workspace missing or too small (%zu < %zu)", ws_bytes, spmm_ws_bytes(A, d));
     return GODE_EWORKSPACE;
   }
+  const bool sub = row_begin != 0 || (row_end >= 0 && row_end != A.n_rows);
+  if (sub && !(vec_ok && d == 128 && ldx == 128)) {
+    set_error("spmm: a row-range call needs d = 128 with contiguous, 16-byte aligned rows (the k_spmm_t2 path)");
+    return GODE_EINVAL;
+  }
   if (vec_ok) {
     float* w = static_cast<float*>(ws);
     static const int use_bulk = [] {
       const char* e = getenv("GODE_SPMM_BULK");
       return e ? atoi(e) : 0;   // 0: register-staged (default), 1: LDGSTS pipeline, 2: TMA bulk-copy pipeline
     }();
-    if (use_bulk == 1 && d == 128) return launch_bulk<1, 1>(A, X, ldx, Y, ldy, ep, w, st);
-    if (use_bulk == 2 && d == 128) return launch_bulk<1, 0>(A, X, ldx, Y, ldy, ep, w, st);
+    if (use_bulk == 1 && d == 128 && !sub) return launch_bulk<1, 1>(A, X, ldx, Y, ldy, ep, w, st);
+    if (use_bulk == 2 && d == 128 && !sub) return launch_bulk<1, 0>(A, X, ldx, Y, ldy, ep, w, st);
     switch (d) {
       case 8: return launch_vec<2, 1>(A, X, ldx, Y, ldy, ep, w, st);
       case 16: return launch_vec<4, 1>(A, X, ldx, Y, ldy, ep, w, st);
       case 32: return launch_vec<8, 1>(A, X, ldx, Y, ldy, ep, w, st);
       case 64: return launch_vec<16, 1>(A, X, ldx, Y, ldy, ep, w, st);
-      case 128: return launch_vec<32, 1>(A, X, ldx, Y, ldy, ep, w, st);
+      case 128: return launch_vec<32, 1>(A, X, ldx, Y, ldy, ep, w, st, row_begin, row_end);
       case 256: return launch_vec<32, 2>(A, X, ldx, Y, ldy, ep, w, st);
       default: break;
     }
   }
   GODE_REQUIRE(!ep.push.ptr, "spmm: a fused halo push needs a vectorised width (8..256, 16-byte aligned operands)");
+  GODE_REQUIRE(row_begin == 0 && (row_end < 0 || row_end == A.n_rows), "spmm: a row-range call needs the vectorised d = 128 path");
   if (A.n_rows > 0) {
     unsigned grid = static_cast<unsigned>((A.n_rows + 7) / 8);
     k_spmm_generic<<<grid, 256, 0, st>>>(A.n_rows, A.rowptr, A.colidx, A.vals, X, ldx, d, Y, ldy, ep);

@@ -24,7 +24,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from ._lib import lib, check
+from ._lib import lib, check, MAX_STAGES
 
 
 def init_process_group(device, backend="nccl"):
@@ -42,6 +42,15 @@ def init_process_group(device, backend="nccl"):
 
 
 MODES = ("sync", "async", "split", "p2p", "p2p-async", "p2p-fused")
+
+
+def pipe_g_chunks(world):
+    """Row chunks of the pipelined forward stage (GODE_PIPE_G; default 0 = off).  Measured at 2 GPUs (N = 10 M,
+    profiles/r02_multi_gpu.md): 113.0 ms per step without, 112.9 with 2 chunks, 114.1 with 4 -- the exposed exchange time
+    drops by 4 ms and the gathers the pushes now run next to slow down by as much, the same trade GODE_PIPE_S showed in
+    round 1.  Parity-tested (tests/test_gpu_parallel.py, modes p2p-fused:g2 / :g3), opt-in."""
+    import os
+    return int(os.environ.get("GODE_PIPE_G", "0"))
 
 
 def partition_bounds(n, world):
@@ -167,6 +176,13 @@ class HaloKernelMixin:
         # with 4 chunks vs 119.9 ms without -- what the overlap hides (outside 16.8 -> 8.3 ms) the concurrent push takes back
         # from the kernels it runs next to (transform 9.3 -> 14.5, A^T gather 18.8 -> 20.5 ms) -- so it stays opt-in.
         self.pipe_S = int(os.environ.get("GODE_PIPE_S", "0")) if (self.fused and not self.fused_S and self.peer.side) else 0
+        # GODE_PIPE_G = number of row chunks (default 0 = off, see pipe_g_chunks): a forward stage is GATHERED in row chunks -- chunk c's rows of y_next are transformed and pushed on the side
+        # stream while chunk c+1 is still being gathered on the main stream (posted NVLink stores next to a kernel with 64
+        # resident warps per SM, as the fused gP push), so only the last chunk's push stays exposed.  Needs the tile gather
+        # (d = 128) and the side stream.
+        self.pipe_G = (pipe_g_chunks(plan.world)
+                       if (self.fused and not self.fused_S and not self.pipe_S and self.peer.side and self.d == 128
+                           and plan.split is None) else 0)
         if plan.split is not None:
             from . import _lib
             # descriptor for the second (halo-column) pass: same parameters, halo blocks, operand offset
@@ -302,8 +318,35 @@ class HaloKernelMixin:
         self._exchange(self.plan.halo, out)
         return out
 
+    def _stage_pipelined(self, S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next):
+        """One forward stage in ``pipe_G`` row chunks: gather chunk c (+ its Runge-Kutta combination) and transform its rows
+        on the main stream; push chunk c's boundary rows of S_next on the side stream underneath chunk c+1's gather."""
+        from . import odeint as _od
+        self.nfe += 1
+        bounds = self.peer.part_bounds(self.pipe_G)
+        ws = self._ws()
+        if _od.MASK_LOG is not None and k_out is None:
+            k_out = self.new()
+        karr = (C.c_void_p * MAX_STAGES)(*[k.data_ptr() for k in kprev])
+        carr = (C.c_float * MAX_STAGES)(*[float(c) for c in coefs])
+
+        def produce(c):
+            r0, nr = bounds[c], bounds[c + 1] - bounds[c]
+            check(lib.gode_gcn_stage_fwd_rows(C.byref(self.f), ops._p(S), ops._p(k_out), ops._p(y0), karr, carr, len(kprev),
+                                              float(coef_self), ops._p(y_next), r0, nr, ops._p(ws), self.ws_bytes,
+                                              ops._stream()), "gode_gcn_stage_fwd_rows")
+            check(lib.gode_gcn_transform_rows(C.byref(self.f), ops._p(y_next), float(t_next), ops._p(S_next), r0, nr,
+                                              ops._p(ws), self.ws_bytes, ops._stream()), "gode_gcn_transform_rows")
+
+        self.pending[S_next.data_ptr()] = self.peer.push_pipelined(self.plan.halo, S_next, self.pipe_G, produce)
+        if _od.MASK_LOG is not None:
+            _od.MASK_LOG.append(k_out > 0)
+
     def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0, S_next=None):
         run = lambda: super(HaloKernelMixin, self).stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next)
+        if self.pipe_G and S_next is not None and y_next is not None:
+            self._wait(S)
+            return self._stage_pipelined(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next)
         if self.pipe_S:
             self._wait(S)
             super(HaloKernelMixin, self).stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, None)
@@ -452,7 +495,8 @@ class PartitionedPlan:
             from . import peer
             try:
                 import os
-                side = self.mode == "p2p-async" or (self.mode == "p2p-fused" and os.environ.get("GODE_PIPE_S", "0") != "0")
+                side = self.mode == "p2p-async" or (self.mode == "p2p-fused" and (
+                    os.environ.get("GODE_PIPE_S", "0") != "0" or pipe_g_chunks(self.world) > 0))
                 ph = self._peer[d] = peer.PeerHalo(self, d, push_stream=self.comm_stream if side else None)
             except peer.PeerSetupError as e:
                 # raised on every rank together: all of them switch to the NCCL exchange on the side stream

@@ -304,6 +304,13 @@ int gode_gcn_stage_fwd(const gode_gcn_odefunc_t* f, const float* S, float* k_out
                        float coef_self, float* y_next, float t_next, float* S_next,
                        void* ws, size_t ws_bytes, void* stream);
 
+/* The same stage for the rows [row0, row0 + n_rows) of the block only (d = 128; no fused transform).  Lets a row-partitioned
+ * caller pipeline a stage: chunk c's rows of y_next are transformed (gode_gcn_transform_rows) and pushed to the peers while
+ * chunk c+1 is still being gathered. */
+int gode_gcn_stage_fwd_rows(const gode_gcn_odefunc_t* f, const float* S, float* k_out, const float* y0,
+                            const float* const* kprev, const float* coef, int32_t n_prev, float coef_self, float* y_next,
+                            int64_t row0, int64_t n_rows, void* ws, size_t ws_bytes, void* stream);
+
 /* One evaluation of the augmented (adjoint) dynamics at (t, y, a) with upstream = sign * a:
  *   k_y  = f(t, y)                                   [n_rows, d]
  *   k_a  = sign * a^T df/dy                          [n_rows, d]

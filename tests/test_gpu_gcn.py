@@ -303,7 +303,7 @@ def test_odefunc2_golden(dev):
 
 CASES = ["odeblock16_cora_rk4", "odeblock16_cora_dopri5", "odeblock16_sub_rk4_h0.25", "odeblock16_sub_euler_h0.5",
          "odeblock16_sub_midpoint", "odeblock128_sub_rk4", "odeblock128_sub_dopri5", "odeblock64_sub_rk4",
-         ]
+         "odeblock64_sub_dopri5"]
 # (odeblock64_sub_dopri5 stays a CPU-oracle case only: with two channels per GroupNorm group the adjoint of
 #  near-equal pairs is cancellation noise scaled by rstd <= 316; the reference's own backward solve there rejects
 #  11 of 39 steps on that noise, so neither its step sequence nor its 0.5 % of outlier gradients are reproducible

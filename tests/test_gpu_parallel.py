@@ -42,7 +42,10 @@ def test_partitioned_plan_world1_matches_plain_plan():
                                                 ("rk4", "relu", "p2p-async"), ("rk4", "smooth", "p2p-async"),
                                                 ("dopri5", "smooth", "p2p"), ("dopri5", "relu", "p2p-async"),
                                                 ("rk4", "smooth", "p2p-fused"), ("rk4", "relu", "p2p-fused"),
-                                                ("dopri5", "smooth", "p2p-fused")])
+                                                ("dopri5", "smooth", "p2p-fused"),
+                                                # forward stages gathered in row chunks, S pushed underneath (GODE_PIPE_G)
+                                                ("rk4", "relu", "p2p-fused:g2"), ("rk4", "smooth", "p2p-fused:g3"),
+                                                ("dopri5", "relu", "p2p-fused:g2")])
 def test_two_gpus_match_one(method, regime, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
@@ -50,5 +53,6 @@ def test_two_gpus_match_one(method, regime, mode):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "_parallel_worker.py"), method,
            "20000" if method == "rk4" else "6000", "128", regime]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, GODE_HALO_MODE=mode))
+    env = dict(os.environ, GODE_HALO_MODE=mode.split(":")[0], GODE_PIPE_G=mode.split(":g")[1] if ":g" in mode else "0")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
