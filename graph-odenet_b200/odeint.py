@@ -550,15 +550,18 @@ def _gcn_aug_dopri5(kern, tab, y1, g1, a_t1, t_start, t_end, S, rtol, atol, stat
         small_new = (wb[:, None] * gth).sum(0)
         small_err = (we[:, None] * gth).sum(0)
         th_new, at_new = th + small_new[:P - 1], at + small_new[P - 1:]
-        msr = max(kern.scalar(_msr(kern, y, y_new, ky, cerr, rtol, atol)) / n_el,
-                  kern.scalar(_msr(kern, a, a_new, ka, cerr, rtol, atol)) / n_el,
-                  _small_msr(small_err[P - 1:], at, at_new, rtol, atol),
-                  _small_msr(small_err[:P - 1], th, th_new, rtol, atol))
+        msrs = (kern.scalar(_msr(kern, y, y_new, ky, cerr, rtol, atol)) / n_el,
+                kern.scalar(_msr(kern, a, a_new, ka, cerr, rtol, atol)) / n_el,
+                _small_msr(small_err[P - 1:], at, at_new, rtol, atol),
+                _small_msr(small_err[:P - 1], th, th_new, rtol, atol))
+        msr = max(msrs)
         accept = msr <= 1.0
         dt_next = _optimal_step(dt, msr)
         if stats is not None:
             key = "accepted" if accept else "rejected"
             stats[key] = stats.get(key, 0) + 1
+            if "trace" in stats:     # per-step diagnostics (tests/d64_noise.py): (t, dt, per-tensor error ratios)
+                stats["trace"].append((float(t), float(dt), [float(m) for m in msrs]))
         if accept:
             t_new = F32(t + h)
             if t_new <= t_end:

@@ -238,6 +238,8 @@ def _solve_dopri5(func, y0, t, rtol, atol, stats, max_steps=2 ** 31 - 1):
             if stats is not None:
                 key = "accepted" if accept else "rejected"
                 stats[key] = stats.get(key, 0) + 1
+                if "trace" in stats:     # per-step diagnostics (tests/d64_noise.py): (t, dt, per-tensor error ratios)
+                    stats["trace"].append((float(t0_), float(dt_), [float(m) for m in msr]))
             dt_next = _optimal_step(dt_, msr)
             if accept:
                 state = [y1, f1, t0_, t0_ + dt_, dt_next, _interp_fit(y_, y1, k, dt_)]

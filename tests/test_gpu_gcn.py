@@ -304,10 +304,13 @@ def test_odefunc2_golden(dev):
 CASES = ["odeblock16_cora_rk4", "odeblock16_cora_dopri5", "odeblock16_sub_rk4_h0.25", "odeblock16_sub_euler_h0.5",
          "odeblock16_sub_midpoint", "odeblock128_sub_rk4", "odeblock128_sub_dopri5", "odeblock64_sub_rk4",
          "odeblock64_sub_dopri5"]
-# (odeblock64_sub_dopri5 stays a CPU-oracle case only: with two channels per GroupNorm group the adjoint of
-#  near-equal pairs is cancellation noise scaled by rstd <= 316; the reference's own backward solve there rejects
-#  11 of 39 steps on that noise, so neither its step sequence nor its 0.5 % of outlier gradients are reproducible
-#  across fp32 implementations.  d=64 is covered by the fixed-step case above.)
+# Cases whose BACKWARD step sequence depends on rounding in the reference itself: (accepted, rejected) of the reference
+# arithmetic in float64 and in float32 (the fixture), printed by tests/d64_noise.py from the pinned oracle.  With two
+# channels per GroupNorm group the adjoint has sharp features (pairs of nearly equal channels, rstd up to 316) and several
+# trial steps land within rounding of the acceptance threshold; libgode's own sequence (27 / 7 on a B200, single-evaluation
+# error vs float64 at or below the float32 oracle's for every tensor -- profiles/r02_d64_noise.log) must lie between the
+# reference's two, +-1.
+ROUNDING_DEPENDENT = {"odeblock64_sub_dopri5": {"f64": (26, 8), "f32": (28, 11)}}
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -334,9 +337,17 @@ def test_ode_block_golden(case, dev):
     assert nfe_f == int(g[k + "nfe_f"]), (nfe_f, int(g[k + "nfe_f"]))
     assert blk.stats["forward"].get("accepted", 0) == int(g[k + "acc_f"])
     assert blk.stats["forward"].get("rejected", 0) == int(g[k + "rej_f"])
-    assert blk.nfe == int(g[k + "nfe_b"]), (blk.nfe, int(g[k + "nfe_b"]))
-    assert blk.stats["backward"].get("accepted", 0) == int(g[k + "acc_b"])
-    assert blk.stats["backward"].get("rejected", 0) == int(g[k + "rej_b"])
+    acc_b, rej_b = blk.stats["backward"].get("accepted", 0), blk.stats["backward"].get("rejected", 0)
+    if case in ROUNDING_DEPENDENT:
+        r = ROUNDING_DEPENDENT[case]
+        assert r["f32"] == (int(g[k + "acc_b"]), int(g[k + "rej_b"]))
+        for got_, a_, b_ in ((acc_b, r["f64"][0], r["f32"][0]), (rej_b, r["f64"][1], r["f32"][1])):
+            assert min(a_, b_) - 1 <= got_ <= max(a_, b_) + 1, ((acc_b, rej_b), r)
+        assert blk.nfe == 6 * (acc_b + rej_b) + 3       # FSAL: six evaluations per trial step + f(t1) + the two h0 probes
+    else:
+        assert blk.nfe == int(g[k + "nfe_b"]), (blk.nfe, int(g[k + "nfe_b"]))
+        assert acc_b == int(g[k + "acc_b"])
+        assert rej_b == int(g[k + "rej_b"])
     # Fixed-step solvers: 1e-5, step for step.  dopri5: the step-size controller turns rounding-level differences of the error
     # norm into slightly different step sizes, so two fp32 implementations agree to the solver's tolerance (rtol = atol =
     # 1e-5 per step, ~1e-4 accumulated), not to fp32 rounding; north_star compares adaptive solvers on the accepted-step
@@ -344,6 +355,26 @@ def test_ode_block_golden(case, dev):
     adaptive = method == "dopri5"
     tol = TOL if not adaptive else dict(rtol=1e-4, atol_scale=1e-4)
     G.assert_close(y, g[k + "out"], **tol, what="y(1)")
+    if case in ROUNDING_DEPENDENT:
+        # Gradients of this case are not reproducible by the reference itself: its float32 (fixture) and float64 runs differ
+        # by 0.41 of grad_x's max, 12 % of the entries by more than 1e-4, parameter gradients by 0.16 .. 0.35.  The bar is the
+        # models' rule (tests/test_gpu_models_golden.py): 1e-4 of scale plus four times that distance, measured here by
+        # running the pinned oracle in float64, and no more entries outside 1e-4 than twice the reference's own count.
+        from oracle import gcn_ref
+        p64 = {kk: v.double().clone().requires_grad_(True) for kk, v in G.params(g, k + "p/").items()}
+        x64 = G.rnd(40 + d, n, d, scale=0.5).double().requires_grad_(True)
+        y64, _ = gcn_ref.ode_block(x64, adj.double(), p64, prefix="odefunc.", method=method)
+        y64.backward(G.rnd(50 + d, n, d, scale=1.0 / n).double())
+        pairs = [("grad_x", x.grad, g[k + "grad_x"], x64.grad)] + [
+            (name, p.grad, g[k + "grad/" + name], p64[name].grad) for name, p in blk.named_parameters()]
+        for name, got, want32, want64 in pairs:
+            want32 = torch.from_numpy(np.asarray(want32)).double()
+            scale = float(want32.abs().max())
+            own = (want32 - want64).abs()
+            err = (got.detach().cpu().double() - want32).abs()
+            assert float(err.max()) <= 1e-4 * scale + 4 * float(own.max()), (name, float(err.max()), float(own.max()), scale)
+            assert int((err > 1e-4 * scale).sum()) <= 2 * int((own > 1e-4 * scale).sum()) + 0.01 * err.numel(), name
+        return
     gtol = TOL if d != 16 else dict(rtol=1e-3, atol_scale=2e-3)
     if d == 64:      # two channels per group: pairs of nearly equal channels have rstd up to 316, and the few rows that
         gtol = dict(TOL, outliers=(5e-3, 1e-2))   # hold one are amplified rounding noise (measured 80 of 32768 elements, 3e-3 of scale)
