@@ -26,6 +26,10 @@ class ODEfunc(nn.Module):
 
     def forward(self, t, x):
         self.nfe += 1
+        from .. import ops
+        from . import layers
+        if isinstance(self.norm1, nn.GroupNorm) and ops.gat_ode_fusable(x, self.norm1.num_groups, self.gc1.heads, self.gc1.out_features):
+            return ops.gat_ode_func(x, t, self.norm1, self.gc1, check_nan=layers.CHECK_NAN)   # one node, no [t || xn] operand
         xn = self.norm1(x)
         tt = torch.ones_like(xn[:, :1]) * t
         return self.gc1(torch.cat([tt, xn], 1))

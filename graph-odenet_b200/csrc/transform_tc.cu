@@ -699,7 +699,8 @@ template <int D, int CPG>
 __global__ void __launch_bounds__(tc::WG_THREADS, 1)
 k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restrict__ G, float* __restrict__ partial /*[grid][D][D]*/,
            float* __restrict__ cs_partial /*[grid][D]: column sums of G over this CTA's rows*/, float eps, int passes,
-           const int pf_chunks /*L2 prefetch distance in chunks of this CTA (0: off)*/, const int rnd_lo /*round the lo residuals*/) {
+           const int pf_chunks /*L2 prefetch distance in chunks of this CTA (0: off)*/, const int rnd_lo /*round the lo residuals*/,
+           const int64_t ldg /*row stride of G in floats*/, const int gcols /*valid columns of G (multiple of 4, <= D); the rest read 0*/) {
   using namespace tc;
   static_assert(D == 128, "the accumulator uses all 128 TMEM lanes");
   // Both operands are [rows, D] row-major in HBM but the reduction runs over rows, so they are transposed on the
@@ -831,12 +832,12 @@ k_wgrad_tc(int64_t n_rows, const float* __restrict__ Yin, const float* __restric
       rb[i] = ra[i];
       if (row < n_rows) {
         ra[i] = __ldcs(reinterpret_cast<const float4*>(Yin + row * D + kc * 4));
-        rb[i] = __ldcs(reinterpret_cast<const float4*>(G + row * D + kc * 4));
+        if (kc * 4 < gcols) rb[i] = __ldcs(reinterpret_cast<const float4*>(G + row * ldg + kc * 4));
       }
       const int64_t prow = row + pf_chunks * (int64_t)gridDim.x * RC;
       if (pf_chunks > 0 && prow < n_rows) {
         prefetch_l2(Yin + prow * D + kc * 4);
-        prefetch_l2(G + prow * D + kc * 4);
+        if (kc * 4 < gcols) prefetch_l2(G + prow * ldg + kc * 4);
       }
     }
   };
@@ -967,12 +968,65 @@ int wgrad_tc(const gode_gcn_odefunc_t* f, const float* y, const float* gS, float
   // and its error against fp64 over 2 M rows is the same either way (1.232e-6 vs 1.234e-6) for 0.45 ms per launch.
   const char* rnd_env = getenv("GODE_WGRAD_RND");
   k_wgrad_tc<D, 4><<<grid, tc::WG_THREADS, smem, st>>>(f->A.n_rows, y, gS, ws, cs_partial, f->gn_eps, passes, pf,
-                                                       rnd_env ? atoi(rnd_env) : 0);
+                                                       rnd_env ? atoi(rnd_env) : 0, D, D);
   GODE_LAUNCH_CHECK();
   k_wgrad_cs<<<1, D, 0, st>>>(grid, D, cs_partial, cs);
   GODE_LAUNCH_CHECK();
   k_wgrad_finish<<<(D * D + 255) / 256, 256, 0, st>>>(grid, D, ws, f->gamma, f->beta, cs, gW1);
   GODE_LAUNCH_CHECK();
+  return GODE_OK;
+}
+
+// out[i][c0 + o] = sum_b partial[b][i][o],  cs[c0 + o] = sum_b cs_partial[b][o]      (o < gcols; fixed order)
+__global__ void k_wgrad_finish_raw(int nblk, int d, int gcols, const float* __restrict__ partial, const float* __restrict__ cs_partial,
+                                   float* __restrict__ out, int64_t ldo, float* __restrict__ cs) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (d + 1) * gcols) return;
+  const int i = idx / gcols, o = idx % gcols;
+  float s = 0.f;
+  if (i < d) {
+    for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * d * d + (size_t)i * d + o];
+    out[(size_t)i * ldo + o] = s;
+  } else {
+    for (int b = 0; b < nblk; ++b) s += cs_partial[(size_t)b * d + o];
+    cs[o] = s;
+  }
+}
+
+size_t gn_wgrad_ws_bytes(int d) { return sizeof(float) * (size_t)sm_count() * (d + 1) * d; }
+
+// out[d, ncols] = xhat(y)^T * G,  cs[ncols] = column sums of G,  xhat = GroupNorm(y) before its affine (4 channels per
+// group): the ODE-function weight gradient of a layer whose input is [t | GroupNorm(y)] and whose output is wider than d
+// (the GAT projection, 2 * heads * oh + 2 * heads columns) -- k_wgrad_tc over 128-column blocks of G.
+int gn_wgrad_tc(int64_t n, int d, int groups, float eps, const float* y, const float* G, int64_t ldg, int ncols, float* out,
+                int64_t ldo, float* cs, float* ws, size_t ws_bytes, int precision, cudaStream_t st) {
+  constexpr int D = 128;
+  GODE_REQUIRE(d == D && groups == 32, "gn_wgrad: the tensor-core kernel covers d = 128 with 32 groups");
+  GODE_REQUIRE(ncols > 0 && ncols % 4 == 0 && ldg % 4 == 0 && ldg >= ncols && ldo >= ncols, "gn_wgrad: ncols and ldg must be multiples of 4");
+  GODE_REQUIRE(al16(y) && al16(G) && al16(ws), "gn_wgrad: operands must be 16-byte aligned");
+  if (n == 0) {
+    GODE_CHECK_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * ncols, d, st));
+    GODE_CHECK_CUDA(cudaMemsetAsync(cs, 0, sizeof(float) * ncols, st));
+    return GODE_OK;
+  }
+  const int64_t n_chunks = (n + 31) / 32;
+  int grid = static_cast<int>(n_chunks < persistent_ctas() ? n_chunks : persistent_ctas());
+  if (grid < 1) grid = 1;
+  if (ws_bytes < sizeof(float) * (size_t)grid * (D + 1) * D) {
+    set_error("gn_wgrad: workspace too small");
+    return GODE_EWORKSPACE;
+  }
+  float* cs_partial = ws + (size_t)grid * D * D;
+  constexpr size_t smem = 2 * 4 * (size_t)(D / 8) * 1168 + 128 + (size_t)D * D * 4;
+  GODE_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad_tc<D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int passes = precision == GODE_PREC_TF32 ? 1 : 3;
+  for (int c0 = 0; c0 < ncols; c0 += D) {
+    const int gcols = ncols - c0 < D ? ncols - c0 : D;
+    k_wgrad_tc<D, 4><<<grid, tc::WG_THREADS, smem, st>>>(n, y, G + c0, ws, cs_partial, eps, passes, 8, 0, ldg, gcols);
+    GODE_LAUNCH_CHECK();
+    k_wgrad_finish_raw<<<((D + 1) * gcols + 255) / 256, 256, 0, st>>>(grid, D, gcols, ws, cs_partial, out + c0, ldo, cs + c0);
+    GODE_LAUNCH_CHECK();
+  }
   return GODE_OK;
 }
 
@@ -1356,4 +1410,15 @@ extern "C" int gode_gemm_tc_f32(int64_t M, int64_t N, int64_t K, const float* A,
 extern "C" int gode_gemm_tc_splitk_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bt, int64_t ldb,
                                        float* C_partials, int64_t ldc, int32_t k_splits, int32_t precision, void* stream) {
   return gode::gemm_tc(M, N, K, A, lda, Bt, ldb, C_partials, ldc, nullptr, 0, precision, gode::as_stream(stream), k_splits);
+}
+
+// out[d, ncols] = GroupNorm-normalised(y)^T * G, cs = column sums of G (see gn_wgrad_tc).
+extern "C" size_t gode_gn_wgrad_workspace_bytes(int32_t d) { return d > 0 ? gode::gn_wgrad_ws_bytes(d) : 0; }
+
+extern "C" int gode_gn_wgrad_f32(int64_t n, int32_t d, int32_t groups, float eps, const float* y, const float* G, int64_t ldg,
+                                 int32_t ncols, float* out, int64_t ldo, float* cs, void* ws, size_t ws_bytes, int32_t precision,
+                                 void* stream) {
+  GODE_REQUIRE(n >= 0 && (n == 0 || (y && G)) && out && cs, "gn_wgrad: null pointer");
+  return gode::gn_wgrad_tc(n, d, groups, eps, y, G, ldg, ncols, out, ldo, cs, static_cast<float*>(ws), ws_bytes, precision,
+                           gode::as_stream(stream));
 }

@@ -678,6 +678,118 @@ class GatConvFn(torch.autograd.Function):
         return gx, gfw, gfb, gww, gwb, None, None, None
 
 
+def gn_wgrad(y, groups, eps, g):
+    """``(xhat(y)^T g, colsum(g))`` with xhat = GroupNorm(y) before its affine -- gode_gn_wgrad_f32 (tcgen05)."""
+    y, g = _rowmajor(y, "y"), _rowmajor(g, "g")
+    d, nc = y.shape[1], g.shape[1]
+    out = torch.empty(d, nc, dtype=torch.float32, device=y.device)
+    cs = torch.empty(nc, dtype=torch.float32, device=y.device)
+    nb = lib.gode_gn_wgrad_workspace_bytes(d)
+    ws = workspace(nb, y.device, "gn_wgrad")
+    check(lib.gode_gn_wgrad_f32(y.shape[0], d, groups, float(eps), _p(y), _p(g), g.stride(0), nc, _p(out), nc, _p(cs), _p(ws), nb,
+                                _lib.PREC_FP32, _stream()), "gode_gn_wgrad_f32")
+    return out, cs
+
+
+def gat_ode_fusable(y, groups, heads, oh):
+    """The fused GAT ODE function covers the widths its tensor-core weight gradient does (d = 128, 32 groups)."""
+    import os
+    return (os.environ.get("GODE_GAT_FUSED", "1") != "0" and y.is_cuda and y.dim() == 2 and y.shape[1] == 128 and groups == 32
+            and y.shape[0] >= 1)
+
+
+class GatOdeFn(torch.autograd.Function):
+    """f(t, y) = GATconv([t*1 || GroupNorm(y)])  (GAT/models.py:161-179 over GAT/layers.py:40-58) as ONE autograd node.
+
+    The t column never materialises: with W_cat = [Wf_src^T | Wf_tgt^T | ww_src^T | ww_tgt^T] ([d+1, ldp], row 0 the t row)
+    the node projection is  P = GroupNorm(y) W_cat[1:] + (t W_cat[0] + b_cat),  a K = d = 128 product on aligned rows (the
+    concatenated [N, 129] operand has 516-byte rows: no 128-bit access, a padded copy per call and a second, 99 % empty
+    column tile in the input-gradient product).  Backward: gode_gat_bwd -> dP; input gradient dP W_cat[1:]^T -> GroupNorm
+    backward; weight gradient xhat(y)^T dP on tcgen05 (gode_gn_wgrad_f32) with the GroupNorm affine, the t row and both
+    biases recovered from the column sums of dP.
+    """
+
+    @staticmethod
+    def forward(ctx, y, t, gamma, beta, f_weight, f_bias, w_weight, w_bias, graph, heads, eps, groups, gn_eps):
+        y = _rowmajor(y, "y")
+        d = y.shape[1]
+        i = d + 1
+        C_, H = f_weight.shape[0], heads
+        oh = C_ // H
+        ldp = 2 * C_ + 2 * H
+        pad = (-ldp) % 4        # rows of P are padded to a multiple of 16 bytes (one head: 2 * oh + 2 columns) with zero weights
+        # Bt [ldp + pad, d]: the K-major right operand (rows = output columns), t columns (0 and i) dropped
+        zp = torch.zeros(pad, d, device=y.device)
+        bt = torch.cat([f_weight[:, 1:i], f_weight[:, i + 1:], w_weight[:, 1:i], w_weight[:, i + 1:], zp], 0).contiguous()
+        w0 = torch.cat([f_weight[:, 0], f_weight[:, i], w_weight[:, 0], w_weight[:, i], zp[:, 0]])   # the t row of W_cat
+        zc, zh = torch.zeros(C_, device=y.device), torch.zeros(H, device=y.device)
+        bcat = torch.cat([zc, f_bias if f_bias is not None else zc, zh, w_bias if w_bias is not None else zh, zp[:, 0]])
+        ldp += pad
+        tt = t.detach().to(torch.float32) if torch.is_tensor(t) else float(t)
+        xn = groupnorm_fwd(y, groups, gamma, beta, gn_eps)
+        P = gemm_tc(xn, bt, w0 * tt + bcat)
+        del xn
+        out = torch.empty(graph.n_nodes, C_, dtype=torch.float32, device=y.device)
+        den = torch.empty(graph.n_nodes, H, dtype=torch.float32, device=y.device)
+        amax = torch.empty(H, dtype=torch.int64, device=y.device)
+        nb = lib.gode_gat_fwd_workspace_bytes(C.byref(graph.c), H, oh)
+        ws = workspace(nb, y.device, "gat_fwd")
+        check(lib.gode_gat_fwd(C.byref(graph.c), H, oh, _p(P), ldp, float(eps), _p(out), out.stride(0), _p(den), _p(amax),
+                               _p(graph.nan_flag), _p(ws), nb, _stream()), "gode_gat_fwd")
+        ctx.graph, ctx.H, ctx.oh, ctx.groups, ctx.gn_eps = graph, H, oh, groups, gn_eps
+        ctx.has_bias = (f_bias is not None, w_bias is not None)
+        ctx.t = tt
+        ctx.save_for_backward(y, gamma, beta, bt, w0, P, out, den, amax)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        y, gamma, beta, bt, w0, P, out, den, amax = ctx.saved_tensors
+        graph, H, oh = ctx.graph, ctx.H, ctx.oh
+        C_ = H * oh
+        ldp = P.shape[1]                # 2 * C_ + 2 * H, padded to a multiple of 4
+        g = _rowmajor(g, "grad").contiguous()
+        dP = torch.empty_like(P)
+        if ldp != 2 * C_ + 2 * H:
+            dP[:, 2 * C_ + 2 * H:].zero_()
+        nb = lib.gode_gat_bwd_workspace_bytes(C.byref(graph.c), H, oh)
+        ws = workspace(nb, y.device, "gat")
+        check(lib.gode_gat_bwd(C.byref(graph.c), H, oh, _p(P), ldp, _p(out), out.stride(0), _p(den), _p(amax), _p(g),
+                               g.stride(0), _p(dP), _p(ws), nb, _stream()), "gode_gat_bwd")
+        need = ctx.needs_input_grad
+        gy = gt = ggam = gbeta = gfw = gfb = gww = gwb = None
+        if need[0] or need[2] or need[3]:
+            dxn = gemm_tc(dP, bt.t().contiguous())                 # [N, ldp] x [ldp, d]: one 128-column tile
+            gy, ggam, gbeta = groupnorm_bwd(y, ctx.groups, gamma, dxn, ctx.gn_eps)
+            del dxn
+        if any(need[4:8]) or need[1]:
+            raw, cs = gn_wgrad(y, ctx.groups, ctx.gn_eps, dP)      # xhat^T dP [d, ldp], colsum(dP) [ldp]
+            if need[1]:
+                gt = (cs * w0).sum()
+                if torch.is_tensor(ctx.t):
+                    gt = gt.reshape(ctx.t.shape)
+            if any(need[4:8]):
+                dw1 = gamma[:, None] * raw + beta[:, None] * cs[None, :]       # rows 1..d of dW_cat
+                dw0 = cs * ctx.t                                               # the t row
+                def half(a, b):   # columns [a, b) of dW_cat, as [b - a, d + 1] (nn.Linear layout: [out, in])
+                    return torch.cat([dw0[a:b, None], dw1[:, a:b].t()], 1)
+                gfw = torch.cat([half(0, C_), half(C_, 2 * C_)], 1)
+                gww = torch.cat([half(2 * C_, 2 * C_ + H), half(2 * C_ + H, 2 * C_ + 2 * H)], 1)
+                gfb = cs[C_:2 * C_] if ctx.has_bias[0] else None
+                gwb = cs[2 * C_ + H:2 * C_ + 2 * H] if ctx.has_bias[1] else None
+        return gy, gt, ggam, gbeta, gfw, gfb, gww, gwb, None, None, None, None, None
+
+
+def gat_ode_func(y, t, norm, conv, check_nan=True):
+    """Fused evaluation of the GAT ODE function for ``norm`` (nn.GroupNorm) and ``conv`` (GAT FixedGraphConvolution)."""
+    graph = gat_graph_for(conv.src, conv.tgt, y.shape[0])
+    out = GatOdeFn.apply(y, t, norm.weight, norm.bias, conv.f.weight, conv.f.bias, conv.w.weight, conv.w.bias, graph,
+                         conv.heads, conv.eps, norm.num_groups, norm.eps)
+    if check_nan:
+        assert int(graph.nan_flag.item()) == 0, "NaN in GAT attention"
+    return out
+
+
 def gat_conv(x, src, tgt, f_weight, f_bias, w_weight, w_bias, heads=1, eps=1e-6, check_nan=True):
     graph = gat_graph_for(src, tgt, x.shape[0])
     out = GatConvFn.apply(x, f_weight, f_bias, w_weight, w_bias, graph, heads, eps)

@@ -227,6 +227,16 @@ int gode_groupnorm_bwd(int64_t n, int32_t d, int32_t groups, float eps, const fl
                        const float* gamma, const float* dy, int64_t lddy, float* dx, int64_t lddx,
                        float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
 
+/* out[d, ncols] (row stride ldo) = xhat(y)^T * G and cs[ncols] = column sums of G, with xhat = GroupNorm(y) BEFORE its
+ * affine, reduced over the n rows on tcgen05 (3xTF32, hierarchical accumulation).  The weight gradient of a layer fed by
+ * [t | GroupNorm(y)] whose output is wider than d -- the GAT ODE function's projection (GAT/models.py:161-179 through
+ * GAT/layers.py:40-45): dW[1:] = gamma * out + beta * cs, dW[0] = t * cs, db = cs.  d = 128 with 32 groups; ncols and ldg
+ * multiples of 4, 16-byte aligned operands; anything else returns GODE_EINVAL (callers use gode_gemm_f32 then). */
+size_t gode_gn_wgrad_workspace_bytes(int32_t d);
+int gode_gn_wgrad_f32(int64_t n, int32_t d, int32_t groups, float eps, const float* y, const float* G, int64_t ldg,
+                      int32_t ncols, float* out, int64_t ldo, float* cs, void* ws, size_t ws_bytes, int32_t precision,
+                      void* stream);
+
 size_t gode_colreduce_workspace_bytes(int32_t width);
 /* out[c] = sum_r x[r, c]   (bias gradients; GCN/layers.py:35 autograd) */
 int gode_colsum_f32(int64_t n, int32_t d, const float* x, int64_t ldx, float* out,

@@ -227,6 +227,53 @@ def test_gat_ode_block_rk4_matches_oracle():
         G.assert_close_l2(p.grad, fo.ps[k.replace(".", "_")].grad, 1e-4, what=k)
 
 
+@pytest.mark.parametrize("heads", [1, 8])
+def test_gat_ode_function_fused_matches_unfused_and_oracle(heads, monkeypatch):
+    """The fused ODE-function node (ops.GatOdeFn: no [t || xn] operand, tcgen05 weight gradient from xhat(y)^T dP) against
+    the layer-by-layer evaluation (GroupNorm -> cat -> GATconv) and the float64 oracle: value, d/dy, d/dt and every
+    parameter gradient.  heads = 1 is the reference's layer (258 projection columns, padded to 260 inside the node)."""
+    _, _, models = _pkg()
+    n, e, d = 3000, 20000, 128
+    oh = d // heads
+    src, tgt = _random_edges(n, e, seed=11)
+    torch.manual_seed(7)
+    f = models.ODEfunc(d, heads=heads)
+    with torch.no_grad():
+        f.norm1.weight.uniform_(0.5, 1.5)
+        f.norm1.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(n, d)
+    gy = torch.randn(n, d) / n
+    p64 = {k: v.detach().double().clone().requires_grad_(True) for k, v in f.state_dict().items()}
+    x64 = x.double().requires_grad_(True)
+    t64 = torch.tensor(0.37, dtype=torch.float64, requires_grad=True)
+    yn = torch.nn.functional.group_norm(x64, 32, p64["norm1.weight"], p64["norm1.bias"], 1e-5)
+    hs = [(p64["gc1.f.weight"][h * oh:(h + 1) * oh], p64["gc1.f.bias"][h * oh:(h + 1) * oh], p64["gc1.w.weight"][h:h + 1],
+           p64["gc1.w.bias"][h:h + 1]) for h in range(heads)]
+    yo = gat_ref.gat_multihead(torch.cat([torch.ones_like(yn[:, :1]) * t64, yn], 1), src, tgt, hs)
+    yo.backward(gy.double())
+    f = f.to(DEV)
+    f.set_adj(src.to(DEV), tgt.to(DEV), None)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GODE_GAT_FUSED", mode)
+        for p in f.parameters():
+            p.grad = None
+        xg = x.to(DEV).requires_grad_(True)
+        tg = torch.tensor(0.37, device=DEV, requires_grad=True)
+        y = f(tg, xg)
+        y.backward(gy.to(DEV))
+        res[mode] = (y.detach(), xg.grad, tg.grad, {k: p.grad.clone() for k, p in f.named_parameters()})
+    for mode, (y, gx, gt, gp) in res.items():
+        what = "fused" if mode == "1" else "unfused"
+        G.assert_close(y, yo.detach(), rtol=1e-5, atol_scale=1e-5, what=what + " f")
+        G.assert_close(gx, x64.grad, rtol=1e-5, atol_scale=1e-5, what=what + " d/dy")
+        assert abs(float(gt) - float(t64.grad)) <= 1e-5 * max(abs(float(t64.grad)), 1e-3), (what, float(gt), float(t64.grad))
+        for k, v in gp.items():
+            if k.endswith("w.bias"):
+                continue                               # mathematically zero (shift invariance of a - max a)
+            G.assert_close(v, p64[k].grad, rtol=1e-5, atol_scale=1e-5, what=what + " " + k)
+
+
 def test_gat_model_surface():
     _, layers, models = _pkg()
     m = models.ODEGCN3(nfeat=12, nhid=16, nclass=3, dropout=0.0)
