@@ -298,6 +298,191 @@ __global__ void __launch_bounds__(128) k_gat_bwd_src(int64_t n_seg, int H, int o
   dpn[2 * C + h] = das;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Lane-group kernels (C = H * oh a multiple of 4 up to 128, oh a power of two >= 4, 16-byte aligned rows).
+// LPN = C / 4 lanes own one segment: lane j holds channels [4j, 4j + 4) of ALL heads' concatenated channels (head
+// h = 4j / oh), so a row of P / out / g is ONE coalesced 128-bit access per lane -- 512 bytes per instruction at C = 128
+// instead of the scalar kernels' 32 lanes x 4 bytes at a 64-byte stride (8x the L1 wavefronts; ncu round 2: 0.92 ms per
+// forward at N = 1 M for 1.8 GB of compulsory traffic).  Per (node, head, channel) the edges are still walked in edge
+// order by one lane: the segmented sums keep the reference's summation order; only the per-head dot products of the
+// backward (over oh channels) become a fixed-shape tree over the head's lanes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+template <int LPN>
+__device__ __forceinline__ float head_sum(float v, int lanes_per_head) {
+#pragma unroll
+  for (int o = 1; o < LPN; o <<= 1)
+    if (o < lanes_per_head) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LPN, bool CHUNK>
+__global__ void __launch_bounds__(128) k_gat_fwd_v(int64_t n_seg, int H, int oh, const int32_t* __restrict__ tptr,
+                                                   const int32_t* __restrict__ t_src, const float* __restrict__ P, int64_t ldp,
+                                                   float eps, const unsigned long long* __restrict__ amax_key,
+                                                   float* __restrict__ out, int64_t ldo, float* __restrict__ den_out,
+                                                   int* __restrict__ nan_flag, GatHeavy hv, float* __restrict__ part, int CH) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t seg = gid / LPN;
+  const int j = static_cast<int>(gid % LPN);
+  if (seg >= n_seg) return;
+  int64_t n;
+  int e0, e1;
+  if (!gat_segment<CHUNK>(seg, tptr, hv, n, e0, e1)) return;
+  const int C = H * oh;
+  const int h = (4 * j) / oh;
+  const float amax = key_max(amax_key[h]);
+  const float* pn = P + n * ldp;
+  const float at = __ldg(pn + 2 * C + H + h);
+  const float4 pt = ldg4(pn + C + 4 * j);
+  float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+  float den = 0.f;
+  for (int e = e0; e < e1; ++e) {
+    const float* ps = P + (int64_t)__ldg(t_src + e) * ldp;
+    const float w = expf(__ldg(ps + 2 * C + h) + at - amax);
+    const float4 v = ldg4(ps + 4 * j);
+    den += w;
+    num.x += fmaxf(v.x + pt.x, 0.f) * w;
+    num.y += fmaxf(v.y + pt.y, 0.f) * w;
+    num.z += fmaxf(v.z + pt.z, 0.f) * w;
+    num.w += fmaxf(v.w + pt.w, 0.f) * w;
+  }
+  const bool head_lead = (4 * j) % oh == 0;
+  if (CHUNK) {
+    float* p = part + (seg * H + h) * (CH + 1) + (4 * j - h * oh);
+    p[0] = num.x; p[1] = num.y; p[2] = num.z; p[3] = num.w;
+    if (head_lead) part[(seg * H + h) * (CH + 1) + CH] = den;
+    return;
+  }
+  den += eps;
+  if (head_lead) den_out[n * H + h] = den;
+  const float4 o = make_float4(num.x / den, num.y / den, num.z / den, num.w / den);
+  if (den != den || o.x != o.x || o.y != o.y || o.z != o.z || o.w != o.w) *nan_flag = 1;
+  *reinterpret_cast<float4*>(out + n * ldo + 4 * j) = o;
+}
+
+template <int LPN, bool CHUNK>
+__global__ void __launch_bounds__(128) k_gat_bwd_tgt_v(int64_t n_seg, int H, int oh, const int32_t* __restrict__ tptr,
+                                                       const int32_t* __restrict__ t_src, const float* __restrict__ P,
+                                                       int64_t ldp, const unsigned long long* __restrict__ amax_key,
+                                                       const float* __restrict__ out, int64_t ldo,
+                                                       const float* __restrict__ den, const float* __restrict__ g, int64_t ldg,
+                                                       float* __restrict__ dP, float* __restrict__ dA, GatHeavy hv,
+                                                       float* __restrict__ part, int CH) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t seg_raw = gid / LPN;
+  const int j = static_cast<int>(gid % LPN);
+  // every lane of a warp takes part in the shuffles: out-of-range / skipped segments run with an empty edge range
+  const bool live = seg_raw < n_seg;
+  const int64_t seg = live ? seg_raw : 0;
+  int64_t n = 0;
+  int e0 = 0, e1 = 0;
+  const bool mine = live && gat_segment<CHUNK>(seg, tptr, hv, n, e0, e1);
+  if (!mine) e0 = e1 = 0;
+  const int C = H * oh;
+  const int h = (4 * j) / oh;
+  const int lph = oh / 4;
+  const float amax = key_max(amax_key[h]);
+  const float* pn = P + n * ldp;
+  float at = 0.f, inv = 0.f, go = 0.f;
+  float4 pt = make_float4(0.f, 0.f, 0.f, 0.f), gn = pt;
+  if (mine) {
+    at = __ldg(pn + 2 * C + H + h);
+    inv = 1.f / den[n * H + h];
+    pt = ldg4(pn + C + 4 * j);
+    const float4 gg = ldg4(g + n * ldg + 4 * j), oo = ldg4(out + n * ldo + 4 * j);
+    gn = make_float4(gg.x * inv, gg.y * inv, gg.z * inv, gg.w * inv);
+    go = gn.x * oo.x + gn.y * oo.y + gn.z * oo.z + gn.w * oo.w;
+  }
+  go = head_sum<LPN>(go, lph);
+  // lanes of one warp walk segments of different lengths: the shuffles below need the whole warp, so the loop runs to the
+  // longest range of the warp and lanes past their own range contribute zeros
+  int len = e1 - e0;
+  int maxlen = len;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+  float4 dpt = make_float4(0.f, 0.f, 0.f, 0.f);
+  float dat = 0.f;
+  const bool head_lead = (4 * j) % oh == 0;
+  for (int i = 0; i < maxlen; ++i) {
+    const bool on = i < len;
+    float w = 0.f, part_dw = 0.f;
+    if (on) {
+      const float* ps = P + (int64_t)__ldg(t_src + e0 + i) * ldp;
+      w = expf(__ldg(ps + 2 * C + h) + at - amax);
+      const float4 v = ldg4(ps + 4 * j);
+      const float zx = v.x + pt.x, zy = v.y + pt.y, zz = v.z + pt.z, zw = v.w + pt.w;
+      if (zx > 0.f) { part_dw += zx * gn.x; dpt.x += w * gn.x; }
+      if (zy > 0.f) { part_dw += zy * gn.y; dpt.y += w * gn.y; }
+      if (zz > 0.f) { part_dw += zz * gn.z; dpt.z += w * gn.z; }
+      if (zw > 0.f) { part_dw += zw * gn.w; dpt.w += w * gn.w; }
+    }
+    const float dw = head_sum<LPN>(part_dw, lph) - go;
+    if (on) {
+      const float da = dw * w;
+      dat += da;
+      if (head_lead) dA[(int64_t)(e0 + i) * H + h] = da;
+    }
+  }
+  if (!mine) return;
+  if (CHUNK) {
+    float* p = part + (seg * H + h) * (CH + 1) + (4 * j - h * oh);
+    p[0] = dpt.x; p[1] = dpt.y; p[2] = dpt.z; p[3] = dpt.w;
+    if (head_lead) part[(seg * H + h) * (CH + 1) + CH] = dat;
+    return;
+  }
+  float* dpn = dP + n * ldp;
+  *reinterpret_cast<float4*>(dpn + C + 4 * j) = dpt;
+  if (head_lead) dpn[2 * C + H + h] = dat;
+}
+
+template <int LPN, bool CHUNK>
+__global__ void __launch_bounds__(128) k_gat_bwd_src_v(int64_t n_seg, int H, int oh, const int32_t* __restrict__ sptr,
+                                                       const int32_t* __restrict__ s_tgt, const int32_t* __restrict__ s_pos,
+                                                       const float* __restrict__ P, int64_t ldp,
+                                                       const unsigned long long* __restrict__ amax_key,
+                                                       const float* __restrict__ den, const float* __restrict__ g, int64_t ldg,
+                                                       const float* __restrict__ dA, float* __restrict__ dP, GatHeavy hv,
+                                                       float* __restrict__ part, int CH) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t seg = gid / LPN;
+  const int j = static_cast<int>(gid % LPN);
+  if (seg >= n_seg) return;
+  int64_t s;
+  int e0, e1;
+  if (!gat_segment<CHUNK>(seg, sptr, hv, s, e0, e1)) return;
+  const int C = H * oh;
+  const int h = (4 * j) / oh;
+  const float amax = key_max(amax_key[h]);
+  const float* psn = P + s * ldp;
+  const float as = __ldg(psn + 2 * C + h);
+  const float4 ps = ldg4(psn + 4 * j);
+  float4 dps = make_float4(0.f, 0.f, 0.f, 0.f);
+  float das = 0.f;
+  for (int e = e0; e < e1; ++e) {
+    const int64_t n = __ldg(s_tgt + e);
+    const float* pt = P + n * ldp;
+    const float w = expf(as + __ldg(pt + 2 * C + H + h) - amax) / __ldg(den + n * H + h);
+    const float4 v = ldg4(pt + C + 4 * j), gg = ldg4(g + n * ldg + 4 * j);
+    if (ps.x + v.x > 0.f) dps.x += w * gg.x;
+    if (ps.y + v.y > 0.f) dps.y += w * gg.y;
+    if (ps.z + v.z > 0.f) dps.z += w * gg.z;
+    if (ps.w + v.w > 0.f) dps.w += w * gg.w;
+    das += __ldg(dA + (int64_t)__ldg(s_pos + e) * H + h);
+  }
+  const bool head_lead = (4 * j) % oh == 0;
+  if (CHUNK) {
+    float* p = part + (seg * H + h) * (CH + 1) + (4 * j - h * oh);
+    p[0] = dps.x; p[1] = dps.y; p[2] = dps.z; p[3] = dps.w;
+    if (head_lead) part[(seg * H + h) * (CH + 1) + CH] = das;
+    return;
+  }
+  float* dpn = dP + s * ldp;
+  *reinterpret_cast<float4*>(dpn + 4 * j) = dps;
+  if (head_lead) dpn[2 * C + h] = das;
+}
+
 // adds a hub's chunk partials in chunk order: dP[n, col0 + h*oh + j] and dP[n, colA + h]
 template <int CH>
 __global__ void __launch_bounds__(128) k_gat_bwd_finish(int H, int oh, GatHeavy hv, const float* __restrict__ part,
@@ -351,17 +536,102 @@ static GatHeavy heavy_of(const gode_gat_graph_t* G, bool by_source) {
 
 static unsigned grid_for(int64_t work) { return static_cast<unsigned>((work + 127) / 128); }
 
+static int ch_of(int oh) { return oh <= 8 ? 8 : oh <= 16 ? 16 : oh <= 32 ? 32 : oh <= 64 ? 64 : 128; }
+
+// ---- lane-group path ----
+static bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// lanes per segment of the lane-group kernels, or 0 when the shape / alignment needs the scalar kernels.  GODE_GAT_VEC=0
+// forces the scalar kernels (tests compare the two).
+static int gat_lpn(int H, int oh, int64_t ldp, const void* P, int64_t ld2, const void* p2, int64_t ld3, const void* p3) {
+  const char* e = getenv("GODE_GAT_VEC");
+  if (e && atoi(e) == 0) return 0;
+  const int C = H * oh;
+  if (oh < 4 || (oh & (oh - 1)) || C > 128) return 0;
+  const int lpn = C / 4;
+  if (lpn != 4 && lpn != 8 && lpn != 16 && lpn != 32) return 0;
+  if (ldp % 4 || ld2 % 4 || ld3 % 4 || !al16p(P) || !al16p(p2) || !al16p(p3)) return 0;
+  return lpn;
+}
+
+template <int LPN>
+static int gat_fwd_v(const gode_gat_graph_t* G, int H, int oh, const float* P, int64_t ldp, float eps, float* out, int64_t ldo,
+                     float* den, unsigned long long* amax_key, int* nan_flag, float* part, cudaStream_t st) {
+  const GatHeavy hv = heavy_of(G, false);
+  const int CH = ch_of(oh);
+  k_gat_fwd_v<LPN, false><<<grid_for(G->n_nodes * LPN), 128, 0, st>>>(G->n_nodes, H, oh, G->tptr, G->t_src, P, ldp, eps, amax_key,
+                                                                      out, ldo, den, nan_flag, hv, nullptr, CH);
+  GODE_LAUNCH_CHECK();
+  if (hv.n_chunks > 0) {
+    k_gat_fwd_v<LPN, true><<<grid_for((int64_t)hv.n_chunks * LPN), 128, 0, st>>>(hv.n_chunks, H, oh, G->tptr, G->t_src, P, ldp, eps,
+                                                                                 amax_key, out, ldo, den, nan_flag, hv, part, CH);
+    GODE_LAUNCH_CHECK();
+  }
+  return GODE_OK;
+}
+
+template <int LPN>
+static int gat_bwd_v(const gode_gat_graph_t* G, int H, int oh, const float* P, int64_t ldp, const float* out, int64_t ldo,
+                     const float* den, const unsigned long long* amax_key, const float* g, int64_t ldg, float* dP, float* dA,
+                     float* part, cudaStream_t st, int phase /*0: target pass, 1: source pass*/) {
+  const int CH = ch_of(oh);
+  if (phase == 0) {
+    const GatHeavy ht = heavy_of(G, false);
+    k_gat_bwd_tgt_v<LPN, false><<<grid_for(G->n_nodes * LPN), 128, 0, st>>>(G->n_nodes, H, oh, G->tptr, G->t_src, P, ldp, amax_key,
+                                                                            out, ldo, den, g, ldg, dP, dA, ht, nullptr, CH);
+    GODE_LAUNCH_CHECK();
+    if (ht.n_chunks > 0) {
+      k_gat_bwd_tgt_v<LPN, true><<<grid_for((int64_t)ht.n_chunks * LPN), 128, 0, st>>>(ht.n_chunks, H, oh, G->tptr, G->t_src, P, ldp,
+                                                                                       amax_key, out, ldo, den, g, ldg, dP, dA, ht,
+                                                                                       part, CH);
+      GODE_LAUNCH_CHECK();
+    }
+    return GODE_OK;
+  }
+  const GatHeavy hs = heavy_of(G, true);
+  k_gat_bwd_src_v<LPN, false><<<grid_for(G->n_nodes * LPN), 128, 0, st>>>(G->n_nodes, H, oh, G->sptr, G->s_tgt, G->s_pos, P, ldp,
+                                                                          amax_key, den, g, ldg, dA, dP, hs, nullptr, CH);
+  GODE_LAUNCH_CHECK();
+  if (hs.n_chunks > 0) {
+    k_gat_bwd_src_v<LPN, true><<<grid_for((int64_t)hs.n_chunks * LPN), 128, 0, st>>>(hs.n_chunks, H, oh, G->sptr, G->s_tgt, G->s_pos,
+                                                                                     P, ldp, amax_key, den, g, ldg, dA, dP, hs, part,
+                                                                                     CH);
+    GODE_LAUNCH_CHECK();
+  }
+  return GODE_OK;
+}
+
+#define GODE_GAT_LPN_DISPATCH(lpn, CALL)       \
+  switch (lpn) {                               \
+    case 4: rc = CALL(4); break;               \
+    case 8: rc = CALL(8); break;               \
+    case 16: rc = CALL(16); break;             \
+    default: rc = CALL(32); break;             \
+  }
+
+
 template <int CH>
 static int gat_fwd_t(const gode_gat_graph_t* G, int H, int oh, const float* P, int64_t ldp, float eps, float* out, int64_t ldo,
                      float* den, unsigned long long* amax_key, int* nan_flag, float* part, cudaStream_t st) {
   const GatHeavy hv = heavy_of(G, false);
-  k_gat_fwd<CH, false><<<grid_for(G->n_nodes * H), 128, 0, st>>>(G->n_nodes, H, oh, G->tptr, G->t_src, P, ldp, eps, amax_key, out,
-                                                                 ldo, den, nan_flag, hv, nullptr);
-  GODE_LAUNCH_CHECK();
-  if (hv.n_chunks > 0) {
-    k_gat_fwd<CH, true><<<grid_for((int64_t)hv.n_chunks * H), 128, 0, st>>>(hv.n_chunks, H, oh, G->tptr, G->t_src, P, ldp, eps,
-                                                                            amax_key, out, ldo, den, nan_flag, hv, part);
+  const int lpn = gat_lpn(H, oh, ldp, P, ldo, out, 4, P);
+  if (lpn) {
+    int rc;
+#define GODE_CALL_(L) gat_fwd_v<L>(G, H, oh, P, ldp, eps, out, ldo, den, amax_key, nan_flag, part, st)
+    GODE_GAT_LPN_DISPATCH(lpn, GODE_CALL_)
+#undef GODE_CALL_
+    if (rc) return rc;
+  } else {
+    k_gat_fwd<CH, false><<<grid_for(G->n_nodes * H), 128, 0, st>>>(G->n_nodes, H, oh, G->tptr, G->t_src, P, ldp, eps, amax_key, out,
+                                                                   ldo, den, nan_flag, hv, nullptr);
     GODE_LAUNCH_CHECK();
+    if (hv.n_chunks > 0) {
+      k_gat_fwd<CH, true><<<grid_for((int64_t)hv.n_chunks * H), 128, 0, st>>>(hv.n_chunks, H, oh, G->tptr, G->t_src, P, ldp, eps,
+                                                                              amax_key, out, ldo, den, nan_flag, hv, part);
+      GODE_LAUNCH_CHECK();
+    }
+  }
+  if (hv.n_chunks > 0) {
     k_gat_fwd_finish<CH><<<grid_for((int64_t)hv.n_heavy * H), 128, 0, st>>>(H, oh, eps, hv, part, out, ldo, den, nan_flag);
     GODE_LAUNCH_CHECK();
   }
@@ -374,30 +644,48 @@ static int gat_bwd_t(const gode_gat_graph_t* G, int H, int oh, const float* P, i
                      float* part, cudaStream_t st) {
   const int C = H * oh;
   const GatHeavy ht = heavy_of(G, false), hs = heavy_of(G, true);
-  k_gat_bwd_tgt<CH, false><<<grid_for(G->n_nodes * H), 128, 0, st>>>(G->n_nodes, H, oh, G->tptr, G->t_src, P, ldp, amax_key, out,
-                                                                     ldo, den, g, ldg, dP, dA, ht, nullptr);
-  GODE_LAUNCH_CHECK();
-  if (ht.n_chunks > 0) {
-    k_gat_bwd_tgt<CH, true><<<grid_for((int64_t)ht.n_chunks * H), 128, 0, st>>>(ht.n_chunks, H, oh, G->tptr, G->t_src, P, ldp,
-                                                                                amax_key, out, ldo, den, g, ldg, dP, dA, ht, part);
+  const int lpn = (gat_lpn(H, oh, ldp, P, ldo, out, ldg, g) && al16p(dP)) ? C / 4 : 0;
+  int rc;
+  if (lpn) {
+#define GODE_CALL_(L) gat_bwd_v<L>(G, H, oh, P, ldp, out, ldo, den, amax_key, g, ldg, dP, dA, part, st, 0)
+    GODE_GAT_LPN_DISPATCH(lpn, GODE_CALL_)
+#undef GODE_CALL_
+    if (rc) return rc;
+  } else {
+    k_gat_bwd_tgt<CH, false><<<grid_for(G->n_nodes * H), 128, 0, st>>>(G->n_nodes, H, oh, G->tptr, G->t_src, P, ldp, amax_key, out,
+                                                                       ldo, den, g, ldg, dP, dA, ht, nullptr);
     GODE_LAUNCH_CHECK();
+    if (ht.n_chunks > 0) {
+      k_gat_bwd_tgt<CH, true><<<grid_for((int64_t)ht.n_chunks * H), 128, 0, st>>>(ht.n_chunks, H, oh, G->tptr, G->t_src, P, ldp,
+                                                                                  amax_key, out, ldo, den, g, ldg, dP, dA, ht, part);
+      GODE_LAUNCH_CHECK();
+    }
+  }
+  if (ht.n_chunks > 0) {
     k_gat_bwd_finish<CH><<<grid_for((int64_t)ht.n_heavy * H), 128, 0, st>>>(H, oh, ht, part, dP, ldp, C, 2 * C + H);
     GODE_LAUNCH_CHECK();
   }
-  k_gat_bwd_src<CH, false><<<grid_for(G->n_nodes * H), 128, 0, st>>>(G->n_nodes, H, oh, G->sptr, G->s_tgt, G->s_pos, P, ldp,
-                                                                     amax_key, den, g, ldg, dA, dP, hs, nullptr);
-  GODE_LAUNCH_CHECK();
-  if (hs.n_chunks > 0) {
-    k_gat_bwd_src<CH, true><<<grid_for((int64_t)hs.n_chunks * H), 128, 0, st>>>(hs.n_chunks, H, oh, G->sptr, G->s_tgt, G->s_pos, P,
-                                                                                ldp, amax_key, den, g, ldg, dA, dP, hs, part);
+  if (lpn) {
+#define GODE_CALL_(L) gat_bwd_v<L>(G, H, oh, P, ldp, out, ldo, den, amax_key, g, ldg, dP, dA, part, st, 1)
+    GODE_GAT_LPN_DISPATCH(lpn, GODE_CALL_)
+#undef GODE_CALL_
+    if (rc) return rc;
+  } else {
+    k_gat_bwd_src<CH, false><<<grid_for(G->n_nodes * H), 128, 0, st>>>(G->n_nodes, H, oh, G->sptr, G->s_tgt, G->s_pos, P, ldp,
+                                                                       amax_key, den, g, ldg, dA, dP, hs, nullptr);
     GODE_LAUNCH_CHECK();
+    if (hs.n_chunks > 0) {
+      k_gat_bwd_src<CH, true><<<grid_for((int64_t)hs.n_chunks * H), 128, 0, st>>>(hs.n_chunks, H, oh, G->sptr, G->s_tgt, G->s_pos, P,
+                                                                                  ldp, amax_key, den, g, ldg, dA, dP, hs, part);
+      GODE_LAUNCH_CHECK();
+    }
+  }
+  if (hs.n_chunks > 0) {
     k_gat_bwd_finish<CH><<<grid_for((int64_t)hs.n_heavy * H), 128, 0, st>>>(H, oh, hs, part, dP, ldp, 0, 2 * C);
     GODE_LAUNCH_CHECK();
   }
   return GODE_OK;
 }
-
-static int ch_of(int oh) { return oh <= 8 ? 8 : oh <= 16 ? 16 : oh <= 32 ? 32 : oh <= 64 ? 64 : 128; }
 
 static size_t part_bytes(const gode_gat_graph_t* G, int H, int oh) {
   const int64_t nc = G->t_heavy.n_chunks > G->s_heavy.n_chunks ? G->t_heavy.n_chunks : G->s_heavy.n_chunks;

@@ -631,11 +631,13 @@ class GatConvFn(torch.autograd.Function):
         i = x.shape[1]
         C_, H = f_weight.shape[0], heads
         oh = C_ // H
-        ldp = 2 * C_ + 2 * H
-        # W_cat [i, ldp] = [Wf_src^T | Wf_tgt^T | ww_src^T | ww_tgt^T]; biases ride on the target halves
-        wcat = torch.cat([f_weight[:, :i].t(), f_weight[:, i:].t(), w_weight[:, :i].t(), w_weight[:, i:].t()], 1).contiguous()
+        pad = (-(2 * C_ + 2 * H)) % 4      # rows of P padded to a multiple of 16 bytes (zero weights): 128-bit kernels
+        ldp = 2 * C_ + 2 * H + pad
+        # W_cat [i, ldp] = [Wf_src^T | Wf_tgt^T | ww_src^T | ww_tgt^T | 0]; biases ride on the target halves
+        zp = torch.zeros(i, pad, device=x.device)
+        wcat = torch.cat([f_weight[:, :i].t(), f_weight[:, i:].t(), w_weight[:, :i].t(), w_weight[:, i:].t(), zp], 1).contiguous()
         zc, zh = torch.zeros(C_, device=x.device), torch.zeros(H, device=x.device)
-        bcat = torch.cat([zc, f_bias if f_bias is not None else zc, zh, w_bias if w_bias is not None else zh])
+        bcat = torch.cat([zc, f_bias if f_bias is not None else zc, zh, w_bias if w_bias is not None else zh, zp[0]])
         P = linear(x, wcat, bcat)
         out = torch.empty(graph.n_nodes, C_, dtype=torch.float32, device=x.device)
         den = torch.empty(graph.n_nodes, H, dtype=torch.float32, device=x.device)
@@ -654,9 +656,11 @@ class GatConvFn(torch.autograd.Function):
         x, wcat, P, out, den, amax = ctx.saved_tensors
         graph, H, oh, i = ctx.graph, ctx.H, ctx.oh, ctx.i
         C_ = H * oh
-        ldp = 2 * C_ + 2 * H
+        ldp = P.shape[1]
         g = _rowmajor(g, "grad").contiguous()
         dP = torch.empty_like(P)
+        if ldp != 2 * C_ + 2 * H:
+            dP[:, 2 * C_ + 2 * H:].zero_()
         nb = lib.gode_gat_bwd_workspace_bytes(C.byref(graph.c), H, oh)
         ws = workspace(nb, x.device, "gat")
         check(lib.gode_gat_bwd(C.byref(graph.c), H, oh, _p(P), ldp, _p(out), out.stride(0), _p(den), _p(amax), _p(g),
@@ -671,10 +675,10 @@ class GatConvFn(torch.autograd.Function):
             # (5.7 ms at N = 1 M); transposing both for the K-major tensor-core kernel costs more than it saves here
             dw = gemm(x, dP, trans_a=True, splits=_splits_for(x.shape[0], i, ldp))       # [i, ldp]
             gfw = torch.cat([dw[:, :C_].t(), dw[:, C_:2 * C_].t()], 1)
-            gww = torch.cat([dw[:, 2 * C_:2 * C_ + H].t(), dw[:, 2 * C_ + H:].t()], 1)
+            gww = torch.cat([dw[:, 2 * C_:2 * C_ + H].t(), dw[:, 2 * C_ + H:2 * C_ + 2 * H].t()], 1)
             db = colsum(dP)
             gfb = db[C_:2 * C_] if ctx.has_bias[0] else None
-            gwb = db[2 * C_ + H:] if ctx.has_bias[1] else None
+            gwb = db[2 * C_ + H:2 * C_ + 2 * H] if ctx.has_bias[1] else None
         return gx, gfw, gfb, gww, gwb, None, None, None
 
 

@@ -86,9 +86,14 @@ def _random_edges(n, e, seed, isolated=5):
     return torch.from_numpy(src.astype(np.int64)), torch.from_numpy(tgt.astype(np.int64))
 
 
-@pytest.mark.parametrize("i,o,heads", [(16, 7, 1), (9, 16, 1), (33, 16, 8), (12, 3, 2), (20, 64, 1)])
-def test_gat_matches_oracle(i, o, heads):
-    """Single- and multi-head layers against the oracle (H independent reference heads, concatenated)."""
+@pytest.mark.parametrize("vec", ["1", "0"], ids=["lane-group", "scalar"])
+@pytest.mark.parametrize("i,o,heads", [(16, 7, 1), (9, 16, 1), (33, 16, 8), (12, 3, 2), (20, 64, 1), (10, 32, 1), (14, 8, 4),
+                                       (11, 128, 1), (13, 4, 4)])
+def test_gat_matches_oracle(i, o, heads, vec, monkeypatch):
+    """Single- and multi-head layers against the oracle (H independent reference heads, concatenated), on the lane-group
+    kernels (128-bit rows; widths 16 / 32 / 64 / 128 with power-of-two heads) and on the scalar kernels (GODE_GAT_VEC=0,
+    and every other width)."""
+    monkeypatch.setenv("GODE_GAT_VEC", vec)
     ops, layers, _ = _pkg()
     n, e = 700, 5000
     src, tgt = _random_edges(n, e, seed=i + o)
@@ -116,10 +121,12 @@ def test_gat_matches_oracle(i, o, heads):
         G.assert_close(p.grad, pc[k].grad, rtol=1e-5, atol_scale=2e-5, what=k, atol_abs=1e-5 if k == "w.bias" else 0.0)
 
 
+@pytest.mark.parametrize("vec", ["1", "0"], ids=["lane-group", "scalar"])
 @pytest.mark.parametrize("heads,o", [(1, 16), (8, 16)])
-def test_gat_hub_nodes_are_chunked(heads, o):
+def test_gat_hub_nodes_are_chunked(heads, o, vec, monkeypatch):
     """Power-law hubs: nodes with more than GODE_GAT_CHUNK (64) in- or out-edges are reduced by several threads whose
     partial sums are added in chunk order; one hub has exactly 64 edges, one 65, one 1000 -- against the oracle."""
+    monkeypatch.setenv("GODE_GAT_VEC", vec)
     ops, layers, _ = _pkg()
     n, i = 1500, 12
     rng = np.random.default_rng(5)
