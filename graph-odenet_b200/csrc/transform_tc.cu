@@ -412,7 +412,8 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1)
 k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, const float* __restrict__ W /*[D+1, D]*/,
           const float* __restrict__ gamma, const float* __restrict__ beta, float t, float eps, int passes,
           const gode_push_route_t push, const int pf_tiles /*L2 prefetch distance in tiles of this CTA (0: off)*/,
-          const int cfg_rt /*accuracy configuration of the 3xTF32 product, see rows_acc_cfg()*/) {
+          const int cfg_rt /*accuracy configuration of the 3xTF32 product, see rows_acc_cfg()*/,
+          const int64_t ldx /*row stride of X*/, const int64_t ldo /*row stride of Out*/, const int64_t ldw /*row stride of W*/) {
   using namespace tc;
   static_assert(D == 128, "k_rows_ws is laid out for 128 channels");
   // cfg: bit 0 round the lo residuals to tf32 | bit 1 correction terms (lo*hi, hi*lo[, lo*lo]) in their own TMEM
@@ -461,12 +462,12 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, 4 * D);
-  const float* W1 = W + D;
+  const float* W1 = W + ldw;
   for (int n = tid; n < D; n += WS_THREADS) {
     float r = 0.f;
     if (MODE == 0) {
       r = t * __ldg(W + n);
-      for (int k = 0; k < D; ++k) r = fmaf(__ldg(beta + k), __ldg(W1 + (int64_t)k * D + n), r);
+      for (int k = 0; k < D; ++k) r = fmaf(__ldg(beta + k), __ldg(W1 + (int64_t)k * ldw + n), r);
     }
     sRow[n] = r;
   }
@@ -476,12 +477,12 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
     float4 b;
     if (MODE == 0) {
       const int k = kc * 4;
-      b.x = __ldg(gamma + k) * __ldg(W1 + (int64_t)k * D + n);
-      b.y = __ldg(gamma + k + 1) * __ldg(W1 + (int64_t)(k + 1) * D + n);
-      b.z = __ldg(gamma + k + 2) * __ldg(W1 + (int64_t)(k + 2) * D + n);
-      b.w = __ldg(gamma + k + 3) * __ldg(W1 + (int64_t)(k + 3) * D + n);
+      b.x = __ldg(gamma + k) * __ldg(W1 + (int64_t)k * ldw + n);
+      b.y = __ldg(gamma + k + 1) * __ldg(W1 + (int64_t)(k + 1) * ldw + n);
+      b.z = __ldg(gamma + k + 2) * __ldg(W1 + (int64_t)(k + 2) * ldw + n);
+      b.w = __ldg(gamma + k + 3) * __ldg(W1 + (int64_t)(k + 3) * ldw + n);
     } else {
-      b = __ldg(reinterpret_cast<const float4*>(W1 + (int64_t)n * D + kc * 4));
+      b = __ldg(reinterpret_cast<const float4*>(W1 + (int64_t)n * ldw + kc * 4));
     }
     float4 hi, lo;
     split4(b, hi, lo, rnd_lo);
@@ -511,12 +512,12 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int64_t row = tile * 128 + (warp * NI + i) * 4 + (lane >> 3);
-        const float* src = X + row * D + q * KQ + (lane & 7) * 4;
+        const float* src = X + row * ldx + q * KQ + (lane & 7) * 4;
         r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live && row < n_rows) r[i] = __ldcs(reinterpret_cast<const float4*>(src));
         if (pf) {                                     // same bytes of the tile pf_tiles visits ahead
           const int64_t prow = row + pf_tiles * (int64_t)gridDim.x * 128;
-          if (prow < n_rows) prefetch_l2(src + pf_tiles * (int64_t)gridDim.x * 128 * D);
+          if (prow < n_rows) prefetch_l2(src + pf_tiles * (int64_t)gridDim.x * 128 * ldx);
         }
       }
     };
@@ -627,7 +628,7 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
         }
         bar_sync_named(2, 128);
         // 128 rows x 16 chunks: a warp instruction stores two 256-byte half rows; 16 chunks per thread
-        float* obase = Out + (tile * 128) * D + h * HC;
+        float* obase = Out + (tile * 128) * ldo + h * HC;
         if (full && !do_push) {
 #pragma unroll
           for (int i0 = 0; i0 < 16; i0 += 8) {
@@ -642,7 +643,7 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
             for (int i = 0; i < 8; ++i) {
               const int idx = (i0 + i) * 128 + et;
               const int r = idx / CHH, c = idx % CHH;
-              __stcs(reinterpret_cast<float4*>(obase + (int64_t)r * D + c * 4), o[i]);
+              __stcs(reinterpret_cast<float4*>(obase + (int64_t)r * ldo + c * 4), o[i]);
             }
           }
         } else {
@@ -653,7 +654,7 @@ k_rows_ws(int64_t n_rows, const float* __restrict__ X, float* __restrict__ Out, 
             const int64_t grow = tile * 128 + r;
             if (grow < n_rows) {
               const float4 o = *reinterpret_cast<const float4*>(stage + r * HC + ((c ^ (r & (CHH - 1))) * 4));
-              __stcs(reinterpret_cast<float4*>(obase + (int64_t)r * D + c * 4), o);
+              __stcs(reinterpret_cast<float4*>(obase + (int64_t)r * ldo + c * 4), o);
               if (do_push) {                       // fused halo push over NVLink (posted stores)
                 const int p1 = __ldg(push.ptr + grow + 1);
                 for (int e = __ldg(push.ptr + grow); e < p1; ++e) {
@@ -1050,7 +1051,8 @@ static bool rows_ws_enabled() {
 
 template <int CPG, int MODE>
 static int launch_rows_ws(int64_t n_rows, const float* X, float* Out, const float* W, const float* gamma, const float* beta,
-                          float t, float eps, int passes, cudaStream_t st, const gode_push_route_t& pr, int grid) {
+                          float t, float eps, int passes, cudaStream_t st, const gode_push_route_t& pr, int grid,
+                          int64_t ldx = 128, int64_t ldo = 128, int64_t ldw = 128) {
   constexpr int D = 128;
   constexpr size_t smem = 2 * (size_t)D * D * 4 + 4 * (size_t)128 * 32 * 4 + (size_t)128 * (D / 2) * 4 + D * 4 + 128;
   static bool configured = false;
@@ -1065,9 +1067,9 @@ static int launch_rows_ws(int64_t n_rows, const float* X, float* Out, const floa
     return e ? atoi(e) : 0;                       // 2.28 ms without vs 2.39 ms with, N = 10 M; the loads are not the limit)
   }();
   const int cfg = rows_acc_cfg(MODE);
-  if (cfg == 3) k_rows_ws<D, CPG, MODE, 3><<<grid, tc::WS_THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf, cfg);
-  else if (cfg == 19) k_rows_ws<D, CPG, MODE, 19><<<grid, tc::WS_THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf, cfg);
-  else k_rows_ws<D, CPG, MODE, -1><<<grid, tc::WS_THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf, cfg);
+  if (cfg == 3) k_rows_ws<D, CPG, MODE, 3><<<grid, tc::WS_THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf, cfg, ldx, ldo, ldw);
+  else if (cfg == 19) k_rows_ws<D, CPG, MODE, 19><<<grid, tc::WS_THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf, cfg, ldx, ldo, ldw);
+  else k_rows_ws<D, CPG, MODE, -1><<<grid, tc::WS_THREADS, smem, st>>>(n_rows, X, Out, W, gamma, beta, t, eps, passes, pr, pf, cfg, ldx, ldo, ldw);
   GODE_LAUNCH_CHECK();
   return GODE_OK;
 }
@@ -1128,6 +1130,116 @@ int input_grad_tc(const gode_gcn_odefunc_t* f, const float* gS, float* gz, cudaS
   return GODE_EINVAL;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Out[r, c] = sum_k GroupNorm(y)[r, k] * W[1 + k, c] + t * W[0, c]  for a layer wider than d (the GAT node projection,
+// 2 * heads * oh + 2 * heads columns): 128-column blocks on k_rows_ws (strided W / Out), the remaining 4 / 8 / 16 / 32
+// attention-logit columns on a warp-per-row SIMT kernel (0.3 % of the flops; K = 128 in fp32 FMAs).
+// ------------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(256) k_gn_cols(int64_t n_rows, const float* __restrict__ Y, const float* __restrict__ W /*row 0 = t row*/,
+                                                 int64_t ldw, const float* __restrict__ gamma, const float* __restrict__ beta, float t,
+                                                 float eps, float* __restrict__ Out, int64_t ldo) {
+  constexpr int D = 128;
+  // gamma[k] * W[1 + k, c] at (k / 4) * LS + (k % 4) * NC + c: a lane reads the four rows of its group as float4s, and
+  // LS / 4 odd spreads the lanes of a quarter warp over all eight 16-byte bank groups (LS = 4 * NC put every lane on the
+  // same banks: 32-way conflicts, 2.15 ms per launch at N = 1 M)
+  constexpr int LS = 4 * NC + 4;
+  __shared__ __align__(16) float sW[(D / 4) * LS];
+  __shared__ float sR[NC];                       // t * W[0, c] + sum_k beta[k] W[1 + k, c]
+  for (int i = threadIdx.x; i < D * NC; i += blockDim.x) {
+    const int k = i / NC, c = i % NC;
+    sW[(k >> 2) * LS + (k & 3) * NC + c] = __ldg(gamma + k) * __ldg(W + (int64_t)(1 + k) * ldw + c);
+  }
+  if (threadIdx.x < NC) {
+    const int c = threadIdx.x;
+    float r = t * __ldg(W + c);
+    for (int k = 0; k < D; ++k) r = fmaf(__ldg(beta + k), __ldg(W + (int64_t)(1 + k) * ldw + c), r);
+    sR[c] = r;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < n_rows; r += nwarps) {
+    const float4 x = tc::normalize4<4>(__ldcs(reinterpret_cast<const float4*>(Y + r * D + lane * 4)), eps);   // lane = one group
+    float acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c += 4) {
+      const float4 w0 = *reinterpret_cast<const float4*>(sW + lane * LS + 0 * NC + c);
+      const float4 w1 = *reinterpret_cast<const float4*>(sW + lane * LS + 1 * NC + c);
+      const float4 w2 = *reinterpret_cast<const float4*>(sW + lane * LS + 2 * NC + c);
+      const float4 w3 = *reinterpret_cast<const float4*>(sW + lane * LS + 3 * NC + c);
+      acc[c + 0] = x.x * w0.x + x.y * w1.x + x.z * w2.x + x.w * w3.x;
+      acc[c + 1] = x.x * w0.y + x.y * w1.y + x.z * w2.y + x.w * w3.y;
+      acc[c + 2] = x.x * w0.z + x.y * w1.z + x.z * w2.z + x.w * w3.z;
+      acc[c + 3] = x.x * w0.w + x.y * w1.w + x.z * w2.w + x.w * w3.w;
+    }
+    // transposed butterfly: every exchange halves the number of columns a lane still carries (NC - 1 + log2(32 / NC)
+    // shuffles instead of 5 * NC); lane bits, from the top, select the column a lane ends up with
+    int col = 0;
+    bool writer = true;
+    {
+      int nv = NC;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        if (nv > 1) {
+          const int half = nv / 2;
+          const bool up = (lane & o) != 0;
+#pragma unroll
+          for (int i = 0; i < NC / 2; ++i)
+            if (i < half) {
+              const float send = up ? acc[i] : acc[i + half];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, o);
+              acc[i] = (up ? acc[i + half] : acc[i]) + recv;
+            }
+          if (up) col += half;
+          nv = half;
+        } else {
+          acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+          writer = writer && (lane & o) == 0;
+        }
+      }
+    }
+    if (writer) Out[r * ldo + col] = acc[0] + sR[col];
+  }
+}
+
+bool gn_linear_tc_supported(int d, int groups, int ncols) {
+  const int rem = ncols % 128;
+  return (tc_mask() & 1) && rows_ws_enabled() && d == 128 && groups == 32 && ncols >= 4 &&
+         (rem == 0 || rem == 4 || rem == 8 || rem == 16 || rem == 32);
+}
+
+int gn_linear_tc(int64_t n, int d, int groups, float eps, const float* y, const float* gamma, const float* beta, const float* W,
+                 int64_t ldw, float t, int ncols, float* out, int64_t ldo, int precision, cudaStream_t st) {
+  GODE_REQUIRE(gn_linear_tc_supported(d, groups, ncols), "gn_linear: d = 128 with 32 groups; columns = k * 128 + {0, 4, 8, 16, 32}");
+  GODE_REQUIRE(ldw >= ncols && ldo >= ncols && ldo % 4 == 0 && al16(y) && al16(out), "gn_linear: bad leading dimension / alignment");
+  if (n == 0) return GODE_OK;
+  const int passes = precision == GODE_PREC_TF32 ? 1 : 3;
+  const int64_t n_tiles = (n + 127) / 128;
+  const int grid = static_cast<int>(n_tiles < persistent_ctas() ? n_tiles : persistent_ctas());
+  gode_push_route_t pr;
+  memset(&pr, 0, sizeof(pr));
+  int c0 = 0;
+  for (; c0 + 128 <= ncols; c0 += 128) {
+    int rc = launch_rows_ws<4, 0>(n, y, out + c0, W + c0, gamma, beta, t, eps, passes, st, pr, grid, 128, ldo, ldw);
+    if (rc) return rc;
+  }
+  const int rem = ncols - c0;
+  if (rem > 0) {
+    const int64_t want = (n * 32 + 255) / 256;
+    const int64_t cap = 8LL * sm_count();
+    const unsigned g = static_cast<unsigned>(want < cap ? want : cap);
+    float* o = out + c0;
+    const float* w = W + c0;
+    if (rem == 4) k_gn_cols<4><<<g, 256, 0, st>>>(n, y, w, ldw, gamma, beta, t, eps, o, ldo);
+    else if (rem == 8) k_gn_cols<8><<<g, 256, 0, st>>>(n, y, w, ldw, gamma, beta, t, eps, o, ldo);
+    else if (rem == 16) k_gn_cols<16><<<g, 256, 0, st>>>(n, y, w, ldw, gamma, beta, t, eps, o, ldo);
+    else k_gn_cols<32><<<g, 256, 0, st>>>(n, y, w, ldw, gamma, beta, t, eps, o, ldo);
+    GODE_LAUNCH_CHECK();
+  }
+  return GODE_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // k_gemm_tc: general  C[M, N] = act(A[M, K] * Bt[N, K]^T + bias)  on tcgen05, 3xTF32 -- the dense products that are
@@ -1421,4 +1533,16 @@ extern "C" int gode_gn_wgrad_f32(int64_t n, int32_t d, int32_t groups, float eps
   GODE_REQUIRE(n >= 0 && (n == 0 || (y && G)) && out && cs, "gn_wgrad: null pointer");
   return gode::gn_wgrad_tc(n, d, groups, eps, y, G, ldg, ncols, out, ldo, cs, static_cast<float*>(ws), ws_bytes, precision,
                            gode::as_stream(stream));
+}
+
+// out[n, ncols] = [t | GroupNorm(y)] * W  with W [d + 1, ncols] (row 0 the t row), see gn_linear_tc.
+extern "C" int gode_gn_linear_supported(int32_t d, int32_t groups, int32_t ncols) {
+  return gode::gn_linear_tc_supported(d, groups, ncols) ? 1 : 0;
+}
+
+extern "C" int gode_gn_linear_f32(int64_t n, int32_t d, int32_t groups, float eps, const float* y, const float* gamma,
+                                  const float* beta, const float* W, int64_t ldw, float t, int32_t ncols, float* out, int64_t ldo,
+                                  int32_t precision, void* stream) {
+  GODE_REQUIRE(n >= 0 && (n == 0 || (y && out)) && gamma && beta && W, "gn_linear: null pointer");
+  return gode::gn_linear_tc(n, d, groups, eps, y, gamma, beta, W, ldw, t, ncols, out, ldo, precision, gode::as_stream(stream));
 }

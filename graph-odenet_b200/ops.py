@@ -722,17 +722,26 @@ class GatOdeFn(torch.autograd.Function):
         oh = C_ // H
         ldp = 2 * C_ + 2 * H
         pad = (-ldp) % 4        # rows of P are padded to a multiple of 16 bytes (one head: 2 * oh + 2 columns) with zero weights
-        # Bt [ldp + pad, d]: the K-major right operand (rows = output columns), t columns (0 and i) dropped
-        zp = torch.zeros(pad, d, device=y.device)
-        bt = torch.cat([f_weight[:, 1:i], f_weight[:, i + 1:], w_weight[:, 1:i], w_weight[:, i + 1:], zp], 0).contiguous()
-        w0 = torch.cat([f_weight[:, 0], f_weight[:, i], w_weight[:, 0], w_weight[:, i], zp[:, 0]])   # the t row of W_cat
+        # W1 [d, ldp + pad] = rows 1.. of W_cat ([in, out] layout), the t columns (0 and i) of the Linear weights dropped
+        zp = torch.zeros(d, pad, device=y.device)
+        w1 = torch.cat([f_weight[:, 1:i].t(), f_weight[:, i + 1:].t(), w_weight[:, 1:i].t(), w_weight[:, i + 1:].t(), zp], 1)
+        w0 = torch.cat([f_weight[:, 0], f_weight[:, i], w_weight[:, 0], w_weight[:, i], zp[0]])      # the t row of W_cat
         zc, zh = torch.zeros(C_, device=y.device), torch.zeros(H, device=y.device)
-        bcat = torch.cat([zc, f_bias if f_bias is not None else zc, zh, w_bias if w_bias is not None else zh, zp[:, 0]])
+        bcat = torch.cat([zc, f_bias if f_bias is not None else zc, zh, w_bias if w_bias is not None else zh, zp[0]])
         ldp += pad
         tt = t.detach().to(torch.float32) if torch.is_tensor(t) else float(t)
-        xn = groupnorm_fwd(y, groups, gamma, beta, gn_eps)
-        P = gemm_tc(xn, bt, w0 * tt + bcat)
-        del xn
+        row0 = w0 * tt + bcat                      # stays on the device: t is a device scalar inside the adjoint solve
+        if lib.gode_gn_linear_supported(d, groups, ldp):
+            # GroupNorm inside the producer of the tcgen05 product; [row0; W1] is the [d + 1, ldp] weight with "t" = 1
+            wfull = torch.cat([row0[None], w1], 0).contiguous()
+            P = torch.empty(y.shape[0], ldp, dtype=torch.float32, device=y.device)
+            check(lib.gode_gn_linear_f32(y.shape[0], d, groups, float(gn_eps), _p(y), _p(gamma.contiguous()), _p(beta.contiguous()),
+                                         _p(wfull), ldp, 1.0, ldp, _p(P), ldp, _lib.PREC_FP32, _stream()), "gode_gn_linear_f32")
+        else:
+            xn = groupnorm_fwd(y, groups, gamma, beta, gn_eps)
+            P = gemm_tc(xn, w1.t().contiguous(), row0)
+            del xn
+        w1 = w1.contiguous()
         out = torch.empty(graph.n_nodes, C_, dtype=torch.float32, device=y.device)
         den = torch.empty(graph.n_nodes, H, dtype=torch.float32, device=y.device)
         amax = torch.empty(H, dtype=torch.int64, device=y.device)
@@ -743,12 +752,12 @@ class GatOdeFn(torch.autograd.Function):
         ctx.graph, ctx.H, ctx.oh, ctx.groups, ctx.gn_eps = graph, H, oh, groups, gn_eps
         ctx.has_bias = (f_bias is not None, w_bias is not None)
         ctx.t = tt
-        ctx.save_for_backward(y, gamma, beta, bt, w0, P, out, den, amax)
+        ctx.save_for_backward(y, gamma, beta, w1, w0, P, out, den, amax)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        y, gamma, beta, bt, w0, P, out, den, amax = ctx.saved_tensors
+        y, gamma, beta, w1, w0, P, out, den, amax = ctx.saved_tensors
         graph, H, oh = ctx.graph, ctx.H, ctx.oh
         C_ = H * oh
         ldp = P.shape[1]                # 2 * C_ + 2 * H, padded to a multiple of 4
@@ -763,7 +772,7 @@ class GatOdeFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         gy = gt = ggam = gbeta = gfw = gfb = gww = gwb = None
         if need[0] or need[2] or need[3]:
-            dxn = gemm_tc(dP, bt.t().contiguous())                 # [N, ldp] x [ldp, d]: one 128-column tile
+            dxn = gemm_tc(dP, w1)                                  # dP [N, ldp] x W1^T [ldp, d]: one 128-column tile
             gy, ggam, gbeta = groupnorm_bwd(y, ctx.groups, gamma, dxn, ctx.gn_eps)
             del dxn
         if any(need[4:8]) or need[1]:

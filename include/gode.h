@@ -232,6 +232,15 @@ int gode_groupnorm_bwd(int64_t n, int32_t d, int32_t groups, float eps, const fl
  * [t | GroupNorm(y)] whose output is wider than d -- the GAT ODE function's projection (GAT/models.py:161-179 through
  * GAT/layers.py:40-45): dW[1:] = gamma * out + beta * cs, dW[0] = t * cs, db = cs.  d = 128 with 32 groups; ncols and ldg
  * multiples of 4, 16-byte aligned operands; anything else returns GODE_EINVAL (callers use gode_gemm_f32 then). */
+/* out[n, ncols] (row stride ldo) = [t*1 | GroupNorm(y)] * W, W [d+1, ncols] row-major (row stride ldw, row 0 the t row):
+ * the node projection of the GAT ODE function (GAT/models.py:172-179 feeding GAT/layers.py:40-45) without the [N, d+1]
+ * concatenation; GroupNorm is applied inside the producer of the tcgen05 product.  gode_gn_linear_supported: d = 128 with
+ * 32 groups, ncols = k*128 + {0, 4, 8, 16, 32}. */
+int gode_gn_linear_supported(int32_t d, int32_t groups, int32_t ncols);
+int gode_gn_linear_f32(int64_t n, int32_t d, int32_t groups, float eps, const float* y, const float* gamma, const float* beta,
+                       const float* W, int64_t ldw, float t, int32_t ncols, float* out, int64_t ldo, int32_t precision,
+                       void* stream);
+
 size_t gode_gn_wgrad_workspace_bytes(int32_t d);
 int gode_gn_wgrad_f32(int64_t n, int32_t d, int32_t groups, float eps, const float* y, const float* G, int64_t ldg,
                       int32_t ncols, float* out, int64_t ldo, float* cs, void* ws, size_t ws_bytes, int32_t precision,

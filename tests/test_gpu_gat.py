@@ -261,8 +261,9 @@ def test_gat_ode_function_fused_matches_unfused_and_oracle(heads, monkeypatch):
     f = f.to(DEV)
     f.set_adj(src.to(DEV), tgt.to(DEV), None)
     res = {}
-    for mode in ("1", "0"):
-        monkeypatch.setenv("GODE_GAT_FUSED", mode)
+    for mode in ("1", "1-gemm", "0"):     # fused with the GroupNorm-fused projection, fused over gn + the general GEMM, layer by layer
+        monkeypatch.setenv("GODE_GAT_FUSED", mode[0])
+        monkeypatch.setenv("GODE_TC", "6" if mode == "1-gemm" else "7")
         for p in f.parameters():
             p.grad = None
         xg = x.to(DEV).requires_grad_(True)
@@ -271,7 +272,7 @@ def test_gat_ode_function_fused_matches_unfused_and_oracle(heads, monkeypatch):
         y.backward(gy.to(DEV))
         res[mode] = (y.detach(), xg.grad, tg.grad, {k: p.grad.clone() for k, p in f.named_parameters()})
     for mode, (y, gx, gt, gp) in res.items():
-        what = "fused" if mode == "1" else "unfused"
+        what = {"1": "fused", "1-gemm": "fused (general GEMM)", "0": "unfused"}[mode]
         G.assert_close(y, yo.detach(), rtol=1e-5, atol_scale=1e-5, what=what + " f")
         G.assert_close(gx, x64.grad, rtol=1e-5, atol_scale=1e-5, what=what + " d/dy")
         assert abs(float(gt) - float(t64.grad)) <= 1e-5 * max(abs(float(t64.grad)), 1e-3), (what, float(gt), float(t64.grad))
