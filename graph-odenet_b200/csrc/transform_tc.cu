@@ -1160,8 +1160,15 @@ __global__ void __launch_bounds__(256) k_gn_cols(int64_t n_rows, const float* __
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // the row loop is latency-bound (one 512-byte load, ~100 dependent instructions, one store per row): the next two rows'
+  // loads are issued before this row's arithmetic
+  float4 nx0 = make_float4(0.f, 0.f, 0.f, 0.f), nx1 = nx0;
+  if (warp0 < n_rows) nx0 = __ldcs(reinterpret_cast<const float4*>(Y + warp0 * D + lane * 4));
+  if (warp0 + nwarps < n_rows) nx1 = __ldcs(reinterpret_cast<const float4*>(Y + (warp0 + nwarps) * D + lane * 4));
   for (int64_t r = warp0; r < n_rows; r += nwarps) {
-    const float4 x = tc::normalize4<4>(__ldcs(reinterpret_cast<const float4*>(Y + r * D + lane * 4)), eps);   // lane = one group
+    const float4 x = tc::normalize4<4>(nx0, eps);   // lane = one group
+    nx0 = nx1;
+    if (r + 2 * nwarps < n_rows) nx1 = __ldcs(reinterpret_cast<const float4*>(Y + (r + 2 * nwarps) * D + lane * 4));
     float acc[NC];
 #pragma unroll
     for (int c = 0; c < NC; c += 4) {
@@ -1268,10 +1275,24 @@ constexpr int GT_KG = 8;       // stages (K = 256 = 32 MMA K steps) accumulated 
 // 1e-5 bar.  So GT_KG stages go into one of two TMEM accumulator sets (hi*hi and the correction terms apart), and the four
 // epilogue warps add every finished set into fp32 running sums in shared memory (round-to-nearest adds) while the MMAs
 // continue into the other set; after a tile's last group the sums get bias / ReLU and are stored as full rows.
+// Output tile of work item t.  Tiles are visited in bands of `gm` row tiles, column tile by column tile inside a band, so
+// that the ~148 tiles in flight at any time share ~gm A panels and ~148 / gm B panels (both L2 resident) instead of 148
+// distinct A panels and one B panel: with the row-tile-fastest order every A panel of the QC edge encoder ([146 618, 2667],
+// 1.56 GB) came back from HBM once per column tile (42 x 1.56 GB per product).
+__device__ __forceinline__ void gemm_tile_of(int64_t t, int64_t tiles_m, int64_t tiles_n, int gm, int64_t& tm, int64_t& tn) {
+  const int64_t per_band = (int64_t)gm * tiles_n;
+  const int64_t band = t / per_band, within = t - band * per_band;
+  const int64_t m0 = band * gm;
+  const int64_t rows = tiles_m - m0 < gm ? tiles_m - m0 : gm;
+  tn = within / rows;
+  tm = m0 + (within - tn * rows);
+}
+
 __global__ void __launch_bounds__(tc::WS_THREADS, 1)
 k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ Bt, int64_t ldb,
           float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int relu, int passes, int vec_in, int vec_out,
-          int k_splits /*> 1: the K range is cut into k_splits slabs, slab s writes its partial product to C + s * M * ldc*/) {
+          int k_splits /*> 1: the K range is cut into k_splits slabs, slab s writes its partial product to C + s * M * ldc*/,
+          int band /*row tiles per band of the tile order, see gemm_tile_of*/) {
   using namespace tc;
   constexpr int BK = 32;                          // K per stage: one 128-byte swizzle atom of tf32
   constexpr int NI = 4;                           // warp-instructions per producer warp per operand per stage
@@ -1315,37 +1336,66 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
     // =============================== producers ============================================================
     // registers of one step: 4 chunks of A and 4 of B (row = (warp * 4 + i) * 4 + lane / 8, 16-byte chunk = lane % 8)
     float4 raw[2][2 * NI];
-    auto load_op = [&](const float* __restrict__ P, int64_t ld, int64_t rows, int64_t row, int64_t k) -> float4 {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < rows && k < K) {
-        const float* src = P + row * ld + k;
-        if (vec_in) {
-          v = __ldg(reinterpret_cast<const float4*>(src));     // in bounds of the padded row (ld % 4 == 0, ld >= K)
-          if (k + 3 >= K) {
-            if (k + 1 >= K) v.y = 0.f;
-            if (k + 2 >= K) v.z = 0.f;
-            v.w = 0.f;
-          }
-        } else {
-          v.x = __ldg(src);
-          if (k + 1 < K) v.y = __ldg(src + 1);
-          if (k + 2 < K) v.z = __ldg(src + 2);
-          if (k + 3 < K) v.w = __ldg(src + 3);
-        }
-      }
-      return v;
-    };
-    auto load_raw = [&](float4 (&r)[2 * NI], int64_t step) {
-      if (step >= n_steps) return;
-      const int64_t v = blockIdx.x + (step / KS) * (int64_t)gridDim.x;
+    // Load cursor.  The stages are loaded strictly in order, so the position (tile of this CTA, stage of the tile) is kept
+    // in counters and the tile's coordinates / row pointers are recomputed once per tile: with the divisions
+    // (step / KS, v % mn_tiles, the band order) evaluated per stage the producers executed 740 instructions per warp per
+    // stage -- ncu round 2: 43 % issue-slot utilisation against 22 % tensor-pipe utilisation, 3 300 cycles per stage.
+    int64_t ld_it = 0;                              // tile iteration of this CTA
+    int64_t ld_ks = 0;                              // stage inside the tile
+    bool ld_done = false;
+    const float* pa[NI];
+    const float* pb[NI];
+    bool va[NI], vb[NI];
+    int64_t kbase = 0;
+    auto ld_setup = [&]() {
+      const int64_t v = blockIdx.x + ld_it * (int64_t)gridDim.x;
+      ld_done = v >= n_tiles;
+      if (ld_done) return;
       const int64_t t = v % mn_tiles, sp = v / mn_tiles;
-      const int64_t tm = t % tiles_m, tn = t / tiles_m;
-      const int64_t k = (sp * KS + step % KS) * BK + (lane & 7) * 4;
+      int64_t tm, tn;
+      gemm_tile_of(t, tiles_m, tiles_n, band, tm, tn);
+      kbase = sp * KS * BK + (lane & 7) * 4;
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int rr = (warp * NI + i) * 4 + (lane >> 3);
-        r[i] = load_op(A, lda, M, tm * 128 + rr, k);
-        r[NI + i] = load_op(Bt, ldb, N, tn * 128 + rr, k);
+        const int64_t ra = tm * 128 + rr, rb = tn * 128 + rr;
+        va[i] = ra < M;
+        vb[i] = rb < N;
+        pa[i] = A + (va[i] ? ra : 0) * lda;
+        pb[i] = Bt + (vb[i] ? rb : 0) * ldb;
+      }
+    };
+    ld_setup();
+    auto load_raw = [&](float4 (&r)[2 * NI]) {
+      if (ld_done) return;
+      const int64_t k = kbase + ld_ks * BK;
+      const bool kin = k < K, ktail = k + 3 >= K;
+#pragma unroll
+      for (int i = 0; i < 2 * NI; ++i) {
+        const float* __restrict__ src = (i < NI ? pa[i % NI] : pb[i % NI]) + k;
+        const bool ok = kin && (i < NI ? va[i % NI] : vb[i % NI]);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+          if (vec_in) {
+            v = __ldg(reinterpret_cast<const float4*>(src));     // in bounds of the padded row (ld % 4 == 0, ld >= K)
+            if (ktail) {
+              if (k + 1 >= K) v.y = 0.f;
+              if (k + 2 >= K) v.z = 0.f;
+              v.w = 0.f;
+            }
+          } else {
+            v.x = __ldg(src);
+            if (k + 1 < K) v.y = __ldg(src + 1);
+            if (k + 2 < K) v.z = __ldg(src + 2);
+            if (k + 3 < K) v.w = __ldg(src + 3);
+          }
+        }
+        r[i] = v;
+      }
+      if (++ld_ks == KS) {
+        ld_ks = 0;
+        ++ld_it;
+        ld_setup();
       }
     };
     auto do_step = [&](float4 (&r)[2 * NI], int64_t step) {
@@ -1366,12 +1416,12 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
         *reinterpret_cast<float4*>(base + 2 * T_BYTES + off) = hi;
         *reinterpret_cast<float4*>(base + 3 * T_BYTES + off) = lo;
       }
-      load_raw(r, step + 2);
+      load_raw(r);                                 // the stage two ahead, into the registers just consumed
       fence_async_smem();
       mbar_arrive(&bars[s]);
     };
-    load_raw(raw[0], 0);
-    load_raw(raw[1], 1);
+    load_raw(raw[0]);
+    load_raw(raw[1]);
     for (int64_t step = 0; step < n_steps; step += 2) {
       do_step(raw[0], step);
       do_step(raw[1], step + 1);
@@ -1380,9 +1430,10 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
     // =============================== MMA issue (one thread) ===============================================
     if (lane == 0) {
       int64_t g = 0;                                 // accumulation groups issued so far (over all tiles of this CTA)
+      int64_t ks = -1;                               // stage inside the tile (a counter: no division per stage)
       for (int64_t step = 0; step < n_steps; ++step) {
         const int s = static_cast<int>(step % GT_STAGES);
-        const int64_t ks = step % KS;
+        if (++ks == KS) ks = 0;
         const int set = static_cast<int>(g & 1);
         const bool first = ks % GT_KG == 0;          // first stage of its group
         if (first && g >= 2) mbar_wait(&bars[2 * GT_STAGES + 2 + set], static_cast<uint32_t>(((g >> 1) - 1) & 1));
@@ -1419,7 +1470,8 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t v = blockIdx.x + it * (int64_t)gridDim.x;
       const int64_t t = v % mn_tiles, sp = v / mn_tiles;
-      const int64_t tm = t % tiles_m, tn = t / tiles_m;
+      int64_t tm, tn;
+      gemm_tile_of(t, tiles_m, tiles_n, band, tm, tn);
       float* __restrict__ Cs = C + sp * M * ldc;
       for (int64_t gi = 0; gi < n_groups; ++gi, ++g) {
         const int set = static_cast<int>(g & 1);
@@ -1503,8 +1555,12 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const 
   const int grid = static_cast<int>(n_tiles < persistent_ctas() ? n_tiles : persistent_ctas());
   const int vec_in = (lda % 4 == 0) && (ldb % 4 == 0) && al16(A) && al16(Bt);
   const int vec_out = (ldc % 4 == 0) && al16(C) && (k_splits == 1 || (M * ldc) % 4 == 0);
+  // GODE_GEMM_BAND: row tiles per band of the tile order (default 16: 16 A panels + ~9 B panels in flight)
+  const char* be = getenv("GODE_GEMM_BAND");
+  int band = be ? atoi(be) : 16;
+  if (band < 1) band = 1;
   k_gemm_tc<<<grid, tc::WS_THREADS, smem, st>>>(M, N, K, A, lda, Bt, ldb, C, ldc, bias, relu,
-                                                precision == GODE_PREC_TF32 ? 1 : 3, vec_in, vec_out, k_splits);
+                                                precision == GODE_PREC_TF32 ? 1 : 3, vec_in, vec_out, k_splits, band);
   GODE_LAUNCH_CHECK();
   return GODE_OK;
 }
