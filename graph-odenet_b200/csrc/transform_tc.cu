@@ -1292,7 +1292,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1)
 k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ Bt, int64_t ldb,
           float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int relu, int passes, int vec_in, int vec_out,
           int k_splits /*> 1: the K range is cut into k_splits slabs, slab s writes its partial product to C + s * M * ldc*/,
-          int band /*row tiles per band of the tile order, see gemm_tile_of*/) {
+          int band /*row tiles per band of the tile order, see gemm_tile_of*/, int pf_stages /*L2 prefetch distance of A, in stages*/) {
   using namespace tc;
   constexpr int BK = 32;                          // K per stage: one 128-byte swizzle atom of tf32
   constexpr int NI = 4;                           // warp-instructions per producer warp per operand per stage
@@ -1366,14 +1366,15 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
       }
     };
     ld_setup();
-    auto load_raw = [&](float4 (&r)[2 * NI]) {
+    // one 16-byte chunk of A (slot i) and of B (slot NI + i) of the stage at the cursor
+    auto load_slot = [&](float4 (&r)[2 * NI], int i) {
       if (ld_done) return;
       const int64_t k = kbase + ld_ks * BK;
       const bool kin = k < K, ktail = k + 3 >= K;
 #pragma unroll
-      for (int i = 0; i < 2 * NI; ++i) {
-        const float* __restrict__ src = (i < NI ? pa[i % NI] : pb[i % NI]) + k;
-        const bool ok = kin && (i < NI ? va[i % NI] : vb[i % NI]);
+      for (int h = 0; h < 2; ++h) {
+        const float* __restrict__ src = (h == 0 ? pa[i] : pb[i]) + k;
+        const bool ok = kin && (h == 0 ? va[i] : vb[i]);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ok) {
           if (vec_in) {
@@ -1389,14 +1390,24 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
             if (k + 2 < K) v.z = __ldg(src + 2);
             if (k + 3 < K) v.w = __ldg(src + 3);
           }
+          // ask L2 for this row's line `pf_stages` stages ahead (no registers; one request per 128-byte line)
+          if (h == 0 && pf_stages > 0 && (lane & 7) == 0 && k + pf_stages * BK < K) prefetch_l2(src + pf_stages * BK);
         }
-        r[i] = v;
+        r[h * NI + i] = v;
       }
+    };
+    auto ld_advance = [&]() {
+      if (ld_done) return;
       if (++ld_ks == KS) {
         ld_ks = 0;
         ++ld_it;
         ld_setup();
       }
+    };
+    auto load_raw = [&](float4 (&r)[2 * NI]) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i) load_slot(r, i);
+      ld_advance();
     };
     auto do_step = [&](float4 (&r)[2 * NI], int64_t step) {
       if (step >= n_steps) return;
@@ -1416,7 +1427,8 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
         *reinterpret_cast<float4*>(base + 2 * T_BYTES + off) = hi;
         *reinterpret_cast<float4*>(base + 3 * T_BYTES + off) = lo;
       }
-      load_raw(r);                                 // the stage two ahead, into the registers just consumed
+      load_raw(r);     // the stage two ahead, into the registers just consumed (issuing these chunk by chunk between the
+                       // stores above measured SLOWER: 47 vs 36 ms on the QC forward product)
       fence_async_smem();
       mbar_arrive(&bars[s]);
     };
@@ -1539,6 +1551,291 @@ k_gemm_tc(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t 
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_gemm_tc2: the same product for 16-byte-aligned operands (lda, ldb % 4 == 0), with the operand loads taken out of the
+// registers.  k_gemm_tc keeps two stages of raw operands in registers: a load is issued one stage period before it is used,
+// so the period cannot drop below the loaded L2 latency (ncu round 2: 2 350 cycles per stage against ~750 of tensor work).
+// Here every producer thread copies its own 16-byte chunks of the next GT2_RING stages into a raw ring in shared memory
+// with cp.async (thread-private slots: no barrier, cp.async.wait_group orders a thread's own copies; out-of-range rows and
+// the K tail are zero-filled by the copy's src-size operand), reads them back, splits and stores the hi / lo MMA stages.
+// Room for the ring comes from moving the running sums out of shared memory: they live in a fourth TMEM accumulator that
+// the epilogue warps update with tcgen05.ld -> fp32 add -> tcgen05.st (TMEM: hi*hi set 0 | hi*hi set 1 | correction terms
+// | running sums, 128 columns each; the correction terms are 2^-11 of the product and accumulate over the whole tile).
+// ------------------------------------------------------------------------------------------------
+namespace tc {
+constexpr int GT2_RING = 3;    // raw stages in flight per CTA (32 KB each)
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+}  // namespace tc
+
+__global__ void __launch_bounds__(tc::WS_THREADS, 1)
+k_gemm_tc2(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ Bt, int64_t ldb,
+           float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int relu, int passes, int vec_out, int k_splits,
+           int band) {
+  using namespace tc;
+  constexpr int BK = 32;
+  constexpr int NI = 4;
+  constexpr uint32_t T_BYTES = 128 * BK * 4;      // one of hi / lo of one operand of one stage (16 KB)
+  constexpr uint32_t STAGE_BYTES = 4 * T_BYTES;   // A_hi | A_lo | B_hi | B_lo
+  constexpr uint32_t RAW_BYTES = 2 * T_BYTES;     // raw A | raw B of one stage (32 KB)
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* ring = smem + GT_STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + GT2_RING * RAW_BYTES);
+  // bars: [0, S) full, [S, 2S) empty, [2S, 2S+2) set_full, [2S+2, 2S+4) set_drained, [2S+4] tile_drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GT_STAGES + 5);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tiles_m = (M + 127) / 128, tiles_n = (N + 127) / 128;
+  const int64_t mn_tiles = tiles_m * tiles_n;
+  const int64_t n_tiles = mn_tiles * k_splits;
+  if ((int64_t)blockIdx.x >= n_tiles) return;
+  const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int64_t KS = ((K + BK - 1) / BK + k_splits - 1) / k_splits;
+  const int64_t n_steps = my_tiles * KS;
+  const int64_t n_groups = (KS + GT_KG - 1) / GT_KG;
+
+  if (tid == 0) {
+    for (int s = 0; s < GT_STAGES; ++s) {
+      mbar_init(&bars[s], WS_PRODUCERS);
+      mbar_init(&bars[GT_STAGES + s], 1);
+    }
+    mbar_init(&bars[2 * GT_STAGES + 0], 1);
+    mbar_init(&bars[2 * GT_STAGES + 1], 1);
+    mbar_init(&bars[2 * GT_STAGES + 2], 128);
+    mbar_init(&bars[2 * GT_STAGES + 3], 128);
+    mbar_init(&bars[2 * GT_STAGES + 4], 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t IDESC = make_idesc(128, 128, false, false);
+  constexpr uint32_t T_CORR = 256, T_SUM = 384;
+
+  if (warp < 8) {
+    // =============================== producers ============================================================
+    int64_t ld_it = 0, ld_ks = 0;                   // load cursor: tile iteration of this CTA, stage inside the tile
+    bool ld_done = false;
+    const float* pa[NI];
+    const float* pb[NI];
+    bool va[NI], vb[NI];
+    int64_t kbase = 0;
+    auto ld_setup = [&]() {
+      const int64_t v = blockIdx.x + ld_it * (int64_t)gridDim.x;
+      ld_done = v >= n_tiles;
+      if (ld_done) return;
+      const int64_t t = v % mn_tiles, sp = v / mn_tiles;
+      int64_t tm, tn;
+      gemm_tile_of(t, tiles_m, tiles_n, band, tm, tn);
+      kbase = sp * KS * BK + (lane & 7) * 4;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int rr = (warp * NI + i) * 4 + (lane >> 3);
+        const int64_t ra = tm * 128 + rr, rb = tn * 128 + rr;
+        va[i] = ra < M;
+        vb[i] = rb < N;
+        pa[i] = A + (va[i] ? ra : 0) * lda;
+        pb[i] = Bt + (vb[i] ? rb : 0) * ldb;
+      }
+    };
+    ld_setup();
+    const uint32_t ring_u32 = smem_u32(ring) + tid * 16;    // chunk i of slot r: ring + r * RAW_BYTES + i * 4096 + tid * 16
+    // copies of the stage at the cursor into ring slot `slot` (nothing when the CTA's work is exhausted); always one group
+    auto issue = [&](int slot) {
+      if (!ld_done) {
+        const int64_t k = kbase + ld_ks * BK;
+        const int64_t left = K - k;                 // valid floats from k on (<= 0: whole chunk zero-filled)
+        const uint32_t kb = left >= 4 ? 16u : (left > 0 ? static_cast<uint32_t>(left) * 4u : 0u);
+        const int64_t ko = left > 0 ? k : 0;        // keep the address inside the row when nothing is read
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          cp_async16(ring_u32 + slot * RAW_BYTES + i * 4096, pa[i] + ko, va[i] ? kb : 0u);
+          cp_async16(ring_u32 + slot * RAW_BYTES + (NI + i) * 4096, pb[i] + ko, vb[i] ? kb : 0u);
+        }
+        if (++ld_ks == KS) {
+          ld_ks = 0;
+          ++ld_it;
+          ld_setup();
+        }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int r = 0; r < GT2_RING; ++r) issue(r);
+    int slot = 0;
+    for (int64_t step = 0; step < n_steps; ++step) {
+      const int s = static_cast<int>(step % GT_STAGES);
+      const int64_t use = step / GT_STAGES;
+      cp_async_wait<GT2_RING - 1>();                // this thread's copies of stage `step` have landed
+      float4 raw[2 * NI];
+      const unsigned char* rs = ring + (size_t)slot * RAW_BYTES + tid * 16;
+#pragma unroll
+      for (int i = 0; i < 2 * NI; ++i) raw[i] = *reinterpret_cast<const float4*>(rs + i * 4096);
+      if (use >= 1) mbar_wait(&bars[GT_STAGES + s], static_cast<uint32_t>((use - 1) & 1));
+      unsigned char* base = smem + (size_t)s * STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int rr = (warp * NI + i) * 4 + (lane >> 3);
+        const uint32_t off = (rr >> 3) * 1024 + (rr & 7) * 128 + (((lane & 7) ^ (rr & 7)) << 4);
+        float4 hi, lo;
+        split4(raw[i], hi, lo);
+        *reinterpret_cast<float4*>(base + off) = hi;
+        *reinterpret_cast<float4*>(base + T_BYTES + off) = lo;
+        split4(raw[NI + i], hi, lo);
+        *reinterpret_cast<float4*>(base + 2 * T_BYTES + off) = hi;
+        *reinterpret_cast<float4*>(base + 3 * T_BYTES + off) = lo;
+      }
+      issue(slot);                                  // stage step + GT2_RING into the slot just read (values are in registers)
+      fence_async_smem();
+      mbar_arrive(&bars[s]);
+      if (++slot == GT2_RING) slot = 0;
+    }
+    cp_async_wait<0>();
+  } else if (warp == 12) {
+    // =============================== MMA issue (one thread) ===============================================
+    if (lane == 0) {
+      int64_t g = 0;                                 // accumulation groups issued so far (over all tiles of this CTA)
+      int64_t ks = -1;
+      int64_t tile_it = 0;
+      for (int64_t step = 0; step < n_steps; ++step) {
+        const int s = static_cast<int>(step % GT_STAGES);
+        if (++ks == KS) {
+          ks = 0;
+          ++tile_it;
+        }
+        const int set = static_cast<int>(g & 1);
+        const bool first = ks % GT_KG == 0;          // first stage of its group
+        if (first && g >= 2) mbar_wait(&bars[2 * GT_STAGES + 2 + set], static_cast<uint32_t>(((g >> 1) - 1) & 1));
+        // the correction accumulator and the running sums belong to one tile at a time
+        if (ks == 0 && tile_it >= 1) mbar_wait(&bars[2 * GT_STAGES + 4], static_cast<uint32_t>((tile_it - 1) & 1));
+        mbar_wait(&bars[s], static_cast<uint32_t>((step / GT_STAGES) & 1));
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t tmem_d = tmem_base + set * 128;
+#pragma unroll
+        for (int q = 0; q < BK / 8; ++q) {
+          const uint64_t a_hi = make_desc_sw128(base + q * 32), a_lo = make_desc_sw128(base + T_BYTES + q * 32);
+          const uint64_t b_hi = make_desc_sw128(base + 2 * T_BYTES + q * 32), b_lo = make_desc_sw128(base + 3 * T_BYTES + q * 32);
+          mma_tf32(tmem_d, a_hi, b_hi, IDESC, (first && q == 0) ? 0u : 1u);
+          if (passes == 3) {
+            mma_tf32(tmem_base + T_CORR, a_lo, b_hi, IDESC, (ks == 0 && q == 0) ? 0u : 1u);
+            mma_tf32(tmem_base + T_CORR, a_hi, b_lo, IDESC, 1u);
+          }
+        }
+        mma_commit(&bars[GT_STAGES + s]);
+        if (ks % GT_KG == GT_KG - 1 || ks == KS - 1) {
+          mma_commit(&bars[2 * GT_STAGES + set]);
+          ++g;
+        }
+      }
+    }
+  } else {
+    // =============================== drain + epilogue (warps 8-11) ========================================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                   // TMEM lane = tile row = the row this thread stores
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    int64_t g = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t v = blockIdx.x + it * (int64_t)gridDim.x;
+      const int64_t t = v % mn_tiles, sp = v / mn_tiles;
+      int64_t tm, tn;
+      gemm_tile_of(t, tiles_m, tiles_n, band, tm, tn);
+      float* __restrict__ Cs = C + sp * M * ldc;
+      const int64_t grow = tm * 128 + row;
+      for (int64_t gi = 0; gi < n_groups; ++gi, ++g) {
+        const int set = static_cast<int>(g & 1);
+        const bool last = gi == n_groups - 1;
+        mbar_wait(&bars[2 * GT_STAGES + set], static_cast<uint32_t>((g >> 1) & 1));
+        tc_fence_after();
+        const uint32_t t_main = tmem_base + set * 128 + lane_off;
+#pragma unroll 1
+        for (int cb = 0; cb < 128; cb += 32) {
+          float acc[32];
+          tmem_ld32(t_main + cb, acc);
+          if (gi > 0) {
+            float w[32];
+            tmem_ld32(tmem_base + T_SUM + lane_off + cb, w);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] += w[j];
+          }
+          if (!last) {
+            tmem_st32(tmem_base + T_SUM + lane_off + cb, acc);
+            continue;
+          }
+          if (passes == 3) {
+            float w[32];
+            tmem_ld32(tmem_base + T_CORR + lane_off + cb, w);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] += w[j];
+          }
+          if (cb == 96) {                            // every accumulator of the tile has been read out
+            tc_fence_before();
+            mbar_arrive(&bars[2 * GT_STAGES + 2 + set]);
+            mbar_arrive(&bars[2 * GT_STAGES + 4]);
+          }
+          if (grow < M) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int64_t col = tn * 128 + cb + j;
+              if (col >= N) break;
+              float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+              if (bias) {
+                o.x += __ldg(bias + col);
+                if (col + 1 < N) o.y += __ldg(bias + col + 1);
+                if (col + 2 < N) o.z += __ldg(bias + col + 2);
+                if (col + 3 < N) o.w += __ldg(bias + col + 3);
+              }
+              if (relu) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+              }
+              float* dst = Cs + grow * ldc + col;
+              if (vec_out && col + 3 < N) {
+                *reinterpret_cast<float4*>(dst) = o;
+              } else {
+                dst[0] = o.x;
+                if (col + 1 < N) dst[1] = o.y;
+                if (col + 2 < N) dst[2] = o.z;
+                if (col + 3 < N) dst[3] = o.w;
+              }
+            }
+          }
+        }
+        if (!last) {
+          tc_fence_before();
+          mbar_arrive(&bars[2 * GT_STAGES + 2 + set]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 int gemm_tc(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc,
             const float* bias, int relu, int precision, cudaStream_t st, int k_splits) {
   GODE_REQUIRE(M >= 0 && N >= 0 && K >= 1 && lda >= K && ldb >= K && ldc >= N, "gemm_tc: bad shape");
@@ -1559,8 +1856,24 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const 
   const char* be = getenv("GODE_GEMM_BAND");
   int band = be ? atoi(be) : 16;
   if (band < 1) band = 1;
+  const char* pe = getenv("GODE_GEMM_PREFETCH");    // L2 prefetch distance of the A operand in stages of 32 columns (0 = off)
+  const int pf_stages = pe ? atoi(pe) : 0;
+  // GODE_GEMM_V: 2 (default) = k_gemm_tc2 (cp.async raw ring, TMEM running sums) for aligned operands, 1 = k_gemm_tc
+  const char* ve = getenv("GODE_GEMM_V");
+  if (vec_in && (!ve || atoi(ve) != 1)) {
+    constexpr size_t smem2 = tc::GT_STAGES * 4 * (size_t)128 * 32 * 4 + tc::GT2_RING * 2 * (size_t)128 * 32 * 4 + 256;
+    static bool configured2 = false;
+    if (!configured2) {
+      GODE_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      configured2 = true;
+    }
+    k_gemm_tc2<<<grid, tc::WS_THREADS, smem2, st>>>(M, N, K, A, lda, Bt, ldb, C, ldc, bias, relu,
+                                                    precision == GODE_PREC_TF32 ? 1 : 3, vec_out, k_splits, band);
+    GODE_LAUNCH_CHECK();
+    return GODE_OK;
+  }
   k_gemm_tc<<<grid, tc::WS_THREADS, smem, st>>>(M, N, K, A, lda, Bt, ldb, C, ldc, bias, relu,
-                                                precision == GODE_PREC_TF32 ? 1 : 3, vec_in, vec_out, k_splits, band);
+                                                precision == GODE_PREC_TF32 ? 1 : 3, vec_in, vec_out, k_splits, band, pf_stages);
   GODE_LAUNCH_CHECK();
   return GODE_OK;
 }
