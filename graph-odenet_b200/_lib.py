@@ -88,6 +88,7 @@ _PROTOS = {
     "gode_gemm_tc_splitk_f32": (C.c_int, [i64, i64, i64, vp, i64, vp, i64, vp, i64, i32, i32, vp]),
     "gode_groupnorm_fwd": (C.c_int, [i64, i32, i32, f32, vp, i64, vp, vp, vp, i64, vp]),
     "gode_groupnorm_bwd": (C.c_int, [i64, i32, i32, f32, vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, sz, vp]),
+    "gode_qc_collate": (C.c_int, [i32, vp, vp, vp, vp, vp, i32, i64, i64, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
     "gode_gn_linear_supported": (C.c_int, [i32, i32, i32]),
     "gode_gn_linear_f32": (C.c_int, [i64, i32, i32, f32, vp, vp, vp, vp, i64, f32, i32, vp, i64, i32, vp]),
     "gode_gn_wgrad_workspace_bytes": (sz, [i32]),

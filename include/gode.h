@@ -439,6 +439,25 @@ int gode_segment_attend_bwd(int32_t n_graphs, int32_t h, const int32_t* gptr, co
                             float* dx, int64_t lddx, float* dq, int64_t lddq, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Device-side collate of molecule graphs into one block-diagonal batch.
+ * replaces: collate_g_concat_edge_data -- QC/datasets/utils.py:153-217 (the DataLoader's collate_fn, a Python loop per
+ *           batch): node ids shifted by the atoms before the molecule, every undirected edge emitted as
+ *           (src -> tgt) at m_acc + i and (tgt -> src) at M + m_acc + i with the same feature row, B[j] = position of
+ *           node j's molecule in the batch.
+ * The dataset is a ragged store on the device: node_ptr / edge_ptr [n_molecules + 1] (int64), X_all [sum atoms, n_d],
+ * per undirected edge (in the reference's sorted((src, tgt)) order inside a molecule) local node ids e_src_local /
+ * e_tgt_local (int32) and E_all [sum edges, e_d].  sel [n_sel] (int32) are the molecule ids of the batch in batch order;
+ * node_off / edge_off [n_sel + 1] the exclusive scans of their atom / edge counts, N = node_off[n_sel], M = edge_off[n_sel].
+ * Outputs: B [N] int64, X [N, n_d], E_d [2M, e_d], E_src [2M] int64, E_tgt [2M] int64 (the target node of every
+ * directed edge: the row index of the reference's one-hot E_tgt [N, 2M]).  shift = 0 keeps the endpoints as numbered
+ * inside the molecule (the reference, utils.py:196-203); shift = 1 adds the molecule's node offset in the batch.
+ * ---------------------------------------------------------------------------------------------- */
+int gode_qc_collate(int32_t n_sel, const int32_t* sel, const int64_t* node_ptr, const int64_t* edge_ptr,
+                    const int64_t* node_off, const int64_t* edge_off, int32_t shift, int64_t N, int64_t M,
+                    const float* X_all, int32_t n_d, const int32_t* e_src_local, const int32_t* e_tgt_local, const float* E_all, int32_t e_d,
+                    int64_t* B, float* X, float* E_d, int64_t* E_src, int64_t* E_tgt, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Halo pack for the row-partitioned (multi-GPU) path: dst[i, :] = src[idx[i], :].
  * The reference is single-device; this packs the rows of the SpMM operand of
  * torch.spmm(adj, support) (GCN/layers.py:71) that peer ranks reference, ordered by destination rank,

@@ -126,3 +126,33 @@ def assert_close_l2(a, b, tol, what=""):
     assert a.shape == b.shape, (what, a.shape, b.shape)
     err = float((a - b).norm() / (b.norm() + 1e-300))
     assert err <= tol, "%s: relative L2 error %.3e > %.1e" % (what, err, tol)
+
+
+def synthetic_molecules(sizes=(6, 1, 9, 3, 2, 7, 4), seed=33, n_d=13, e_d=5, o_d=12, global_ids=False):
+    """Dataset items of the reference's QC datasets, ``((M, x, e), o)`` (QC/datasets/qm9.py __getitem__): adjacency matrix,
+    node feature rows, ``{(src, tgt): edge feature row}`` with one entry per undirected edge, target row.  A spanning tree
+    plus a few extra bonds per molecule; the single-atom molecule has no edge.  Values are float64 with more than 24
+    significant bits, so the float32 rounding of the collate is exercised."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for n in sizes:
+        pairs = set()
+        for i in range(1, n):
+            pairs.add((int(rng.randint(0, i)), i))
+        for _ in range(n // 3):
+            a, b = sorted(int(v) for v in rng.randint(0, n, 2))
+            if a != b:
+                pairs.add((a, b))
+        order = list(pairs)
+        rng.shuffle(order)                       # dict insertion order is not the sorted order the collate must produce
+        M = np.zeros([n, n])
+        e = {}
+        for a, b in order:
+            if rng.rand() < 0.5:
+                a, b = b, a                      # keys are not always (low, high)
+            M[a, b] = M[b, a] = 1.0
+            e[(a, b)] = list(rng.standard_normal(e_d))
+        x = [list(rng.standard_normal(n_d)) for _ in range(n)]
+        o = list(rng.standard_normal(o_d))
+        out.append(((M, x, e), o))
+    return out

@@ -18,6 +18,7 @@ Outputs (all small, committed):
   gcn_golden.npz       GraphConvolution / ODEfunc / ODEfunc2 / ODEBlock / whole-model outputs + grads
   gat_golden.npz       GAT GraphConvolution + ODEfunc outputs + grads
   qc_golden.npz        QC EdgeGraphConvolution / EdgeEncoderMLP / EdgeGCN_K_Sum outputs + grads
+  qc_collate_golden.npz  the DataLoader collate of QC/datasets/utils.py on synthetic molecules (``--only-qc-collate``)
   set2set_golden.npz   QC Set2Set readout and EdgeGCN_K_Set2Set outputs + grads (``--only-set2set`` regenerates it alone)
 """
 from __future__ import annotations
@@ -589,8 +590,34 @@ def make_qc_models():
     print("qc_models_golden.npz", os.path.getsize(os.path.join(HERE, "qc_models_golden.npz")) // 1024, "KiB")
 
 
+def make_qc_collate():
+    """qc_collate_golden.npz: the reference's DataLoader collate (QC/datasets/utils.py:153-217) on synthetic molecules.
+    ``QC/datasets/utils.py`` imports rdkit and networkx at module level (utils.py:15-19) for its file parsers; empty stub
+    modules satisfy the import, the collate itself is numpy + torch."""
+    from tests import _golden as TG
+    for name in ("rdkit", "networkx"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except ImportError:
+                sys.modules[name] = types.ModuleType(name)
+    spec = importlib.util.spec_from_file_location("ref_qc_datasets_utils", os.path.join(REF, "QC", "datasets", "utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = {}
+    for tag, kw in (("a", {}), ("b", {"sizes": (3, 5, 1, 1, 8), "seed": 5})):
+        mols = TG.synthetic_molecules(**kw)
+        bs, G_, B, X, E_d, E_src, E_tgt, Y = mod.collate_g_concat_edge_data(mols)
+        out.update({tag + "/bs": np.int64(bs), tag + "/G": G_.numpy(), tag + "/B": B.numpy(), tag + "/X": X.numpy(),
+                    tag + "/E_d": E_d.numpy(), tag + "/E_src": E_src.numpy(), tag + "/E_tgt": E_tgt.numpy(), tag + "/Y": Y.numpy()})
+    np.savez_compressed(os.path.join(HERE, "qc_collate_golden.npz"), **out)
+    print("qc_collate_golden.npz", os.path.getsize(os.path.join(HERE, "qc_collate_golden.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    if "--only-qc-models" in sys.argv:
+    if "--only-qc-collate" in sys.argv:
+        make_qc_collate()
+    elif "--only-qc-models" in sys.argv:
         make_qc_models()
     elif "--only-set2set" in sys.argv:
         make_set2set()
@@ -600,3 +627,4 @@ if __name__ == "__main__":
         main()
         make_models()
         make_qc_models()
+        make_qc_collate()
