@@ -472,16 +472,22 @@ def run_ours(a):
     def launch_streams(method):
         """[N,d] streams (besides S) of every agg_fwd launch of one fwd+bwd step on grid [0,1]."""
         tab = _od.TABLEAUS[method]
+        running = _od._running_final(tab)
         out = []
+        ks = [None] * tab.s
         for aug in (False, True):
             if aug:
                 out.append(1)                                        # f(t1): writes k only
             for i in range(tab.s):
                 last = i == tab.s - 1
-                row = tab.b if last else tab.a[i + 1]
-                n_prev = sum(1 for c in row[:i] if c != 0)
-                store = (not last) and _od._needed_later(tab, i)
-                out.append((1 if store else 0) + 1 + n_prev + 1 + (2 if aug else 0))   # k_i, y0, k_j.., y_next, (a, gP)
+                _, kprev, _, _, sec = _od._stage_plan(tab, i, 1.0, ks, running)
+                if aug and last:
+                    out.append(2)                                    # the adjoint's last stage forms no y(t0): a, gP only
+                    continue
+                second = sec is not None and not aug                 # running final combination (the adjoint's y needs none)
+                store = (not last) and _od._needed_later(tab, i) and sec is None
+                # k_i, base state, k_j.., y_next, (running final combination), (a, gP)
+                out.append((1 if store else 0) + 1 + len(kprev) + 1 + (1 if second else 0) + (2 if aug else 0))
         return out
 
     if a.method in _od.FIXED_METHODS:

@@ -29,15 +29,21 @@ class PushRoute(C.Structure):
     _fields_ = [("ptr", vp), ("ent", vp), ("base", vp * MAX_PEERS)]
 
 
+class RkSecond(C.Structure):
+    _fields_ = [("coef", f32 * MAX_STAGES), ("coef_self", f32), ("out", vp)]
+
+
 class SpmmEpilogue(C.Structure):
     _fields_ = [("bias", vp), ("relu", i32), ("residual", vp), ("y0", vp), ("kprev", vp * MAX_STAGES),
                 ("coef", f32 * MAX_STAGES), ("n_prev", i32), ("coef_self", f32), ("ynext", vp),
-                ("mask_src", vp), ("mask_scale", f32), ("gp_out", vp), ("acc_in", vp), ("push", PushRoute)]
+                ("mask_src", vp), ("mask_scale", f32), ("gp_out", vp), ("acc_in", vp), ("push", PushRoute),
+                ("second", RkSecond), ("gp_row_scale", vp)]
 
 
 class Csr(C.Structure):
     _fields_ = [("n_rows", i64), ("n_cols", i64), ("rowptr", vp), ("colidx", vp), ("vals", vp), ("row_vals", vp),
-                ("heavy_rows", vp), ("heavy_chunk_ptr", vp), ("n_heavy", i32), ("n_chunks", i32)]
+                ("heavy_rows", vp), ("heavy_chunk_ptr", vp), ("n_heavy", i32), ("n_chunks", i32), ("tile_sched", vp),
+                ("n_tile_sched", i32)]
 
 
 GAT_CHUNK = 64
@@ -55,7 +61,7 @@ class GatGraph(C.Structure):
 class GcnOdeFunc(C.Structure):
     _fields_ = [("A", Csr), ("At", Csr), ("d", i32), ("groups", i32), ("gn_eps", f32), ("precision", i32),
                 ("W", vp), ("b", vp), ("gamma", vp), ("beta", vp), ("gather_row_offset", i64), ("partial_in", vp),
-                ("push_S", PushRoute), ("push_gP", PushRoute)]
+                ("push_S", PushRoute), ("push_gP", PushRoute), ("second", RkSecond), ("gp_row_scale", vp)]
 
 
 class PeerGroup(C.Structure):

@@ -19,6 +19,6 @@ int groupnorm_bwd(int64_t n, int d, int groups, float eps, const float* x, int64
 int groupnorm_bwd_rk(int64_t n, int d, int groups, float eps, const float* x, int64_t ldx, const float* gamma,
                      const float* dy, int64_t lddy, float* dx, int64_t lddx, float* dgamma, float* dbeta, void* ws,
                      size_t ws_bytes, cudaStream_t st, const float* a0, const float* const* kprev, const float* coef,
-                     int n_prev, float coef_self, float* a_next);
+                     int n_prev, float coef_self, float* a_next, const gode_rk_second_t* second = nullptr);
 int rk_combine(int64_t n, const float* y0, const float* const* k, const float* c, int nk, float* out, cudaStream_t st);
 }  // namespace gode

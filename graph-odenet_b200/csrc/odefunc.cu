@@ -117,6 +117,19 @@ __global__ void k_time_terms(int d, float t, const float* __restrict__ cs, const
   }
 }
 
+// The descriptor's per-call second combination (header: gode_gcn_odefunc_t.second) joins the epilogue of this gather; it
+// shares y0 and the k_j list with y_next (which may itself be off).
+static int set_second(gode_spmm_epilogue_t& ep, const gode_gcn_odefunc_t* f, const float* y0, const float* const* kprev_host,
+                      int n_prev) {
+  if (!f->second.out) return GODE_OK;
+  GODE_REQUIRE(y0, "gcn: the second Runge-Kutta combination needs y0");
+  ep.second = f->second;
+  ep.y0 = y0;
+  ep.n_prev = n_prev;
+  for (int j = 0; j < n_prev; ++j) ep.kprev[j] = kprev_host[j];
+  return GODE_OK;
+}
+
 static int transform_impl(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, GcnWs& w, cudaStream_t st) {
   ProfScope prof(GODE_PROF_TRANSFORM, st);
   if (transform_tc_supported(f)) return transform_tc(f, y, t, S, st);
@@ -200,6 +213,7 @@ extern "C" int gode_gcn_stage_fwd(const gode_gcn_odefunc_t* f, const float* S, f
     ep.coef_self = coef_self;
     ep.ynext = y_next;
   }
+  if ((rc = set_second(ep, f, y0, kprev_host, n_prev))) return rc;
   {
     ProfScope prof(GODE_PROF_AGG_FWD, st);
     ep.acc_in = f->partial_in;
@@ -240,6 +254,7 @@ extern "C" int gode_gcn_stage_fwd_rows(const gode_gcn_odefunc_t* f, const float*
     ep.coef_self = coef_self;
     ep.ynext = y_next;
   }
+  if ((rc = set_second(ep, f, y0, kprev_host, n_prev))) return rc;
   ep.acc_in = f->partial_in;
   ProfScope prof(GODE_PROF_AGG_FWD, st);
   return spmm_dispatch(f->A, S + f->gather_row_offset * f->d, f->d, f->d, k_out, f->d, ep, w.heavy, w.heavy_bytes, st, row0,
@@ -275,6 +290,8 @@ extern "C" int gode_gcn_vjp_phase1(const gode_gcn_odefunc_t* f, const float* S, 
       ep.coef[j] = coef_host[j];
     }
   }
+  if ((rc = set_second(ep, f, y0, kprev_host, n_prev))) return rc;
+  ep.gp_row_scale = f->gp_row_scale;
   ep.acc_in = f->partial_in;
   ProfScope prof(GODE_PROF_AGG_FWD, as_stream(stream));
   return spmm_dispatch(f->A, S + f->gather_row_offset * f->d, f->d, f->d, k_y, f->d, ep, w.heavy, w.heavy_bytes,
@@ -287,8 +304,11 @@ extern "C" int gode_gcn_vjp_phase2_rk(const gode_gcn_odefunc_t* f, const float* 
                                       size_t ws_bytes, void* stream) {
   int rc = check(f);
   if (rc) return rc;
-  GODE_REQUIRE(f->At.rowptr && (f->A.n_rows == 0 || (y && gP && (k_a || a_next))) && gtheta, "gcn_vjp_phase2: null pointer");
-  GODE_REQUIRE(n_prev >= 0 && n_prev <= GODE_MAX_STAGES && (!a_next || a0), "gcn_vjp_phase2: bad RK arguments");
+  GODE_REQUIRE(f->At.rowptr && (f->A.n_rows == 0 || (y && gP && (k_a || a_next || f->second.out))) && gtheta,
+               "gcn_vjp_phase2: null pointer");
+  GODE_REQUIRE(n_prev >= 0 && n_prev <= GODE_MAX_STAGES && ((!a_next && !f->second.out) || a0),
+               "gcn_vjp_phase2: bad RK arguments");
+  GODE_REQUIRE(!f->gp_row_scale || f->At.row_vals, "gcn_vjp_phase2: gp_row_scale needs the unit pattern of A_hat^T in At");
   GcnWs w;
   rc = carve(f, ws, ws_bytes, w);
   if (rc) return rc;
@@ -314,8 +334,8 @@ extern "C" int gode_gcn_vjp_phase2_rk(const gode_gcn_odefunc_t* f, const float* 
   }
   if (rc) return rc;
   ProfScope prof_dense(GODE_PROF_VJP_DENSE, st);
-  // bias gradient
-  if ((rc = colsum(n, d, gP, d, gb, w.red, w.red_bytes, st))) return rc;
+  // bias gradient: column sums of gP -- or, with gp_row_scale (gP holds row-scaled rows), of gS (below)
+  if (!f->gp_row_scale && (rc = colsum(n, d, gP, d, gb, w.red, w.red_bytes, st))) return rc;
   // gW[1:,:] = z^T gS, and cs = column sums of gS (tensor-core path: same pass over gS)
   if (wgrad_tc_supported(f)) {
     if ((rc = wgrad_tc(f, y, gS, cs, gW + d, w.splitk, w.splitk_bytes, st))) return rc;
@@ -325,6 +345,7 @@ extern "C" int gode_gcn_vjp_phase2_rk(const gode_gcn_odefunc_t* f, const float* 
     if ((rc = gemm_simt(1, 0, d, d, n, 1.f, z, d, gS, d, 0.f, gW + d, d, splits_for(n), w.splitk, w.splitk_bytes, st, nullptr, 0.f)))
       return rc;
   }
+  if (f->gp_row_scale) GODE_CHECK_CUDA(cudaMemcpyAsync(gb, cs, sizeof(float) * d, cudaMemcpyDeviceToDevice, st));
   // the two time-column terms: gW[0,:] = t cs, gt = <cs, W[0,:]>
   k_time_terms<<<1, 128, 0, st>>>(d, t, cs, f->W, gW, gt);
   GODE_LAUNCH_CHECK();
@@ -335,7 +356,7 @@ extern "C" int gode_gcn_vjp_phase2_rk(const gode_gcn_odefunc_t* f, const float* 
     return rc;
   }
   return groupnorm_bwd_rk(n, d, f->groups, f->gn_eps, y, d, f->gamma, gz, d, k_a, d, ggamma, gbeta, w.red, w.red_bytes, st,
-                          a0, kprev_host, coef_host, n_prev, coef_self, a_next);
+                          a0, kprev_host, coef_host, n_prev, coef_self, a_next, f->second.out ? &f->second : nullptr);
 }
 
 extern "C" int gode_gcn_vjp_phase2(const gode_gcn_odefunc_t* f, const float* y, float t, const float* gP, float* k_a,
@@ -351,6 +372,7 @@ extern "C" int gode_gcn_stage_vjp(const gode_gcn_odefunc_t* f, const float* y, f
   if (rc) return rc;
   GODE_REQUIRE(f->A.n_cols == f->A.n_rows && f->At.n_cols == f->A.n_rows && f->gather_row_offset == 0 && !f->partial_in,
                "gcn_stage_vjp: partitioned graphs must call phase1 / exchange / phase2");
+  GODE_REQUIRE(!f->second.out, "gcn_stage_vjp: a second Runge-Kutta combination needs the phase1 / phase2 calls");
   GcnWs w;
   rc = carve(f, ws, ws_bytes, w);
   if (rc) return rc;

@@ -4,6 +4,7 @@
 // Reference call sites: nn.GroupNorm(min(32,d), d) GCN/models.py:165,175 (and its autograd);
 // bias gradient of GCN/layers.py:35; torchdiffeq rk_common/_compute_error_ratio (restated in oracle/odeint.py).
 #include "internal.cuh"
+#include <string.h>
 
 namespace gode {
 
@@ -139,6 +140,7 @@ struct RkTail {
   KList kl;
   float c_self;
   float* anext;
+  gode_rk_second_t second;   // out2 = a0 + sum_j second.coef[j] k[j] + second.coef_self * dx   (out NULL: off)
 };
 
 // backward: dx and per-block partial sums of dgamma / dbeta.  blockDim.x is a multiple of `groups`, so a
@@ -182,20 +184,27 @@ __global__ void __launch_bounds__(256) k_gn_bwd(int64_t n, int groups, float eps
 #pragma unroll
     for (int c = 0; c < CPG; ++c) o[c] = rstd * (u[c] - m1 - v[c] * m2);
     if (dx) store_grp<CPG>(dx + r * lddx + g * CPG, o, vec);
-    if (rk.anext) {   // contiguous [n, d] operands (ld = d)
+    if (rk.anext || rk.second.out) {   // contiguous [n, d] operands (ld = d)
       const int64_t off = r * (int64_t)(groups * CPG) + g * CPG;
-      float acc[CPG], w[CPG];
+      float acc[CPG], acc2[CPG], w[CPG];
       load_grp<CPG>(rk.a0 + off, acc, vec);
 #pragma unroll
-      for (int c = 0; c < CPG; ++c) acc[c] += rk.c_self * o[c];
+      for (int c = 0; c < CPG; ++c) {
+        acc2[c] = acc[c] + rk.second.coef_self * o[c];
+        acc[c] += rk.c_self * o[c];
+      }
 #pragma unroll
       for (int j = 0; j < GODE_MAX_STAGES; ++j)
         if (j < rk.kl.n) {
           load_grp<CPG>(rk.kl.k[j] + off, w, vec);
 #pragma unroll
-          for (int c = 0; c < CPG; ++c) acc[c] += rk.kl.c[j] * w[c];
+          for (int c = 0; c < CPG; ++c) {
+            acc[c] += rk.kl.c[j] * w[c];
+            acc2[c] += rk.second.coef[j] * w[c];
+          }
         }
-      store_grp<CPG>(rk.anext + off, acc, vec);
+      if (rk.anext) store_grp<CPG>(rk.anext + off, acc, vec);
+      if (rk.second.out) store_grp<CPG>(rk.second.out + off, acc2, vec);
     }
   }
 #pragma unroll
@@ -306,8 +315,8 @@ static int gn_bwd_t(int64_t n, int groups, float eps, const float* x, int64_t ld
                     int64_t lddy, float* dx, int64_t lddx, float* dgamma, float* dbeta, float* part, cudaStream_t st,
                     const RkTail& rk) {
   bool vec = al16(x) && al16(dy) && al16(dx) && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0;
-  if (rk.anext) {
-    vec = vec && al16(rk.a0) && al16(rk.anext) && (groups * CPG) % 4 == 0;
+  if (rk.anext || rk.second.out) {
+    vec = vec && al16(rk.a0) && al16(rk.anext) && al16(rk.second.out) && (groups * CPG) % 4 == 0;
     for (int j = 0; j < rk.kl.n; ++j) vec = vec && al16(rk.kl.k[j]);
   }
   const int d = groups * CPG;
@@ -347,13 +356,14 @@ static int fill_klist(KList& kl, const float* const* k, const float* c, int n);
 int groupnorm_bwd_rk(int64_t n, int d, int groups, float eps, const float* x, int64_t ldx, const float* gamma,
                      const float* dy, int64_t lddy, float* dx, int64_t lddx, float* dgamma, float* dbeta, void* ws,
                      size_t ws_bytes, cudaStream_t st, const float* a0, const float* const* kprev, const float* coef,
-                     int n_prev, float coef_self, float* a_next) {
+                     int n_prev, float coef_self, float* a_next, const gode_rk_second_t* second) {
   if (ws_bytes < gode_colreduce_workspace_bytes(2 * d) || !ws) {
     set_error("groupnorm_bwd: workspace too small");
     return GODE_EWORKSPACE;
   }
-  GODE_REQUIRE(dx || a_next, "groupnorm_bwd: nothing to write");
-  GODE_REQUIRE(!a_next || a0, "groupnorm_bwd: a_next needs a0");
+  float* out2 = second ? second->out : nullptr;
+  GODE_REQUIRE(dx || a_next || out2, "groupnorm_bwd: nothing to write");
+  GODE_REQUIRE((!a_next && !out2) || a0, "groupnorm_bwd: a_next needs a0");
   if (n == 0) {
     GODE_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * d, st));
     GODE_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * d, st));
@@ -363,7 +373,8 @@ int groupnorm_bwd_rk(int64_t n, int d, int groups, float eps, const float* x, in
   rk.a0 = a0;
   rk.c_self = coef_self;
   rk.anext = a_next;
-  int rc = fill_klist(rk.kl, kprev, coef, a_next ? n_prev : 0);
+  if (second) rk.second = *second; else memset(&rk.second, 0, sizeof(rk.second));
+  int rc = fill_klist(rk.kl, kprev, coef, (a_next || out2) ? n_prev : 0);
   if (rc) return rc;
   float* part = static_cast<float*>(ws);
   const int cpg = d / groups;
@@ -381,7 +392,7 @@ int groupnorm_bwd(int64_t n, int d, int groups, float eps, const float* x, int64
                   const float* dy, int64_t lddy, float* dx, int64_t lddx, float* dgamma, float* dbeta, void* ws,
                   size_t ws_bytes, cudaStream_t st) {
   return groupnorm_bwd_rk(n, d, groups, eps, x, ldx, gamma, dy, lddy, dx, lddx, dgamma, dbeta, ws, ws_bytes, st, nullptr,
-                          nullptr, nullptr, 0, 0.f, nullptr);
+                          nullptr, nullptr, 0, 0.f, nullptr, nullptr);
 }
 
 static int fill_klist(KList& kl, const float* const* k, const float* c, int n) {

@@ -49,28 +49,45 @@ __device__ __forceinline__ void epilogue(const gode_spmm_epilogue_t& ep, int64_t
       }
       st_stream4(Y + o, w);
     }
-    if (ep.ynext) {
+    if (ep.ynext || ep.second.out) {
+      // one pass over (y0, k_j) serves both combinations
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 t2 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < GODE_MAX_STAGES; ++j) {
         if (j < ep.n_prev) {
           float4 k = ld_stream4(ep.kprev[j] + o);
           const float cj = ep.coef[j];
           t.x += cj * k.x; t.y += cj * k.y; t.z += cj * k.z; t.w += cj * k.w;
+          if (ep.second.out) {
+            const float c2 = ep.second.coef[j];
+            t2.x += c2 * k.x; t2.y += c2 * k.y; t2.z += c2 * k.z; t2.w += c2 * k.w;
+          }
         }
       }
-      t.x += ep.coef_self * v.x; t.y += ep.coef_self * v.y; t.z += ep.coef_self * v.z; t.w += ep.coef_self * v.w;
-      float4 y = ld_stream4(ep.y0 + o);
-      y.x += t.x; y.y += t.y; y.z += t.z; y.w += t.w;
-      st_stream4(ep.ynext + o, y);
+      const float4 y0 = ld_stream4(ep.y0 + o);
+      if (ep.ynext) {
+        t.x += ep.coef_self * v.x; t.y += ep.coef_self * v.y; t.z += ep.coef_self * v.z; t.w += ep.coef_self * v.w;
+        float4 y = y0;
+        y.x += t.x; y.y += t.y; y.z += t.z; y.w += t.w;
+        st_stream4(ep.ynext + o, y);
+      }
+      if (ep.second.out) {
+        const float cs = ep.second.coef_self;
+        t2.x += cs * v.x; t2.y += cs * v.y; t2.z += cs * v.z; t2.w += cs * v.w;
+        float4 y = y0;
+        y.x += t2.x; y.y += t2.y; y.z += t2.z; y.w += t2.w;
+        st_stream4(ep.second.out + o, y);
+      }
     }
     if (ep.gp_out) {
       float4 a = ld_stream4(ep.mask_src + o);
+      const float ms = ep.gp_row_scale ? ep.mask_scale * __ldg(ep.gp_row_scale + row) : ep.mask_scale;
       float4 g;
-      g.x = v.x > 0.f ? ep.mask_scale * a.x : 0.f;
-      g.y = v.y > 0.f ? ep.mask_scale * a.y : 0.f;
-      g.z = v.z > 0.f ? ep.mask_scale * a.z : 0.f;
-      g.w = v.w > 0.f ? ep.mask_scale * a.w : 0.f;
+      g.x = v.x > 0.f ? ms * a.x : 0.f;
+      g.y = v.y > 0.f ? ms * a.y : 0.f;
+      g.z = v.z > 0.f ? ms * a.z : 0.f;
+      g.w = v.w > 0.f ? ms * a.w : 0.f;
       st_stream4(ep.gp_out + o, g);
       if (ep.push.ptr) {   // fused halo push: the peers that reference this row get it now, over NVLink
         const int p1 = __ldg(ep.push.ptr + row + 1);
@@ -97,7 +114,7 @@ __device__ __forceinline__ void epilogue_prefetch(const gode_spmm_epilogue_t& ep
     const int64_t ou = o + u * 4;
     if (ep.acc_in) prefetch_l2(ep.acc_in + ou);
     if (ep.residual) prefetch_l2(ep.residual + ou);
-    if (ep.ynext) {
+    if (ep.ynext || ep.second.out) {
       prefetch_l2(ep.y0 + ou);
 #pragma unroll
       for (int j = 0; j < GODE_MAX_STAGES; ++j)
@@ -490,20 +507,21 @@ __device__ __forceinline__ void acc_row(float2& a0, float2& a1, const float v, c
   }
 }
 
-// Hub rows (> GODE_HEAVY_ROW entries) INSIDE the tile's CTA.  Round 2 ncu on the separate hub kernel (profiles/r02_gather.md):
-// L2 hit rate 18 %, 11.7 GB of DRAM reads for 15.6 GB gathered -- swept on their own, the hubs' chunks find nothing of their
-// band in L2 (the reuse distance between two hubs that share neighbours is about the size of L2), while the tile sweep of
-// the light rows has exactly that band resident when it passes a hub's id.  So (opt-in, GODE_SPMM_HUBS_INLINE=1: it measured
-// SLOWER, 8.55 vs 7.08 ms per bare gather -- a CTA that meets a hub parks its 8 warps behind two block barriers and holds its
-// SM slot for the hub's whole length, which costs more than the L2 misses it avoids) the tile that contains a hub also gathers
-// it: after the light rows (block barrier) the tile's hub chunks (256 entries each) are pulled from a second shared
-// counter by all 8 warps, their partial sums go to the caller's workspace, and after another barrier one warp per hub adds
-// the chunks IN CHUNK ORDER (deterministic) and applies the epilogue.  A 100 000-entry hub keeps its CTA for ~1 ms, well
-// inside the kernel's 6 ms; the other CTAs of the wave are unaffected (dynamic CTA scheduling).
+// Hub rows (> GODE_HEAVY_ROW entries) are cut into 256-entry chunks gathered by single warps (partial[chunk][128]) and summed in
+// chunk order by k_spmm_heavy_finish (deterministic, no atomics).  Round 2 ncu on the SEPARATE hub kernel (k_spmm_heavy2,
+// profiles/r02_gather.md): L2 hit rate 18 %, 11.7 GB of DRAM reads for 15.6 GB gathered -- swept on their own, the hubs' chunks
+// find nothing of their band in L2 (the reuse distance between two hubs that share neighbours is about the size of L2), while
+// the tile sweep of the light rows has exactly that band resident when it passes a hub's id.  Gathering a hub inside the CTA of
+// the tile that contains it was measured slower (8.55 vs 7.08 ms per bare gather: the CTA parks its 8 warps behind two block
+// barriers and holds its SM slot for the hub's whole length).  So the hub chunks become CTAs OF THE SAME GRID instead: the plan's
+// work order (gode_csr_t.tile_sched) lists the 32-row tiles in id order with every group of 8 hub chunks inserted right after the
+// tile that contains its hub -- the block scheduler issues CTAs in blockIdx order, so a chunk group runs while the tiles around
+// its hub (and with them the hub's band) are in flight; a 100 000-entry hub is 49 consecutive CTAs spread over the SMs.
 struct HubArgs {
-  const int32_t* rows;        // sorted hub row ids (gode_csr_t.heavy_rows), nullptr: hubs are left to the separate kernels
+  const int32_t* sched;       // gode_csr_t.tile_sched or nullptr (blockIdx = tile; hubs left to k_spmm_heavy2)
+  const int32_t* rows;        // sorted hub row ids (gode_csr_t.heavy_rows)
   const int32_t* chunk_ptr;   // first chunk of each hub in the workspace (gode_csr_t.heavy_chunk_ptr)
-  int n_heavy;
+  int n_heavy, n_chunks;
   float4* partial;            // [n_chunks][32] float4 workspace
 };
 
@@ -519,10 +537,60 @@ __global__ void __launch_bounds__(256, MINB) k_spmm_t2(int64_t n_rows, const int
   __shared__ int s_idx[TS_CAP];
   __shared__ float s_val[ROWVAL ? 1 : TS_CAP];
   __shared__ int s_next;
-  __shared__ int s_nhub, s_next2, s_hub[TS_ROWS], s_hub_first[TS_ROWS + 1], s_hub_gbase[TS_ROWS];
-  if (threadIdx.x == 0) { s_nhub = 0; s_next2 = 0; }
   const int tid = threadIdx.x, lane = tid & 31;
-  const int64_t row0 = row_begin + blockIdx.x * (int64_t)TS_ROWS;
+  const float4* __restrict__ xb = X4 + lane;        // row c, this lane's four channels: xb[c * 32]
+  int item = blockIdx.x;
+  if (hub.sched) {
+    item = __ldg(hub.sched + blockIdx.x);
+    if (item < 0) {                                  // (uniform) a group of 8 hub chunks, one per warp
+      const int w = tid >> 5;
+      const int chunk = (-item - 1) * 8 + w;
+      if (chunk >= hub.n_chunks) return;
+      // the hub row this chunk belongs to = last one whose first chunk is <= chunk: a 32-way search (as k_spmm_heavy2)
+      int lo = 0, hi = hub.n_heavy;
+      while (hi - lo > 1) {
+        const int step = (hi - lo + 31) >> 5;
+        const int p = lo + lane * step;
+        const bool le = p < hi && __ldg(hub.chunk_ptr + p) <= chunk;
+        const int k = __popc(__ballot_sync(0xffffffffu, le)) - 1;
+        lo += k * step;
+        hi = min(lo + step, hi);
+      }
+      const int row = __ldg(hub.rows + lo);
+      const int r1 = __ldg(rowptr + row + 1);
+      const int ce0 = __ldg(rowptr + row) + (chunk - __ldg(hub.chunk_ptr + lo)) * GODE_HEAVY_CHUNK;
+      const int cnt = min(r1 - ce0, GODE_HEAVY_CHUNK);
+      int* __restrict__ my_idx = s_idx + w * 128;    // 128 entries at a time through this warp's slice of the index buffer
+      float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+      for (int half = 0; half < cnt; half += 128) {
+        const int hc = min(128, cnt - half);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = q * 32 + lane;
+          if (i < hc) my_idx[i] = __ldcs(colidx + ce0 + half + i);
+        }
+        __syncwarp();
+        const float* __restrict__ vp = vals + ce0 + half;   // values straight from global memory (broadcast loads of one line)
+        int i = 0;
+#pragma unroll 1
+        for (; i + 4 <= hc; i += 4) {
+          const unsigned c0 = my_idx[i], c1 = my_idx[i + 1], c2 = my_idx[i + 2], c3 = my_idx[i + 3];
+          const float4 x0 = __ldg(xb + (size_t)c0 * 32), x1 = __ldg(xb + (size_t)c1 * 32);
+          const float4 x2 = __ldg(xb + (size_t)c2 * 32), x3 = __ldg(xb + (size_t)c3 * 32);
+          const float v0 = __ldg(vp + i), v1 = __ldg(vp + i + 1), v2 = __ldg(vp + i + 2), v3 = __ldg(vp + i + 3);
+          acc_row<false>(a0, a1, v0, x0);
+          acc_row<false>(a0, a1, v1, x1);
+          acc_row<false>(a0, a1, v2, x2);
+          acc_row<false>(a0, a1, v3, x3);
+        }
+        for (; i < hc; ++i) acc_row<false>(a0, a1, __ldg(vp + i), __ldg(xb + (size_t)(unsigned)my_idx[i] * 32));
+      }
+      hub.partial[(size_t)chunk * 32 + lane] = make_float4(a0.x, a0.y, a1.x, a1.y);
+      return;
+    }
+  }
+  const int64_t row0 = row_begin + item * (int64_t)TS_ROWS;
   const int nr = static_cast<int>(min((int64_t)TS_ROWS, n_rows - row0));
   if (tid <= nr) s_ptr[tid] = __ldg(rowptr + row0 + tid);
   if (tid == 0) s_next = 0;
@@ -534,17 +602,13 @@ __global__ void __launch_bounds__(256, MINB) k_spmm_t2(int64_t n_rows, const int
     if (!ROWVAL) s_val[i] = __ldcs(vals + t0 + i);
   }
   __syncthreads();
-  const float4* __restrict__ xb = X4 + lane;        // row c, this lane's four channels: xb[c * 32]
   for (;;) {
     int r = 0;
     if (lane == 0) r = atomicAdd(&s_next, 1);
     r = __shfl_sync(0xffffffffu, r, 0);
     if (r >= nr) break;
     const int e0 = s_ptr[r], e1 = s_ptr[r + 1];
-    if (e1 - e0 > GODE_HEAVY_ROW) {                  // hub row: gathered below (or by k_spmm_heavy2 / finish when hub.rows is null)
-      if (hub.rows && lane == 0) s_hub[atomicAdd(&s_nhub, 1)] = r;
-      continue;
-    }
+    if (e1 - e0 > GODE_HEAVY_ROW) continue;          // hub row: its chunks are other CTAs' (or k_spmm_heavy2's) work, then k_spmm_heavy_finish
     const int64_t row = row0 + r;
     if (prefetch) epilogue_prefetch<1>(ep, row, lane * 4, 128);
     float4 one[1];
@@ -590,99 +654,6 @@ __global__ void __launch_bounds__(256, MINB) k_spmm_t2(int64_t n_rows, const int
       one[0] = make_float4(0.f, 0.f, 0.f, 0.f);
       gather_range<32, 1, 4>(one, e0, e1, e1 - e0, 0, lane, colidx, vals, reinterpret_cast<const float*>(xb), 128);
     }
-    epilogue<1>(ep, row, lane * 4, one, Y, 128);
-  }
-  if (!hub.rows) return;
-  // ---- the tile's hub rows --------------------------------------------------------------------------------------
-  __syncthreads();                                   // every light row is done: the index buffer is free, s_nhub is final
-  const int nhub = s_nhub;
-  if (nhub == 0) return;                             // (uniform over the CTA)
-  const int w = tid >> 5;
-  if (w == 0) {                                      // per hub: its first chunk in the workspace, and the tile's chunk prefix
-    int nch = 0;
-    if (lane < nhub) {
-      const int r = s_hub[lane];
-      nch = (s_ptr[r + 1] - s_ptr[r] + GODE_HEAVY_CHUNK - 1) / GODE_HEAVY_CHUNK;
-      const int grow = static_cast<int>(row0) + r;
-      int lo = 0, hi = hub.n_heavy - 1;              // position of this row in the sorted hub list
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(hub.rows + mid) < grow) lo = mid + 1; else hi = mid;
-      }
-      s_hub_gbase[lane] = __ldg(hub.chunk_ptr + lo);
-    }
-    int incl = nch;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane < nhub) s_hub_first[lane] = incl - nch;
-    if (lane == 31) s_hub_first[nhub] = incl;        // lanes >= nhub carry nch = 0: the total
-  }
-  __syncthreads();
-  const int total = s_hub_first[nhub];
-  int* __restrict__ my_idx = s_idx + w * 128;
-  for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(&s_next2, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= total) break;
-    int k = 0;
-    while (k + 1 < nhub && s_hub_first[k + 1] <= item) ++k;
-    const int j = item - s_hub_first[k];
-    const int r = s_hub[k];
-    const int ce0 = s_ptr[r] + j * GODE_HEAVY_CHUNK;
-    const int cnt = min(s_ptr[r + 1] - ce0, GODE_HEAVY_CHUNK);
-    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
-    for (int half = 0; half < cnt; half += 128) {    // 128 entries at a time through this warp's slice of the index buffer
-      const int hc = min(128, cnt - half);
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int i = q * 32 + lane;
-        if (i < hc) my_idx[i] = __ldcs(colidx + ce0 + half + i);
-      }
-      __syncwarp();
-      int i = 0;
-#pragma unroll 1
-      for (; i + 4 <= hc; i += 4) {
-        const unsigned c0 = my_idx[i], c1 = my_idx[i + 1], c2 = my_idx[i + 2], c3 = my_idx[i + 3];
-        const float4 x0 = __ldg(xb + (size_t)c0 * 32), x1 = __ldg(xb + (size_t)c1 * 32);
-        const float4 x2 = __ldg(xb + (size_t)c2 * 32), x3 = __ldg(xb + (size_t)c3 * 32);
-        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-        if (!ROWVAL) {                               // values straight from global memory (broadcast loads, L1-resident line)
-          const float* vp = vals + ce0 + half + i;
-          v0 = __ldg(vp); v1 = __ldg(vp + 1); v2 = __ldg(vp + 2); v3 = __ldg(vp + 3);
-        }
-        acc_row<ROWVAL>(a0, a1, v0, x0);
-        acc_row<ROWVAL>(a0, a1, v1, x1);
-        acc_row<ROWVAL>(a0, a1, v2, x2);
-        acc_row<ROWVAL>(a0, a1, v3, x3);
-      }
-      for (; i < hc; ++i) {
-        const float v = ROWVAL ? 0.f : __ldg(vals + ce0 + half + i);
-        acc_row<ROWVAL>(a0, a1, v, __ldg(xb + (size_t)(unsigned)my_idx[i] * 32));
-      }
-    }
-    hub.partial[(size_t)(s_hub_gbase[k] + j) * 32 + lane] = make_float4(a0.x, a0.y, a1.x, a1.y);
-  }
-  __syncthreads();                                   // the tile's partial sums are written (and visible to this CTA)
-  for (int k = w; k < nhub; k += 8) {                // one warp per hub: chunks in order, then the row epilogue
-    const int r = s_hub[k];
-    const int nch = s_hub_first[k + 1] - s_hub_first[k];
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* __restrict__ pp = hub.partial + (size_t)s_hub_gbase[k] * 32 + lane;
-    for (int j = 0; j < nch; ++j) {
-      const float4 p = pp[(size_t)j * 32];
-      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
-    }
-    const int64_t row = row0 + r;
-    if (ROWVAL) {
-      const float rv = __ldg(row_vals + row);
-      acc.x *= rv; acc.y *= rv; acc.z *= rv; acc.w *= rv;
-    }
-    float4 one[1] = {acc};
     epilogue<1>(ep, row, lane * 4, one, Y, 128);
   }
 }
@@ -1129,7 +1100,16 @@ __global__ void __launch_bounds__(256) k_spmm_generic(int64_t n_rows, const int3
         t += ep.coef_self * v;
         ep.ynext[o] = ep.y0[o] + t;
       }
-      if (ep.gp_out) ep.gp_out[o] = v > 0.f ? ep.mask_scale * ep.mask_src[o] : 0.f;
+      if (ep.second.out) {
+        float t = 0.f;
+        for (int j = 0; j < ep.n_prev; ++j) t += ep.second.coef[j] * ep.kprev[j][o];
+        t += ep.second.coef_self * v;
+        ep.second.out[o] = ep.y0[o] + t;
+      }
+      if (ep.gp_out) {
+        const float ms = ep.gp_row_scale ? ep.mask_scale * ep.gp_row_scale[row] : ep.mask_scale;
+        ep.gp_out[o] = v > 0.f ? ms * ep.mask_src[o] : 0.f;
+      }
     }
   }
 }
@@ -1212,23 +1192,26 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
       }();
       const bool rv = use_rowval && A.row_vals != nullptr;
       const float4* X4 = reinterpret_cast<const float4*>(X);
-      static const int hubs_inline = [] {
-        const char* e = getenv("GODE_SPMM_HUBS_INLINE");   // 1: a tile's CTA also gathers its hub rows; 0 (default): separate kernels.
-        return e ? atoi(e) : 0;                            // Measured: 8.55 / 8.50 / 11.53 ms inline vs 7.08 / 7.98 / 9.97 separate (bare, A^T, fused)
+      static const int use_sched = [] {
+        const char* e = getenv("GODE_SPMM_SCHED");   // 1 (default): hub chunks are CTAs of the tile grid, in the plan's work order
+        return e ? atoi(e) : 1;                      // (gode_csr_t.tile_sched); 0: separate hub kernel after the tiles
       }();
       static const int t3 = [] {
         const char* e = getenv("GODE_SPMM_T3");      // 1: aligned staging + LDS.128 index reads (k_spmm_t3).  Default off: measured
         return e ? atoi(e) : 0;                      // 6.68 / 7.93 / 9.59 ms against k_spmm_t2's 6.47 / 7.59 / 9.04 (bare A, A^T, fused epilogue)
       }();
       HubArgs hub;
-      hub.rows = (hubs_inline && A.n_heavy > 0 && !(t2_rows == 32 && t3)) ? A.heavy_rows : nullptr;
+      hub.sched = (use_sched && A.n_heavy > 0 && A.tile_sched && A.n_tile_sched > 0 && t2_rows == 32 && !t3 && !sub) ? A.tile_sched
+                                                                                                                   : nullptr;
+      hub.rows = A.heavy_rows;
       hub.chunk_ptr = A.heavy_chunk_ptr;
       hub.n_heavy = A.n_heavy;
+      hub.n_chunks = A.n_chunks;
       hub.partial = reinterpret_cast<float4*>(ws);
       if (row_end > row_begin) {
 #define GODE_T2_LAUNCH(R, MB)                                                                                           \
   do {                                                                                                                  \
-    unsigned grid = static_cast<unsigned>((row_end - row_begin + R - 1) / R);                                           \
+    unsigned grid = hub.sched ? static_cast<unsigned>(A.n_tile_sched) : static_cast<unsigned>((row_end - row_begin + R - 1) / R); \
     if (rv) k_spmm_t2<R, MB, true><<<grid, 256, 0, st>>>(row_end, A.rowptr, A.colidx, A.vals, A.row_vals, X4, Y, ep, prefetch_t2, hub, row_begin); \
     else k_spmm_t2<R, MB, false><<<grid, 256, 0, st>>>(row_end, A.rowptr, A.colidx, A.vals, nullptr, X4, Y, ep, prefetch_t2, hub, row_begin);    \
   } while (0)
@@ -1255,11 +1238,13 @@ static int launch_vec(const gode_csr_t& A, const float* X, int64_t ldx, float* Y
 #undef GODE_T2_LAUNCH
         GODE_LAUNCH_CHECK();
       }
-      if (A.n_heavy > 0 && !hub.rows) {
-        unsigned g1 = static_cast<unsigned>((A.n_chunks + 7) / 8);
-        k_spmm_heavy2<6><<<g1, 256, 0, st>>>(A.n_heavy, A.n_chunks, A.heavy_rows, A.heavy_chunk_ptr, A.rowptr, A.colidx, A.vals,
-                                             X4, reinterpret_cast<float4*>(ws), row_begin, row_end);
-        GODE_LAUNCH_CHECK();
+      if (A.n_heavy > 0) {
+        if (!hub.sched) {
+          unsigned g1 = static_cast<unsigned>((A.n_chunks + 7) / 8);
+          k_spmm_heavy2<6><<<g1, 256, 0, st>>>(A.n_heavy, A.n_chunks, A.heavy_rows, A.heavy_chunk_ptr, A.rowptr, A.colidx, A.vals,
+                                               X4, reinterpret_cast<float4*>(ws), row_begin, row_end);
+          GODE_LAUNCH_CHECK();
+        }
         unsigned g2 = static_cast<unsigned>((A.n_heavy + RPB - 1) / RPB);
         k_spmm_heavy_finish<LPR, VPL><<<g2, 256, 0, st>>>(A.n_heavy, A.heavy_rows, A.heavy_chunk_ptr, ws, Y, ldy, ep, row_begin, row_end);
         GODE_LAUNCH_CHECK();
@@ -1627,7 +1612,7 @@ int spmm_dispatch(const gode_csr_t& A, const float* X, int64_t ldx, int32_t d, f
                   const gode_spmm_epilogue_t& ep, void* ws, size_t ws_bytes, cudaStream_t st, int64_t row_begin, int64_t row_end) {
   bool vec_ok = vec_width(d) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y) && aligned16(ep.bias) &&
                 aligned16(ep.residual) && aligned16(ep.y0) && aligned16(ep.ynext) && aligned16(ep.mask_src) &&
-                aligned16(ep.gp_out) && aligned16(ep.acc_in) && aligned16(ws);
+                aligned16(ep.gp_out) && aligned16(ep.acc_in) && aligned16(ep.second.out) && aligned16(ws);
   for (int j = 0; j < ep.n_prev; ++j) vec_ok = vec_ok && aligned16(ep.kprev[j]);
   if (vec_ok && A.n_heavy > 0 && (!ws || ws_bytes < spmm_ws_bytes(A, d) || !A.heavy_rows || !A.heavy_chunk_ptr)) {
     set_error("spmm: heavy-row workspace missing or too small (%zu < %zu)", ws_bytes, spmm_ws_bytes(A, d));
@@ -1685,9 +1670,9 @@ extern "C" int gode_spmm_csr_f32(const gode_csr_t* A, const float* X, int64_t ld
     memset(&ep, 0, sizeof(ep));
   }
   GODE_REQUIRE(ep.n_prev >= 0 && ep.n_prev <= GODE_MAX_STAGES, "spmm: n_prev out of range");
-  GODE_REQUIRE(!ep.ynext || ep.y0, "spmm: ynext needs y0");
+  GODE_REQUIRE((!ep.ynext && !ep.second.out) || ep.y0, "spmm: ynext / second.out need y0");
   GODE_REQUIRE(!ep.gp_out || ep.mask_src, "spmm: gp_out needs mask_src");
-  GODE_REQUIRE(Y || ep.ynext || ep.gp_out, "spmm: no output requested");
+  GODE_REQUIRE(Y || ep.ynext || ep.gp_out || ep.second.out, "spmm: no output requested");
   if (!Y && ldy < d) ldy = d;  // every epilogue operand shares the leading dimension ldy
   ProfScope prof(GODE_PROF_OTHER, as_stream(stream));
   return spmm_dispatch(*A, X, ldx, d, Y, ldy, ep, ws, ws_bytes, as_stream(stream));

@@ -19,6 +19,7 @@ Time values and step sizes are float32 on the host, as torchdiffeq keeps them in
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -156,6 +157,15 @@ class GcnKernel:
         f.d, f.groups, f.gn_eps, f.precision = self.d, groups, eps, precision
         f.W, f.gamma, f.beta = self.weight.data_ptr(), self.gamma.data_ptr(), self.beta.data_ptr()
         f.b = self.bias.data_ptr() if self.bias is not None else None
+        # Row-stochastic, row-constant A_hat (the reference's normalisation): the adjoint's A_hat^T gather runs on the 0/1
+        # pattern with gP pre-scaled by its producer, and the bias gradient comes out of the weight-gradient pass
+        # (gode_gcn_odefunc_t.gp_row_scale; GODE_UNIT_T=0 keeps values per entry and the separate column-sum pass).
+        self.unit_t = None
+        if plan.rowptr_t is not None and os.environ.get("GODE_UNIT_T", "1") != "0" and hasattr(plan, "unit_transpose"):
+            self.unit_t = plan.unit_transpose()
+            if self.unit_t is not None:
+                f.At = self.unit_t[1]
+                f.gp_row_scale = self.unit_t[0].data_ptr()
         self.f = f
         self.ws_bytes = lib.gode_gcn_workspace_bytes(C.byref(f))
         self.n_theta = (self.d + 1) * self.d + 3 * self.d + 1
@@ -195,21 +205,47 @@ class GcnKernel:
                                      ops._stream()), "gode_gcn_transform")
         return out
 
-    def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0, S_next=None):
-        """k_out = f(.) from its support S; fused y_next = y0 + sum coefs*kprev + coef_self*k; S_next = transform."""
+    def _second(self, second, n_prev):
+        """Context: the descriptor's per-call second combination ``(coefs2, coef2_self, out2)`` -- out2 = y0 + sum
+        coefs2*kprev + coef2_self*k over the SAME (y0, kprev) as the call's own combination -- set for one library call."""
+        kern = self
+
+        class _Ctx:
+            def __enter__(self_):
+                if second is not None:
+                    c2, c2s, out2 = second
+                    if len(c2) != n_prev:
+                        raise ValueError("second combination: %d coefficients for %d stage tensors" % (len(c2), n_prev))
+                    r = _lib.RkSecond()
+                    for j, c in enumerate(c2):
+                        r.coef[j] = float(c)
+                    r.coef_self, r.out = float(c2s), out2.data_ptr()
+                    kern.f.second = r
+
+            def __exit__(self_, *exc):
+                if second is not None:
+                    kern.f.second = _lib.RkSecond()
+                return False
+        return _Ctx()
+
+    def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0, S_next=None,
+                  second=None):
+        """k_out = f(.) from its support S; fused y_next = y0 + sum coefs*kprev + coef_self*k; S_next = transform;
+        ``second`` = (coefs2, coef2_self, out2): a second combination of the same operands (see ``_second``)."""
         self.nfe += 1
         ws = self._ws()
         if MASK_LOG is not None and k_out is None:
             k_out = self.new()
         karr = (C.c_void_p * _lib.MAX_STAGES)(*[k.data_ptr() for k in kprev])
         carr = (C.c_float * _lib.MAX_STAGES)(*[float(c) for c in coefs])
-        check(lib.gode_gcn_stage_fwd(C.byref(self.f), ops._p(S), ops._p(k_out), ops._p(y0), karr, carr, len(kprev),
-                                     float(coef_self), ops._p(y_next), float(t_next), ops._p(S_next), ops._p(ws),
-                                     self.ws_bytes, ops._stream()), "gode_gcn_stage_fwd")
+        with self._second(second, len(kprev)):
+            check(lib.gode_gcn_stage_fwd(C.byref(self.f), ops._p(S), ops._p(k_out), ops._p(y0), karr, carr, len(kprev),
+                                         float(coef_self), ops._p(y_next), float(t_next), ops._p(S_next), ops._p(ws),
+                                         self.ws_bytes, ops._stream()), "gode_gcn_stage_fwd")
         if MASK_LOG is not None:
             MASK_LOG.append(k_out > 0)
 
-    def vjp_phase1(self, S, a, sign, k_y, gP, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None):
+    def vjp_phase1(self, S, a, sign, k_y, gP, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, second=None):
         """k_y = f(.), gP = sign*a*(k_y>0), fused y_next = y0 + sum coefs*kprev + coef_self*k_y -- one SpMM launch."""
         self.nfe += 1
         ws = self._ws()
@@ -217,21 +253,24 @@ class GcnKernel:
             k_y = self.new()
         karr = (C.c_void_p * _lib.MAX_STAGES)(*[k.data_ptr() for k in kprev])
         carr = (C.c_float * _lib.MAX_STAGES)(*[float(c) for c in coefs])
-        check(lib.gode_gcn_vjp_phase1(C.byref(self.f), ops._p(S), ops._p(a), float(sign), ops._p(k_y), ops._p(gP),
-                                      ops._p(y0), karr, carr, len(kprev), float(coef_self), ops._p(y_next),
-                                      ops._p(ws), self.ws_bytes, ops._stream()), "gode_gcn_vjp_phase1")
+        with self._second(second, len(kprev)):
+            check(lib.gode_gcn_vjp_phase1(C.byref(self.f), ops._p(S), ops._p(a), float(sign), ops._p(k_y), ops._p(gP),
+                                          ops._p(y0), karr, carr, len(kprev), float(coef_self), ops._p(y_next),
+                                          ops._p(ws), self.ws_bytes, ops._stream()), "gode_gcn_vjp_phase1")
         if MASK_LOG is not None:
             MASK_LOG.append(k_y > 0)
 
-    def vjp_phase2(self, y, t, gP, k_a, gtheta, a0=None, kprev=(), coefs=(), coef_self=0.0, a_next=None):
+    def vjp_phase2(self, y, t, gP, k_a, gtheta, a0=None, kprev=(), coefs=(), coef_self=0.0, a_next=None, second=None):
         """k_a = (gP^T A_hat) d[.]/dy (k_a may be None when no later stage reads it), gtheta = parameter / time terms;
-        fused a_next = a0 + sum coefs*kprev + coef_self*k_a in the tail of the GroupNorm backward."""
+        fused a_next = a0 + sum coefs*kprev + coef_self*k_a in the tail of the GroupNorm backward (``second``: as in
+        ``stage_fwd``, over a0 / kprev / k_a)."""
         ws = self._ws()
         karr = (C.c_void_p * _lib.MAX_STAGES)(*[k.data_ptr() for k in kprev])
         carr = (C.c_float * _lib.MAX_STAGES)(*[float(c) for c in coefs])
-        check(lib.gode_gcn_vjp_phase2_rk(C.byref(self.f), ops._p(y), float(t), ops._p(gP), ops._p(k_a), ops._p(gtheta),
-                                         ops._p(a0), karr, carr, len(kprev), float(coef_self), ops._p(a_next),
-                                         ops._p(ws), self.ws_bytes, ops._stream()), "gode_gcn_vjp_phase2_rk")
+        with self._second(second, len(kprev)):
+            check(lib.gode_gcn_vjp_phase2_rk(C.byref(self.f), ops._p(y), float(t), ops._p(gP), ops._p(k_a), ops._p(gtheta),
+                                             ops._p(a0), karr, carr, len(kprev), float(coef_self), ops._p(a_next),
+                                             ops._p(ws), self.ws_bytes, ops._stream()), "gode_gcn_vjp_phase2_rk")
 
 
 def _nz(ks, coefs):
@@ -267,22 +306,52 @@ def gcn_solve_forward(kern, y0, t0, t1, method="dopri5", step_size=None, rtol=1e
     return _gcn_dopri5(kern, tab, y0, F32(t0), F32(t1), rtol, atol, stats)
 
 
+def _running_final(tab):
+    """May the step keep a running partial sum of its final combination instead of the last-but-one stage derivative?
+    In an explicit s-stage step k_{s-2} is read, after its own stage's combination, by the final weights b only; so that
+    stage stores  V = y0 + dt * sum_{j <= s-2} b_j k_j  in place of k_{s-2} (a second combination of operands it reads
+    anyway) and the last stage computes y1 = V + dt * b_{s-1} k_{s-1} from ONE tensor instead of y0 and every k_j -- for
+    rk4 three [N, d] streams less per state and step.  GODE_RK_RUNNING=0 restores the plain form."""
+    return (tab.s >= 2 and any(c != 0 for c in tab.b[:tab.s - 1]) and tab.c_err is None
+            and os.environ.get("GODE_RK_RUNNING", "1") != "0")
+
+
+def _stage_plan(tab, i, dt, ks, running):
+    """Operands of stage i's fused combinations: (base is y0?, kprev, coefs, coef_self, second coefficients or None)."""
+    s = tab.s
+    last = i == s - 1
+    row = tab.b if last else tab.a[i + 1]
+    coefs = [F32(dt * F32(c)) for c in row[:i + 1]]
+    if running and last:
+        # y1 = V + dt * b_{s-1} * k_{s-1}
+        return False, [], [], coefs[i], None
+    if running and i == s - 2:
+        b = [F32(dt * F32(c)) for c in tab.b[:i + 1]]
+        keep = [j for j in range(i) if coefs[j] != 0 or b[j] != 0]
+        return True, [ks[j] for j in keep], [coefs[j] for j in keep], coefs[i], ([b[j] for j in keep], b[i])
+    kprev, cprev = _nz(ks[:i], coefs[:i])
+    return True, kprev, cprev, coefs[i], None
+
+
 def _gcn_fixed_step(kern, tab, t0, dt, y0, S0, want_S):
     s = tab.s
     ks, S = [], S0
     scratch_y = [kern.new(), kern.new()]
-    y1 = None
+    y1 = V = None
+    running = _running_final(tab)
     for i in range(s):
         last = i == s - 1
-        row = tab.b if last else tab.a[i + 1]
-        coefs = [F32(dt * F32(c)) for c in row[:i + 1]]
         t_n = F32(t0 + dt) if last else F32(t0 + F32(tab.c[i + 1]) * dt)
-        kprev, cprev = _nz(ks[:i], coefs[:i])
-        store = (not last) and _needed_later(tab, i)
+        base_y0, kprev, cprev, c_self, sec = _stage_plan(tab, i, dt, ks, running)
+        store = (not last) and _needed_later(tab, i) and sec is None
         k_i = kern.new() if store else None
         y_next = kern.new() if last else scratch_y[i & 1]
         S_next = kern.new_S() if (not last or want_S) else None
-        kern.stage_fwd(S, k_i, y0, kprev, cprev, coefs[i], y_next, t_n, S_next)
+        second = None
+        if sec is not None:
+            V = kern.new()
+            second = (sec[0], sec[1], V)
+        kern.stage_fwd(S, k_i, y0 if base_y0 else V, kprev, cprev, c_self, y_next, t_n, S_next, second=second)
         ks.append(k_i)
         S = S_next
         y1 = y_next
@@ -389,7 +458,8 @@ def gcn_solve_adjoint(kern, y1, g1, t0, t1, method="dopri5", step_size=None, rto
         y, a = y1, g1
         for g0_, g1_ in zip(grid[:-1], grid[1:]):
             h = F32(g1_ - g0_)
-            y, a, S, dth = _gcn_aug_fixed_step(kern, tab, g0_, h, y, a, S, want_S=g1_ != grid[-1])
+            y, a, S, dth = _gcn_aug_fixed_step(kern, tab, g0_, h, y, a, S, want_S=g1_ != grid[-1],
+                                               want_y=g1_ != grid[-1])
             a_theta += dth
             if stats is not None:
                 stats["accepted"] = stats.get("accepted", 0) + 1
@@ -399,8 +469,9 @@ def gcn_solve_adjoint(kern, y1, g1, t0, t1, method="dopri5", step_size=None, rto
     return _gcn_aug_dopri5(kern, tab, y1, g1, a_t, F32(t1), F32(t0), S, rtol, atol, stats)
 
 
-def _gcn_aug_fixed_step(kern, tab, t0, h, y0, a0, S0, want_S):
-    """One explicit RK step of the augmented system with step h (negative: backwards in time)."""
+def _gcn_aug_fixed_step(kern, tab, t0, h, y0, a0, S0, want_S, want_y=True):
+    """One explicit RK step of the augmented system with step h (negative: backwards in time).  ``want_y`` False (the
+    last step of the grid: nothing reads y(t0) any more) drops the y-combination of the last stage altogether."""
     s = tab.s
     P = kern.n_theta
     ky, ka = [], []
@@ -411,18 +482,28 @@ def _gcn_aug_fixed_step(kern, tab, t0, h, y0, a0, S0, want_S):
     Ybuf, Abuf = [kern.new(), kern.new()], [kern.new(), kern.new()]
     Y_i, A_i, S_i = y0, a0, S0
     y_out = a_out = S_out = None
+    Vy = Va = None
+    running = _running_final(tab)
     for i in range(s):
         last = i == s - 1
         t_i = F32(t0 + F32(tab.c[i]) * h)
-        row = tab.b if last else tab.a[i + 1]
-        coefs = [F32(h * F32(c)) for c in row[:i + 1]]
         t_n = F32(t0 + h) if last else F32(t0 + F32(tab.c[i + 1]) * h)
-        store = (not last) and _needed_later(tab, i)
-        ky_i = kern.new() if store else None
-        Y_n = kern.new() if last else Ybuf[i & 1]
-        kyp, cyp = _nz(ky[:i], coefs[:i])
+        base_y0, kyp, cyp, c_self, sec = _stage_plan(tab, i, h, ky, running)
+        _, kap, cap, _, _ = _stage_plan(tab, i, h, ka, running)
+        sec_y = sec if want_y else None          # without y(t0) the y-state needs no final combination at all
+        store_y = (not last) and _needed_later(tab, i) and sec is None
+        ky_i = kern.new() if store_y else None
+        need_Y = (not last) or want_y
+        Y_n = (kern.new() if last else Ybuf[i & 1]) if need_Y else None
         gP = gPs[i & 1]
-        kern.vjp_phase1(S_i, A_i, -1.0, ky_i, gP, y0, kyp, cyp, coefs[i], Y_n)
+        second = None
+        if sec_y is not None:
+            Vy = kern.new()
+            second = (sec_y[0], sec_y[1], Vy)
+        if need_Y:
+            kern.vjp_phase1(S_i, A_i, -1.0, ky_i, gP, y0 if base_y0 else Vy, kyp, cyp, c_self, Y_n, second=second)
+        else:
+            kern.vjp_phase1(S_i, A_i, -1.0, None, gP)
         # The next stage's support only needs Y_n, which phase 1 has just produced: issue its transform BEFORE
         # phase 2, so that on the row-partitioned path both halo exchanges (gP, then S_n) are in flight underneath
         # the transform and phase 2's dense chain instead of being exposed.
@@ -431,11 +512,14 @@ def _gcn_aug_fixed_step(kern, tab, t0, h, y0, a0, S0, want_S):
         else:
             S_n = None
         # k_a of this stage and the adjoint state of the next one in the same pass (k_a is stored only if a later
-        # combination reads it)
-        ka_i = kern.new() if store else None
+        # combination reads it; the last-but-one stage stores the running final combination instead)
+        ka_i = kern.new() if store_y else None
         A_n = kern.new() if last else Abuf[i & 1]
-        kap, cap = _nz(ka[:i], coefs[:i])
-        kern.vjp_phase2(Y_i, t_i, gP, ka_i, gth[i], a0, kap, cap, coefs[i], A_n)
+        second = None
+        if sec is not None:
+            Va = kern.new()
+            second = (sec[0], sec[1], Va)
+        kern.vjp_phase2(Y_i, t_i, gP, ka_i, gth[i], a0 if base_y0 else Va, kap, cap, c_self, A_n, second=second)
         ky.append(ky_i)
         ka.append(ka_i)
         Y_i, A_i, S_i = Y_n, A_n, S_n

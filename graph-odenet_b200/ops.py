@@ -117,6 +117,40 @@ class GraphPlan:
                                   self.chunk_ptr, self.n_heavy, self.n_chunks, self.row_vals)
         return self._csr
 
+    def row_stochastic_scale(self):
+        """``row_vals`` when the matrix is row-constant AND every row sums to one (the reference's D^-1 (A + I),
+        GCN/utils.py:205-212: row value = fp32(1 / row count)), else None.  Decides ``unit_transpose``."""
+        if not hasattr(self, "_rs_scale"):
+            self._rs_scale = None
+            if self.row_vals is not None and self.n_rows > 0:
+                cnt = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.float32)
+                if bool(((self.row_vals * cnt - 1.0).abs() <= 1e-6).all().item()):
+                    self._rs_scale = self.row_vals
+        return self._rs_scale
+
+    def unit_pattern_csr(self):
+        """``gode_csr_t`` of this matrix's 0/1 PATTERN (same index arrays, every value one, row-constant)."""
+        if getattr(self, "_unit_csr", None) is None:
+            self._unit_vals = torch.ones(max(self.nnz, 1), dtype=torch.float32, device=self.device)
+            self._unit_row_vals = torch.ones(max(self.n_rows, 1), dtype=torch.float32, device=self.device)
+            self._unit_csr = _make_csr(self.n_rows, self.n_cols, self.rowptr, self.colidx, self._unit_vals, self.heavy,
+                                       self.chunk_ptr, self.n_heavy, self.n_chunks, self._unit_row_vals)
+        return self._unit_csr
+
+    def unit_transpose(self):
+        """(row scale, pattern CSR of A^T) when the adjoint may gather ``A_hat^T gP`` without a values stream: for a
+        row-constant, row-stochastic A_hat column i of A_hat^T is the constant rv_i, so the producer of gP stores
+        ``rv_i * gP_i`` and the gather adds plain rows; the bias gradient ``sum_i gP_i`` equals the column sums of the
+        gathered result because every row of A_hat sums to one (gode_gcn_odefunc_t.gp_row_scale).  Else None."""
+        if self.rowptr_t is None or self.n_rows != self.n_cols:
+            return None
+        scale = self.row_stochastic_scale()
+        if scale is None:
+            return None
+        if getattr(self, "_unit_t_view", None) is None:
+            self._unit_t_view = self.transposed()      # shares the index arrays; owns the unit values
+        return scale, self._unit_t_view.unit_pattern_csr()
+
     def _build_transpose(self):
         dev = self.device
         nnz = self.nnz
@@ -181,8 +215,30 @@ class GraphPlan:
         return t
 
 
+def tile_schedule(n_rows, heavy, chunk_ptr, n_heavy, n_chunks):
+    """Work order of the d = 128 tile gather (gode_csr_t.tile_sched): the 32-row tiles in id order, every group of 8 hub
+    chunks right behind the tile that contains the hub of its first chunk.  int32 on the device, or None without hubs."""
+    if not n_heavy or n_rows == 0:
+        return None
+    dev = heavy.device
+    n_tiles = (n_rows + 31) // 32
+    groups = (n_chunks + 7) // 8
+    first = torch.arange(groups, device=dev, dtype=torch.int64) * 8
+    hub = torch.searchsorted(chunk_ptr[:n_heavy + 1].to(torch.int64), first, right=True) - 1
+    row = heavy[hub.clamp_(0, n_heavy - 1)].to(torch.int64)
+    keys = torch.cat([torch.arange(n_tiles, device=dev, dtype=torch.int64) * 2, (row // 32) * 2 + 1])
+    items = torch.cat([torch.arange(n_tiles, device=dev, dtype=torch.int64),
+                       -(torch.arange(groups, device=dev, dtype=torch.int64) + 1)])
+    order = torch.sort(keys, stable=True).indices
+    return items[order].to(torch.int32).contiguous()
+
+
 def _make_csr(n_rows, n_cols, rowptr, colidx, vals, heavy, chunk_ptr, n_heavy, n_chunks, row_vals=None):
     c = _lib.Csr()
+    sched = tile_schedule(n_rows, heavy, chunk_ptr, n_heavy, n_chunks)
+    if sched is not None:
+        c._keep_sched = sched        # the struct instance is cached on its plan: the table lives as long as the plan
+        c.tile_sched, c.n_tile_sched = sched.data_ptr(), int(sched.numel())
     c.n_rows, c.n_cols = n_rows, n_cols
     c.rowptr, c.colidx, c.vals = rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr()
     c.row_vals = row_vals.data_ptr() if row_vals is not None else None

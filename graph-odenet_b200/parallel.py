@@ -318,7 +318,7 @@ class HaloKernelMixin:
         self._exchange(self.plan.halo, out)
         return out
 
-    def _stage_pipelined(self, S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next):
+    def _stage_pipelined(self, S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next, second=None):
         """One forward stage in ``pipe_G`` row chunks: gather chunk c (+ its Runge-Kutta combination) and transform its rows
         on the main stream; push chunk c's boundary rows of S_next on the side stream underneath chunk c+1's gather."""
         from . import odeint as _od
@@ -338,18 +338,22 @@ class HaloKernelMixin:
             check(lib.gode_gcn_transform_rows(C.byref(self.f), ops._p(y_next), float(t_next), ops._p(S_next), r0, nr,
                                               ops._p(ws), self.ws_bytes, ops._stream()), "gode_gcn_transform_rows")
 
-        self.pending[S_next.data_ptr()] = self.peer.push_pipelined(self.plan.halo, S_next, self.pipe_G, produce)
+        with self._second(second, len(kprev)):
+            self.pending[S_next.data_ptr()] = self.peer.push_pipelined(self.plan.halo, S_next, self.pipe_G, produce)
         if _od.MASK_LOG is not None:
             _od.MASK_LOG.append(k_out > 0)
 
-    def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0, S_next=None):
-        run = lambda: super(HaloKernelMixin, self).stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next)
+    def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0, S_next=None,
+                  second=None):
+        run = lambda: super(HaloKernelMixin, self).stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next,
+                                                             second=second)
         if self.pipe_G and S_next is not None and y_next is not None:
             self._wait(S)
-            return self._stage_pipelined(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next)
+            return self._stage_pipelined(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next, second)
         if self.pipe_S:
             self._wait(S)
-            super(HaloKernelMixin, self).stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, None)
+            super(HaloKernelMixin, self).stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, None,
+                                                   second=second)
             if S_next is not None:
                 self._transform_pipelined(y_next, t_next, S_next)
             return
@@ -370,8 +374,9 @@ class HaloKernelMixin:
         if S_next is not None:
             self._exchange(self.plan.halo, S_next)
 
-    def vjp_phase1(self, S, a, sign, k_y, gP, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None):
-        run = lambda: super(HaloKernelMixin, self).vjp_phase1(S, a, sign, k_y, gP, y0, kprev, coefs, coef_self, y_next)
+    def vjp_phase1(self, S, a, sign, k_y, gP, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, second=None):
+        run = lambda: super(HaloKernelMixin, self).vjp_phase1(S, a, sign, k_y, gP, y0, kprev, coefs, coef_self, y_next,
+                                                              second=second)
         if self.fused:
             self._wait(S)
             epoch = self._fused_begin("push_gP", self.plan.halo_t, gP)     # the gather's epilogue pushes gP
@@ -386,8 +391,9 @@ class HaloKernelMixin:
             self._with_halo_pass(part, run)
         self._exchange(self.plan.halo_t, gP)
 
-    def vjp_phase2(self, y, t, gP, k_a, gtheta, a0=None, kprev=(), coefs=(), coef_self=0.0, a_next=None):
-        run = lambda: super(HaloKernelMixin, self).vjp_phase2(y, t, gP, k_a, gtheta, a0, kprev, coefs, coef_self, a_next)
+    def vjp_phase2(self, y, t, gP, k_a, gtheta, a0=None, kprev=(), coefs=(), coef_self=0.0, a_next=None, second=None):
+        run = lambda: super(HaloKernelMixin, self).vjp_phase2(y, t, gP, k_a, gtheta, a0, kprev, coefs, coef_self, a_next,
+                                                              second=second)
         if self.plan.split is None:
             self._wait(gP)
             return run()
@@ -485,6 +491,19 @@ class PartitionedPlan:
 
     def csr(self, transpose=False):
         return (self.At if transpose else self.A).csr(False)
+
+    def unit_transpose(self):
+        """(row scale of the owned rows, 0/1 pattern of this rank's A_hat^T block) when EVERY rank's block of A_hat is
+        row-constant and row-stochastic (``ops.GraphPlan.unit_transpose``: the owner of a row pre-scales its gP row, so
+        the halo rows of gP arrive scaled and all ranks have to agree) and gathers are not column-split; else None.
+        Collective on first use."""
+        if not hasattr(self, "_unit_t"):
+            scale = None if self.split is not None else self.A.row_stochastic_scale()
+            ok = torch.tensor([1 if scale is not None else 0], dtype=torch.int32, device=self.device)
+            if self.world > 1 and dist.is_initialized():
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            self._unit_t = (scale, self.At.unit_pattern_csr()) if int(ok.item()) == 1 else None
+        return self._unit_t
 
     def peer_for(self, d):
         """The peer-memory arena / exchange state for feature width ``d`` (collective on first use)."""

@@ -106,6 +106,12 @@ typedef struct {
   const int32_t* heavy_chunk_ptr;   /* [n_heavy + 1], or NULL */
   int32_t n_heavy;
   int32_t n_chunks;
+  const int32_t* tile_sched;        /* [n_tile_sched] or NULL.  Work order of the d = 128 tile gather (one CTA per entry): an entry
+                                       >= 0 is a 32-row tile index; an entry < 0 is -(g + 1), the hub chunks [8g, 8g + 8).  Tiles are
+                                       in id order and every chunk group follows the tile that contains its (first chunk's) hub, so
+                                       a hub's chunks are gathered while the band around its id is L2-resident; NULL: the hub chunks
+                                       are gathered by a separate launch after the tiles (same sums, same order, same result). */
+  int32_t n_tile_sched;
 } gode_csr_t;
 
 /* row_vals_out[r] = the common value of row r's entries (0 for an empty row); *is_const_out (device int32) = 1
@@ -138,7 +144,19 @@ typedef struct {
  *   fused Runge-Kutta stage combination (torchdiffeq rk_common._runge_kutta_step, restated in
  *   oracle/odeint.py):  Ynext = y0 + sum_j coef[j]*kprev[j] + coef_self*v     (if ynext)
  *   fused adjoint preparation:   gP = mask_scale * mask_src * (v > 0)         (if gp_out)
+ *   second combination of the SAME operands (if second.out; needs y0):
+ *                                out = y0 + sum_j second.coef[j]*kprev[j] + second.coef_self*v
+ *     -- the solver keeps a running partial sum of the step's final weights b this way (written INSTEAD of the
+ *        stage derivative), so that the last stage of a step reads one tensor rather than every earlier k_j.
+ *   gp_row_scale (with gp_out): gP rows are multiplied by gp_row_scale[row] -- the A_hat^T gather of a row-constant
+ *     A_hat then needs no values stream (column i of A_hat^T is the constant row value of row i of A_hat).
  * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  float coef[GODE_MAX_STAGES];
+  float coef_self;
+  float* out;              /* [n_rows, ld] or NULL: off */
+} gode_rk_second_t;
+
 typedef struct {
   const float* bias;       /* [d] or NULL */
   int32_t relu;            /* 0/1 */
@@ -156,6 +174,8 @@ typedef struct {
                               another column block of the same rows -- the row-partitioned path gathers the owned
                               columns while the halo is in flight, then the halo columns with acc_in) */
   gode_push_route_t push;  /* gp_out rows are also stored into the peers' buffers (ptr NULL: off) */
+  gode_rk_second_t second; /* second combination of (y0, kprev, v); out NULL: off */
+  const float* gp_row_scale; /* [n_rows] or NULL */
 } gode_spmm_epilogue_t;
 
 /* ws: n_chunks * d floats of scratch for the heavy-row partial sums (0 bytes when n_heavy == 0) */
@@ -302,6 +322,16 @@ typedef struct {
    * VJP writes are also stored into the peers' halo tails.  Needs the tensor-core transform (gode_gcn_push_fusable). */
   gode_push_route_t push_S;
   gode_push_route_t push_gP;
+  /* Per-call (out NULL: off): the second Runge-Kutta combination of the NEXT gode_gcn_stage_fwd / _stage_fwd_rows /
+   * _vjp_phase1 (over y0, kprev, k) or gode_gcn_vjp_phase2_rk (over a0, kprev, k_a) call -- see gode_spmm_epilogue_t. */
+  gode_rk_second_t second;
+  /* Non-NULL ([n_rows], = A.row_vals of the FULL row block): A_hat is row-constant AND row-stochastic (the reference's
+   * D^-1 (A + I), GCN/utils.py:205-212) and At holds the 0/1 pattern of A_hat^T (values and row_vals all one).  Phase 1
+   * then stores gP pre-multiplied by gp_row_scale[row] (column i of A_hat^T is the constant row value of row i), the
+   * A_hat^T gather reads no values, and the bias gradient (column sums of the unscaled gP) is taken from the column sums
+   * of gS = A_hat^T gP, which the weight-gradient pass forms anyway: sum_i (sum_j A_ij) gP_i = sum_i gP_i.
+   * NULL: values per entry, separate column-sum pass over gP. */
+  const float* gp_row_scale;
 } gode_gcn_odefunc_t;
 
 size_t gode_gcn_workspace_bytes(const gode_gcn_odefunc_t* f);

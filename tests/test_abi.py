@@ -50,9 +50,11 @@ def test_struct_layouts_match_header():
     from graph_odenet_b200 import _lib
     route = 8 + 8 + 16 * 8
     assert ctypes.sizeof(_lib.PushRoute) == route
-    assert ctypes.sizeof(_lib.SpmmEpilogue) == 8 + 8 + 8 + 8 + 8 * 8 + 4 * 8 + 4 + 4 + 8 + 8 + 8 + 8 + 8 + route
-    assert ctypes.sizeof(_lib.Csr) == 2 * 8 + 6 * 8 + 2 * 4
-    assert ctypes.sizeof(_lib.GcnOdeFunc) == 2 * ctypes.sizeof(_lib.Csr) + 4 * 4 + 4 * 8 + 8 + 8 + 2 * route
+    second = 4 * 8 + 4 + 4 + 8        # coef[8], coef_self, padding, out
+    assert ctypes.sizeof(_lib.RkSecond) == second
+    assert ctypes.sizeof(_lib.SpmmEpilogue) == 8 + 8 + 8 + 8 + 8 * 8 + 4 * 8 + 4 + 4 + 8 + 8 + 8 + 8 + 8 + route + second + 8
+    assert ctypes.sizeof(_lib.Csr) == 2 * 8 + 6 * 8 + 2 * 4 + 8 + 4 + 4     # ..., tile_sched, n_tile_sched, padding
+    assert ctypes.sizeof(_lib.GcnOdeFunc) == 2 * ctypes.sizeof(_lib.Csr) + 4 * 4 + 4 * 8 + 8 + 8 + 2 * route + second + 8
     assert ctypes.sizeof(_lib.PeerGroup) == 4 + 4 + 16 * 8
 
 
@@ -73,3 +75,28 @@ def test_model_surface_matches_reference_keys():
         models.RGCN2(10, 2, 3, 0.5)
     k = models.RESKnorm(10, 16, 3, 0.5, nlayers=5, residue_layers=3)
     assert [n for n, _ in k.named_parameters()][:2] == ["gcs.0.weight", "gcs.0.bias"] and len(k.norms) == 3
+
+
+def test_tile_schedule_is_a_merge_of_tiles_and_hub_chunk_groups():
+    """gode_csr_t.tile_sched (ops.tile_schedule): every 32-row tile once, in id order; every group of 8 hub chunks once, right
+    behind the tile that contains the hub of its first chunk (index work, checked on CPU tensors)."""
+    import torch
+    from graph_odenet_b200 import ops
+    n_rows = 10_000
+    heavy = torch.tensor([5, 31, 32, 700, 701, 9_999], dtype=torch.int32)
+    nch = torch.tensor([3, 1, 17, 2, 40, 9])
+    chunk_ptr = torch.cat([torch.zeros(1, dtype=torch.int64), nch.cumsum(0)]).to(torch.int32)
+    n_chunks = int(nch.sum())
+    sched = ops.tile_schedule(n_rows, heavy, chunk_ptr, len(heavy), n_chunks)
+    n_tiles, groups = (n_rows + 31) // 32, (n_chunks + 7) // 8
+    assert sched.dtype == torch.int32 and sched.numel() == n_tiles + groups
+    tiles = sched[sched >= 0]
+    assert torch.equal(tiles, torch.arange(n_tiles, dtype=torch.int32))
+    grp = (-sched[sched < 0] - 1).tolist()
+    assert sorted(grp) == list(range(groups))
+    pos = {int(v): i for i, v in enumerate(sched.tolist())}
+    for g in range(groups):
+        hub = int(torch.searchsorted(chunk_ptr.to(torch.int64), torch.tensor([8 * g]), right=True)) - 1
+        tile = int(heavy[hub]) // 32
+        assert pos[tile] < pos[-(g + 1)] and (tile + 1 == n_tiles or pos[-(g + 1)] < pos[tile + 1])
+    assert ops.tile_schedule(n_rows, None, None, 0, 0) is None

@@ -505,6 +505,52 @@ def test_relu_regime_gradient_parity(n, deg, seed, dev):
     assert all(v < bound for v in e_plain.values()), ("unconditioned", e_plain, feed.flips)
 
 
+@pytest.mark.parametrize("method,options", [("rk4", None), ("rk4", {"step_size": 0.5}), ("midpoint", None), ("euler", {"step_size": 0.25})])
+def test_running_final_and_unit_transpose_match_plain(method, options, dev, monkeypatch):
+    """Two rewrites of the fixed-step adjoint's data flow that change no arithmetic beyond fp32 rounding: (1) the last-but-one
+    stage stores the running final combination y0 + dt*sum b_j k_j instead of its derivative (odeint._running_final) and the
+    last adjoint step forms no y(t0); (2) on the reference's row-stochastic A_hat the A_hat^T gather runs on the 0/1 pattern
+    over pre-scaled gP rows and the bias gradient is read off the column sums of gS (gode_gcn_odefunc_t.gp_row_scale).  Each
+    must reproduce the plain form (GODE_RK_RUNNING=0, GODE_UNIT_T=0) on a problem without ReLU mask sensitivity (smooth
+    regime: positive pre-activations), one step and two steps, and unit_transpose must be OFF for a matrix that is not
+    row-stochastic."""
+    ops, odeint, synth, _, models = _pkg()
+    n, d = 30000, 128
+    row, col, val = synth.powerlaw_graph(n, avg_degree=16, seed=3, device=dev)
+    adj = torch.sparse_coo_tensor(torch.stack([row, col]), val, (n, n))
+    torch.manual_seed(1)
+    blk = models.ODEBlock(models.ODEfunc(d), method=method, options=options).to(dev)
+    with torch.no_grad():
+        blk.odefunc.norm1.weight.uniform_(0.5, 1.5)
+        blk.odefunc.norm1.bias.uniform_(-0.5, 0.5)
+        blk.odefunc.gc1.bias.fill_(4.0)          # every pre-activation positive: no mask element near zero
+    x0 = 0.5 * torch.randn(n, d, device=dev)
+    g = torch.randn(n, d, device=dev) / n
+
+    def run(running, unit):
+        monkeypatch.setenv("GODE_RK_RUNNING", running)
+        monkeypatch.setenv("GODE_UNIT_T", unit)
+        for p in blk.parameters():
+            p.grad = None
+        x = x0.clone().requires_grad_(True)
+        y = blk(x, adj)
+        y.backward(g)
+        return [y.detach(), x.grad] + [p.grad.clone() for p in blk.parameters()]
+
+    plain = run("0", "0")
+    names = ["y1", "grad_x"] + [k for k, _ in blk.named_parameters()]
+    for running, unit in (("1", "0"), ("0", "1"), ("1", "1")):
+        got = run(running, unit)
+        for nm, a, b in zip(names, got, plain):
+            err = float((a.double() - b.double()).norm() / b.double().norm())
+            assert err < 2e-6, (method, options, running, unit, nm, err)
+    # a matrix whose rows do not sum to one keeps values per entry
+    plan2 = ops.GraphPlan.from_coo(row, col, 0.5 * val, n, n)
+    assert plan2.row_vals is not None and plan2.unit_transpose() is None
+    plan1 = ops.GraphPlan.from_coo(row, col, val, n, n)
+    assert plan1.unit_transpose() is not None
+
+
 def test_weight_gradient_accuracy_long_reduction(dev):
     """The weight gradient z^T gS is a reduction over ALL rows, accumulated in TMEM by k_wgrad_tc: against fp64 at 2 M rows
     (13 500 rows = 1 700 accumulating MMA steps per CTA) it must stay within 1e-5 relative L2.  Identity adjacency, so gS = gP
