@@ -37,7 +37,7 @@ class SpmmEpilogue(C.Structure):
     _fields_ = [("bias", vp), ("relu", i32), ("residual", vp), ("y0", vp), ("kprev", vp * MAX_STAGES),
                 ("coef", f32 * MAX_STAGES), ("n_prev", i32), ("coef_self", f32), ("ynext", vp),
                 ("mask_src", vp), ("mask_scale", f32), ("gp_out", vp), ("acc_in", vp), ("push", PushRoute),
-                ("second", RkSecond), ("gp_row_scale", vp)]
+                ("push_y", PushRoute), ("second", RkSecond), ("gp_row_scale", vp)]
 
 
 class Csr(C.Structure):
@@ -61,7 +61,7 @@ class GatGraph(C.Structure):
 class GcnOdeFunc(C.Structure):
     _fields_ = [("A", Csr), ("At", Csr), ("d", i32), ("groups", i32), ("gn_eps", f32), ("precision", i32),
                 ("W", vp), ("b", vp), ("gamma", vp), ("beta", vp), ("gather_row_offset", i64), ("partial_in", vp),
-                ("push_S", PushRoute), ("push_gP", PushRoute), ("second", RkSecond), ("gp_row_scale", vp)]
+                ("push_S", PushRoute), ("push_gP", PushRoute), ("push_y", PushRoute), ("second", RkSecond), ("gp_row_scale", vp)]
 
 
 class PeerGroup(C.Structure):

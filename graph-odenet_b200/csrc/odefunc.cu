@@ -169,7 +169,8 @@ extern "C" int gode_gcn_transform_rows(const gode_gcn_odefunc_t* f, const float*
                                        int64_t n_rows, void* ws, size_t ws_bytes, void* stream) {
   int rc = check(f);
   if (rc) return rc;
-  GODE_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= f->A.n_rows, "gcn_transform_rows: row range outside the block");
+  const int64_t row_limit = (transform_tc_supported(f) && f->A.n_cols > f->A.n_rows) ? f->A.n_cols : f->A.n_rows;
+  GODE_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= row_limit, "gcn_transform_rows: row range outside the block");
   if (n_rows == 0) return GODE_OK;
   GODE_REQUIRE(y && S, "gcn_transform_rows: null pointer");
   GcnWs w;
@@ -212,6 +213,7 @@ extern "C" int gode_gcn_stage_fwd(const gode_gcn_odefunc_t* f, const float* S, f
     }
     ep.coef_self = coef_self;
     ep.ynext = y_next;
+    ep.push_y = f->push_y;
   }
   if ((rc = set_second(ep, f, y0, kprev_host, n_prev))) return rc;
   {
@@ -253,6 +255,7 @@ extern "C" int gode_gcn_stage_fwd_rows(const gode_gcn_odefunc_t* f, const float*
     }
     ep.coef_self = coef_self;
     ep.ynext = y_next;
+    ep.push_y = f->push_y;
   }
   if ((rc = set_second(ep, f, y0, kprev_host, n_prev))) return rc;
   ep.acc_in = f->partial_in;
@@ -283,6 +286,7 @@ extern "C" int gode_gcn_vjp_phase1(const gode_gcn_odefunc_t* f, const float* S, 
   if (y_next) {
     ep.y0 = y0;
     ep.ynext = y_next;
+    ep.push_y = f->push_y;
     ep.n_prev = n_prev;
     ep.coef_self = coef_self;
     for (int j = 0; j < n_prev; ++j) {

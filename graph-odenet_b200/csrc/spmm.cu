@@ -71,6 +71,14 @@ __device__ __forceinline__ void epilogue(const gode_spmm_epilogue_t& ep, int64_t
         float4 y = y0;
         y.x += t.x; y.y += t.y; y.z += t.z; y.w += t.w;
         st_stream4(ep.ynext + o, y);
+        if (ep.push_y.ptr) {   // fused halo push of the next stage state: the peers transform these rows themselves
+          const int p1 = __ldg(ep.push_y.ptr + row + 1);
+          for (int e = __ldg(ep.push_y.ptr + row); e < p1; ++e) {
+            const int64_t ent = __ldg(ep.push_y.ent + e);
+            float* dst = ep.push_y.base[ent >> 40] + (ent & 0xFFFFFFFFFFll) * ldy + c;
+            *reinterpret_cast<float4*>(dst) = y;
+          }
+        }
       }
       if (ep.second.out) {
         const float cs = ep.second.coef_self;

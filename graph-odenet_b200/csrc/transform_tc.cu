@@ -1110,7 +1110,9 @@ int transform_tc(const gode_gcn_odefunc_t* f, const float* y, float t, float* S,
     row0 = 0;
     n_rows = f->A.n_rows;
   }
-  GODE_REQUIRE(row0 >= 0 && row0 + n_rows <= f->A.n_rows, "transform_tc: row range outside the block");
+  // rows beyond the owned block are the halo rows of a partitioned block (y and S then have A.n_cols rows)
+  GODE_REQUIRE(row0 >= 0 && row0 + n_rows <= (f->A.n_cols > f->A.n_rows ? f->A.n_cols : f->A.n_rows),
+               "transform_tc: row range outside the block");
   GODE_REQUIRE(!push || row0 == 0, "transform_tc: a fused push addresses rows from 0");
   y += row0 * f->d;
   S += row0 * f->d;

@@ -187,6 +187,19 @@ class GcnKernel:
         """Buffer for gP (operand of the A_hat^T gather)."""
         return self.new()
 
+    def new_Y(self):
+        """Buffer for a stage state the NEXT evaluation's transform reads (the row-partitioned kernel hands out one with a
+        halo tail: the producing gather stores the peers' rows there, parallel.HaloKernelMixin)."""
+        return self.new()
+
+    def transform_rows(self, y, t, out, row0, n_rows):
+        """out[row0 : row0 + n_rows] = transform(y[row0 : row0 + n_rows], t)  (base pointers; rows past the owned block
+        are the halo rows of a partitioned block)."""
+        ws = self._ws()
+        check(lib.gode_gcn_transform_rows(C.byref(self.f), ops._p(y), float(t), ops._p(out), int(row0), int(n_rows),
+                                          ops._p(ws), self.ws_bytes, ops._stream()), "gode_gcn_transform_rows")
+        return out
+
     def numel_global(self):
         """Number of state elements over the whole graph (denominator of the RMS norms)."""
         return self.n * self.d
@@ -336,7 +349,7 @@ def _stage_plan(tab, i, dt, ks, running):
 def _gcn_fixed_step(kern, tab, t0, dt, y0, S0, want_S):
     s = tab.s
     ks, S = [], S0
-    scratch_y = [kern.new(), kern.new()]
+    scratch_y = [kern.new_Y(), kern.new_Y()]
     y1 = V = None
     running = _running_final(tab)
     for i in range(s):
@@ -345,7 +358,7 @@ def _gcn_fixed_step(kern, tab, t0, dt, y0, S0, want_S):
         base_y0, kprev, cprev, c_self, sec = _stage_plan(tab, i, dt, ks, running)
         store = (not last) and _needed_later(tab, i) and sec is None
         k_i = kern.new() if store else None
-        y_next = kern.new() if last else scratch_y[i & 1]
+        y_next = (kern.new_Y() if want_S else kern.new()) if last else scratch_y[i & 1]
         S_next = kern.new_S() if (not last or want_S) else None
         second = None
         if sec is not None:
@@ -479,7 +492,7 @@ def _gcn_aug_fixed_step(kern, tab, t0, h, y0, a0, S0, want_S, want_y=True):
     # two gP buffers in turn: with the peer-memory exchange a push of stage i+1's gP must not land in the buffer a
     # peer's phase 2 of stage i may still be gathering from (peer.py)
     gPs = [kern.new_gP(), kern.new_gP()]
-    Ybuf, Abuf = [kern.new(), kern.new()], [kern.new(), kern.new()]
+    Ybuf, Abuf = [kern.new_Y(), kern.new_Y()], [kern.new(), kern.new()]
     Y_i, A_i, S_i = y0, a0, S0
     y_out = a_out = S_out = None
     Vy = Va = None
@@ -494,7 +507,7 @@ def _gcn_aug_fixed_step(kern, tab, t0, h, y0, a0, S0, want_S, want_y=True):
         store_y = (not last) and _needed_later(tab, i) and sec is None
         ky_i = kern.new() if store_y else None
         need_Y = (not last) or want_y
-        Y_n = (kern.new() if last else Ybuf[i & 1]) if need_Y else None
+        Y_n = ((kern.new_Y() if want_S else kern.new()) if last else Ybuf[i & 1]) if need_Y else None
         gP = gPs[i & 1]
         second = None
         if sec_y is not None:

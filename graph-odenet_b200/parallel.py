@@ -183,6 +183,14 @@ class HaloKernelMixin:
         self.pipe_G = (pipe_g_chunks(plan.world)
                        if (self.fused and not self.fused_S and not self.pipe_S and self.peer.side and self.d == 128
                            and plan.split is None) else 0)
+        # GODE_PUSH_Y (default 1 with the fused exchange): the halo exchange moves from the transform's OUTPUT to its INPUT.
+        # The gather that produces a stage state y_next stores the rows its peers reference into their copies of the
+        # buffer (gode_gcn_odefunc_t.push_y: posted NVLink writes underneath a kernel with 64 resident warps per SM, as
+        # the gP push) and every rank transforms [owned | halo] rows itself -- the owned rows while the peers' rows are
+        # still landing.  The stand-alone push of S (8 per rk4 step, nothing to hide under in the forward chain
+        # gather -> transform -> push -> gather) and its exposed wait disappear; the price is the transform of the halo rows.
+        self.push_y = (self.fused and not self.fused_S and not self.pipe_S and not self.pipe_G and plan.split is None
+                       and os.environ.get("GODE_PUSH_Y", "1") != "0")
         if plan.split is not None:
             from . import _lib
             # descriptor for the second (halo-column) pass: same parameters, halo blocks, operand offset
@@ -207,6 +215,40 @@ class HaloKernelMixin:
         if self.peer is not None:
             return self.peer.new(plan.n_rows + plan.halo_t.n_halo)
         return torch.empty(plan.n_rows + plan.halo_t.n_halo, self.d, dtype=torch.float32, device=self.dev)
+
+    def new_Y(self):
+        if not self.push_y:
+            return self.new()
+        plan = self.plan
+        full = self.peer.new(plan.n_rows + plan.halo.n_halo)
+        view = self._own_rows(full)
+        if view is full:
+            full._gode_y = True          # (the protocol simulator's buffers stand for both)
+        else:
+            view._gode_full = full       # the solver passes this very object on to stage_fwd / vjp_phase1 / transform
+        return view
+
+    def _ybuf(self, y):
+        """The [owned | halo] arena buffer behind a stage state handed out by ``new_Y`` (None for any other tensor)."""
+        if not self.push_y or y is None:
+            return None
+        full = getattr(y, "_gode_full", None)
+        if full is None and getattr(y, "_gode_y", False):
+            full = y
+        return full
+
+    def _own_rows(self, full):
+        return full[:self.plan.n_rows]
+
+    def _transform_local(self, y, full, t, out):
+        """S = transform(y) without an exchange of S: ``full`` holds this rank's rows of y and -- once the exchange issued by
+        y's producer has completed -- the peers' rows in its halo tail."""
+        n, nh = self.plan.n_rows, self.plan.halo.n_halo
+        self.transform_rows(full, t, out, 0, n)          # owned rows: no wait
+        self._wait(full)                                 # the peers' rows of y have landed (and: this reads the tail)
+        if nh:
+            self.transform_rows(full, t, out, n, nh)
+        return out
 
     def numel_global(self):
         return self.plan.n_global * self.d
@@ -251,15 +293,23 @@ class HaloKernelMixin:
             done.record(cs)
         self.pending[buf.data_ptr()] = done
 
-    def _wait(self, buf):
+    def _await(self, buf):
+        """Enqueue the wait for ``buf``'s in-flight exchange (if any) without stamping the read."""
         ev = self.pending.pop(buf.data_ptr(), None)
         if self.peer is not None:
             if ev is not None:
                 self.peer.wait(ev)       # ev is the exchange's epoch
-            self.peer.note_read(buf)     # a gather from buf is about to be enqueued
             return
         if ev is not None:
             torch.cuda.current_stream().wait_event(ev)
+
+    def _wait(self, buf):
+        """... and stamp it: a gather from ``buf`` is the NEXT thing enqueued on the consumer stream.  A kernel that gathers
+        AND produces a fused push calls ``_await`` and passes the buffer as ``reads`` to ``_fused_begin`` instead, so that
+        the stamp is taken after that call's hazard exchanges (peer.ExchangeProtocol.begin)."""
+        self._await(buf)
+        if self.peer is not None:
+            self.peer.note_read(buf)     # a gather from buf is about to be enqueued
 
     def _own_pass(self, csr, X):
         """partial = (owned-column block) @ X[:n_own]  -- runs while X's halo tail is still arriving."""
@@ -282,16 +332,25 @@ class HaloKernelMixin:
     def _push_fusable(self):
         return bool(lib.gode_gcn_push_fusable(C.byref(self.f)))
 
-    def _fused_begin(self, field, halo, buf):
-        """The next producer of ``buf`` also stores the peers' rows (gode_push_route_t in the descriptor)."""
-        epoch, _ = self.peer.begin(buf)
+    def _fused_begin(self, field, halo, buf, also=(), reads=()):
+        """The next producer of ``buf`` also stores the peers' rows (gode_push_route_t in the descriptor).  ``also``:
+        (field, halo, buffer) of further operands the same kernel produces (one epoch for all); ``reads``: halo operands
+        it gathers from."""
+        epoch, _ = self.peer.begin(buf, also=[b for _, _, b in also], reads=reads)
         setattr(self.f, field, self.peer.fused_route(halo, buf))
+        for f2, h2, b2 in also:
+            setattr(self.f, f2, self.peer.fused_route(h2, b2))
         return epoch
 
-    def _fused_end(self, field, buf, epoch):
+    def _fused_end(self, field, buf, epoch, also=()):
         from . import _lib
         setattr(self.f, field, _lib.PushRoute())
-        self.pending[buf.data_ptr()] = self.peer.finish(epoch)
+        for f2, _, _ in also:
+            setattr(self.f, f2, _lib.PushRoute())
+        e = self.peer.finish(epoch)
+        self.pending[buf.data_ptr()] = e
+        for _, _, b2 in also:
+            self.pending[b2.data_ptr()] = e
 
     def _transform_pipelined(self, y, t, out):
         """S = transform(y, t) in row chunks on the current stream, each chunk's boundary rows pushed on the side stream."""
@@ -307,6 +366,9 @@ class HaloKernelMixin:
         return out
 
     def transform(self, y, t, out):
+        full = self._ybuf(y)
+        if full is not None and full.data_ptr() in self.pending:
+            return self._transform_local(y, full, t, out)     # y's producer pushed the peers' rows (vjp_phase1)
         if self.pipe_S:
             return self._transform_pipelined(y, t, out)
         if self.fused_S:
@@ -339,7 +401,7 @@ class HaloKernelMixin:
                                               ops._p(ws), self.ws_bytes, ops._stream()), "gode_gcn_transform_rows")
 
         with self._second(second, len(kprev)):
-            self.pending[S_next.data_ptr()] = self.peer.push_pipelined(self.plan.halo, S_next, self.pipe_G, produce)
+            self.pending[S_next.data_ptr()] = self.peer.push_pipelined(self.plan.halo, S_next, self.pipe_G, produce, reads=[S])
         if _od.MASK_LOG is not None:
             _od.MASK_LOG.append(k_out > 0)
 
@@ -347,8 +409,15 @@ class HaloKernelMixin:
                   second=None):
         run = lambda: super(HaloKernelMixin, self).stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next,
                                                              second=second)
+        full = self._ybuf(y_next) if S_next is not None else None
+        if full is not None:
+            self._await(S)
+            epoch = self._fused_begin("push_y", self.plan.halo, full, reads=[S])      # the gather's epilogue pushes y_next
+            super(HaloKernelMixin, self).stage_fwd(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, None, second=second)
+            self._fused_end("push_y", full, epoch)
+            return self._transform_local(y_next, full, t_next, S_next)
         if self.pipe_G and S_next is not None and y_next is not None:
-            self._wait(S)
+            self._await(S)
             return self._stage_pipelined(S, k_out, y0, kprev, coefs, coef_self, y_next, t_next, S_next, second)
         if self.pipe_S:
             self._wait(S)
@@ -358,10 +427,11 @@ class HaloKernelMixin:
                 self._transform_pipelined(y_next, t_next, S_next)
             return
         if self.fused_S:
-            self._wait(S)
             if S_next is None:
+                self._wait(S)
                 return run()
-            epoch = self._fused_begin("push_S", self.plan.halo, S_next)   # the transform inside stage_fwd pushes S_next
+            self._await(S)
+            epoch = self._fused_begin("push_S", self.plan.halo, S_next, reads=[S])   # the transform inside stage_fwd pushes S_next
             run()
             return self._fused_end("push_S", S_next, epoch)
         if self.plan.split is None:
@@ -378,10 +448,13 @@ class HaloKernelMixin:
         run = lambda: super(HaloKernelMixin, self).vjp_phase1(S, a, sign, k_y, gP, y0, kprev, coefs, coef_self, y_next,
                                                               second=second)
         if self.fused:
-            self._wait(S)
-            epoch = self._fused_begin("push_gP", self.plan.halo_t, gP)     # the gather's epilogue pushes gP
+            self._await(S)
+            full = self._ybuf(y_next)
+            # the gather's epilogue pushes gP -- and y_next, when the next transform will be local -- under ONE epoch
+            also = [("push_y", self.plan.halo, full)] if full is not None else []
+            epoch = self._fused_begin("push_gP", self.plan.halo_t, gP, also=also, reads=[S])
             run()
-            return self._fused_end("push_gP", gP, epoch)
+            return self._fused_end("push_gP", gP, epoch, also=also)
         if self.plan.split is None:
             self._wait(S)
             run()

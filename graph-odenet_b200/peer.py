@@ -128,18 +128,28 @@ class ExchangeProtocol:
         """consumer stream waits for the recorded completion of push ``epoch``"""
 
     # protocol -----------------------------------------------------------------------------------------------------
-    def begin(self, buf):
-        """Hazard handling for an exchange into ``buf``'s slot; returns (epoch, slot).  What follows is either
-        ``_emit_push`` of the data (``push``) or a producer kernel that stores the peers' rows itself, then ``finish``."""
-        slot = self._slot(buf)
-        n_empty, wait_epoch = self.track.before_push(slot)
-        if n_empty:
-            if self.side:
-                self._emit_side_after_main()
-            self._emit_push(self.track.issued, None, None, None)
-        if wait_epoch is not None:
-            self._emit_wait(wait_epoch)
-        return self.track.push(), slot
+    def begin(self, buf, also=(), reads=()):
+        """Hazard handling for an exchange into ``buf``'s slot (and the slots of ``also``: further buffers the SAME producer
+        kernel fills, sharing the epoch); returns (epoch, slot).  What follows is either ``_emit_push`` of the data (``push``)
+        or a producer kernel that stores the peers' rows itself, then ``finish``.
+
+        ``reads``: halo operands that producer kernel itself GATHERS from.  They are stamped here -- after the hazard
+        exchanges of this call, before the epoch is assigned -- because the stamp has to name the last epoch published
+        BEFORE the gather is enqueued: an empty exchange inserted by the hazard rule is published ahead of the gather, so a
+        peer that has published it has not necessarily finished that gather (found by replaying the adaptive solver, whose
+        single gP buffer makes the rule act, through tests/test_peer_protocol_cpu.py; stamping at the wait in front of the
+        call let a faster rank overwrite the support a slower rank was still gathering from)."""
+        for b in (buf,) + tuple(also):
+            n_empty, wait_epoch = self.track.before_push(self._slot(b))
+            if n_empty:
+                if self.side:
+                    self._emit_side_after_main()
+                self._emit_push(self.track.issued, None, None, None)
+            if wait_epoch is not None:
+                self._emit_wait(wait_epoch)
+        for r in reads:
+            self.track.note_read(self._slot(r))
+        return self.track.push(), self._slot(buf)
 
     def push(self, halo, buf):
         """Issue the exchange that fills the peers' halo tails of ``buf``'s slot; returns its epoch."""
@@ -163,12 +173,12 @@ class ExchangeProtocol:
             self.done.add(epoch)
         return epoch
 
-    def push_pipelined(self, halo, buf, n_parts, produce):
+    def push_pipelined(self, halo, buf, n_parts, produce, reads=()):
         """One exchange in ``n_parts`` row chunks: ``produce(c)`` enqueues the producer of chunk c on the consumer stream,
         the rows of that chunk are pushed on the side stream while the next chunk is produced; the last part publishes
         the epoch.  Needs the side stream (flag writes stay on one stream)."""
         assert self.side, "the pipelined exchange needs the side stream"
-        epoch, slot = self.begin(buf)
+        epoch, slot = self.begin(buf, reads=reads)      # ``produce`` may gather from ``reads`` (see begin)
         for c in range(n_parts):
             produce(c)
             self._emit_side_after_main()
@@ -218,7 +228,7 @@ class PeerHalo(ExchangeProtocol):
         self.plan, self.d = plan, d
         self.world, self.rank, self.group = plan.world, plan.rank, plan.group
         dev = plan.device
-        n_slots = n_slots or int(os.environ.get("GODE_PEER_SLOTS", "8"))
+        n_slots = n_slots or int(os.environ.get("GODE_PEER_SLOTS", "12"))    # S x3, gP x2, stage states x2 (+ multi-step grids)
         self.timeout_ns = int(float(timeout_s or os.environ.get("GODE_PEER_TIMEOUT_S", "30")) * 1e9)
         self.max_ctas = int(max_ctas or os.environ.get("GODE_PUSH_CTAS", "0"))
         # slot size: the largest operand buffer over all ranks (same offsets everywhere)

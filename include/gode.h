@@ -174,6 +174,9 @@ typedef struct {
                               another column block of the same rows -- the row-partitioned path gathers the owned
                               columns while the halo is in flight, then the halo columns with acc_in) */
   gode_push_route_t push;  /* gp_out rows are also stored into the peers' buffers (ptr NULL: off) */
+  gode_push_route_t push_y;/* ynext rows are also stored into the peers' buffers (ptr NULL: off): the row-partitioned solver
+                              exchanges the transform's INPUT this way and transforms [owned | halo] rows locally, so no
+                              exchange of the support S stands between two gathers */
   gode_rk_second_t second; /* second combination of (y0, kprev, v); out NULL: off */
   const float* gp_row_scale; /* [n_rows] or NULL */
 } gode_spmm_epilogue_t;
@@ -322,6 +325,8 @@ typedef struct {
    * VJP writes are also stored into the peers' halo tails.  Needs the tensor-core transform (gode_gcn_push_fusable). */
   gode_push_route_t push_S;
   gode_push_route_t push_gP;
+  gode_push_route_t push_y;   /* rows of every y_next the fused Runge-Kutta combination writes (gode_gcn_stage_fwd, _stage_fwd_rows,
+                                 _vjp_phase1); the caller then transforms owned AND halo rows (gode_gcn_transform_rows) */
   /* Per-call (out NULL: off): the second Runge-Kutta combination of the NEXT gode_gcn_stage_fwd / _stage_fwd_rows /
    * _vjp_phase1 (over y0, kprev, k) or gode_gcn_vjp_phase2_rk (over a0, kprev, k_a) call -- see gode_spmm_epilogue_t. */
   gode_rk_second_t second;
@@ -342,7 +347,9 @@ int gode_gcn_push_fusable(const gode_gcn_odefunc_t* f);
 int gode_gcn_transform(const gode_gcn_odefunc_t* f, const float* y, float t, float* S,
                        void* ws, size_t ws_bytes, void* stream);
 /* The same transform on rows [row0, row0 + n_rows) of the block (y and S are the block's base pointers): lets the caller
- * pipeline the transform of one row chunk with the halo push of the previous one. */
+ * pipeline the transform of one row chunk with the halo push of the previous one.  With the tensor-core transform the range
+ * may extend over the halo rows of a partitioned block (row0 + n_rows <= A.n_cols = owned + halo: y and S then have that
+ * many rows) -- the transform is row-local, so a rank that holds its peers' rows of y (push_y) needs no exchange of S. */
 int gode_gcn_transform_rows(const gode_gcn_odefunc_t* f, const float* y, float t, float* S, int64_t row0, int64_t n_rows,
                             void* ws, size_t ws_bytes, void* stream);
 

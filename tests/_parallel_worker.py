@@ -13,6 +13,9 @@ sys.path.insert(0, ROOT)
 
 def main():
     method = sys.argv[1] if len(sys.argv) > 1 else "rk4"
+    step_size = None
+    if ":" in method:                      # "rk4:0.5" = fixed-step method on a grid of that step size
+        method, step_size = method.split(":")[0], float(method.split(":")[1])
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
     d = int(sys.argv[3]) if len(sys.argv) > 3 else 128
     smooth = (sys.argv[4] == "smooth") if len(sys.argv) > 4 else False
@@ -26,7 +29,7 @@ def main():
 
     row, col, val = synth.powerlaw_graph(n, avg_degree=12, locality=0.6, window=512, seed=5, device=dev)
     torch.manual_seed(7)
-    blk = models.ODEBlock(models.ODEfunc(d), method=method).to(dev)
+    blk = models.ODEBlock(models.ODEfunc(d), method=method, options={"step_size": step_size} if step_size else None).to(dev)
     with torch.no_grad():
         blk.odefunc.norm1.weight.uniform_(0.5, 1.5)
         blk.odefunc.norm1.bias.uniform_(-0.5, 0.5)

@@ -52,9 +52,9 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.PushRoute) == route
     second = 4 * 8 + 4 + 4 + 8        # coef[8], coef_self, padding, out
     assert ctypes.sizeof(_lib.RkSecond) == second
-    assert ctypes.sizeof(_lib.SpmmEpilogue) == 8 + 8 + 8 + 8 + 8 * 8 + 4 * 8 + 4 + 4 + 8 + 8 + 8 + 8 + 8 + route + second + 8
+    assert ctypes.sizeof(_lib.SpmmEpilogue) == 8 + 8 + 8 + 8 + 8 * 8 + 4 * 8 + 4 + 4 + 8 + 8 + 8 + 8 + 8 + 2 * route + second + 8
     assert ctypes.sizeof(_lib.Csr) == 2 * 8 + 6 * 8 + 2 * 4 + 8 + 4 + 4     # ..., tile_sched, n_tile_sched, padding
-    assert ctypes.sizeof(_lib.GcnOdeFunc) == 2 * ctypes.sizeof(_lib.Csr) + 4 * 4 + 4 * 8 + 8 + 8 + 2 * route + second + 8
+    assert ctypes.sizeof(_lib.GcnOdeFunc) == 2 * ctypes.sizeof(_lib.Csr) + 4 * 4 + 4 * 8 + 8 + 8 + 3 * route + second + 8
     assert ctypes.sizeof(_lib.PeerGroup) == 4 + 4 + 16 * 8
 
 

@@ -45,14 +45,19 @@ def test_partitioned_plan_world1_matches_plain_plan():
                                                 ("dopri5", "smooth", "p2p-fused"),
                                                 # forward stages gathered in row chunks, S pushed underneath (GODE_PIPE_G)
                                                 ("rk4", "relu", "p2p-fused:g2"), ("rk4", "smooth", "p2p-fused:g3"),
-                                                ("dopri5", "relu", "p2p-fused:g2")])
+                                                ("dopri5", "relu", "p2p-fused:g2"),
+                                                # the supports S exchanged instead of the stage states (GODE_PUSH_Y=0); two-step grid
+                                                ("rk4", "relu", "p2p-fused:noY"), ("rk4", "smooth", "p2p-fused:noY"),
+                                                ("rk4:0.5", "relu", "p2p-fused"), ("rk4:0.5", "smooth", "p2p-fused:noY"),
+                                                ("midpoint", "smooth", "p2p-fused")])
 def test_two_gpus_match_one(method, regime, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     world = min(torch.cuda.device_count(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "_parallel_worker.py"), method,
-           "20000" if method == "rk4" else "6000", "128", regime]
-    env = dict(os.environ, GODE_HALO_MODE=mode.split(":")[0], GODE_PIPE_G=mode.split(":g")[1] if ":g" in mode else "0")
+           "6000" if method == "dopri5" else "20000", "128", regime]
+    env = dict(os.environ, GODE_HALO_MODE=mode.split(":")[0], GODE_PIPE_G=mode.split(":g")[1] if ":g" in mode else "0",
+               GODE_PUSH_Y="0" if mode.endswith(":noY") else "1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

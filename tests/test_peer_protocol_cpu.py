@@ -47,13 +47,14 @@ class RecProtocol(peer.ExchangeProtocol):
     def _slot(self, buf):
         return buf.slot
 
-    def begin(self, buf):
-        epoch, slot = super().begin(buf)
-        buf.version = epoch
+    def begin(self, buf, also=(), reads=()):
+        epoch, slot = super().begin(buf, also=also, reads=reads)
+        for b in (buf,) + tuple(also):
+            b.version = epoch
         return epoch, slot
 
     def fused_route(self, halo, buf):
-        return None
+        return "route"
 
     def _emit_push(self, epoch, halo, buf, slot):
         stream = "side" if self.side else "main"
@@ -120,9 +121,23 @@ class RecBase:
         self._produce(out)
         return out
 
+    def new_Y(self):
+        return self.new()
+
+    def transform_rows(self, y, t, out, row0, n_rows):
+        if row0 > 0:                           # the halo rows of y: a read of the tail the peers' gathers have pushed into,
+            self._gather(y)                    # and a LOCAL write of the support's tail (no peer ever stores into it)
+            self.prog.append(("main", "lwrite", out.slot, out.version))
+        return out
+
+    def _push_y(self, y_next):
+        if y_next is not None and getattr(self.f, "push_y", None) == "route":     # the gather's epilogue stores the peers' rows of y_next
+            self.prog.append(("main", "rwrite", y_next.version, y_next.slot))
+
     def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0, S_next=None, second=None):
         self.nfe += 1
         self._gather(S)
+        self._push_y(y_next)
         if S_next is not None:
             self._produce(S_next)
 
@@ -130,6 +145,7 @@ class RecBase:
         self.nfe += 1
         self._gather(S)
         self._produce(gP, "gP")
+        self._push_y(y_next)
 
     def vjp_phase2(self, y, t, gP, k_a, gtheta, a0=None, kprev=(), coefs=(), coef_self=0.0, a_next=None, second=None):
         gtheta.zero_()
@@ -142,6 +158,9 @@ class RecKernel(parallel.HaloKernelMixin, RecBase):
 
     def _push_fusable(self):
         return True
+
+    def _own_rows(self, full):                      # a FakeBuf stands for the buffer and for its owned-rows view
+        return full
 
     def _transform_pipelined(self, y, t, out):      # the CUDA chunk launches replaced by nothing: only the protocol is replayed
         self.pending[out.data_ptr()] = self.peer.push_pipelined(self.plan.halo, out, self.pipe_S, lambda c: None)
@@ -205,6 +224,10 @@ def simulate(prog, world, rng, max_ops=10 ** 7):
                         return "rank %d stored epoch %d into slot %d while rank %d gathers version %d" % (
                             r, epoch, slot, p, active[p][slot])
                     ver[p][(slot, r)] = epoch
+            elif kind == "lwrite":
+                for p in range(world):
+                    if p != r:
+                        ver[r][(op[1], p)] = op[2]
             elif kind == "signal":
                 epoch = op[1]
                 for p in range(world):
@@ -236,14 +259,23 @@ def _no_cuda_combine(monkeypatch):
     monkeypatch.setattr(ops, "rk_combine", lambda y0, ks, cs, out=None: out)
 
 
-@pytest.mark.parametrize("mode", ["p2p", "p2p-async", "p2p-fused", "p2p-fused+S", "p2p-fused+pipe"])
+@pytest.mark.parametrize("mode", ["p2p", "p2p-async", "p2p-fused", "p2p-fused-noY", "p2p-fused+S", "p2p-fused+pipe"])
 @pytest.mark.parametrize("method,step_size", [("rk4", None), ("rk4", 0.25), ("midpoint", 0.5), ("euler", 0.5)])
 def test_protocol_is_safe_under_random_interleaving(mode, method, step_size, monkeypatch):
+    """"p2p-fused" is the shipped default: gP and the stage states y_next are pushed by the gathers that produce them and the
+    transform of [owned | halo] rows is local (GODE_PUSH_Y); "-noY" exchanges the supports S instead."""
     monkeypatch.setenv("GODE_FUSE_S", "1" if mode.endswith("+S") else "0")
     monkeypatch.setenv("GODE_PIPE_S", "3" if mode.endswith("+pipe") else "0")
-    mode = mode.replace("+S", "").replace("+pipe", "")
-    prog, proto = record_program(RecProtocol, mode, method, step_size, n_steps=3)
+    monkeypatch.setenv("GODE_PUSH_Y", "0" if mode.endswith("-noY") else "1")
+    y_mode = mode == "p2p-fused"
+    mode = mode.replace("+S", "").replace("+pipe", "").replace("-noY", "")
+    prog, proto = record_program(RecProtocol, mode, method, step_size, n_steps=3, n_slots=12)
     assert any(op[1] == "rwrite" for op in prog) and any(op[1] == "signal" for op in prog)
+    if y_mode and method != "euler":
+        # the stage states are read through their halo tails (gathers of Y slots) and no support is pushed between stages
+        n_rw = sum(1 for op in prog if op[1] == "rwrite")
+        n_sig = sum(1 for op in prog if op[1] == "signal")
+        assert n_sig < n_rw
     rng = random.Random(1234)
     for world in (2, 4):
         for _ in range(40):
@@ -252,13 +284,16 @@ def test_protocol_is_safe_under_random_interleaving(mode, method, step_size, mon
 
 def test_rk4_steady_state_needs_no_empty_exchange(monkeypatch):
     """With the solver's buffer rotation (two gP buffers, fresh S per stage, round-robin slots) the hazard rule never
-    has to insert an empty exchange: 12 exchanges per rk4 fwd+bwd step on grid [0, 1] (4 + 4 supports -- the adjoint's
-    first stage reuses the support of f(t1) -- and 4 masked adjoints), as PartitionedPlan.halo_bytes_per_step counts."""
-    for mode, pipe in (("p2p", "0"), ("p2p-async", "0"), ("p2p-fused", "0"), ("p2p-fused", "4")):
+    has to insert an empty exchange: 12 exchanges per rk4 fwd+bwd step on grid [0, 1] when supports are exchanged (4 + 4
+    supports -- the adjoint's first stage reuses the support of f(t1) -- and 4 masked adjoints), as
+    PartitionedPlan.halo_bytes_per_step counts; 9 epochs when the stage states are (default fused mode)."""
+    for mode, pipe, per_step in (("p2p", "0", 12), ("p2p-async", "0", 12), ("p2p-fused", "0", 9), ("p2p-fused", "4", 12)):
         monkeypatch.setenv("GODE_PIPE_S", pipe)
-        prog, proto = record_program(RecProtocol, mode, "rk4", None, n_steps=4)
+        prog, proto = record_program(RecProtocol, mode, "rk4", None, n_steps=4, n_slots=12)
         assert proto.n_empty == 0
-        assert proto.track.issued == 4 * 12
+        # the default fused mode exchanges stage states, one epoch per producing gather: forward 1 support + 3 states, adjoint
+        # 1 support + 4 (gP, with the next state riding along on three of them)
+        assert proto.track.issued == 4 * per_step
 
 
 def _single_buffer_program(proto_cls, side, rounds=6):
@@ -339,3 +374,54 @@ def test_fused_route_and_chunk_ranges_are_exact_index_maps():
                 assert bool(((rows >= bounds[c]) & (rows < bounds[c + 1])).all())
                 pos = e[p]
             assert pos == send_ptr[p + 1]
+
+
+class ScriptedKernel(RecKernel):
+    """RecKernel for the ADAPTIVE solver: the error norms the controller reads are scripted (every ``reject_every``-th
+    decision fails), so that accepted and rejected dopri5 steps -- one gP buffer, two supports swapped on acceptance -- are
+    replayed through the same simulator."""
+    calls = 0
+    reject_every = 5
+
+    def numel_global(self):
+        return 1
+
+    def scalar(self, dev_scalar):
+        ScriptedKernel.calls += 1
+        return 4.0 if ScriptedKernel.calls % ScriptedKernel.reject_every == 0 else 0.25
+
+
+def record_dopri5_program(mode, n_steps=2, n_slots=12, reject_every=5):
+    import os
+    prog = []
+    side = mode == "p2p-async" or (mode == "p2p-fused" and os.environ.get("GODE_PIPE_S", "0") != "0")
+    proto = RecProtocol(n_slots, side, prog)
+    plan = types.SimpleNamespace(mode=mode, world=4, split=None, n_rows=10, n_global=40,
+                                 halo=types.SimpleNamespace(n_halo=3), halo_t=types.SimpleNamespace(n_halo=3),
+                                 group=None, comm_stream=None, peer_for=lambda d: proto, check_peers=lambda: None)
+    ScriptedKernel.calls, ScriptedKernel.reject_every = 0, reject_every
+    stats = {}
+    for _ in range(n_steps):
+        kf = ScriptedKernel(plan, prog)
+        y1 = odeint.gcn_solve_forward(kf, torch.zeros(1), 0.0, 1.0, "dopri5", None, stats=stats)
+        kb = ScriptedKernel(plan, prog)
+        odeint.gcn_solve_adjoint(kb, y1, torch.zeros(1), 0.0, 1.0, "dopri5", None, stats=stats)
+        del kf, kb
+    return prog, proto, stats
+
+
+@pytest.mark.parametrize("mode", ["p2p", "p2p-async", "p2p-fused", "p2p-fused+S"])
+@pytest.mark.parametrize("reject_every", [7, 11, 1000])
+def test_adaptive_solver_protocol_is_safe(mode, reject_every, monkeypatch):
+    """dopri5 forward + adjoint (one gP buffer: the hazard rule has to insert empty exchanges) with scripted accept / reject
+    decisions.  This replay found the read-stamp bug described in peer.ExchangeProtocol.begin: on 2 B200 the fused mode gave
+    run-to-run different adjoint step sequences (a faster rank's support rows landing under a slower rank's gather)."""
+    monkeypatch.setenv("GODE_FUSE_S", "1" if mode.endswith("+S") else "0")
+    mode = mode.replace("+S", "")
+    monkeypatch.setattr(ops, "rk_error_sumsq", lambda *a, **k: torch.ones(1))
+    prog, proto, stats = record_dopri5_program(mode, reject_every=reject_every)
+    assert stats.get("accepted", 0) > 2 and (reject_every > 100 or stats.get("rejected", 0) > 0)
+    rng = random.Random(99)
+    for world in (2, 3):
+        for _ in range(60):
+            assert simulate(prog, world, rng) is None
