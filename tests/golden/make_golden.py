@@ -25,6 +25,8 @@ from __future__ import annotations
 
 import functools
 import importlib
+import importlib.util
+import json
 import os
 import sys
 import types
@@ -614,8 +616,71 @@ def make_qc_collate():
     print("qc_collate_golden.npz", os.path.getsize(os.path.join(HERE, "qc_collate_golden.npz")) // 1024, "KiB")
 
 
+def orbit_problem(n_sys=3, bodies=4):
+    """Relation structure of ``prototypes/orbit/train_IN.py:process_instance`` (every ordered pair of distinct bodies of a
+    system is a relation) for a block-diagonal batch: (n, m, src[m], tgt[m])."""
+    src, tgt = [], []
+    for s_ in range(n_sys):
+        for a in range(bodies):
+            for b in range(bodies):
+                if a != b:
+                    src.append(s_ * bodies + a)
+                    tgt.append(s_ * bodies + b)
+    return n_sys * bodies, len(src), np.array(src, dtype=np.int64), np.array(tgt, dtype=np.int64)
+
+
+def make_orbit():
+    """orbit_golden.npz: the reference's Interaction Network and IN-ODE (prototypes/orbit/model.py:29-171) on a small batch
+    of n-body systems -- outputs, input gradients and parameter gradients, the ODE model with the fixed-step rk4 solver
+    (arithmetic pinned step by step) and with the reference's default dopri5 (NFE and step counts as well)."""
+    _install_shims()
+    spec = importlib.util.spec_from_file_location("ref_orbit_model", os.path.join(REF, "prototypes", "orbit", "model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    n, m, src, tgt = orbit_problem()
+    Msrc = torch.zeros(n, m)
+    Mtgt = torch.zeros(n, m)
+    Msrc[torch.from_numpy(src), torch.arange(m)] = 1
+    Mtgt[torch.from_numpy(tgt), torch.arange(m)] = 1
+    out = {"n": np.int64(n), "m": np.int64(m), "src": src, "tgt": tgt}
+    O = rnd(301, n, 5)
+    G = rnd(302, n, 2)
+
+    def grads(model, key, fwd):
+        model.zero_grad()
+        o = O.clone().requires_grad_(True)
+        P = fwd(model, o)
+        (P * G).sum().backward()
+        out[key + "/P"] = P.detach().numpy()
+        out[key + "/grad_O"] = o.grad.numpy()
+        for k, p_ in model.named_parameters():
+            if p_.grad is not None:
+                out[key + "/grad/" + k] = p_.grad.numpy().copy()
+
+    torch.manual_seed(31)
+    net = mod.IN(5, 0, 0, 2)
+    out.update(sd_np(net, "IN/sd/"))
+    grads(net, "IN", lambda mdl, o: mdl(o, None, None, Msrc, Mtgt))
+
+    torch.manual_seed(32)
+    ode = mod.IN_ODE(5, 0, 0, 2)
+    out.update(sd_np(ode, "IN_ODE/sd/"))
+    for method in ("rk4", "dopri5"):
+        stats = {}
+        mod.odeint = functools.partial(restated.odeint_adjoint, method=method, stats=stats)
+        ode.nfe = 0
+        grads(ode, "IN_ODE_" + method, lambda mdl, o: mdl(o, None, None, Msrc, Mtgt))
+        out["IN_ODE_%s/nfe" % method] = np.int64(ode.nfe)
+        out["IN_ODE_%s/stats" % method] = np.array(json.dumps(stats))
+    np.savez_compressed(os.path.join(HERE, "orbit_golden.npz"), **out)
+    print("orbit_golden.npz", os.path.getsize(os.path.join(HERE, "orbit_golden.npz")) // 1024, "KiB",
+          {k: v for k, v in out.items() if k.endswith("/nfe") or k.endswith("/stats")})
+
+
 if __name__ == "__main__":
-    if "--only-qc-collate" in sys.argv:
+    if "--only-orbit" in sys.argv:
+        make_orbit()
+    elif "--only-qc-collate" in sys.argv:
         make_qc_collate()
     elif "--only-qc-models" in sys.argv:
         make_qc_models()
@@ -628,3 +693,4 @@ if __name__ == "__main__":
         make_models()
         make_qc_models()
         make_qc_collate()
+        make_orbit()
