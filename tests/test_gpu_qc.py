@@ -178,9 +178,16 @@ def test_edge_ode_block_matches_oracle():
     y.backward(gy.to(DEV))
     assert nfe_f == 4 and blk.nfe == fo.nfe == 9
     G.assert_close(y, yo, rtol=1e-5, atol_scale=1e-5, what="y(1)")
-    G.assert_close_l2(xg.grad, xo.grad, 1e-4, what="grad_x")
+    def rel(a, b_):
+        return float((a.detach().cpu().double() - b_.double()).norm() / b_.double().norm())
+
+    errs = {"grad_x": rel(xg.grad, xo.grad)}
+    errs.update({k: rel(p.grad, fo.ps[k.replace(".", "_")].grad) for k, p in blk.odefunc.named_parameters()})
+    print("edge-ODE block gradients, relative L2 vs the restated solver:", errs)
+    # measured on B200 (round 2, tcgen05 products with rounded residuals): 2.7e-7 .. 5.1e-7 -- the fp32 bar holds
+    G.assert_close_l2(xg.grad, xo.grad, 1e-5, what="grad_x")
     for k, p in blk.odefunc.named_parameters():
-        G.assert_close_l2(p.grad, fo.ps[k.replace(".", "_")].grad, 1e-4, what=k)
+        G.assert_close_l2(p.grad, fo.ps[k.replace(".", "_")].grad, 1e-5, what=k)
 
 
 def test_qc_model_surface():
