@@ -579,20 +579,28 @@ __global__ void __launch_bounds__(256, MINB) k_spmm_t2(int64_t n_rows, const int
           if (i < hc) my_idx[i] = __ldcs(colidx + ce0 + half + i);
         }
         __syncwarp();
-        const float* __restrict__ vp = vals + ce0 + half;   // values straight from global memory (broadcast loads of one line)
+        // ROWVAL: plain row sums, scaled once below (as the light rows are) -- no values stream, and the four row loads of a
+        // batch stay in flight together within the 32-register budget; else values straight from global memory (broadcast
+        // loads of one line)
+        const float* __restrict__ vp = vals + ce0 + half;
         int i = 0;
 #pragma unroll 1
         for (; i + 4 <= hc; i += 4) {
           const unsigned c0 = my_idx[i], c1 = my_idx[i + 1], c2 = my_idx[i + 2], c3 = my_idx[i + 3];
           const float4 x0 = __ldg(xb + (size_t)c0 * 32), x1 = __ldg(xb + (size_t)c1 * 32);
           const float4 x2 = __ldg(xb + (size_t)c2 * 32), x3 = __ldg(xb + (size_t)c3 * 32);
-          const float v0 = __ldg(vp + i), v1 = __ldg(vp + i + 1), v2 = __ldg(vp + i + 2), v3 = __ldg(vp + i + 3);
-          acc_row<false>(a0, a1, v0, x0);
-          acc_row<false>(a0, a1, v1, x1);
-          acc_row<false>(a0, a1, v2, x2);
-          acc_row<false>(a0, a1, v3, x3);
+          float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+          if (!ROWVAL) { v0 = __ldg(vp + i); v1 = __ldg(vp + i + 1); v2 = __ldg(vp + i + 2); v3 = __ldg(vp + i + 3); }
+          acc_row<ROWVAL>(a0, a1, v0, x0);
+          acc_row<ROWVAL>(a0, a1, v1, x1);
+          acc_row<ROWVAL>(a0, a1, v2, x2);
+          acc_row<ROWVAL>(a0, a1, v3, x3);
         }
-        for (; i < hc; ++i) acc_row<false>(a0, a1, __ldg(vp + i), __ldg(xb + (size_t)(unsigned)my_idx[i] * 32));
+        for (; i < hc; ++i) acc_row<ROWVAL>(a0, a1, ROWVAL ? 0.f : __ldg(vp + i), __ldg(xb + (size_t)(unsigned)my_idx[i] * 32));
+      }
+      if (ROWVAL) {
+        const float rv = __ldg(row_vals + row);
+        a0.x *= rv; a0.y *= rv; a1.x *= rv; a1.y *= rv;
       }
       hub.partial[(size_t)chunk * 32 + lane] = make_float4(a0.x, a0.y, a1.x, a1.y);
       return;

@@ -24,13 +24,15 @@ echo
 echo "## Excerpt: the MMA issue loop of the transform (\`k_rows_ws<128,4,0,19>\`)"
 echo
 echo '```'
-cuobjdump -sass -fun '_ZN4gode9k_rows_wsILi128ELi4ELi0ELi19EEEvlPKfPfS2_S2_S2_ffi17gode_push_route_tii' $SO 2>/dev/null | grep -E "UTCHMMA|UTCBAR|LDTM|SYNCS" | sed -E 's#/\* 0x[0-9a-f]+ \*/##; s/^\s+//' | head -28
+ROWS_WS=$(cuobjdump -sass $SO 2>/dev/null | grep "Function :" | grep -o "_ZN4gode9k_rows_wsILi128ELi4ELi0ELi19E[A-Za-z0-9_]*" | head -1)   # the mangled name follows the signature
+cuobjdump -sass -fun "$ROWS_WS" $SO 2>/dev/null | grep -E "UTCHMMA|UTCBAR|LDTM|SYNCS" | sed -E 's#/\* 0x[0-9a-f]+ \*/##; s/^\s+//' | head -28
 echo '```'
 echo
 echo "## Excerpt: the inner loop of the gather (\`k_spmm_t2<32,8,true>\`): 4 LDS + 4 IMAD.WIDE.U32 + 4 LDG.E.128 + 8 FADD2 per four neighbour rows"
 echo
 echo '```'
-cuobjdump -sass -fun '_ZN4gode9k_spmm_t2ILi32ELi8ELb1EEEvlPKiS2_PKfS4_PK6float4Pf20gode_spmm_epilogue_ti' $SO 2>/dev/null | grep -E "/\*[0-9a-f]{4}\*/" | sed -E 's#/\* 0x[0-9a-f]+ \*/##; s/^\s+//' | awk '/LDS R[0-9]+, \[R[0-9]+\] ;/ && !p {p=1} p {print; n++} n>=26 {exit}'
+T2=$(cuobjdump -sass $SO 2>/dev/null | grep "Function :" | grep -o "_ZN4gode9k_spmm_t2ILi32ELi8ELb1E[A-Za-z0-9_]*" | head -1)
+cuobjdump -sass -fun "$T2" $SO 2>/dev/null | grep -E "/\*[0-9a-f]{4}\*/" | sed -E 's#/\* 0x[0-9a-f]+ \*/##; s/^\s+//' | awk '/LDS R[0-9]+, \[R[0-9]+\] ;/ && !p {p=1} p {print; n++} n>=26 {exit}'
 echo '```'
 } > $OUT
 wc -l $OUT
