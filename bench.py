@@ -590,12 +590,20 @@ def run_ours(a):
                        "l2": "inputs larger than L2 (every [N,d] tensor is %.2f GB)" % (n * d * 4 / 1e9),
                        "optimizer": "Adam on the ODE function's parameters (in the timed region)",
                        "relabelling": relabel_info,
-                       "partition": None if world == 1 else dict(halo_info, scheme="contiguous row blocks; halo exchange "
-                                                                  "of the gather operand per evaluation (" + (
-                                                                      "libgode kernel storing rows into the peers' halo "
-                                                                      "tails over NVLink peer memory"
-                                                                      if plan.mode.startswith("p2p") else
-                                                                      "pack + NCCL all-to-all-v") + ")")},
+                       "partition": None if world == 1 else dict(
+                           halo_info,
+                           scheme="contiguous row blocks; " + (
+                               ("the gathers that produce a stage state / a masked adjoint store the rows their peers reference "
+                                "into the peers' halo tails over NVLink peer memory from their epilogues; every rank transforms "
+                                "[owned | halo] rows itself (no exchange of the support between two gathers)"
+                                if os.environ.get("GODE_PUSH_Y", "1") != "0" and plan.mode == "p2p-fused" else
+                                "halo exchange of the gather operand per evaluation (libgode kernels storing rows into the peers' "
+                                "halo tails over NVLink peer memory)")
+                               if plan.mode.startswith("p2p") else
+                               "halo exchange of the gather operand per evaluation (pack + NCCL all-to-all-v)"),
+                           # what the exchange leaves exposed on rank 0: the step minus the CUDA-event time of the libgode compute
+                           # classes (gathers, transforms, dense VJP chain) -- flag waits, pushes not hidden, loss, Adam
+                           ms_outside_compute_classes=ms - sum(v["ms_total"] for v in prof.values()) / a.steps)},
             "func_evals_per_sec": nfe_per_step / (ms / 1e3), "final_loss": float(loss_total.item()),
             "roofline": roofline, "cpu_baseline": cpu, "library_baseline": lib_base, "e2e": e2e, "gpu_launches": launches,
             "clocks": clk.summary()}

@@ -10,9 +10,10 @@ maps once (cudaIpc handles shipped with ``all_gather_object``); slots have the s
 
 Write-after-read across ranks.  A push overwrites the halo tail of the peers' slot X; the peers may still be gathering
 from the previous contents of X.  All ranks run the same program, so the rule is decided locally and identically
-everywhere: a gather from X is stamped with the number of exchanges issued so far (``c``); a later push into X needs a
-completed wait on an exchange ``j >= c + 1`` to have been enqueued first (a peer that has published ``j`` has finished
-everything it enqueued before its push ``j``, in particular that gather).  If none was, one is enqueued (an empty
+everywhere: a gather from X is stamped with the number of exchanges issued when the gather is ENQUEUED (``c``: for a
+kernel that gathers and produces a fused push, after that call's own hazard exchanges -- ``ExchangeProtocol.begin``);
+a later push into X needs a completed wait on an exchange ``j >= c + 1`` to have been enqueued first (a peer that has
+published ``j`` has finished everything it enqueued before its push ``j``, in particular that gather).  If none was, one is enqueued (an empty
 exchange when no exchange was issued since the gather).  The solver's buffer rotation makes this the rare path.
 """
 from __future__ import annotations
