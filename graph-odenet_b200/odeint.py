@@ -18,6 +18,7 @@ Time values and step sizes are float32 on the host, as torchdiffeq keeps them in
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 
@@ -218,28 +219,25 @@ class GcnKernel:
                                      ops._stream()), "gode_gcn_transform")
         return out
 
+    @contextlib.contextmanager
     def _second(self, second, n_prev):
-        """Context: the descriptor's per-call second combination ``(coefs2, coef2_self, out2)`` -- out2 = y0 + sum
-        coefs2*kprev + coef2_self*k over the SAME (y0, kprev) as the call's own combination -- set for one library call."""
-        kern = self
-
-        class _Ctx:
-            def __enter__(self_):
-                if second is not None:
-                    c2, c2s, out2 = second
-                    if len(c2) != n_prev:
-                        raise ValueError("second combination: %d coefficients for %d stage tensors" % (len(c2), n_prev))
-                    r = _lib.RkSecond()
-                    for j, c in enumerate(c2):
-                        r.coef[j] = float(c)
-                    r.coef_self, r.out = float(c2s), out2.data_ptr()
-                    kern.f.second = r
-
-            def __exit__(self_, *exc):
-                if second is not None:
-                    kern.f.second = _lib.RkSecond()
-                return False
-        return _Ctx()
+        """The descriptor's per-call second combination ``(coefs2, coef2_self, out2)`` -- out2 = y0 + sum coefs2*kprev +
+        coef2_self*k over the SAME (y0, kprev) as the call's own combination -- set for the one library call inside the block."""
+        if second is None:
+            yield
+            return
+        c2, c2s, out2 = second
+        if len(c2) != n_prev:
+            raise ValueError("second combination: %d coefficients for %d stage tensors" % (len(c2), n_prev))
+        r = _lib.RkSecond()
+        for j, c in enumerate(c2):
+            r.coef[j] = float(c)
+        r.coef_self, r.out = float(c2s), out2.data_ptr()
+        self.f.second = r
+        try:
+            yield
+        finally:
+            self.f.second = _lib.RkSecond()
 
     def stage_fwd(self, S, k_out, y0=None, kprev=(), coefs=(), coef_self=0.0, y_next=None, t_next=0.0, S_next=None,
                   second=None):
