@@ -15,6 +15,12 @@ here is the published algorithm of the 0.0.x line (contemporary with the 2019 re
   ``(y, a_y, a_t, a_theta)`` from t1 to t0 with the same method and tolerances (decreasing time is
   handled by negating ``t`` and ``f``).
 
+Pinned nevertheless, against an independent implementation in the image (tests/test_oracle_golden.py::
+test_solver_pieces_against_scipy, float64, 1e-14): one Dormand-Prince step (stages, solution, FSAL derivative) vs scipy's RK45
+``rk_step``; the initial step vs scipy's ``select_initial_step``; the fixed-step increments vs the textbook formulas.  NOT
+pinned: torchdiffeq's own error coefficients (``_DP_CERR`` ends in -1/60, Dormand-Prince's pair in -1/40), controller and
+dense output.
+
 States are tuples of tensors throughout, exactly as in the package.  ``stats`` (optional dict) receives
 accepted/rejected step counts so adaptive solves can be compared "on the accepted-step count".
 """

@@ -158,6 +158,56 @@ def test_solver_against_analytic_solutions():
     assert abs(float(y) - 0.375) < 1e-6
 
 
+def test_solver_pieces_against_scipy():
+    """torchdiffeq is absent, so the restated solver cannot be compared with it.  Its published building blocks
+    can be pinned against an independent implementation that IS in the image -- scipy's RK45 (Dormand-Prince 5(4), the same
+    tableau) and Hairer's initial-step rule (scipy.integrate._ivp.common.select_initial_step) -- in float64:
+      * one Dormand-Prince step: the six stage derivatives, the 5th-order solution and the FSAL derivative;
+      * the first step size (torchdiffeq passes order 4 for dopri5: exponent 1/5, as scipy's error_estimator_order);
+      * the fixed-step methods against their textbook formulas on a nonlinear system.
+    What stays unpinned is torchdiffeq's own: its error coefficients (c_error ends in -1/60 where Dormand-Prince's embedded
+    pair has -1/40 -- restated as torchdiffeq has them), its step-size controller and its quartic dense output."""
+    from scipy.integrate._ivp import rk as srk
+    from scipy.integrate._ivp.common import select_initial_step
+    rng = np.random.RandomState(5)
+    M = rng.standard_normal((6, 6)) * 0.4
+
+    def f_np(t, y):
+        return np.tanh(M @ y) + np.sin(3.0 * t) * 0.3
+
+    def f_t(t, ys):
+        (y,) = ys
+        return (torch.tanh(torch.from_numpy(M) @ y) + torch.sin(3.0 * t) * 0.3,)
+
+    y0 = rng.standard_normal(6)
+    t0, h = 0.3, 0.17
+    K = np.empty((srk.RK45.n_stages + 1, 6))
+    y_new, f_new = srk.rk_step(f_np, t0, y0, f_np(t0, y0), h, srk.RK45.A, srk.RK45.B, srk.RK45.C, K)
+    ty0 = (torch.from_numpy(y0),)
+    tt0, th = torch.tensor(t0, dtype=torch.float64), torch.tensor(h, dtype=torch.float64)
+    y1, f1, err, k = odeint._dp_step(f_t, ty0, f_t(tt0, ty0), tt0, th)
+    np.testing.assert_allclose(y1[0].numpy(), y_new, rtol=0, atol=1e-14)
+    np.testing.assert_allclose(f1[0].numpy(), f_new, rtol=0, atol=1e-14)
+    np.testing.assert_allclose(torch.stack(k[0]).numpy(), K, rtol=0, atol=1e-14)
+    # torchdiffeq's error combination differs from Dormand-Prince's embedded pair only in its coefficients: same stages
+    np.testing.assert_allclose(err[0].numpy(), h * (np.array(odeint._DP_CERR) @ K), rtol=0, atol=1e-15)
+    assert abs(odeint._DP_CERR[-1] + 1.0 / 60.0) < 1e-15 and abs(srk.RK45.E[-1] - 1.0 / 40.0) < 1e-15
+
+    for rtol, atol in ((1e-5, 1e-5), (1e-7, 1e-9)):
+        want = select_initial_step(f_np, t0, y0, 1e9, np.inf, f_np(t0, y0), 1.0, 4, rtol, atol)
+        got = odeint._initial_step(f_t, tt0, ty0, 4, (rtol,), (atol,), f_t(tt0, ty0))
+        assert abs(float(got) - want) <= 1e-12 * want, (float(got), want)
+
+    # fixed-step methods: increments against the textbook formulas (Kutta's 3/8 rule, explicit midpoint, Euler)
+    k1 = f_np(t0, y0)
+    k2 = f_np(t0 + h / 3, y0 + h * k1 / 3)
+    k3 = f_np(t0 + 2 * h / 3, y0 + h * (-k1 / 3 + k2))
+    k4 = f_np(t0 + h, y0 + h * (k1 - k2 + k3))
+    np.testing.assert_allclose(odeint._rk4_38_step(f_t, tt0, th, ty0)[0].numpy(), h * (k1 + 3 * k2 + 3 * k3 + k4) / 8, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(odeint._midpoint_step(f_t, tt0, th, ty0)[0].numpy(), h * f_np(t0 + h / 2, y0 + h * k1 / 2), rtol=0, atol=1e-15)
+    np.testing.assert_allclose(odeint._euler_step(f_t, tt0, th, ty0)[0].numpy(), h * k1, rtol=0, atol=1e-15)
+
+
 def test_gat_matches_reference():
     g = G.load("gat_golden")
     c = G.load("planetoid_cora")
