@@ -100,3 +100,34 @@ def test_tile_schedule_is_a_merge_of_tiles_and_hub_chunk_groups():
         tile = int(heavy[hub]) // 32
         assert pos[tile] < pos[-(g + 1)] and (tile + 1 == n_tiles or pos[-(g + 1)] < pos[tile + 1])
     assert ops.tile_schedule(n_rows, None, None, 0, 0) is None
+
+
+def test_row_stochastic_detection_decides_the_pattern_only_transpose():
+    """ops.GraphPlan.row_stochastic_scale: the adjoint may gather A_hat^T gP on the 0/1 pattern (and take the bias gradient from
+    the column sums of the result) only when every row of A_hat is constant AND sums to one -- an empty row, or a scaled matrix,
+    must keep the values (index / float work on CPU tensors through an uninitialised plan object)."""
+    import numpy as np
+    import torch
+    from graph_odenet_b200 import ops
+
+    def plan(rowptr, row_vals):
+        p = object.__new__(ops.GraphPlan)
+        p.n_rows = len(rowptr) - 1
+        p.rowptr = torch.tensor(rowptr, dtype=torch.int32)
+        p.row_vals = None if row_vals is None else torch.tensor(row_vals, dtype=torch.float32)
+        return p
+
+    third = float(np.float32(1.0 / 3.0))
+    ok = plan([0, 2, 3, 6], [0.5, 1.0, third])
+    assert ok.row_stochastic_scale() is ok.row_vals
+    assert plan([0, 2, 3, 6], [0.5, 1.0, 0.25]).row_stochastic_scale() is None          # a row that sums to 0.75
+    assert plan([0, 2, 2, 5], [0.5, 0.0, third]).row_stochastic_scale() is None         # an empty row
+    assert plan([0, 2, 3, 6], [0.25, 0.5, third / 2]).row_stochastic_scale() is None    # 0.5 * A_hat
+    assert plan([0, 2, 3, 6], None).row_stochastic_scale() is None                      # not row-constant
+    # degrees up to 100 000: fp32(1 / deg) * deg stays within the 1e-6 window
+    deg = torch.tensor([1, 2, 3, 7, 1000, 99_991, 100_000])
+    big = object.__new__(ops.GraphPlan)
+    big.n_rows = deg.numel()
+    big.rowptr = torch.cat([torch.zeros(1, dtype=torch.int64), deg.cumsum(0)]).to(torch.int32)
+    big.row_vals = (1.0 / deg.double()).float()
+    assert big.row_stochastic_scale() is big.row_vals
