@@ -105,6 +105,7 @@ class ExchangeProtocol:
         self.pool = SlotPool(n_slots)
         self.track = HazardTracker()
         self.done = set()                      # epochs whose own push (side stream) no consumer has waited for yet
+        self.own_side = {}                     # slot -> epoch of this rank's last side-stream push into it (while in ``done``)
 
     # primitives ---------------------------------------------------------------------------------------------------
     def _slot(self, buf):
@@ -141,6 +142,14 @@ class ExchangeProtocol:
         single gP buffer makes the rule act, through tests/test_peer_protocol_cpu.py; stamping at the wait in front of the
         call let a faster rank overwrite the support a slower rank was still gathering from)."""
         for b in (buf,) + tuple(also):
+            # write-after-write inside this rank: an earlier push of OURS into the same slot may still be running on the side
+            # stream (the buffer was re-produced, or released and its slot re-allocated, without a wait in between); a fused
+            # producer stores from the consumer stream, so that stream first waits for the old push (found by
+            # tests/test_peer_protocol_cpu.py::test_random_api_programs_are_safe)
+            e_own = self.own_side.pop(self._slot(b), None)
+            if e_own is not None and e_own in self.done:
+                self._emit_wait_done(e_own)
+                self.done.discard(e_own)
             n_empty, wait_epoch = self.track.before_push(self._slot(b))
             if n_empty:
                 if self.side:
@@ -161,6 +170,7 @@ class ExchangeProtocol:
         if self.side:
             self._emit_done(epoch)
             self.done.add(epoch)
+            self.own_side[slot] = epoch
         return epoch
 
     def finish(self, epoch):
@@ -186,6 +196,7 @@ class ExchangeProtocol:
             self._emit_push_part(epoch, halo, buf, slot, c, n_parts)
         self._emit_done(epoch)
         self.done.add(epoch)
+        self.own_side[slot] = epoch
         return epoch
 
     def wait(self, epoch):
