@@ -443,7 +443,7 @@ def _random_program(rng, side, n_ops, n_slots=6):
             proto.wait(e)
 
     for _ in range(n_ops):
-        op = rng.choice(["new", "push", "fused", "gather", "gather", "free"])
+        op = rng.choice(["new", "push", "fused", "gather", "gather", "free"] + (["pipe"] if side else []))
         if op == "new" and len(live) < n_slots - 1:
             live.append(proto.new(1))
         elif op == "push" and live:
@@ -463,6 +463,19 @@ def _random_program(rng, side, n_ops, n_slots=6):
             e = proto.finish(epoch)
             for b in outs:
                 pending[id(b)] = e
+        elif op == "pipe" and live:                         # an exchange in row chunks: chunk c produced (gathering) on the
+            b = rng.choice(live)                            # consumer stream, pushed on the side stream underneath chunk c + 1
+            reads = [x for x in live if x is not b and x.version > 0 and rng.random() < 0.5]
+            for r in reads:
+                await_(r)
+
+            def produce(c, reads=reads):
+                for r_ in reads:
+                    prog.append(("main", "gather_begin", r_.slot, r_.version))
+                    prog.append(("main", "gather_end", r_.slot, r_.version))
+
+            pending[id(b)] = proto.push_pipelined(object(), b, rng.randint(1, 3), produce, reads=reads)
+            produce = None
         elif op == "gather" and live:
             b = rng.choice(live)
             if b.version == 0:
