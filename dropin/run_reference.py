@@ -4,6 +4,7 @@
     cd /path/to/graph-odenet            # the reference's checkout: its scripts read ./data
     python /path/to/repo/dropin/run_reference.py GCN/train_res.py --model ode3 --dataset cora
     python /path/to/repo/dropin/run_reference.py --keep-models GCN/train_res.py --model ode3   # reference models.py + our layers + solver
+    python /path/to/repo/dropin/run_reference.py prototypes/orbit/train_IN.py ...              # ``from model import IN, IN_ODE`` -> dropin/orbit
 
 The reference imports its siblings by bare name (``import models``, ``from utils import ...``, ``from layers import ...``).
 Running ``python GCN/train_res.py`` puts the script's directory first on sys.path, so PYTHONPATH cannot override them
@@ -32,7 +33,7 @@ def main(argv):
     family = os.path.basename(os.path.dirname(script))
     shim_dir = os.path.join(HERE, family)
     if not os.path.isdir(shim_dir):
-        sys.exit("no drop-in for %r (have GCN, GAT, QC)" % family)
+        sys.exit("no drop-in for %r (have GCN, GAT, QC, orbit)" % family)
     sys.path.insert(0, HERE)                      # torchdiffeq stand-in
     if keep_models:
         # the reference's own models.py, found by bare name AFTER the shims for everything else
@@ -44,6 +45,9 @@ def main(argv):
         spec.loader.exec_module(mod)
     else:
         sys.path.insert(0, shim_dir)
+    # the script's own directory LAST: siblings the drop-in does not replace (prototypes/orbit/prepare_dataset.py ...) still
+    # resolve, as they do under ``python script.py``, but never ahead of a shim
+    sys.path.append(os.path.dirname(script))
     sys.argv = [script] + argv[1:]
     runpy.run_path(script, run_name="__main__")
 

@@ -48,6 +48,26 @@ def test_shim_modules_export_what_the_reference_imports():
         assert r.returncode == 0 and "dropin" in r.stdout, r.stderr[-2000:]
 
 
+def test_orbit_script_resolves_model_to_the_dropin(tmp_path):
+    """``prototypes/orbit/train_IN.py:16`` does ``from model import IN, IN_ODE`` next to imports of its own siblings
+    (``prepare_dataset``): through the launcher ``model`` is the drop-in and a sibling of the script still resolves.  (The
+    reference's trainer itself needs ``fire`` and a generated dataset, neither of which exists here; a probe with the same
+    imports stands in.  Construction and state_dict need no GPU.)"""
+    d = tmp_path / "orbit"
+    d.mkdir()
+    (d / "prepare_dataset.py").write_text("def get_epoch():\n    return 'sibling'\n")
+    (d / "probe.py").write_text(
+        "from prepare_dataset import get_epoch\n"
+        "import model\n"
+        "from model import IN, IN_ODE\n"
+        "net, ode = IN(5, 0, 0, 2), IN_ODE(5, 0, 0, 2)\n"
+        "assert 'fR.mlp.0.weight' in net.state_dict() and 'odefunc.fO.output_linear.bias' in ode.state_dict()\n"
+        "print('PROBE OK', get_epoch(), model.__file__)\n")
+    r = subprocess.run([sys.executable, LAUNCH, str(d / "probe.py")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "PROBE OK sibling" in r.stdout and os.path.join("dropin", "orbit", "model.py") in r.stdout
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("keep", [False])
 def test_bare_name_script_trains_on_the_dropin(keep):
