@@ -52,6 +52,18 @@ class MLP(nn.Module):
         return self.output_linear(x)
 
 
+# layer widths of the two learned functions (model.py:55-63,83-96,143-151: the same numbers in all three classes)
+_RELATION_HIDDEN = 4 * [150]     # fR: relation model, four hidden layers
+_EFFECT_WIDTH = 50               # d_E
+_OBJECT_HIDDEN = 1 * [100]       # fO: object model, one hidden layer
+
+
+def _learned_functions(relation_in, external_in, d_P):
+    """(fR, fO) = (MLP(relation_in -> 150 x4 -> d_E), MLP(d_E + external_in -> 100 -> d_P))"""
+    return (MLP(relation_in, list(_RELATION_HIDDEN), _EFFECT_WIDTH),
+            MLP(_EFFECT_WIDTH + external_in, list(_OBJECT_HIDDEN), d_P))
+
+
 def _plans(Msrc, Mtgt):
     return ops.plan_for(Msrc), ops.plan_for(Mtgt)
 
@@ -66,10 +78,7 @@ class IN(nn.Module):
 
     def __init__(self, d_O, d_R, d_X, d_P):
         super().__init__()
-        E_num_hidden_layers, d_E_hidden, d_E = 4, 150, 50
-        P_num_hidden_layers, d_P_hidden = 1, 100
-        self.fR = MLP(d_R + 2 * d_O, E_num_hidden_layers * [d_E_hidden], d_E)
-        self.fO = MLP(d_E + d_X, P_num_hidden_layers * [d_P_hidden], d_P)
+        self.fR, self.fO = _learned_functions(d_R + 2 * d_O, d_X, d_P)
 
     def forward(self, O, R, X, Msrc, Mtgt):
         psrc, ptgt = _plans(Msrc, Mtgt)
@@ -87,12 +96,8 @@ class IN_ODEfunc(nn.Module):
 
     def __init__(self, d_O, d_R, d_X, d_P):
         super().__init__()
-        E_num_hidden_layers, d_E_hidden, d_E = 4, 150, 50
-        P_num_hidden_layers, d_P_hidden = 1, 100
-        d_X = 0
-        d_R = 0
-        self.fR = MLP(d_R + 2 * d_O + 1, E_num_hidden_layers * [d_E_hidden], d_E)
-        self.fO = MLP(d_E + d_X, P_num_hidden_layers * [d_P_hidden], d_P)
+        # the ODE function takes neither relation nor external inputs (d_R = d_X = 0 whatever is passed); + 1 = the time column
+        self.fR, self.fO = _learned_functions(2 * d_O + 1, 0, d_P)
         self.nfe = 0
 
     def set_fixed(self, Otail, Msrc, Mtgt):
@@ -115,10 +120,7 @@ class IN_ODE(nn.Module):
 
     def __init__(self, d_O, d_R, d_X, d_P, tol=1e-5, method=None, options=None):
         super().__init__()
-        E_num_hidden_layers, d_E_hidden, d_E = 4, 150, 50
-        P_num_hidden_layers, d_P_hidden = 1, 100
-        self.fR = MLP(d_R + 2 * d_O, E_num_hidden_layers * [d_E_hidden], d_E)
-        self.fO = MLP(d_E + d_X, P_num_hidden_layers * [d_P_hidden], d_P)
+        self.fR, self.fO = _learned_functions(d_R + 2 * d_O, d_X, d_P)
         self.odefunc = IN_ODEfunc(d_O, d_R, d_X, d_P)
         self.integration_time = torch.tensor([0, 1]).float()
         self.tol = tol
