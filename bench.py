@@ -513,7 +513,13 @@ def run_ours(a):
     roofline = {"bound": "hbm", "kernel": "k_spmm_t2<32,8> (A_hat*S gather + bias + relu + RK combine)%s" % (
                     "" if world == 1 else " on rank 0's row block"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": traffic, "algorithmic_bytes_per_launch": b_compulsory, "ms_per_launch": agg["ms_avg"],
+                "traffic": traffic,
+                "traffic_note": None if traffic is None else (
+                    "ncu dram__bytes_read + dram__bytes_write, average of five consecutive launches of one step (profiles/traffic.json): "
+                    "25.4 GB for the bare gather incl. hub rows (2.15x the compulsory bytes: the non-local 10 % of the entries and "
+                    "the hubs' bands miss L2) + 5.1 GB per [N,d] operand of the fused Runge-Kutta / adjoint epilogue, which the "
+                    "compulsory count of SURVEY 8d leaves out (with_fused_epilogue_operands counts them)"),
+                "algorithmic_bytes_per_launch": b_compulsory, "ms_per_launch": agg["ms_avg"],
                 "launches_timed": agg["launches"], "peak_source": peak_src,
                 "model": "SURVEY 8d compulsory bytes per function evaluation: nnz*8 + (N+1)*4 + 2*N*d*4",
                 "with_fused_epilogue_operands": {
